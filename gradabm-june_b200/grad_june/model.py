@@ -1,0 +1,107 @@
+"""One simulation timestep (reference: grad_june/model.py).
+
+``GradJune.forward(data, timer)`` keeps the reference's contract — it returns the same ``data`` object
+with ``transmission``, ``susceptibility``, ``is_infected``, ``infection_time`` and the symptoms dict
+replaced by new (differentiable) tensors — but runs the whole step (transmission update, infection
+networks under the active policies, Gumbel-softmax draw, state update, symptoms) as one fused
+forward of ``gj_step_forward`` with a hand-written backward, instead of ~430 torch ops.
+"""
+import torch
+import yaml
+
+from . import ops
+from .infection import IsInfectedSampler
+from .infection_networks import InfectionNetworks
+from .infection_networks.base import _quarantine_thresholds, beta_vector, leisure_table
+from .paths import ensure_default_config
+from .policies import Policies
+from .symptoms import SymptomsUpdater
+from .transmission import TransmissionUpdater, profile_tensors
+from .world import get_device_world
+
+
+class GradJune(torch.nn.Module):
+    def __init__(self, symptoms_updater=None, policies=None, infection_networks=None, device="cpu"):
+        super().__init__()
+        self.symptoms_updater = SymptomsUpdater.from_file() if symptoms_updater is None else symptoms_updater
+        self.policies = Policies.from_file() if policies is None else policies
+        self.infection_networks = InfectionNetworks.from_file() if infection_networks is None else infection_networks
+        self.transmission_updater = TransmissionUpdater()
+        self.is_infected_sampler = IsInfectedSampler()
+        self.device = device
+
+    @classmethod
+    def from_file(cls, fpath=None):
+        with open(fpath or ensure_default_config(), "r") as f:
+            return cls.from_parameters(yaml.safe_load(f))
+
+    @classmethod
+    def from_parameters(cls, params):
+        return cls(
+            symptoms_updater=SymptomsUpdater.from_parameters(params),
+            policies=Policies.from_parameters(params),
+            infection_networks=InfectionNetworks.from_parameters(params),
+            device=params["system"]["device"],
+        )
+
+    def infect_people(self, data, timer, new_infected):
+        """model.py:90-110 (maximum variant: the gradient splits 1/2-1/2 where s - n == 0)."""
+        agent = data["agent"]
+        agent.susceptibility = torch.maximum(torch.tensor(0.0, device=agent.susceptibility.device),
+                                             agent.susceptibility - new_infected)
+        agent.is_infected = agent.is_infected + new_infected
+        agent.infection_time = agent.infection_time + new_infected * (timer.now - agent.infection_time)
+
+    # ------------------------------------------------------------------------------------------
+    def _static(self, data, device):
+        world = get_device_world(data, device)
+        maxinf, shape, rate, shift, k0 = profile_tensors(data)
+        table, rows = leisure_table(list(self.infection_networks.networks.values()), device)
+        cache = data.__dict__.setdefault("_gj_cache", {})
+        key = ("static", id(world), id(k0), id(self.symptoms_updater.symptoms_sampler.stage_transition_probabilities))
+        hit = cache.get("static")
+        if hit is None or hit[0] != key:
+            static = ops.StepStatic(world=world, maxinf=maxinf, shape=shape, rate=rate, shift=shift, k0=k0,
+                                    leisure_prob=table,
+                                    symptoms=self.symptoms_updater.symptoms_sampler.tables(device))
+            cache["static"] = hit = (key, static, rows)
+        return hit[1], hit[2]
+
+    def step(self, data, timer, age_bins=None, mode=ops.MODE_STEP, seed_fraction=None, noise=None):
+        """Fused step; returns (data, reductions) where reductions = [cases, deaths, cases by age bin...]
+        (None unless ``age_bins`` is given)."""
+        agent = data["agent"]
+        ops.require_cuda(agent.susceptibility, "data['agent'].susceptibility")
+        dev = agent.susceptibility.device
+        static, rows = self._static(data, dev)
+        policies = self.policies
+        if mode == ops.MODE_SEED:
+            nets, phases = [], ops.PHASE_SAMPLE | ops.PHASE_INFECT | ops.PHASE_SYMPTOMS
+        else:
+            nets, phases = self.infection_networks.active_networks(timer, policies), ops.PHASE_ALL
+        spec = ops.StepSpec(
+            now=timer.now, dt=timer.duration, day_type=0 if timer.day_type == "weekday" else 1,
+            nets=[net.net_spec(rows.get(id(net), -1)) for net in nets],
+            quarantine=_quarantine_thresholds(policies, timer), phases=phases, mode=mode,
+            age_bins=tuple(int(b) for b in age_bins) if age_bins is not None else (),
+            want_reductions=age_bins is not None)
+        sym = agent["symptoms"]
+        state = {"s": agent.susceptibility, "inf": agent.is_infected, "tinf": agent.infection_time,
+                 "cur": sym["current_stage"], "nxt": sym["next_stage"], "ttn": sym["time_to_next_stage"]}
+        beta = beta_vector(nets, policies, timer, dev) if nets else None
+        out = ops.infection_step(static, spec, beta, state, seed_fraction=seed_fraction, noise=noise)
+        if out["T"] is not None:
+            agent.transmission = out["T"]
+        agent.susceptibility = out["s"]
+        agent.is_infected = out["inf"]
+        agent.infection_time = out["tinf"]
+        sym["current_stage"] = out["cur"]
+        sym["next_stage"] = out["nxt"]
+        sym["time_to_next_stage"] = out["ttn"]
+        data["agent"]["new_infected"] = out["n"]
+        if out["q"] is not None:
+            data["agent"]["not_infected_probs"] = out["q"]
+        return data, out["red"]
+
+    def forward(self, data, timer):
+        return self.step(data, timer)[0]

@@ -1,0 +1,476 @@
+"""Autograd operators over the C ABI (``include/gradjune_b200.h``).
+
+``infection_step`` is the fused timestep (GradJune.forward, model.py:112-144); the stand-alone module
+classes call the same entry point with a sub-set of phases.  All tensors must live on a CUDA device;
+there is no CPU fallback.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import (KIND_CARE_VISIT, KIND_HOUSEHOLD, KIND_LEISURE, KIND_PLAIN, MODE_SEED, MODE_STEP, PHASE_ALL,
+                   PHASE_INFECT, PHASE_NETWORKS, PHASE_SAMPLE, PHASE_SYMPTOMS)
+from .world import DeviceWorld
+
+TAU = 0.1
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise _lib.GradJuneLibraryError(
+            f"{what} lives on {t.device}: the infection step runs only as CUDA kernels on a B200 "
+            "(there is no CPU fallback); move the world to a cuda device (system.device: cuda:0)."
+        )
+
+
+def _f32(t: Optional[torch.Tensor], device=None):
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous() or (device is not None and t.device != device):
+        t = t.to(device=device or t.device, dtype=torch.float32).contiguous()
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+# --------------------------------------------------------------------------------------
+# noise control
+# --------------------------------------------------------------------------------------
+class NoiseSource:
+    """Where the step's random draws come from.
+
+    Default: counter-based Philox inside the kernels; each call takes a fresh 62-bit key from
+    torch's CPU generator, so ``torch.manual_seed`` makes runs reproducible like the reference.
+    ``inject`` replaces it by explicit arrays (parity tests): a callable ``call_index -> (E, u, z)``.
+    """
+
+    def __init__(self):
+        self.injected = None
+        self.fixed_seed = None
+        self.calls = 0
+
+    def next(self, n_agents, device):
+        """-> (seed, call_index, E, u, z)"""
+        c = self.calls
+        self.calls += 1
+        if self.injected is not None:
+            E, u, z = self.injected(c)
+            return 0, c, _f32(torch.as_tensor(E), device), _f32(torch.as_tensor(u), device), _f32(torch.as_tensor(z), device)
+        if self.fixed_seed is not None:
+            return int(self.fixed_seed), c, None, None, None
+        seed = int(torch.randint(0, 2**62, (1,)).item())
+        return seed, 0, None, None, None
+
+
+NOISE = NoiseSource()
+
+
+class inject_noise:
+    """``with inject_noise(lambda c: (E, u, z)):`` — feed explicit noise arrays to every sampler /
+    symptoms call inside the block; call c = 0, 1, 2, ... in call order."""
+
+    def __init__(self, provider):
+        self.provider = provider
+
+    def __enter__(self):
+        self._saved = (NOISE.injected, NOISE.calls)
+        NOISE.injected, NOISE.calls = self.provider, 0
+        return NOISE
+
+    def __exit__(self, *exc):
+        NOISE.injected, NOISE.calls = self._saved
+
+
+class philox_seed:
+    """``with philox_seed(1234):`` — fixed Philox key, call_index counts calls inside the block."""
+
+    def __init__(self, seed):
+        self.seed = seed
+
+    def __enter__(self):
+        self._saved = (NOISE.fixed_seed, NOISE.calls)
+        NOISE.fixed_seed, NOISE.calls = self.seed, 0
+        return NOISE
+
+    def __exit__(self, *exc):
+        NOISE.fixed_seed, NOISE.calls = self._saved
+
+
+def philox_fill(seed: int, call_index: int, n: int, device):
+    """The exact (E[2,N], u[N], z[N]) draws the kernels make for (seed, call_index)."""
+    E = torch.empty(2, n, device=device)
+    u = torch.empty(n, device=device)
+    z = torch.empty(n, device=device)
+    _lib.check(_lib.lib().gj_philox_fill(seed, call_index, n, E.data_ptr(), u.data_ptr(), z.data_ptr(), _stream(E.device)),
+               "gj_philox_fill")
+    return E, u, z
+
+
+# --------------------------------------------------------------------------------------
+# step description
+# --------------------------------------------------------------------------------------
+@dataclass
+class NetSpec:
+    name: str
+    edge_type: str
+    kind: int
+    prob_row: int = -1
+
+
+@dataclass
+class SymptomsTables:
+    n_stages: int
+    stage_prob: torch.Tensor                  # [S, 100] device
+    trans: Dict[int, Optional[tuple]]         # i -> (kind, loc, scale) | None
+    rec: Dict[int, Optional[tuple]]
+
+
+@dataclass
+class StepSpec:
+    now: float
+    dt: float
+    day_type: int
+    nets: List[NetSpec]
+    quarantine: Optional[Sequence[float]]     # None / thresholds of the active policies
+    phases: int = PHASE_ALL
+    mode: int = MODE_STEP
+    age_bins: Sequence[int] = ()
+    want_reductions: bool = True
+    want_lam: bool = False
+
+
+def _scratch(world: DeviceWorld):
+    sc = getattr(world, "_scratch", None)
+    if sc is None:
+        nbytes = _lib.lib().gj_scratch_bytes(C.byref(world.desc()))
+        sc = torch.zeros(nbytes, dtype=torch.uint8, device=world.device)
+        world._scratch = sc
+    return sc
+
+
+def _buffer(world: DeviceWorld, name: str, n: int):
+    """Reusable per-world workspace (transient between the launches of one call)."""
+    cache = world.__dict__.setdefault("_buffers", {})
+    t = cache.get(name)
+    if t is None or t.numel() < n:
+        t = torch.empty(max(n, 1), dtype=torch.float32, device=world.device)
+        cache[name] = t
+    return t
+
+
+def _fill_params(world: DeviceWorld, spec: StepSpec, sym: Optional[SymptomsTables], seed: int, call_index: int):
+    p = _lib.StepParams()
+    p.mode, p.phases = spec.mode, spec.phases
+    p.now, p.dt, p.day_type = float(spec.now), float(spec.dt), int(spec.day_type)
+    if len(spec.nets) > _lib.GJ_MAX_NETS:
+        raise ValueError(f"at most {_lib.GJ_MAX_NETS} networks per step")
+    p.n_nets = len(spec.nets)
+    off = 0
+    for k, net in enumerate(spec.nets):
+        ti = world.types.index(net.edge_type)
+        p.nets[k].type, p.nets[k].kind, p.nets[k].prob_row, p.nets[k].s_off = ti, net.kind, net.prob_row, off
+        off += world.type_group_off[ti + 1] - world.type_group_off[ti]
+    if off >= (1 << 31):
+        raise ValueError("group-sum buffer too large")
+    if spec.quarantine is None:
+        p.n_quar = -1
+    else:
+        if len(spec.quarantine) > _lib.GJ_MAX_QUAR:
+            raise ValueError(f"at most {_lib.GJ_MAX_QUAR} simultaneous quarantine policies")
+        p.n_quar = len(spec.quarantine)
+        for i, thr in enumerate(spec.quarantine):
+            p.quar_thr[i] = float(thr)
+    if sym is not None:
+        if sym.n_stages > _lib.GJ_MAX_STAGES:
+            raise ValueError("too many symptom stages")
+        p.n_stages = sym.n_stages
+        for i in range(_lib.GJ_MAX_STAGES):
+            for arr, table in ((p.trans_time, sym.trans), (p.rec_time, sym.rec)):
+                e = table.get(i)
+                if e is None:
+                    arr[i].kind = -1
+                else:
+                    arr[i].kind, arr[i].loc, arr[i].scale = int(e[0]), float(e[1]), float(e[2])
+    else:
+        p.n_stages = 8
+        for i in range(_lib.GJ_MAX_STAGES):
+            p.trans_time[i].kind = p.rec_time[i].kind = -1
+    bins = list(spec.age_bins)
+    if len(bins) - 1 > _lib.GJ_MAX_AGE_BINS:
+        raise ValueError("too many age bins")
+    p.n_age_bins = max(len(bins) - 1, 0)
+    for i, b in enumerate(bins):
+        p.age_bins[i] = int(b)
+    p.tau = TAU
+    p.seed, p.call_index = int(seed), int(call_index)
+    return p, off
+
+
+@dataclass
+class StepStatic:
+    """Per-world constants of the step: profile parameters and lookup tables (device tensors)."""
+    world: DeviceWorld
+    maxinf: Optional[torch.Tensor] = None
+    shape: Optional[torch.Tensor] = None
+    rate: Optional[torch.Tensor] = None
+    shift: Optional[torch.Tensor] = None
+    k0: Optional[torch.Tensor] = None
+    leisure_prob: Optional[torch.Tensor] = None   # [n_tables, 2, 2, 100]
+    symptoms: Optional[SymptomsTables] = None
+
+
+def profile_k0(shape: torch.Tensor) -> torch.Tensor:
+    require_cuda(shape, "infection_parameters['shape']")
+    shape = _f32(shape)
+    k0 = torch.empty_like(shape)
+    _lib.check(_lib.lib().gj_profile_prepare(shape.numel(), shape.data_ptr(), k0.data_ptr(), _stream(shape.device)),
+               "gj_profile_prepare")
+    return k0
+
+
+class _Transmission(torch.autograd.Function):
+    """TransmissionUpdater.forward (transmission.py:38-51) and its derivative."""
+
+    @staticmethod
+    def forward(ctx, now, tinf, inf, maxinf, shape, rate, shift, k0):
+        dev = tinf.device
+        tinf, inf = _f32(tinf), _f32(inf)
+        T = torch.empty_like(tinf)
+        _lib.check(_lib.lib().gj_transmission_forward(
+            tinf.numel(), float(now), tinf.data_ptr(), inf.data_ptr(), maxinf.data_ptr(), shape.data_ptr(),
+            rate.data_ptr(), shift.data_ptr(), k0.data_ptr(), T.data_ptr(), _stream(dev)), "gj_transmission_forward")
+        ctx.save_for_backward(tinf, inf, maxinf, shape, rate, shift, k0)
+        ctx.now = float(now)
+        return T
+
+    @staticmethod
+    def backward(ctx, gT):
+        tinf, inf, maxinf, shape, rate, shift, k0 = ctx.saved_tensors
+        gT = _f32(gT)
+        g_tinf = torch.empty_like(tinf)
+        g_inf = torch.empty_like(tinf)
+        _lib.check(_lib.lib().gj_transmission_backward(
+            tinf.numel(), ctx.now, tinf.data_ptr(), inf.data_ptr(), maxinf.data_ptr(), shape.data_ptr(),
+            rate.data_ptr(), shift.data_ptr(), k0.data_ptr(), gT.data_ptr(), g_tinf.data_ptr(), g_inf.data_ptr(),
+            _stream(tinf.device)), "gj_transmission_backward")
+        return None, g_tinf, g_inf, None, None, None, None, None
+
+
+def transmission(now, tinf, inf, maxinf, shape, rate, shift, k0=None):
+    for t, name in ((tinf, "infection_time"), (inf, "is_infected"), (shape, "infection_parameters")):
+        require_cuda(t, name)
+    maxinf, shape, rate, shift = _f32(maxinf), _f32(shape), _f32(rate), _f32(shift)
+    if k0 is None:
+        k0 = profile_k0(shape)
+    return _Transmission.apply(now, tinf, inf, maxinf, shape, rate, shift, k0)
+
+
+_STATE = ("s", "inf", "tinf", "cur", "nxt", "ttn")
+
+
+class _Step(torch.autograd.Function):
+    """gj_step_forward / gj_step_backward.
+
+    Differentiable inputs: beta[K], the six state tensors, T_in / q_in / n_in (stand-alone phases)
+    and the seeding fraction.  Outputs: six new state tensors, T, q, n, reductions.
+    """
+
+    @staticmethod
+    def forward(ctx, static: StepStatic, spec: StepSpec, noise, beta, s, inf, tinf, cur, nxt, ttn, T_in, q_in, n_in,
+                seed_fraction):
+        world = static.world
+        dev = world.device
+        N = world.n_agents
+        L = _lib.lib()
+        seed, call_index, E, u, z = noise
+        p, s_total = _fill_params(world, spec, static.symptoms, seed, call_index)
+        io = _lib.FwdIO()
+        keep = []
+
+        def put(name, t):
+            t = _f32(t, dev)
+            if t is not None:
+                keep.append(t)
+                setattr(io, name, t.data_ptr())
+            return t
+
+        phases, seed_mode = spec.phases, spec.mode == MODE_SEED
+        nets_on = bool(phases & PHASE_NETWORKS) and not seed_mode
+        beta = put("beta", beta) if nets_on else None
+        put("leisure_prob", static.leisure_prob)
+        if static.symptoms is not None:
+            put("stage_prob", static.symptoms.stage_prob)
+        seed_fraction = put("seed_fraction", seed_fraction) if seed_mode else None
+        put("inj_E", E), put("inj_u", u), put("inj_z", z)
+        st = {}
+        for name, t in zip(_STATE, (s, inf, tinf, cur, nxt, ttn)):
+            st[name] = put(name, t)
+        fused_T = nets_on and T_in is None
+        if fused_T:
+            for name in ("maxinf", "shape", "rate", "shift", "k0"):
+                put(name, getattr(static, name))
+        T_in, q_in, n_in = put("T_in", T_in), put("q_in", q_in), put("n_in", n_in)
+
+        def new(name):
+            t = torch.empty(N, dtype=torch.float32, device=dev)
+            setattr(io, name, t.data_ptr())
+            return t
+
+        out = {}
+        if phases & PHASE_INFECT:
+            for name in ("s_o", "inf_o", "tinf_o"):
+                out[name] = new(name)
+        if phases & PHASE_SYMPTOMS:
+            for name in ("cur_o", "nxt_o", "ttn_o"):
+                out[name] = new(name)
+        T = None
+        if fused_T:
+            T = new("T")
+            io.Tq = _buffer(world, "Tq", N).data_ptr() if p.n_quar > 0 else T.data_ptr()
+        elif nets_on and p.n_quar > 0:
+            io.Tq = _buffer(world, "Tq", N).data_ptr()
+        q = new("q") if nets_on else None
+        lam = new("lam") if (nets_on and spec.want_lam) else None
+        n = new("n") if (phases & PHASE_SAMPLE) else None
+        tape_v = new("tape_v") if nets_on else None
+        tape_y0 = new("tape_y0") if (phases & PHASE_SAMPLE) else None
+        S_un = None
+        if nets_on:
+            io.S_scaled = _buffer(world, "S_scaled", s_total).data_ptr()
+            S_un = torch.empty(max(s_total, 1), dtype=torch.float32, device=dev)
+            io.S_unscaled = S_un.data_ptr()
+        red = None
+        if spec.want_reductions:
+            red = torch.empty(2 + p.n_age_bins, dtype=torch.float32, device=dev)
+            io.red = red.data_ptr()
+        io.scratch = _scratch(world).data_ptr()
+        desc = world.desc()
+        _lib.check(L.gj_step_forward(C.byref(desc), C.byref(p), C.byref(io), _stream(dev)), "gj_step_forward")
+
+        ctx.static, ctx.spec, ctx.noise_key = static, spec, (seed, call_index)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(beta, st["s"], st["inf"], st["tinf"], st["cur"], st["nxt"], st["ttn"], T_in, q_in, n_in,
+                              seed_fraction, out.get("inf_o"), tape_v, tape_y0, S_un, E, u, z, q, n)
+        outs = (out.get("s_o"), out.get("inf_o"), out.get("tinf_o"), out.get("cur_o"), out.get("nxt_o"),
+                out.get("ttn_o"), T, q, n, red, lam)
+        nd = [t for t in (T,) if t is not None]
+        if (phases & PHASE_SAMPLE) and q is not None:
+            nd.append(q)   # fused: q is a by-product; its cotangent path runs through the sampler
+        if (phases & PHASE_INFECT) and n is not None:
+            nd.append(n)
+        ctx.mark_non_differentiable(*nd)
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_s_o, g_inf_o, g_tinf_o, g_cur_o, g_nxt_o, g_ttn_o, g_T, g_q, g_n, g_red, g_lam):
+        static, spec = ctx.static, ctx.spec
+        world = static.world
+        dev, N = world.device, world.n_agents
+        (beta, s, inf, tinf, cur, nxt, ttn, T_in, q_in, n_in, seed_fraction, inf_o, tape_v, tape_y0, S_un, E, u, z,
+         q_saved, n_saved) = ctx.saved_tensors
+        seed, call_index = ctx.noise_key
+        p, s_total = _fill_params(world, spec, static.symptoms, seed, call_index)
+        phases, seed_mode = spec.phases, spec.mode == MODE_SEED
+        nets_on = bool(phases & PHASE_NETWORKS) and not seed_mode
+        io = _lib.BwdIO()
+        keep = []
+
+        def put(name, t):
+            t = _f32(t, dev)
+            if t is not None:
+                keep.append(t)
+                setattr(io, name, t.data_ptr())
+            return t
+
+        put("beta", beta), put("leisure_prob", static.leisure_prob)
+        if static.symptoms is not None:
+            put("stage_prob", static.symptoms.stage_prob)
+        put("seed_fraction", seed_fraction)
+        put("inj_E", E), put("inj_u", u), put("inj_z", z)
+        for name, t in zip(_STATE, (s, inf, tinf, cur, nxt, ttn)):
+            put(name, t)
+        fused_T = nets_on and T_in is None
+        if fused_T:
+            for name in ("maxinf", "shape", "rate", "shift", "k0"):
+                put(name, getattr(static, name))
+        put("inf_o", inf_o)
+        if inf_o is None:
+            put("n_in", n_in if n_in is not None else n_saved)
+        put("T_in", T_in), put("q_in", q_in if q_in is not None else None)
+        put("tape_v", tape_v), put("tape_y0", tape_y0), put("S_unscaled", S_un)
+        for name, g in (("g_s_o", g_s_o), ("g_inf_o", g_inf_o), ("g_tinf_o", g_tinf_o), ("g_cur_o", g_cur_o),
+                        ("g_nxt_o", g_nxt_o), ("g_ttn_o", g_ttn_o), ("g_red", g_red)):
+            put(name, g)
+        if nets_on and not (phases & PHASE_SAMPLE):
+            put("g_q", g_q)
+        if nets_on:
+            put("g_lam", g_lam)
+        if (phases & PHASE_SAMPLE) and not (phases & PHASE_INFECT):
+            put("g_n", g_n)
+
+        need = ctx.needs_input_grad  # (static, spec, noise, beta, s, inf, tinf, cur, nxt, ttn, T_in, q_in, n_in, frac)
+
+        def new(name, n=N, zero=False):
+            t = (torch.zeros if zero else torch.empty)(n, dtype=torch.float32, device=dev)
+            setattr(io, name, t.data_ptr())
+            return t
+
+        grads = {}
+        for i, name in enumerate(_STATE):
+            src = (s, inf, tinf, cur, nxt, ttn)[i]
+            if src is not None and need[4 + i]:
+                grads[name] = new("g_" + name)
+        # the gather pass accumulates into g_inf / g_tinf, so they must exist when the fused networks ran
+        if fused_T:
+            for name in ("inf", "tinf"):
+                if name not in grads:
+                    grads[name] = new("g_" + name)
+        g_T_in = new("g_T") if (nets_on and T_in is not None and need[10]) else None
+        g_q_in = new("g_q_out") if (q_in is not None and need[11]) else None
+        g_n_in = new("g_n_out") if (n_in is not None and need[12]) else None
+        g_beta = new("g_beta", max(p.n_nets, 1), zero=True) if nets_on else None
+        g_frac = new("g_seed_fraction", 1, zero=True) if seed_mode else None
+        if nets_on:
+            io.w = _buffer(world, "w", N).data_ptr()
+            io.wq = _buffer(world, "wq", N).data_ptr() if p.n_quar > 0 else io.w
+            io.R = _buffer(world, "R", s_total).data_ptr()
+            io.cR = _buffer(world, "cR", s_total).data_ptr()
+        io.scratch = _scratch(world).data_ptr()
+        desc = world.desc()
+        _lib.check(_lib.lib().gj_step_backward(C.byref(desc), C.byref(p), C.byref(io), _stream(dev)), "gj_step_backward")
+        if g_beta is not None:
+            g_beta = g_beta[: p.n_nets]
+        return (None, None, None, g_beta if need[3] else None,
+                grads.get("s") if need[4] else None, grads.get("inf") if need[5] else None,
+                grads.get("tinf") if need[6] else None, grads.get("cur") if need[7] else None,
+                grads.get("nxt") if need[8] else None, grads.get("ttn") if need[9] else None,
+                g_T_in, g_q_in, g_n_in, g_frac if need[13] else None)
+
+
+def infection_step(static: StepStatic, spec: StepSpec, beta, state: dict, T_in=None, q_in=None, n_in=None,
+                   seed_fraction=None, noise=None):
+    """Run one (fused or partial) step.  ``state``: s, inf, tinf, cur, nxt, ttn (any may be None when
+    the phases do not need it).  Returns a dict with s, inf, tinf, cur, nxt, ttn, T, q, n, red."""
+    world = static.world
+    if world.device.type != "cuda":
+        raise _lib.GradJuneLibraryError(
+            "the infection step runs only as CUDA kernels on a B200 (no CPU fallback): world is on "
+            f"{world.device}; use system.device: cuda:0")
+    if noise is None:
+        if spec.phases & (PHASE_SAMPLE | PHASE_SYMPTOMS):
+            noise = NOISE.next(world.n_agents, world.device)
+        else:
+            noise = (0, 0, None, None, None)
+    outs = _Step.apply(static, spec, noise, beta, state.get("s"), state.get("inf"), state.get("tinf"),
+                       state.get("cur"), state.get("nxt"), state.get("ttn"), T_in, q_in, n_in, seed_fraction)
+    names = ("s", "inf", "tinf", "cur", "nxt", "ttn", "T", "q", "n", "red", "lam")
+    return dict(zip(names, outs))

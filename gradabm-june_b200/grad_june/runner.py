@@ -1,0 +1,174 @@
+"""Simulation driver (reference: grad_june/runner.py).
+
+Builds model, world and timer from the YAML parameters, keeps a backup of the initial state so that
+``runner()`` can be re-run for every calibration iteration, seeds the initial cases and loops the
+fused step.  The per-step result reductions (cases, differentiable deaths, cases by age bin —
+runner.py:167-171,198-224) are produced inside the step kernel, so the loop issues no extra passes
+over the agents.
+"""
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import torch
+import yaml
+
+from . import ops
+from .model import GradJune
+from .paths import ensure_default_config
+from .timer import Timer
+from .transmission import PROFILE_KEYS, TransmissionSampler
+from .utils import read_path
+from .world import load_world
+
+_STATE_KEYS = ("susceptibility", "is_infected", "infection_time", "transmission")
+_SYMPTOM_KEYS = ("current_stage", "next_stage", "time_to_next_stage")
+
+
+class Runner(torch.nn.Module):
+    def __init__(self, model, data, timer, log_fraction_initial_cases, save_path, parameters,
+                 age_bins=(0, 18, 65, 100)):
+        super().__init__()
+        self.model = model
+        self.data = data
+        self.data_backup = self.backup_infection_data(data)
+        self.timer = timer
+        self.log_fraction_initial_cases = log_fraction_initial_cases
+        self.device = model.device
+        self.age_bins = torch.tensor(age_bins, device=self.device)
+        self._age_bins_host = tuple(int(b) for b in age_bins)
+        self.ethnicities = np.sort(np.unique(data["agent"].ethnicity))
+        self.n_agents = data["agent"].id.shape[0]
+        self.population_by_age = self.get_people_by_age()
+        self.save_path = Path(save_path)
+        self.input_parameters = parameters
+        self.restore_initial_data()
+
+    @classmethod
+    def from_file(cls, fpath=None):
+        with open(fpath or ensure_default_config(), "r") as f:
+            return cls.from_parameters(yaml.safe_load(f))
+
+    @classmethod
+    def from_parameters(cls, params):
+        return cls(
+            model=GradJune.from_parameters(params),
+            data=cls.get_data(params),
+            timer=Timer.from_parameters(params),
+            log_fraction_initial_cases=params["infection_seed"]["log_fraction_initial_cases"],
+            save_path=params["save_path"],
+            parameters=params,
+            age_bins=params.get("age_bins_to_save", (0, 18, 65, 100)),
+        )
+
+    @staticmethod
+    def get_data(params, data=None):
+        """World + freshly sampled per-agent profile parameters + initial state (runner.py:65-91).
+        ``data`` may be passed directly instead of ``params['data_path']`` (synthetic worlds)."""
+        device = params["system"]["device"]
+        if data is None:
+            data = load_world(read_path(params["data_path"]))
+        data = data.to(device)
+        n_agents = len(data["agent"]["id"])
+        values = TransmissionSampler.from_parameters(params)(n_agents)
+        data["agent"].infection_parameters = {key: values[i, :] for i, key in enumerate(PROFILE_KEYS)}
+        data["agent"].transmission = torch.zeros(n_agents, device=device)
+        data["agent"].susceptibility = torch.ones(n_agents, device=device)
+        data["agent"].is_infected = torch.zeros(n_agents, device=device)
+        data["agent"].infection_time = torch.zeros(n_agents, device=device)
+        data["agent"].symptoms = {
+            "current_stage": torch.ones(n_agents, dtype=torch.long, device=device),
+            "next_stage": torch.ones(n_agents, dtype=torch.long, device=device),
+            "time_to_next_stage": torch.zeros(n_agents, device=device),
+        }
+        return data
+
+    def backup_infection_data(self, data):
+        agent = data["agent"]
+        backup = {key: agent[key].detach().clone() for key in _STATE_KEYS}
+        backup["symptoms"] = {key: agent["symptoms"][key].detach().clone() for key in _SYMPTOM_KEYS}
+        return backup
+
+    def restore_initial_data(self):
+        agent = self.data["agent"]
+        for key in _STATE_KEYS:
+            agent[key] = self.data_backup[key].detach().clone()
+        for key in _SYMPTOM_KEYS:
+            agent.symptoms[key] = self.data_backup["symptoms"][key].detach().clone()
+        self.data["results"] = {"deaths_per_timestep": None}
+
+    def _fraction_tensor(self):
+        fraction = 10.0 ** self.log_fraction_initial_cases
+        if not torch.is_tensor(fraction):
+            fraction = torch.tensor(float(fraction))
+        return fraction.reshape(1).to(device=self.data["agent"].susceptibility.device, dtype=torch.float32)
+
+    def set_initial_cases(self):
+        """infect_fraction_of_people + first symptoms update (runner.py:138-149) as one fused call."""
+        _, red = self.model.step(self.data, self.timer, age_bins=self._age_bins_host, mode=ops.MODE_SEED,
+                                 seed_fraction=self._fraction_tensor())
+        return red
+
+    def forward(self):
+        timer, model, data = self.timer, self.model, self.data
+        timer.reset()
+        self.restore_initial_data()
+        reds = [self.set_initial_cases()]
+        dates = [timer.date]
+        while timer.date < timer.final_date:
+            next(timer)
+            data, red = model.step(data, timer, age_bins=self._age_bins_host)
+            reds.append(red)
+            dates.append(timer.date)
+        table = torch.stack(reds)                      # [T+1, 2 + n_bins]
+        cases_per_timestep = table[:, 0]
+        data["results"]["deaths_per_timestep"] = table[:, 1]
+        results = {
+            "dates": dates,
+            "cases_per_timestep": cases_per_timestep,
+            "daily_cases_per_timestep": torch.diff(
+                cases_per_timestep, prepend=torch.tensor([0.0], device=cases_per_timestep.device)),
+            "deaths_per_timestep": data["results"]["deaths_per_timestep"],
+        }
+        for i, key in enumerate(self._age_bins_host[1:]):
+            results[f"cases_by_age_{key:02d}"] = table[:, 2 + i]
+        return results, data["agent"].is_infected
+
+    def save_results(self, results, is_infected):
+        self.save_path.mkdir(exist_ok=True, parents=True)
+        df = pd.DataFrame(index=results["dates"])
+        df.index.name = "date"
+        for key, value in results.items():
+            if key != "dates":
+                df[key] = value.detach().cpu().numpy()
+        df.to_csv(self.save_path / "results.csv")
+        pd.DataFrame({"is_infected": is_infected.detach().cpu().numpy()}).to_csv(
+            self.save_path / "results_is_infected.csv")
+
+    # --- reference helper reductions, kept for API parity (runner.py:198-242) ----------------------
+    def store_differentiable_deaths(self, data):
+        symptoms = data["agent"].symptoms
+        dead = self.model.symptoms_updater.stages_ids[-1]
+        deaths = ((symptoms["current_stage"] == dead) * symptoms["current_stage"] / dead).sum()
+        prev = data["results"]["deaths_per_timestep"]
+        data["results"]["deaths_per_timestep"] = deaths if prev is None else torch.hstack((prev, deaths))
+
+    def _age_mask(self, i):
+        age = self.data["agent"].age
+        return (age < self.age_bins[i]) * (age > self.age_bins[i - 1])
+
+    def get_cases_by_age(self, data):
+        ret = torch.zeros(self.age_bins.shape[0] - 1, device=self.device)
+        for i in range(1, self.age_bins.shape[0]):
+            ret[i - 1] = (data["agent"].is_infected * self._age_mask(i)).sum()
+        return ret
+
+    def get_people_by_age(self):
+        return {int(self.age_bins[i].item()): self._age_mask(i).sum() for i in range(1, self.age_bins.shape[0])}
+
+    def get_cases_by_ethnicity(self, data):
+        ret = torch.zeros(len(self.ethnicities), device=self.device)
+        for i, ethnicity in enumerate(self.ethnicities):
+            mask = torch.tensor(self.data["agent"].ethnicity == ethnicity, device=self.device)
+            ret[i] = (mask * data["agent"].is_infected).sum()
+        return ret

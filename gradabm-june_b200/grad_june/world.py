@@ -1,0 +1,504 @@
+"""World container and device layout.
+
+``HeteroData`` is a torch_geometric-free stand-in that supports exactly the access patterns the
+reference uses on its world object (runner.py:65-136, infection_networks/base.py:30-45):
+``data["agent"].age``, ``data["agent"]["age"]``, ``data["agent","attends_school","school"].edge_index``,
+``data["attends_school"]``, ``data["rev_attends_school"]``, ``data["school"]["people"]``,
+``data["results"]``, ``del data["rev_attends_school"]`` and ``.to(device)``.  Reference pickles
+(e.g. test/data/data.pkl) load into it through :func:`load_world`.
+
+:func:`build_csr` turns the reference's unsorted int64 ``[2, E]`` edge lists into the CSR-sorted layout
+the kernels read (``gj_world_desc`` in include/gradjune_b200.h); it is plain torch so that it runs on
+the GPU for England-scale worlds and on the CPU for tests.
+"""
+import io
+import pickle
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+MAX_TYPES = 8
+
+
+# --------------------------------------------------------------------------------------
+# container
+# --------------------------------------------------------------------------------------
+class _Store:
+    def __init__(self, key=None):
+        object.__setattr__(self, "_mapping", {})
+        object.__setattr__(self, "_key", key)
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        mapping = self.__dict__.get("_mapping", {})
+        if name in mapping:
+            return mapping[name]
+        raise AttributeError(f"{type(self).__name__} {self.__dict__.get('_key')!r} has no attribute {name!r}")
+
+    def __setattr__(self, name, value):
+        self._mapping[name] = value
+
+    def __getitem__(self, name):
+        return self._mapping[name]
+
+    def __setitem__(self, name, value):
+        self._mapping[name] = value
+
+    def __delitem__(self, name):
+        del self._mapping[name]
+
+    def __contains__(self, name):
+        return name in self._mapping
+
+    def keys(self):
+        return self._mapping.keys()
+
+    def items(self):
+        return self._mapping.items()
+
+    def __setstate__(self, state):  # torch_geometric storage pickles: {"_mapping", "_parent", "_key"}
+        object.__setattr__(self, "_mapping", dict(state.get("_mapping", {})))
+        object.__setattr__(self, "_key", state.get("_key"))
+
+    def __getstate__(self):
+        return {"_mapping": self._mapping, "_key": self._key}
+
+    def __repr__(self):
+        return f"{type(self).__name__}({self._key!r}: {list(self._mapping)})"
+
+
+class NodeStorage(_Store):
+    pass
+
+
+class EdgeStorage(_Store):
+    pass
+
+
+class GlobalStorage(_Store):
+    pass
+
+
+def _move(v, device):
+    if torch.is_tensor(v):
+        return v.to(device)
+    if isinstance(v, dict):
+        return {k: _move(x, device) for k, x in v.items()}
+    return v
+
+
+class HeteroData:
+    def __init__(self):
+        self.__dict__["_global_store"] = GlobalStorage("global")
+        self.__dict__["_node_store_dict"] = {}
+        self.__dict__["_edge_store_dict"] = {}
+        self.__dict__["_gj_cache"] = {}
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self.__dict__.setdefault("_gj_cache", {})
+
+    def __getstate__(self):
+        return {k: v for k, v in self.__dict__.items() if k != "_gj_cache"}
+
+    def _edge_key(self, rel):
+        for k in self._edge_store_dict:
+            if k[1] == rel:
+                return k
+        return None
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple):
+            if key not in self._edge_store_dict:
+                self._edge_store_dict[key] = EdgeStorage(key)
+            return self._edge_store_dict[key]
+        ek = self._edge_key(key)
+        if ek is not None:
+            return self._edge_store_dict[ek]
+        if key in self._global_store:
+            return self._global_store[key]
+        if key not in self._node_store_dict:
+            self._node_store_dict[key] = NodeStorage(key)
+        return self._node_store_dict[key]
+
+    def __setitem__(self, key, value):
+        self._global_store[key] = value
+
+    def __delitem__(self, key):
+        if isinstance(key, tuple):
+            del self._edge_store_dict[key]
+            return
+        ek = self._edge_key(key)
+        if ek is not None:
+            del self._edge_store_dict[ek]
+        elif key in self._node_store_dict:
+            del self._node_store_dict[key]
+        else:
+            del self._global_store[key]
+
+    def __contains__(self, key):
+        return (self._edge_key(key) is not None or key in self._node_store_dict or key in self._global_store)
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        gs = self.__dict__.get("_global_store")
+        if gs is not None and name in gs:
+            return gs[name]
+        raise AttributeError(name)
+
+    @property
+    def node_types(self):
+        return list(self._node_store_dict)
+
+    @property
+    def edge_types(self):
+        return list(self._edge_store_dict)
+
+    def to(self, device):
+        for store in [*self._node_store_dict.values(), *self._edge_store_dict.values(), self._global_store]:
+            for k, v in list(store.items()):
+                store[k] = _move(v, device)
+        self._gj_cache.clear()
+        return self
+
+    def venue_types(self) -> List[str]:
+        """Edge types present, in insertion order: 'school' for ('agent','attends_school','school')."""
+        return [k[1][len("attends_"):] for k in self._edge_store_dict if k[1].startswith("attends_")]
+
+
+class ToUndirected:
+    """Adds (dst, "rev_"+rel, src) edge stores holding ``edge_index.flip(0)`` (same edge order)."""
+
+    def __call__(self, data):
+        for (src, rel, dst) in list(data._edge_store_dict):
+            if rel.startswith("rev_"):
+                continue
+            data[(dst, "rev_" + rel, src)].edge_index = data._edge_store_dict[(src, rel, dst)].edge_index.flip(0)
+        return data
+
+
+class _WorldUnpickler(pickle.Unpickler):
+    """Reads reference pickles without torch_geometric: its classes map onto the stand-ins above."""
+
+    _MAP = {"HeteroData": HeteroData, "NodeStorage": NodeStorage, "EdgeStorage": EdgeStorage,
+            "GlobalStorage": GlobalStorage, "BaseStorage": GlobalStorage}
+
+    def find_class(self, module, name):
+        if module.startswith("torch_geometric"):
+            if name in self._MAP:
+                return self._MAP[name]
+            raise pickle.UnpicklingError(f"unsupported torch_geometric class {module}.{name}")
+        return super().find_class(module, name)
+
+
+def load_world(path_or_file):
+    """Load a world pickle written either by the reference (torch_geometric HeteroData) or by us."""
+    if hasattr(path_or_file, "read"):
+        return _WorldUnpickler(path_or_file).load()
+    with open(path_or_file, "rb") as f:
+        return _WorldUnpickler(f).load()
+
+
+def world_from_arrays(arrays: Dict[str, np.ndarray], types: List[str], device="cpu") -> HeteroData:
+    """Build a world from the plain-array form used by tests/golden/sample_world.npz."""
+    data = HeteroData()
+    n = len(arrays["age"])
+    data["agent"].id = torch.arange(n)
+    data["agent"].age = torch.as_tensor(np.asarray(arrays["age"]).astype(np.int64))
+    data["agent"].sex = torch.as_tensor(np.asarray(arrays["sex"]).astype(np.int64))
+    if "ethnicity" in arrays:
+        data["agent"].ethnicity = np.asarray(arrays["ethnicity"])
+    for t in types:
+        ng = int(arrays[f"{t}_ngroups"])
+        data[t].id = torch.arange(ng)
+        data[t].people = torch.as_tensor(np.asarray(arrays[f"{t}_people"]).astype(np.int64))
+        ei = np.stack([arrays[f"{t}_src"], arrays[f"{t}_dst"]]).astype(np.int64)
+        data["agent", "attends_" + t, t].edge_index = torch.as_tensor(ei)
+    data = ToUndirected()(data)
+    return data.to(device)
+
+
+# --------------------------------------------------------------------------------------
+# CSR layout
+# --------------------------------------------------------------------------------------
+class DeviceWorld:
+    """CSR-sorted device arrays + the ctypes descriptor handed to the library."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def desc(self):
+        from . import _lib
+
+        d = _lib.WorldDesc()
+        d.n_agents, d.n_groups, d.n_edges, d.n_types = self.n_agents, self.n_groups, self.n_edges, len(self.types)
+        for i, off in enumerate(self.type_group_off):
+            d.type_group_off[i] = off
+        for name in ("am_ptr", "am_ent", "gm_ptr", "gm_agent", "pc", "cls", "small_groups", "chunk_group",
+                     "chunk_begin", "chunk_end", "chunk_part", "big_groups", "big_part_ptr"):
+            setattr(d, name, getattr(self, name).data_ptr())
+        d.n_small, d.n_chunks = self.small_groups.numel(), self.chunk_group.numel()
+        d.n_big, d.n_parts = self.big_groups.numel(), self.n_parts
+        return d
+
+
+def p_contact(people: torch.Tensor) -> torch.Tensor:
+    """clamp(1 / (people - 1), 0, 1) evaluated like infection_networks/base.py:64-69 (fp32)."""
+    one = torch.tensor(1.0, device=people.device)
+    zero = torch.tensor(0.0, device=people.device)
+    return torch.maximum(torch.minimum(1.0 / (people - 1), one), zero).to(torch.float32)
+
+
+def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], people: Dict[str, torch.Tensor],
+              n_groups: Dict[str, int], age: torch.Tensor, sex: torch.Tensor, small_group: int, chunk: int,
+              device) -> DeviceWorld:
+    if len(types) > MAX_TYPES:
+        raise ValueError(f"at most {MAX_TYPES} edge types are supported")
+    dev = torch.device(device)
+    offs = [0]
+    for t in types:
+        offs.append(offs[-1] + int(n_groups[t]))
+    G = offs[-1]
+    srcs, gkeys, ents = [], [], []
+    for ti, t in enumerate(types):
+        ei = edges[t].to(dev)
+        if ei.numel():
+            if int(ei[0].max()) >= n_agents or int(ei[0].min()) < 0:
+                raise ValueError(f"edge type {t}: agent index out of range")
+            if int(ei[1].max()) >= n_groups[t] or int(ei[1].min()) < 0:
+                raise ValueError(f"edge type {t}: group index out of range")
+        if n_groups[t] >= (1 << 28):
+            raise ValueError(f"edge type {t}: too many groups")
+        srcs.append(ei[0])
+        gkeys.append(ei[1] + offs[ti])
+        ents.append(ei[1] + (ti << 28))
+    if srcs:
+        src = torch.cat(srcs)
+        gkey = torch.cat(gkeys)
+        ent = torch.cat(ents)
+    else:
+        src = gkey = ent = torch.zeros(0, dtype=torch.long, device=dev)
+    E = src.numel()
+    if E >= (1 << 32) or n_agents >= (1 << 32):
+        raise ValueError("world too large for 32-bit CSR offsets")
+    # group-major: stable sort by global group id keeps the reference's edge order inside each group
+    _, perm = torch.sort(gkey, stable=True)
+    gm_agent = src[perm].to(torch.int32)
+    size = torch.bincount(gkey, minlength=G) if E else torch.zeros(G, dtype=torch.long, device=dev)
+    gm_ptr = torch.zeros(G + 1, dtype=torch.long, device=dev)
+    gm_ptr[1:] = torch.cumsum(size, 0)
+    del perm
+    # agent-major: types were concatenated in order, so a stable sort by agent gives (type, edge order)
+    _, perm = torch.sort(src, stable=True)
+    am_ent = ent[perm].to(torch.int64)
+    deg = torch.bincount(src, minlength=n_agents) if E else torch.zeros(n_agents, dtype=torch.long, device=dev)
+    am_ptr = torch.zeros(n_agents + 1, dtype=torch.long, device=dev)
+    am_ptr[1:] = torch.cumsum(deg, 0)
+    del perm
+    pc = torch.cat([p_contact(people[t].to(dev)) for t in types]) if types else torch.zeros(0, device=dev)
+    if pc.numel() != G:
+        raise ValueError("people arrays do not match the number of groups")
+    age = age.to(dev).long()
+    sex = sex.to(dev).long()
+    if age.numel() and (int(age.min()) < 0 or int(age.max()) > 99 or int(sex.min()) < 0 or int(sex.max()) > 1):
+        raise ValueError("age must be in [0, 99] and sex in {0, 1}")
+    cls = (sex * 100 + age).to(torch.uint8)
+
+    # work lists of the group-major passes
+    gids = torch.arange(G, device=dev)
+    small = gids[size <= small_group]
+    big_mask = size > small_group
+    bg = gids[big_mask]
+    nchunk = (size[big_mask] + chunk - 1) // chunk
+    chunk_group = torch.repeat_interleave(bg, nchunk)
+    first = torch.zeros(nchunk.numel() + 1, dtype=torch.long, device=dev)
+    first[1:] = torch.cumsum(nchunk, 0)
+    within = torch.arange(chunk_group.numel(), device=dev) - torch.repeat_interleave(first[:-1], nchunk)
+    chunk_begin = gm_ptr[chunk_group] + within * chunk
+    chunk_end = torch.minimum(chunk_begin + chunk, gm_ptr[chunk_group + 1])
+    multi = torch.repeat_interleave(nchunk > 1, nchunk)
+    chunk_part = torch.full((chunk_group.numel(),), -1, dtype=torch.long, device=dev)
+    n_parts = int(multi.sum())
+    chunk_part[multi] = torch.arange(n_parts, device=dev)
+    big_groups = bg[nchunk > 1]
+    big_part_ptr = torch.zeros(big_groups.numel() + 1, dtype=torch.long, device=dev)
+    big_part_ptr[1:] = torch.cumsum(nchunk[nchunk > 1], 0)
+
+    def u32(t):  # uint32 values stored as int32 bit patterns (torch has no general uint32 support)
+        t = t.to(torch.int64)
+        return (((t + (1 << 31)) % (1 << 32)) - (1 << 31)).to(torch.int32).contiguous()
+
+    return DeviceWorld(
+        n_agents=n_agents, n_groups=G, n_edges=E, types=list(types), type_group_off=offs,
+        group_size=size, am_ptr=u32(am_ptr), am_ent=u32(am_ent), gm_ptr=u32(gm_ptr), gm_agent=gm_agent.contiguous(),
+        pc=pc.contiguous(), cls=cls.contiguous(), small_groups=u32(small), chunk_group=u32(chunk_group),
+        chunk_begin=u32(chunk_begin), chunk_end=u32(chunk_end), chunk_part=chunk_part.to(torch.int32),
+        big_groups=u32(big_groups), big_part_ptr=u32(big_part_ptr), n_parts=n_parts, device=dev,
+    )
+
+
+def get_device_world(data: HeteroData, device, small_group: Optional[int] = None, chunk: Optional[int] = None):
+    """CSR layout of ``data`` on ``device``; cached on the world object and rebuilt when an edge list,
+    ``people`` or the agent attributes are replaced (identity + version check)."""
+    types = data.venue_types()
+    sig = [str(device)]
+    for t in types:
+        ei = data["attends_" + t].edge_index
+        pp = data[t]["people"]
+        sig.append((t, id(ei), ei._version, tuple(ei.shape), id(pp), getattr(pp, "_version", 0), len(data[t]["id"])))
+    sig.append((id(data["agent"].age), id(data["agent"].sex)))
+    sig = tuple(sig)
+    cache = data.__dict__.setdefault("_gj_cache", {})
+    if cache.get("sig") == sig:
+        return cache["world"]
+    if small_group is None or chunk is None:
+        from . import _lib
+
+        cfg = _lib.config()
+        small_group, chunk = cfg["small_group"], cfg["chunk"]
+    n = len(data["agent"].id)
+    world = build_csr(
+        n, types,
+        {t: data["attends_" + t].edge_index for t in types},
+        {t: torch.as_tensor(data[t]["people"]) for t in types},
+        {t: len(data[t]["id"]) for t in types},
+        torch.as_tensor(data["agent"].age), torch.as_tensor(data["agent"].sex), small_group, chunk, device,
+    )
+    cache["sig"] = sig
+    cache["world"] = world
+    cache.pop("scratch", None)
+    return world
+
+
+# --------------------------------------------------------------------------------------
+# synthetic worlds
+# --------------------------------------------------------------------------------------
+def create_simple_connected_graph(n_agents, device="cpu", params=None):
+    """BASELINE config 1 world (reference utils.py:97-133): even agents share one household, odd
+    agents one school, ``people = n_agents`` for both, uniform ages and sexes."""
+    from .transmission import TransmissionSampler
+
+    data = HeteroData()
+    sampler = TransmissionSampler.from_file() if params is None else TransmissionSampler.from_parameters(params)
+    ids = torch.arange(0, n_agents)
+    data["agent"].id = ids
+    data["agent"].age = torch.randint(0, 100, (n_agents,))
+    data["agent"].sex = torch.randint(0, 2, (n_agents,))
+    values = sampler(n_agents)
+    data["agent"].infection_parameters = {
+        k: values[i] for i, k in enumerate(("max_infectiousness", "shape", "rate", "shift"))
+    }
+    data["agent"].transmission = torch.zeros(n_agents)
+    data["agent"].susceptibility = torch.ones(n_agents)
+    data["agent"].is_infected = torch.zeros(n_agents)
+    data["agent"].infection_time = torch.zeros(n_agents)
+    data["agent"].symptoms = {
+        "current_stage": torch.ones(n_agents, dtype=torch.long),
+        "next_stage": torch.ones(n_agents, dtype=torch.long),
+        "time_to_next_stage": torch.zeros(n_agents),
+    }
+    data["agent"].ethnicity = np.array(["A"] * n_agents)
+    for name, members in (("household", ids[::2]), ("school", ids[1::2])):
+        data[name].id = torch.zeros(1)
+        data[name].people = torch.tensor([n_agents])
+        data["agent", "attends_" + name, name].edge_index = torch.vstack(
+            (members, torch.zeros(members.numel(), dtype=torch.long)))
+    data = ToUndirected()(data)
+    return data.to(device)
+
+
+_HOUSEHOLD_SIZES = torch.tensor([1, 2, 3, 4, 5, 6, 8])
+_HOUSEHOLD_PROBS = torch.tensor([0.41, 0.33, 0.11, 0.09, 0.03, 0.025, 0.005])
+
+
+def make_synthetic_world(n_agents: int, seed: int = 0, device="cpu", agents_per_super_area: int = 7500,
+                         with_reverse: bool = False) -> HeteroData:
+    """England-like synthetic world: area-contiguous agents, contiguous
+    households (1-8 members), schools (ages 5-17, two per super-area), universities (18-22),
+    companies (19-64, log-normal sizes, 80 % local), care homes (over 75 + staff) and three leisure
+    groups per agent (own super-area and the two neighbouring ones).  ``people`` = member count.
+    Generated with torch ops on ``device`` so the 56 M-agent world builds on the GPU in seconds."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    N = int(n_agents)
+    SA = agents_per_super_area
+    ids = torch.arange(N, device=dev)
+    sa = ids // SA
+    n_sa = int((N + SA - 1) // SA)
+
+    def rand(n):
+        return torch.rand(n, generator=g, device=dev)
+
+    # age pyramid: flat to 60, then linearly thinning to 99
+    w_age = torch.ones(100, device=dev)
+    w_age[60:] = torch.linspace(1.0, 0.05, 40, device=dev)
+    age = torch.multinomial(w_age, N, replacement=True, generator=g)
+    sex = (rand(N) < 0.5).long()
+
+    data = HeteroData()
+    data["agent"].id = ids
+    data["agent"].age = age
+    data["agent"].sex = sex
+
+    def add(name, agents, groups, n_groups):
+        data[name].id = torch.arange(n_groups, device=dev)
+        data[name].people = torch.bincount(groups, minlength=n_groups)
+        data["agent", "attends_" + name, name].edge_index = torch.stack((agents, groups))
+
+    # households: contiguous runs of agents
+    m = max(N // 2, 1) + 16
+    hs = _HOUSEHOLD_SIZES.to(dev)[torch.multinomial(_HOUSEHOLD_PROBS.to(dev), m, replacement=True, generator=g)]
+    ends = torch.cumsum(hs, 0)
+    n_hh = int(torch.searchsorted(ends, torch.tensor([N], device=dev), right=False)[0]) + 1
+    hh = torch.searchsorted(ends[:n_hh].contiguous(), ids, right=True)
+    add("household", ids, hh, n_hh)
+
+    r = rand(N)
+    is_school = (age >= 5) & (age <= 17)
+    is_uni = (age >= 18) & (age <= 22) & (r < 0.3)
+    adult = (age >= 19) & (age <= 64) & ~is_uni
+    is_care_worker = adult & (r > 0.998)
+    is_worker = adult & (r < 0.75) & ~is_care_worker
+    is_resident = (age > 75) & (r < 0.04)
+
+    a = ids[is_school]
+    add("school", a, sa[a] * 2 + (rand(a.numel()) < 0.5).long(), n_sa * 2)
+    a = ids[is_uni]
+    n_uni = max(n_sa // 111, 1)
+    add("university", a, torch.clamp(sa[a] // 111, max=n_uni - 1), n_uni)
+
+    # companies: log-normal sizes, home super-area uniform; workers pick proportionally to size
+    a = ids[is_worker]
+    n_comp = max(int(a.numel() / 10.4), 1)
+    csize = torch.exp(1.5 + 1.3 * torch.randn(n_comp, generator=g, device=dev)).clamp(1, 5000)
+    chome = torch.sort(torch.randint(0, n_sa, (n_comp,), generator=g, device=dev))[0]
+    cum = torch.cumsum(csize.double(), 0)
+    first = torch.searchsorted(chome, torch.arange(n_sa + 1, device=dev))      # companies of each super-area
+    lo = torch.where(first[:-1] > 0, cum[(first[:-1] - 1).clamp(min=0)], torch.zeros(n_sa, dtype=cum.dtype, device=dev))
+    hi = torch.where(first[1:] > 0, cum[(first[1:] - 1).clamp(min=0)], torch.zeros(n_sa, dtype=cum.dtype, device=dev))
+    u = rand(a.numel()).double()
+    local = (rand(a.numel()) < 0.8) & (hi[sa[a]] > lo[sa[a]])
+    target = torch.where(local, lo[sa[a]] + u * (hi[sa[a]] - lo[sa[a]]), u * cum[-1])
+    comp = torch.searchsorted(cum, target, right=True).clamp(max=n_comp - 1)
+    add("company", a, comp, n_comp)
+
+    a = torch.cat((ids[is_resident], ids[is_care_worker]))
+    add("care_home", a, sa[a], n_sa)
+
+    # leisure: own super-area and its two neighbours (k = 3 nearest, graph_loader.py:12)
+    left = torch.where(sa == 0, torch.full_like(sa, min(2, n_sa - 1)), sa - 1)
+    right = torch.where(sa == n_sa - 1, torch.full_like(sa, max(n_sa - 3, 0)), sa + 1)
+    if n_sa >= 3:
+        la = torch.cat((ids, ids, ids))
+        lg = torch.cat((sa, left, right))
+    else:
+        la, lg = ids, sa
+    add("leisure", la, lg, n_sa)
+    data["agent"].ethnicity = np.array(["A"])  # one label; per-agent strings are not needed by the step
+    if with_reverse:
+        data = ToUndirected()(data)
+    return data

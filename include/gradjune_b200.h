@@ -1,0 +1,246 @@
+/*
+ * gradjune_b200.h — C ABI of the B200-native per-timestep infection path of GradABM-JUNE.
+ *
+ * One shared library (libgradjune_b200.so, sm_100a), plain pointers and sizes only, no torch types.
+ * The reference has no FFI: its boundary for this path is the Python nn.Module API
+ * (/root/reference/grad_june/model.py:112-144 and the modules it calls).  Each entry point below
+ * names the reference interface it replaces; INTEGRATION.md shows the ctypes stubs that bind them.
+ *
+ * Conventions
+ *   - every array pointer is DEVICE memory owned by the caller and borrowed for the call;
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*), performs no
+ *     allocation and no host synchronisation;
+ *   - return value 0 = ok, negative = error (text via gj_last_error());
+ *   - floating point is fp32, compiled without FMA contraction and without fast-math so that the
+ *     elementwise arithmetic rounds like the reference's op-by-op torch graph.
+ */
+#ifndef GRADJUNE_B200_H
+#define GRADJUNE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GJ_ABI_VERSION 1
+
+#define GJ_MAX_TYPES 8      /* edge types (household, company, school, university, care_home, leisure, ...) */
+#define GJ_MAX_NETS 16      /* infection networks active in one step */
+#define GJ_MAX_STAGES 16    /* symptom stages */
+#define GJ_MAX_QUAR 4       /* simultaneously active quarantine policies */
+#define GJ_MAX_AGE_BINS 8   /* cases-by-age result bins */
+#define GJ_MAX_CHANNELS 8   /* networks sharing one edge type (the six leisure networks) */
+
+/* group-size split of the group-major passes (the world builder must use the same values,
+ * read them through gj_config) */
+#define GJ_SMALL_GROUP 16   /* <= this many members: one lane sums the group sequentially */
+#define GJ_CHUNK 1024       /* larger groups are cut into chunks of this many members, one warp each */
+
+/* how a network masks transmissions / susceptibilities
+ * (grad_june/infection_networks/base.py:47-59,144-149; leisure_network.py:61-85,107-120) */
+enum { GJ_KIND_PLAIN = 0, GJ_KIND_HOUSEHOLD = 1, GJ_KIND_LEISURE = 2, GJ_KIND_CARE_VISIT = 3 };
+
+/* phases of one timestep (grad_june/model.py:112-144); the fused step runs all of them, the
+ * stand-alone module entry points run one */
+enum {
+  GJ_PHASE_NETWORKS = 1, /* InfectionNetworks.forward            base.py:118-141            */
+  GJ_PHASE_SAMPLE = 2,   /* IsInfectedSampler.forward            infection.py:3-18          */
+  GJ_PHASE_INFECT = 4,   /* GradJune.infect_people               model.py:90-110            */
+  GJ_PHASE_SYMPTOMS = 8, /* SymptomsUpdater.forward              symptoms.py:204-247        */
+  GJ_PHASE_ALL = 15
+};
+
+/* mode flags */
+enum {
+  GJ_MODE_STEP = 0,
+  GJ_MODE_SEED = 1 /* infect_fraction_of_people: uniform q = 1 - fraction and the clamp variant of the
+                      susceptibility update (infection.py:21-42, runner.py:138-149) */
+};
+
+/* ------------------------------------------------------------------------------------------
+ * World: CSR-sorted agent<->group edges for every edge type (replaces the int64 [2,E]
+ * edge_index pairs of HeteroData, june_world_loader/graph_loader.py:16-39).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gj_world_desc {
+  int64_t n_agents;
+  int64_t n_groups; /* all types */
+  int64_t n_edges;  /* all types */
+  int32_t n_types;
+  int32_t _pad0;
+  int64_t type_group_off[GJ_MAX_TYPES + 1]; /* global group id range of each type */
+
+  /* agent-major CSR, all types merged; an agent's entries are sorted by (type, reference edge order) */
+  const uint32_t* am_ptr; /* [n_agents+1] */
+  const uint32_t* am_ent; /* [n_edges]  (type << 28) | group id local to the type */
+
+  /* group-major CSR in global group order; members keep the reference's edge order */
+  const uint32_t* gm_ptr;   /* [n_groups+1] */
+  const uint32_t* gm_agent; /* [n_edges] */
+  const float* pc;          /* [n_groups] clamp(1/(people-1), 0, 1)  (base.py:64-69) */
+
+  const uint8_t* cls; /* [n_agents] sex*100 + age */
+
+  /* work lists of the group-major passes */
+  const uint32_t* small_groups; /* [n_small] global ids of groups with <= GJ_SMALL_GROUP members */
+  int64_t n_small;
+  const uint32_t* chunk_group; /* [n_chunks] global group id */
+  const uint32_t* chunk_begin; /* [n_chunks] first entry in gm_agent */
+  const uint32_t* chunk_end;   /* [n_chunks] one past the last entry */
+  const int32_t* chunk_part;   /* [n_chunks] -1: the group's only chunk (write the sum directly);
+                                  else index into the partial-sum buffer */
+  int64_t n_chunks;
+  const uint32_t* big_groups;   /* [n_big] groups with >= 2 chunks */
+  const uint32_t* big_part_ptr; /* [n_big+1] their partial-sum ranges */
+  int64_t n_big;
+  int64_t n_parts; /* total partial sums (= big_part_ptr[n_big]) */
+} gj_world_desc;
+
+typedef struct gj_net {
+  int32_t type;     /* edge type index */
+  int32_t kind;     /* GJ_KIND_* */
+  int32_t prob_row; /* leisure table index for LEISURE / CARE_VISIT, else -1 */
+  int32_t s_off;    /* offset of this network's per-group sums in the S buffers */
+} gj_net;
+
+typedef struct gj_dist {
+  int32_t kind; /* -1 none, 0 LogNormal, 1 Normal (utils.py:75-83 distributions used by default.yaml / tests) */
+  float loc, scale;
+} gj_dist;
+
+/* scalars of one timestep, all host values (timer.py, policies/*.py stay on the host) */
+typedef struct gj_step_params {
+  int32_t mode;   /* GJ_MODE_* */
+  int32_t phases; /* GJ_PHASE_* mask */
+  float now;      /* timer.now   (days) */
+  float dt;       /* timer.duration (days) */
+  int32_t day_type; /* 0 weekday, 1 weekend */
+  int32_t n_nets;
+  gj_net nets[GJ_MAX_NETS]; /* in accumulation order = timer.get_activity_order() minus closed venues */
+  int32_t n_quar;           /* -1: no quarantine collection (mask is the scalar 1.0) */
+  float quar_thr[GJ_MAX_QUAR];
+  int32_t n_stages;
+  gj_dist trans_time[GJ_MAX_STAGES];
+  gj_dist rec_time[GJ_MAX_STAGES];
+  int32_t n_age_bins;
+  int32_t age_bins[GJ_MAX_AGE_BINS + 1];
+  float tau; /* gumbel-softmax temperature (0.1, infection.py:15) */
+  /* noise: Philox4x32-10 keyed by seed, counter (agent, call_index, stream); ignored where an
+   * injected array is given */
+  uint64_t seed;
+  uint32_t call_index;
+  uint32_t _pad1;
+} gj_step_params;
+
+/* device arrays of one forward call; unused ones may be NULL */
+typedef struct gj_fwd_io {
+  const float* beta;         /* [n_nets] beta_eff per network (base.py:36-42 evaluated on the host) */
+  const float* leisure_prob; /* [n_tables][2][2][100] */
+  const float* stage_prob;   /* [n_stages][100] */
+  const float* seed_fraction; /* [1] (GJ_MODE_SEED) */
+  /* injected noise (NULL -> Philox) */
+  const float* inj_E; /* [2][N] */
+  const float* inj_u; /* [N] */
+  const float* inj_z; /* [2*(n_stages-3)][N] */
+  /* state in */
+  const float *s, *inf, *tinf, *cur, *nxt, *ttn;
+  /* per-agent infectiousness profile (transmission.py:8-35); k0 = exp(-lgamma(shape)) */
+  const float *maxinf, *shape, *rate, *shift, *k0;
+  /* phase inputs when the producing phase is not run */
+  const float* T_in; /* transmissions (NETWORKS phase without gj_transmission) */
+  const float* q_in; /* not-infected probabilities (SAMPLE without NETWORKS) */
+  const float* n_in; /* new_infected (INFECT/SYMPTOMS without SAMPLE) */
+  /* state out */
+  float *s_o, *inf_o, *tinf_o, *cur_o, *nxt_o, *ttn_o;
+  float* T;  /* [N] transmissions (written by the fused step, read by the group pass) */
+  float* Tq; /* [N] quarantine-masked transmissions; may alias T when n_quar <= 0 */
+  float* q;  /* [N] optional: not_infected_probs */
+  float* lam; /* [N] optional: summed pressure before the clamp (InfectionNetwork.forward, base.py:61-84) */
+  float* n;  /* [N] optional: new_infected */
+  /* saved for backward */
+  float* tape_v;  /* [N] pressure (s != 0) or pressure per unit susceptibility (s == 0) */
+  float* tape_y0; /* [N] soft not-infected probability */
+  float* S_scaled;   /* [sum_k G(type_k)] beta*pc-weighted group sums (forward operand) */
+  float* S_unscaled; /* [sum_k G(type_k)] plain group sums (saved: d/dbeta) */
+  float* red;        /* [2 + n_age_bins] cases, deaths, cases by age bin */
+  void* scratch;     /* gj_scratch_bytes() bytes, zero-initialised once by the caller */
+} gj_fwd_io;
+
+typedef struct gj_bwd_io {
+  const float* beta;
+  const float* leisure_prob;
+  const float* stage_prob;
+  const float* seed_fraction;
+  const float* inj_E;
+  const float* inj_u;
+  const float* inj_z;
+  /* forward inputs and saved tensors */
+  const float *s, *inf, *tinf, *cur, *nxt, *ttn;
+  const float *maxinf, *shape, *rate, *shift, *k0;
+  const float* inf_o; /* post-step is_infected (new_infected = inf_o - inf) or NULL with n_in */
+  const float* n_in;
+  const float* T_in;
+  const float* q_in; /* stand-alone SAMPLE: the q it was given */
+  const float* tape_v;
+  const float* tape_y0;
+  const float* S_unscaled;
+  /* cotangents of the outputs (NULL = zero) */
+  const float *g_s_o, *g_inf_o, *g_tinf_o, *g_cur_o, *g_nxt_o, *g_ttn_o;
+  const float* g_red; /* [2 + n_age_bins] */
+  const float* g_q;   /* cotangent of q (NETWORKS without SAMPLE) */
+  const float* g_lam; /* cotangent of lam */
+  const float* g_n;   /* extra cotangent of new_infected */
+  /* cotangents of the inputs (NULL = not wanted) */
+  float *g_s, *g_inf, *g_tinf, *g_cur, *g_nxt, *g_ttn;
+  float* g_T;       /* cotangent of T_in (stand-alone NETWORKS) */
+  float* g_q_out;   /* cotangent of q_in (stand-alone SAMPLE) */
+  float* g_n_out;   /* cotangent of n_in (stand-alone INFECT / SYMPTOMS) */
+  float* g_beta;    /* [n_nets] */
+  float* g_seed_fraction; /* [1] */
+  /* workspaces */
+  float* w;   /* [N] */
+  float* wq;  /* [N], may alias w when n_quar <= 0 */
+  float* R;   /* [sum_k G(type_k)] */
+  float* cR;  /* [sum_k G(type_k)] */
+  void* scratch;
+} gj_bwd_io;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int gj_abi_version(void);
+const char* gj_last_error(void);
+/* out[0]=GJ_SMALL_GROUP, out[1]=GJ_CHUNK, out[2]=sizeof(gj_world_desc), out[3]=sizeof(gj_step_params),
+ * out[4]=sizeof(gj_fwd_io), out[5]=sizeof(gj_bwd_io), out[6]=reduction grid size */
+int gj_config(int64_t* out, int n);
+/* bytes of the caller-provided scratch buffer (zero it once; the library leaves it zeroed) */
+int64_t gj_scratch_bytes(const gj_world_desc* w);
+
+/* ---- TransmissionUpdater.forward (grad_june/transmission.py:38-51) ------------------------ */
+/* k0[i] = exp(-lgamma(shape[i])), the time-independent factor of the gamma profile */
+int gj_profile_prepare(int64_t n, const float* shape, float* k0, void* stream);
+int gj_transmission_forward(int64_t n, float now, const float* tinf, const float* inf, const float* maxinf,
+                            const float* shape, const float* rate, const float* shift, const float* k0,
+                            float* T, void* stream);
+int gj_transmission_backward(int64_t n, float now, const float* tinf, const float* inf, const float* maxinf,
+                             const float* shape, const float* rate, const float* shift, const float* k0,
+                             const float* g_T, float* g_tinf, float* g_inf, void* stream);
+
+/* ---- GradJune.forward (grad_june/model.py:112-144) and, through `phases`, its parts:
+ *      InfectionNetworks.forward (infection_networks/base.py:118-141, 61-87; leisure_network.py),
+ *      IsInfectedSampler.forward (infection.py:3-18), infect_people (model.py:90-110,
+ *      infection.py:21-28), SymptomsUpdater.forward (symptoms.py:204-247), plus the per-step result
+ *      reductions of Runner.forward (runner.py:167-171,198-224) ------------------------------- */
+int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fwd_io* io, void* stream);
+/* reverse-mode derivative of gj_step_forward (replaces autograd's replay of the op tape) */
+int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_bwd_io* io, void* stream);
+
+/* ---- noise ------------------------------------------------------------------------------- */
+/* the exact draws gj_step_forward makes for (seed, call_index): E[2][N], u[N], z[N] */
+int gj_philox_fill(uint64_t seed, uint32_t call_index, int64_t n, float* E, float* u, float* z, void* stream);
+/* raw Philox4x32-10 block for known-answer tests: out[4] = philox(ctr[4], key[2]) (host function) */
+void gj_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRADJUNE_B200_H */
