@@ -134,8 +134,21 @@ __device__ __forceinline__ float not_infected_prob(float lam, float dt) {
 
 struct Draw {
   float n;   // new_infected, exactly 0 or 1
-  float y0;  // soft probability of "not infected"
+  float ty;  // tape: the smaller of the two soft probabilities, +y1 (infected) or -y0 (not infected)
 };
+
+// The backward needs BOTH softmax outputs as the forward rounded them (torch's softmax backward uses
+// y1 itself, not 1 - y0: for y1 ~ 1e-9 and q -> 1 the product y0*y1/(1-q) is far from negligible).
+// Storing the smaller one with a sign bit keeps it exact; the larger one is 1 - small to 1 ulp.
+__device__ __forceinline__ void decode_soft(float ty, float& y0, float& y1) {
+  if (signbit(ty)) {
+    y0 = -ty;
+    y1 = 1.0f - y0;
+  } else {
+    y1 = ty;
+    y0 = 1.0f - y1;
+  }
+}
 
 __device__ __forceinline__ Draw gumbel_draw(float q, float E0, float E1, float tau) {
   const float l0 = logf(q);
@@ -152,7 +165,7 @@ __device__ __forceinline__ Draw gumbel_draw(float q, float E0, float E1, float t
   const float y1 = e1 / sum;
   Draw d;
   d.n = (y1 > y0) ? 1.0f : 0.0f;  // max() returns the first index on ties -> not infected
-  d.y0 = y0;
+  d.ty = (y1 <= y0) ? y1 : -y0;
   return d;
 }
 

@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(kBlock) k_agent_forward(gj_world_desc w, gj_st
     if (p.phases & GJ_PHASE_SAMPLE) {
       const Draw d = gumbel_draw(q, nz.E0, nz.E1, p.tau);
       n = d.n;
-      if (io.tape_y0) io.tape_y0[a] = d.y0;
+      if (io.tape_y0) io.tape_y0[a] = d.ty;
     } else if (io.n_in) {
       n = io.n_in[a];
     }
@@ -575,12 +575,14 @@ __global__ void __launch_bounds__(kBlock) k_agent_backward(gj_world_desc w, gj_s
     if (seed_mode) q = 1.0f - io.seed_fraction[0] * 1.0f;
     if (p.phases & GJ_PHASE_SAMPLE) {
       if (!(p.phases & GJ_PHASE_NETWORKS) && !seed_mode && io.q_in) q = io.q_in[a];  // stand-alone sampler
-      const float y0 = io.tape_y0[a];
-      const float y1 = 1.0f - y0;
-      const float gret0 = -gn;                    // new_infected = 1 - ret[0]
-      const float gx0 = gret0 * y0 * y1;          // softmax^T with cotangent (gret0, 0); gx1 = -gx0
-      const float gl0 = gx0 / p.tau, gl1 = -gx0 / p.tau;
-      gq += gl0 / q - gl1 / (1.0f - q);           // logits = log([q, 1-q])
+      float y0, y1;
+      decode_soft(io.tape_y0[a], y0, y1);
+      const float gret0 = -gn;                        // new_infected = 1 - ret[0]
+      const float dot = gret0 * y0;                   // softmax^T: (g - sum(g*y)) * y with g = (gret0, 0)
+      const float gx0 = (gret0 - dot) * y0;
+      const float gx1 = (0.0f - dot) * y1;
+      const float gl0 = gx0 / p.tau, gl1 = gx1 / p.tau;
+      gq += gl0 / q - gl1 / (1.0f - q);               // logits = log([q, 1-q])
     }
     if (io.g_q_out) io.g_q_out[a] = gq;
     if (io.g_n_out) io.g_n_out[a] = gn;

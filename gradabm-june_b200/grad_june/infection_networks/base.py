@@ -106,7 +106,9 @@ def leisure_table(networks, device):
 def beta_vector(networks, policies, timer, device):
     if not networks:
         return torch.zeros(0, device=device)
-    return torch.stack([net.beta_eff(policies, timer).reshape(()).to(torch.float32) for net in networks]).to(device)
+    # log_beta usually lives on the CPU while policy factors follow system.device: move each scalar first
+    return torch.stack([net.beta_eff(policies, timer).reshape(()).to(device=device, dtype=torch.float32)
+                        for net in networks])
 
 
 def _run_networks(networks, data, timer, policies, device, want_lam=False):

@@ -160,7 +160,7 @@ typedef struct gj_fwd_io {
   float* n;  /* [N] optional: new_infected */
   /* saved for backward */
   float* tape_v;  /* [N] pressure (s != 0) or pressure per unit susceptibility (s == 0) */
-  float* tape_y0; /* [N] soft not-infected probability */
+  float* tape_y0; /* [N] the smaller soft probability of the draw: +y1 (infected) or -y0 (not infected) */
   float* S_scaled;   /* [sum_k G(type_k)] beta*pc-weighted group sums (forward operand) */
   float* S_unscaled; /* [sum_k G(type_k)] plain group sums (saved: d/dbeta) */
   float* red;        /* [2 + n_age_bins] cases, deaths, cases by age bin */

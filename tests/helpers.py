@@ -97,3 +97,135 @@ def make_leaf_networks(params):
 
 
 RUNS = {"sample_default": 11, "sample_policies": 12, "sample_deadly": 13}
+
+
+# ------------------------------------------------------------------------------------------
+# gradient parity criterion
+# ------------------------------------------------------------------------------------------
+class perturb_q:
+    """Context manager: every q the oracle computes is moved by a random -1/0/+1 fp32 ulp (values only,
+    same autograd graph).  Measures how much of a parameter gradient is decided by the last bit of
+    expf — the part that legitimately differs between CPU libm (reference) and CUDA libm (kernels)."""
+
+    def __init__(self, seed):
+        self.seed = seed
+
+    def __enter__(self):
+        gen = torch.Generator().manual_seed(self.seed)
+        self.orig = orig = O.not_infected_probs
+
+        def hooked(world, spec, T, s, cur, return_pressure=False):
+            q, lam = orig(world, spec, T, s, cur, True)
+            if q.dtype == torch.float32:
+                r = (torch.randint(0, 3, q.shape, generator=gen) - 1).to(q.device)
+                qp = (q.detach().view(torch.int32) + r.int()).view(torch.float32).clamp(max=1.0)
+                q = q + (qp - q.detach())
+            return (q, lam) if return_pressure else q
+        O.not_infected_probs = hooked
+
+    def __exit__(self, *a):
+        O.not_infected_probs = self.orig
+
+
+def oracle_run(tag, dtype=torch.float32, device="cpu"):
+    """Replay a golden Runner trajectory through the oracle; returns (result dict, grads[11], grad log_frac,
+    masks_equal_to_golden)."""
+    from grad_june.policies import Policies
+    from grad_june.symptoms import SymptomsSampler
+    g = np.load(GOLDEN / f"run_{tag}.npz")
+    params, _ = load_params(tag)
+    arrays = np.load(GOLDEN / "sample_world.npz")
+    w = oracle_world(arrays, SAMPLE_TYPES, device)
+    nets = make_leaf_networks(params)
+    policies = Policies.from_parameters(params)
+    sym = oracle_symptoms(SymptomsSampler.from_parameters(params), device)
+    steps = oracle_schedule(params, nets, policies)
+    if dtype != torch.float32:
+        for s in steps:
+            for n in s.nets:
+                n.beta = n.beta.to(dtype)
+    noises = [O.StepNoise(E=n.E.to(dtype), u=n.u.to(dtype), z=n.z.to(dtype))
+              for n in torch_noise(RUNS[tag], len(steps) + 1, w.n_agents, device)]
+    log_frac = torch.tensor(float(params["infection_seed"]["log_fraction_initial_cases"]), requires_grad=True,
+                            dtype=dtype)
+    prof = {k: v.to(dtype) for k, v in profile_params(g, device).items()}
+    trace = []
+    res = O.run(w, prof, sym, log_frac, steps, noises, age_bins=params.get("age_bins_to_save", (0, 18, 65, 100)),
+                dtype=dtype, trace=trace)
+    wc, wd, wa = g["loss_weights"]
+    cba = res["cases_by_age"]
+    loss = wc * res["cases_per_timestep"].sum() + wd * res["deaths_per_timestep"].sum() \
+        + wa * (cba * torch.arange(1, cba.shape[1] + 1, device=device)).sum()
+    loss.backward()
+    names = [str(n) for n in g["net_names"]]
+    grads = np.array([nets.networks[n].log_beta.grad.item() if nets.networks[n].log_beta.grad is not None else 0.0
+                      for n in names])
+    same = np.array_equal(np.stack([t["is_infected"].cpu().numpy() for t in trace]).astype(np.uint8),
+                          g["trace_is_infected"]) and \
+        np.array_equal(np.stack([t["current_stage"].cpu().numpy() for t in trace]).astype(np.uint8),
+                       g["trace_current_stage"])
+    return res, grads, log_frac.grad.item(), same
+
+
+def assert_grad_parity(mine, ref32, f64, sens=None, rtol=1e-5, slack=4.0, ulp_slack=6.0, what="gradient"):
+    """Parameter-gradient criterion.
+
+    Target: 1e-5 relative agreement with the reference's fp32 gradient.  That is only meaningful where the
+    reference's gradient is itself conditioned to 1e-5: the factor y0*y1*dt/(tau*(1-q)) turns a 1-ulp
+    difference in q (CPU expf vs CUDA expf) into a relative change ulp/(1-q) of the term, i.e. 1e-4..1e-2
+    for agents under a small pressure.  A component therefore passes if
+      (a) it is within ``rtol`` of the reference, or
+      (b) its distance to the fp64 witness of the same trajectory is at most ``slack`` x the reference's own
+          distance to that witness (not less accurate than the reference's fp32 arithmetic), or
+      (c) its distance to the reference is at most ``ulp_slack`` x the change the reference's own gradient
+          shows when its q values are moved by a random +-1 ulp (``sens``, measured with perturb_q)."""
+    mine, ref32, f64 = (np.atleast_1d(np.asarray(x, dtype=np.float64)) for x in (mine, ref32, f64))
+    sens = np.zeros_like(ref32) if sens is None else np.atleast_1d(np.asarray(sens, dtype=np.float64))
+    for i, (m, r, t, sn) in enumerate(zip(mine, ref32, f64, sens)):
+        if abs(m - r) <= rtol * abs(r) + 1e-30:
+            continue
+        e_ref, e_mine = abs(r - t), abs(m - t)
+        if e_mine <= max(slack * e_ref, rtol * abs(t)):
+            continue
+        assert abs(m - r) <= ulp_slack * sn, \
+            (f"{what}[{i}]: mine {m!r} ref32 {r!r} fp64 {t!r}: |mine-ref| = {abs(m - r):.3e} (rel {abs(m - r) / abs(r):.2e}), "
+             f"|mine-f64| = {e_mine:.3e}, |ref32-f64| = {e_ref:.3e}, 1-ulp sensitivity = {sn:.3e}")
+
+
+def run_sensitivity(tag, seeds=(1, 2, 3)):
+    """max over seeds of |grad(perturbed q) - grad| for the golden run ``tag`` (fp32 oracle, CPU)."""
+    _, base, basef, _ = oracle_run(tag)
+    sens, sensf = np.zeros_like(base), 0.0
+    for sd in seeds:
+        with perturb_q(sd):
+            _, gp, gpf, _ = oracle_run(tag)
+        sens = np.maximum(sens, np.abs(gp - base))
+        sensf = max(sensf, abs(gpf - basef))
+    return sens, sensf
+
+
+def oracle_step100(dtype=torch.float32, device="cpu"):
+    """The single-step fixture through the oracle: returns (aux dict, post state, grads[household, company, school])."""
+    from grad_june.symptoms import SymptomsSampler
+    g = np.load(GOLDEN / "step100.npz")
+    w = oracle_world(g, ["school", "company", "household"], device)
+    state = {k: torch.from_numpy(g["pre_" + k]).to(device=device, dtype=dtype) for k in
+             ("susceptibility", "is_infected", "infection_time", "current_stage", "next_stage", "time_to_next_stage")}
+    params = {k: v.to(dtype) for k, v in profile_params(g, device).items()}
+    sym = oracle_symptoms(SymptomsSampler.from_file(), device)
+    lb = {"household": torch.tensor(0.5, requires_grad=True, dtype=dtype),
+          "company": torch.tensor(0.3, requires_grad=True, dtype=dtype),
+          "school": torch.tensor(0.4, requires_grad=True, dtype=dtype)}
+    kinds = {"household": O.KIND_HOUSEHOLD, "company": O.KIND_PLAIN, "school": O.KIND_PLAIN}
+    nets = [O.NetSpec(str(n), str(n), kinds[str(n)], 10.0 ** lb[str(n)]) for n in g["order"]]
+    spec = O.StepSpec(now=float(g["now"]), dt=float(g["dt"]), day_type=0, nets=nets, quarantine=[])
+    nz = torch_noise(8, 1, w.n_agents, device)[0]
+    nz = O.StepNoise(E=nz.E.to(dtype), u=nz.u.to(dtype), z=nz.z.to(dtype))
+    aux = {}
+    O.step(w, state, params, spec, sym, nz, aux)
+    wl = torch.from_numpy(g["loss_w"]).to(device=device, dtype=dtype)
+    w2 = torch.from_numpy(g["loss_w2"]).to(device=device, dtype=dtype)
+    loss = (state["is_infected"] * wl).sum() + (state["current_stage"] * w2).sum() \
+        + 0.5 * (state["susceptibility"] * w2).sum() + 0.1 * (state["infection_time"] * wl).sum()
+    loss.backward()
+    return aux, state, np.array([lb[k].grad.item() for k in ("household", "company", "school")])

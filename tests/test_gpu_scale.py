@@ -1,0 +1,221 @@
+"""GPU parity at larger sizes: a synthetic England-like world (all six edge types, eleven networks,
+quarantine active) stepped once from a mid-epidemic state, teacher-forced against the oracle with the
+kernel's own Philox noise (gj_philox_fill), plus size-independent properties."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle import gj_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def _params(device=DEV):
+    from grad_june.default_config import default_parameters
+    p = default_parameters()
+    p["system"]["device"] = device
+    p["policies"] = {"quarantine": {"quarantine": {1: {"start_date": "2022-01-01", "end_date": "2023-01-01",
+                                                       "stage_threshold": 4}}}}
+    return p
+
+
+def _mid_epidemic_state(n, now, seed, device):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    r = torch.rand(n, generator=g)
+    inf = (r < 0.25)
+    cur = torch.ones(n)
+    nxt = torch.ones(n)
+    stage = torch.randint(2, 7, (n,), generator=g).float()
+    cur[inf] = stage[inf]
+    rec_next = torch.rand(n, generator=g) < 0.4
+    nxt[inf] = torch.where(rec_next[inf], torch.zeros(int(inf.sum())), stage[inf] + 1)
+    done = inf & (torch.rand(n, generator=g) < 0.2)      # already recovered / dead
+    cur[done] = torch.where(torch.rand(int(done.sum()), generator=g) < 0.9, 0.0, 7.0)
+    nxt[done] = cur[done]
+    tinf = torch.where(inf, now - 12.0 * torch.rand(n, generator=g), torch.zeros(n))
+    ttn = torch.where(inf, now + 4.0 * torch.rand(n, generator=g) - 1.5, torch.zeros(n))
+    s = torch.where(inf, torch.zeros(n), torch.ones(n))
+    st = {"susceptibility": s, "is_infected": inf.float(), "infection_time": tinf, "current_stage": cur,
+          "next_stage": nxt, "time_to_next_stage": ttn}
+    return {k: v.to(device) for k, v in st.items()}
+
+
+def _setup(n_agents, seed=1):
+    from grad_june import GradJune, Timer
+    from grad_june.runner import Runner
+    from grad_june.world import make_synthetic_world
+    params = _params()
+    torch.manual_seed(seed)
+    data = make_synthetic_world(n_agents, seed=seed, device=DEV)
+    data = Runner.get_data(params, data=data)
+    model = GradJune.from_parameters(params)
+    for net in model.infection_networks.networks.values():
+        net.log_beta = torch.nn.Parameter(net.log_beta)
+    timer = Timer.from_parameters(params)
+    for _ in range(8):
+        next(timer)
+    state = _mid_epidemic_state(n_agents, timer.now, seed + 5, DEV)
+    for k in ("susceptibility", "is_infected", "infection_time"):
+        data["agent"][k] = state[k]
+    data["agent"].symptoms = {k: state[k] for k in ("current_stage", "next_stage", "time_to_next_stage")}
+    return params, data, model, timer, state
+
+
+def _oracle_inputs(params, data, model, timer, state, device):
+    from grad_june.symptoms import SymptomsSampler
+    w = O.OracleWorld(n_agents=len(data["agent"].id), age=data["agent"].age.to(device), sex=data["agent"].sex.to(device))
+    for t in data.venue_types():
+        ei = data["attends_" + t].edge_index.to(device)
+        w.edges[t] = O.EdgeType(src=ei[0], dst=ei[1], people=data[t]["people"].to(device), n_groups=len(data[t]["id"]))
+    nets = H.make_leaf_networks({**params, "system": {"device": "cpu"}})
+    policies = model.policies
+    specs = []
+    for net in nets.active_networks(timer, policies):
+        prob = getattr(net, "leisure_probabilities", None)
+        specs.append(O.NetSpec(net.name, net.edge_type(), net.kind, net.beta_eff(policies, timer).to(device),
+                               None if prob is None else prob.to(device)))
+    spec = O.StepSpec(now=timer.now, dt=timer.duration, day_type=0 if timer.day_type == "weekday" else 1, nets=specs,
+                      quarantine=policies.quarantine_policies.active_thresholds(timer))
+    sym = H.oracle_symptoms(SymptomsSampler.from_parameters(params), device)
+    prof = {k: v.to(device) for k, v in data["agent"].infection_parameters.items()}
+    st = {k: v.detach().clone().to(device) for k, v in state.items()}
+    return w, nets, spec, sym, prof, st
+
+
+@pytest.mark.parametrize("n_agents,oracle_device", [(30_000, "cpu"), (400_000, DEV)])
+def test_teacher_forced_step_vs_oracle(n_agents, oracle_device):
+    from grad_june import ops
+    params, data, model, timer, state = _setup(n_agents)
+    seed = 2024
+    with ops.philox_seed(seed):
+        res = model(data=data, timer=timer)
+    agent = res["agent"]
+    E, u, z = ops.philox_fill(seed, 0, n_agents, DEV)
+    w, nets, spec, sym, prof, st = _oracle_inputs(params, data, model, timer, state, oracle_device)
+    noise = O.StepNoise(E=E.to(oracle_device), u=u.to(oracle_device), z=z.to(oracle_device).expand(10, n_agents))
+    aux = {}
+    O.step(w, st, prof, spec, sym, noise, aux)
+
+    def cpu(t):
+        return t.detach().cpu().numpy()
+
+    T, To = cpu(agent.transmission), cpu(aux["transmission"])
+    assert np.allclose(T, To, rtol=1e-5, atol=1e-30)
+    q, qo = cpu(agent["not_infected_probs"]), cpu(aux["q"])
+    assert np.max(np.abs(q - qo) / qo) <= 1e-5, np.max(np.abs(q - qo) / qo)
+    n, no = cpu(agent["new_infected"]), cpu(aux["new_infected"])
+    mism = np.nonzero(n != no)[0]
+    # every mask mismatch must be a certified near-tie of the two perturbed logits
+    if len(mism):
+        qm = torch.from_numpy(qo[mism].astype(np.float64))
+        Em = E[:, torch.from_numpy(mism).to(DEV)].double().cpu()
+        x0 = (qm.log() - Em[0].log()) / 0.1
+        x1 = ((1 - torch.from_numpy(qo[mism]).float()).double().log() - Em[1].log()) / 0.1
+        gap = (x0 - x1).abs() / torch.maximum(x0.abs(), x1.abs())
+        assert float(gap.max()) < 2e-5, f"mask mismatch that is not a near-tie: gap {gap}"
+    assert len(mism) <= max(2, int(2e-5 * n_agents)), len(mism)
+    ok = np.ones(n_agents, dtype=bool)
+    ok[mism] = False
+    assert n.sum() > 0.001 * n_agents
+    for mine, theirs, exact in ((agent.susceptibility, st["susceptibility"], True),
+                                (agent.is_infected, st["is_infected"], True),
+                                (agent.symptoms["current_stage"], st["current_stage"], True),
+                                (agent.symptoms["next_stage"], st["next_stage"], True),
+                                (agent.infection_time, st["infection_time"], False),
+                                (agent.symptoms["time_to_next_stage"], st["time_to_next_stage"], False)):
+        a, b = cpu(mine)[ok], cpu(theirs)[ok]
+        if exact:
+            assert np.array_equal(a, b)
+        else:
+            assert np.allclose(a, b, rtol=2e-6, atol=1e-6)
+    # stages really moved (the symptoms machine was exercised)
+    assert (cpu(agent.symptoms["current_stage"]) != cpu(state["current_stage"])).sum() > 0.01 * n_agents
+
+    if len(mism) == 0:
+        gw = torch.Generator(device="cpu").manual_seed(5)
+        wts = [torch.rand(n_agents, generator=gw) for _ in range(4)]
+        keys = list(model.infection_networks.networks.keys())
+
+        def loss_of(inf, cur, s, tinf, dev, dtype=torch.float32):
+            w0, w1, w2, w3 = (t.to(device=dev, dtype=dtype) for t in wts)
+            return (inf * w0).sum() + (cur * w1).sum() + 0.5 * (s * w2).sum() + 0.05 * (tinf * w3).sum()
+
+        def oracle_grads(dtype, perturb=None):
+            wo, netso, speco, symo, profo, sto = _oracle_inputs(params, data, model, timer, state, oracle_device)
+            for sp in speco.nets:
+                sp.beta = sp.beta.to(dtype)
+            sto = {k: v.to(dtype) for k, v in sto.items()}
+            profo = {k: v.to(dtype) for k, v in profo.items()}
+            nz = O.StepNoise(E=noise.E.to(dtype), u=noise.u.to(dtype), z=noise.z.to(dtype))
+            if perturb is None:
+                O.step(wo, sto, profo, speco, symo, nz)
+            else:
+                with H.perturb_q(perturb):
+                    O.step(wo, sto, profo, speco, symo, nz)
+            loss_of(sto["is_infected"], sto["current_stage"], sto["susceptibility"], sto["infection_time"],
+                    oracle_device, dtype).backward()
+            gr = np.array([netso.networks[k].log_beta.grad.item() if netso.networks[k].log_beta.grad is not None
+                           else 0.0 for k in keys])
+            return gr, torch.equal(sto["is_infected"].float(), st["is_infected"])
+
+        loss_of(agent.is_infected, agent.symptoms["current_stage"], agent.susceptibility, agent.infection_time, DEV).backward()
+        mine = np.array([model.infection_networks.networks[k].log_beta.grad.item() for k in keys])
+        ref, _ = oracle_grads(torch.float32)
+        g64, same = oracle_grads(torch.float64)
+        sens = np.zeros_like(ref)
+        for sd in (1, 2, 3):
+            gp, _ = oracle_grads(torch.float32, perturb=sd)
+            sens = np.maximum(sens, np.abs(gp - ref))
+        if same:
+            H.assert_grad_parity(mine, ref, g64, sens, rtol=1e-5, what="d/dlog_beta")
+        else:
+            assert np.allclose(mine, ref, rtol=1e-3)
+
+
+def test_properties_at_scale():
+    """Size-independent checks on a 2M-agent world: reductions equal recomputed sums, run-to-run
+    bit-reproducibility, and pressure is linear in beta (q(2*beta) == q(beta)**2 where unclamped)."""
+    from grad_june import ops
+    n_agents = 2_000_000
+    params, data, model, timer, state = _setup(n_agents, seed=3)
+
+    def reset():
+        for k in ("susceptibility", "is_infected", "infection_time"):
+            data["agent"][k] = state[k]
+        data["agent"].symptoms = {k: state[k] for k in ("current_stage", "next_stage", "time_to_next_stage")}
+
+    outs = []
+    for rep in range(2):
+        reset()
+        with ops.philox_seed(99):
+            _, red = model.step(data, timer, age_bins=(0, 18, 65, 100))
+        outs.append((data["agent"].is_infected.clone(), data["agent"]["not_infected_probs"].clone(), red.clone(),
+                     data["agent"].symptoms["current_stage"].clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    inf, q, red, cur = outs[0]
+    age = data["agent"].age
+    assert red[0].item() == pytest.approx(inf.double().sum().item(), rel=1e-7)
+    assert red[1].item() == pytest.approx((cur == 7).double().sum().item(), rel=1e-7)
+    for i, (lo, hi) in enumerate(((0, 18), (18, 65), (65, 100))):
+        assert red[2 + i].item() == pytest.approx((inf.double() * ((age > lo) & (age < hi))).sum().item(), rel=1e-7)
+    assert float(q.min()) > 0 and float(q.max()) <= 1.0
+    # linearity in beta
+    reset()
+    with torch.no_grad():
+        for net in model.infection_networks.networks.values():
+            net.log_beta += np.log10(2.0)
+    with ops.philox_seed(99):
+        model.step(data, timer)
+    q2 = data["agent"]["not_infected_probs"]
+    mid = (q > 1e-3) & (q < 0.99)       # away from the 1e-6 floor and the 100 cap
+    assert int(mid.sum()) > 1000
+    assert torch.allclose(q2[mid], q[mid] ** 2, rtol=2e-5)
