@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the per-timestep infection path (fwd+bwd), BASELINE.json metric
+"agent-timesteps/sec fwd+bwd ...; HBM GB/s vs roofline".
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # the reference's CPU path (oracle port)
+
+One "step" = one simulation timestep forward AND its backward, over every agent of the synthetic
+England-scale world (config.workload).  K steps are run as BPTT windows (forward w steps, backward
+through them) exactly as Runner.forward() + loss.backward() does; prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT / "gradabm-june_b200", ROOT, ROOT / "tests", ROOT / "tests" / "golden"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+import numpy as np
+import torch
+
+METRIC = "agent_timesteps_per_sec_fwd_bwd"
+UNIT = "agent-timesteps/s"
+# algorithmic HBM bytes per agent-timestep, fwd+bwd, symptoms on (DESIGN.md "Roofline")
+B_ALG_STEP = 279.0
+
+
+def measured_peak_gbs():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.load(open(f))["hbm_gbs"]), "measured"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback"
+
+
+def bench_params(device, steps):
+    from grad_june.default_config import default_parameters
+    p = default_parameters()
+    p["system"]["device"] = device
+    p["policies"] = {}
+    p["timer"]["total_days"] = steps
+    p["infection_seed"]["log_fraction_initial_cases"] = -2.0
+    p["save_path"] = tempfile.gettempdir() + "/gj_bench"
+    return p
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.path or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        os.unlink(self.path)
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline = the oracle port of the reference's path, on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_reference_run(n_agents, steps, repeats=1):
+    """Oracle (torch CPU restatement of the reference) fwd+bwd on a bounded sample of the workload:
+    the same synthetic world generator at n_agents, default 11 networks, `steps` timesteps.
+    Returns (agent-timesteps/s, seconds per fwd+bwd pass, cores)."""
+    import helpers as H
+    from grad_june import Timer
+    from grad_june.policies import Policies
+    from grad_june.symptoms import SymptomsSampler
+    from grad_june.transmission import TransmissionSampler
+    from grad_june.world import make_synthetic_world
+    from oracle import gj_oracle as O
+
+    params = bench_params("cpu", steps)
+    torch.manual_seed(0)
+    data = make_synthetic_world(n_agents, seed=0, device="cpu")
+    w = O.OracleWorld(n_agents=n_agents, age=data["agent"].age, sex=data["agent"].sex)
+    for t in data.venue_types():
+        ei = data["attends_" + t].edge_index
+        w.edges[t] = O.EdgeType(src=ei[0], dst=ei[1], people=data[t]["people"], n_groups=len(data[t]["id"]))
+    vals = TransmissionSampler.from_parameters(params)(n_agents)
+    prof = {k: vals[i] for i, k in enumerate(("max_infectiousness", "shape", "rate", "shift"))}
+    nets = H.make_leaf_networks(params)
+    sym = H.oracle_symptoms(SymptomsSampler.from_parameters(params))
+    sched = H.oracle_schedule(params, nets, Policies.from_parameters(params))
+    g = torch.Generator().manual_seed(1)
+    best = None
+    for _ in range(repeats):
+        noises = [O.StepNoise(E=torch.empty(2, n_agents).exponential_(generator=g), u=torch.rand(n_agents, generator=g),
+                              z=torch.randn(10, n_agents, generator=g)) for _ in range(len(sched) + 1)]
+        for net in nets.networks.values():
+            net.log_beta.grad = None
+        # fresh graph each repeat
+        sched = H.oracle_schedule(params, nets, Policies.from_parameters(params))
+        t0 = time.perf_counter()
+        res = O.run(w, prof, sym, torch.tensor(-2.0), sched, noises)
+        (res["cases_per_timestep"].sum() + res["deaths_per_timestep"].sum()).backward()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_agents * steps / best, best, torch.get_num_threads()
+
+
+def run_reference_arm(args, rank, world_size):
+    if rank != 0:
+        return
+    n_sample = args.cpu_agents
+    # warm-up
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_reference_run(min(n_sample, 100_000), 1)
+    t0 = time.perf_counter()
+    thr, secs, cores = cpu_reference_run(n_sample, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": thr, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": secs * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.agents), "sample_agents": n_sample, "networks": 11,
+                   "note": "reference is pure Python/torch (no compiled oracle/_ref): oracle port of its CPU path"},
+        "cpu_baseline": {"value": thr, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_sample} agents of the same synthetic world x {args.steps} timesteps, fwd+bwd"},
+        "e2e": {"value": thr, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(n_agents):
+    return (f"synthetic England-scale world ({n_agents / 1e6:.0f}M agents, ~4.6 edges/agent over household/company/school/"
+            "university/care_home/leisure), 11 default networks, symptoms on, fwd+bwd wrt log_beta")
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--agents", type=int, default=56_000_000, help="agents per GPU")
+    ap.add_argument("--window", type=int, default=0, help="BPTT window (0 = as many steps as memory allows)")
+    ap.add_argument("--cpu-agents", type=int, default=1_000_000, help="agents of the CPU-baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    world_size = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world_size)
+        return
+
+    import torch.distributed as dist
+    from grad_june import GradJune, Runner, Timer, _lib, ops
+    from grad_june.world import freeze_device_world, make_synthetic_world
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    N = args.agents
+    free, total = torch.cuda.mem_get_info()
+    # bytes retained per agent per step until backward (pre-state 24 + tape 8 + group sums ~3) + margin
+    per_step = 40.0 * N
+    resident = 120.0 * N           # world CSR + static arrays + transient workspaces + initial state backup
+    max_window = int(max(1, (free * 0.85 - resident) // per_step))
+    window = min(args.steps, args.window or max_window, max_window)
+
+    params = bench_params(dev, window)
+    torch.manual_seed(1234 + rank)
+    data = make_synthetic_world(N, seed=0, device=dev)
+    data = Runner.get_data(params, data=data)
+    world = freeze_device_world(data, dev)   # the int64 edge lists are not needed once the CSR exists
+    model = GradJune.from_parameters(params)
+    keys = list(model.infection_networks.networks.keys())
+    # ensemble axis: every rank evaluates its own beta sample on the world (config 5 style sharding)
+    gen = torch.Generator().manual_seed(99)
+    offsets = 0.05 * torch.randn(max(world_size, 1), len(keys), generator=gen)
+    host_log_beta = torch.tensor([float(model.infection_networks.networks[k].log_beta) for k in keys]) + offsets[rank]
+    host_log_beta = host_log_beta.pin_memory()
+
+    def fresh_runner():
+        r = Runner(model=model, data=data, timer=Timer.from_parameters(params), log_fraction_initial_cases=-2.0,
+                   save_path=params["save_path"], parameters=params)
+        return r
+
+    runner = fresh_runner()
+
+    def one_window(e2e):
+        """forward `window` timesteps + backward; returns device-side loss and grads"""
+        if e2e:
+            lb_dev = host_log_beta.to(dev, non_blocking=True)          # H2D of this window's inputs
+        else:
+            lb_dev = resident_log_beta
+        leaves = []
+        for i, k in enumerate(keys):
+            leaf = lb_dev[i].detach().clone().requires_grad_(True)
+            model.infection_networks.networks[k].log_beta = leaf
+            leaves.append(leaf)
+        with ops.philox_seed(7):
+            results, _ = runner()
+        loss = results["cases_per_timestep"].sum() + results["deaths_per_timestep"].sum()
+        loss.backward()
+        grads = torch.stack([l.grad for l in leaves])
+        out = torch.cat([results["cases_per_timestep"], results["deaths_per_timestep"], grads])
+        if e2e:
+            return out.to("cpu")                                     # D2H of the window's results
+        return out
+
+    resident_log_beta = host_log_beta.to(dev)
+    n_windows = max(1, -(-args.steps // window))
+    steps_done = n_windows * window
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up: W >= 3 timesteps
+    wsteps = 0
+    while wsteps < max(args.warmup, 3):
+        one_window(False)
+        wsteps += window
+    barrier()
+
+    # ---- timed region 1: device-resident inputs --------------------------------------------------
+    _lib.profile_enable(True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_windows):
+            out = one_window(False)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    clk = clocks.summary()
+
+    # ---- timed region 2: end to end through Runner with host buffers -------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_windows):
+        host_out = one_window(True)
+    torch.cuda.synchronize()
+    if world_size > 1:
+        dist.barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = host_log_beta.numel() * 4 / window
+    d2h = host_out.numel() * 4 / window
+
+    if world_size > 1:
+        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+        gathered = [torch.zeros_like(out) for _ in range(world_size)]
+        dist.all_gather(gathered, out)      # the ensemble's only exchange: losses + gradients
+
+    if rank == 0:
+        peak, peak_kind = measured_peak_gbs()
+        total_units = N * steps_done * world_size
+        value = total_units / (ms * 1e-3)
+        # dominant kernel + its algorithmic bytes per launch (DESIGN.md "Roofline")
+        e_bar = world.n_edges / N
+        g_bar = world.n_groups / N
+        small = world.group_size <= _lib.config()["small_group"]
+        e_small = float(world.group_size[small].sum()) / N
+        g_small = float(small.sum()) / N
+        alg = kernel_alg_bytes(e_bar, g_bar, e_small, g_small)
+        timed = {k: v for k, v in prof.items() if v[1] > 0}
+        dom = max(timed, key=lambda k: timed[k][0]) if timed else None
+        roof = None
+        if dom is not None:
+            avg_ms = timed[dom][0] / timed[dom][1]
+            achieved = alg.get(dom, 0.0) * N / (avg_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                    "alg_bytes_per_agent": alg.get(dom), "avg_launch_ms": avg_ms,
+                    "step_alg_bytes_per_agent_timestep": B_ALG_STEP,
+                    "step_achieved": B_ALG_STEP * value / world_size / 1e9,
+                    "step_frac": B_ALG_STEP * value / world_size / 1e9 / peak,
+                    "kernel_ms_share": {k: round(v[0] / sum(x[0] for x in timed.values()), 4) for k, v in timed.items()}}
+        launches = int(sum(v[2] for v in prof.values()))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": steps_done,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / steps_done, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(N), "agents_per_gpu": N, "edges_per_agent": round(e_bar, 3),
+                       "groups_per_agent": round(g_bar, 3), "bptt_window": window, "networks": 11,
+                       "parallelism": "ensemble shard (one beta sample per GPU, no data-path collective)" if world_size > 1 else "single GPU",
+                       "l2": "inputs (>= 2 GB per pass) far larger than the 126 MB L2; no flush needed"},
+            "clocks": clk,
+            "e2e": {"value": total_units / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": roof,
+        }
+        if not args.no_cpu_baseline and world_size == 1:
+            thr, secs, cores = cpu_reference_run(args.cpu_agents, args.cpu_steps)
+            line["cpu_baseline"] = {"value": thr, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_agents} agents of the same synthetic world x {args.cpu_steps} "
+                                              f"timesteps fwd+bwd ({secs:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def kernel_alg_bytes(e_bar, g_bar, e_small, g_small, c=1.2):
+    """Algorithmic bytes per agent and launch of each kernel: every operand array touched once,
+    int32 indices, fp32 values (DESIGN.md lists the terms)."""
+    return {
+        # tinf, inf, 4 profile + k0 reads (28) + T write (4)
+        "k_transmission": 32.0,
+        # member ids 4e + T gathers 4e + group ptr/pc 8g + two sums written 8cg
+        "k_group_small<fwd>": 4 * e_small + 4 * min(e_small, 1.0) + 8 * g_small + 8 * c * g_small,
+        "k_group_chunk<fwd>": 4 * (e_bar - e_small) + 4 * min(e_bar - e_small, 1.0) + 8 * (g_bar - g_small)
+        + 8 * c * (g_bar - g_small),
+        "k_group_small<bwd>": 4 * e_small + 4 * min(e_small, 1.0) + 8 * g_small + 8 * c * g_small,
+        "k_group_chunk<bwd>": 4 * (e_bar - e_small) + 4 * min(e_bar - e_small, 1.0) + 8 * (g_bar - g_small)
+        + 8 * c * (g_bar - g_small),
+        # state in 24 + cls 1 + row ptr 4 + entries 4e + group sums 4cg + state out 24 + tape 8
+        "k_agent_forward": 24 + 1 + 4 + 4 * e_bar + 4 * c * g_bar + 24 + 8,
+        # state in 24 + post is_infected 4 + tape 8 + cls 1 + cotangents in 8 (is_infected, stage) + out 20 + w 4
+        "k_agent_backward": 24 + 4 + 8 + 1 + 8 + 20 + 4,
+        # row ptr 4 + entries 4e + cR 4cg + profile/state 28 + cls/cur 5 + RMW of two cotangents 16
+        "k_agent_backward_gather": 4 + 4 * e_bar + 4 * c * g_bar + 28 + 5 + 16,
+    }
+
+
+if __name__ == "__main__":
+    main()

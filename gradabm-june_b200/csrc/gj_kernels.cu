@@ -35,6 +35,41 @@ static int bad(const char* what) {
     if (_e != cudaSuccess) return fail(name, _e);     \
   } while (0)
 
+// ---- optional per-kernel timing with CUDA events on the launching stream (gj_profile_*) -------------
+enum KernelId {
+  K_TRANSMISSION = 0, K_GROUP_SMALL_F, K_GROUP_CHUNK_F, K_GROUP_FIX_F, K_AGENT_FWD,
+  K_AGENT_BWD, K_GROUP_SMALL_B, K_GROUP_CHUNK_B, K_GROUP_FIX_B, K_DBETA, K_AGENT_BWD_GATHER, K_OTHER, K_COUNT
+};
+static const char* kKernelNames[K_COUNT] = {
+  "k_transmission", "k_group_small<fwd>", "k_group_chunk<fwd>", "k_group_fix<fwd>", "k_agent_forward",
+  "k_agent_backward", "k_group_small<bwd>", "k_group_chunk<bwd>", "k_group_fix<bwd>", "k_dbeta",
+  "k_agent_backward_gather", "other"};
+constexpr int kMaxProfiled = 16384;
+struct Profiler {
+  bool on = false;
+  int n = 0;
+  int64_t launches[K_COUNT] = {0};
+  cudaEvent_t ev[kMaxProfiled][2];
+  int id[kMaxProfiled];
+  bool created = false;
+};
+static Profiler g_prof;
+struct ProfScope {
+  int slot = -1;
+  cudaStream_t st;
+  ProfScope(int kid, cudaStream_t s) : st(s) {
+    g_prof.launches[kid]++;
+    if (g_prof.on && g_prof.n < kMaxProfiled) {
+      slot = g_prof.n++;
+      g_prof.id[slot] = kid;
+      cudaEventRecord(g_prof.ev[slot][0], st);
+    }
+  }
+  ~ProfScope() {
+    if (slot >= 0) cudaEventRecord(g_prof.ev[slot][1], st);
+  }
+};
+
 static inline int blocks_for(int64_t n, int per_block) {
   int64_t b = (n + per_block - 1) / per_block;
   return (int)(b < 1 ? 1 : b);
@@ -704,16 +739,19 @@ static int launch_group_pass(const gj_world_desc* w, const gj_step_params* p, co
                              const float* lprob, const float* in0, const float* in1, float* out_a, float* out_b,
                              const Scratch& sc, cudaStream_t st) {
   if (w->n_small > 0) {
+    ProfScope ps(kBwd ? K_GROUP_SMALL_B : K_GROUP_SMALL_F, st);
     k_group_small<kBwd><<<blocks_for(w->n_small, kBlock), kBlock, 0, st>>>(*w, *p, ch, beta, lprob, in0, in1, out_a,
                                                                          out_b);
     GJ_CHECK_LAUNCH("k_group_small");
   }
   if (w->n_chunks > 0) {
+    ProfScope ps(kBwd ? K_GROUP_CHUNK_B : K_GROUP_CHUNK_F, st);
     k_group_chunk<kBwd><<<blocks_for(w->n_chunks * 32, kBlock), kBlock, 0, st>>>(*w, *p, ch, beta, lprob, in0, in1,
                                                                               out_a, out_b, sc.part_a, sc.part_b);
     GJ_CHECK_LAUNCH("k_group_chunk");
   }
   if (w->n_big > 0) {
+    ProfScope ps(kBwd ? K_GROUP_FIX_B : K_GROUP_FIX_F, st);
     k_group_fix<kBwd><<<blocks_for(w->n_big, kBlock), kBlock, 0, st>>>(*w, *p, ch, beta, sc.part_a, sc.part_b, out_a,
                                                                      out_b);
     GJ_CHECK_LAUNCH("k_group_fix");
@@ -738,6 +776,41 @@ int gj_config(int64_t* out, int n) {
 }
 
 int64_t gj_scratch_bytes(const gj_world_desc* w) { return w ? scratch_bytes(w) : -1; }
+
+int gj_profile_enable(int on) {
+  if (on && !g_prof.created) {
+    for (int i = 0; i < kMaxProfiled; ++i) {
+      if (cudaEventCreate(&g_prof.ev[i][0]) != cudaSuccess || cudaEventCreate(&g_prof.ev[i][1]) != cudaSuccess)
+        return fail("cudaEventCreate", cudaGetLastError());
+    }
+    g_prof.created = true;
+  }
+  g_prof.on = on != 0;
+  g_prof.n = 0;
+  for (int i = 0; i < K_COUNT; ++i) g_prof.launches[i] = 0;
+  return 0;
+}
+
+int gj_profile_read(double* ms, int64_t* timed, int64_t* launches, int n) {
+  for (int i = 0; i < n && i < K_COUNT; ++i) {
+    ms[i] = 0.0;
+    timed[i] = 0;
+    launches[i] = g_prof.launches[i];
+  }
+  for (int s = 0; s < g_prof.n; ++s) {
+    if (cudaEventSynchronize(g_prof.ev[s][1]) != cudaSuccess) return fail("cudaEventSynchronize", cudaGetLastError());
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof.ev[s][0], g_prof.ev[s][1]) != cudaSuccess)
+      return fail("cudaEventElapsedTime", cudaGetLastError());
+    if (g_prof.id[s] < n) {
+      ms[g_prof.id[s]] += t;
+      timed[g_prof.id[s]]++;
+    }
+  }
+  return K_COUNT;
+}
+
+const char* gj_profile_kernel_name(int i) { return (i >= 0 && i < K_COUNT) ? kKernelNames[i] : ""; }
 
 int gj_profile_prepare(int64_t n, const float* shape, float* k0, void* stream) {
   if (n <= 0) return 0;
@@ -795,6 +868,7 @@ int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fw
       if (!io->T || !io->tinf || !io->inf || !io->maxinf || !io->k0) return bad("state / T buffers are NULL");
       float* tq = (p->n_quar > 0) ? io->Tq : io->T;
       if (!tq) return bad("Tq is NULL with an active quarantine");
+      ProfScope ps(K_TRANSMISSION, st);
       k_transmission<<<agent_grid(N), kBlock, 0, st>>>(N, p->now, io->tinf, io->inf, io->maxinf, io->shape, io->rate,
                                                       io->shift, io->k0, io->T, *p, io->cur, tq);
       GJ_CHECK_LAUNCH("k_transmission");
@@ -810,7 +884,10 @@ int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fw
                                          st))
       return e;
   }
-  k_agent_forward<<<agent_grid(N), kBlock, 0, st>>>(*w, pp, *io, sc.red_part, sc.tickets);
+  {
+    ProfScope ps(K_AGENT_FWD, st);
+    k_agent_forward<<<agent_grid(N), kBlock, 0, st>>>(*w, pp, *io, sc.red_part, sc.tickets);
+  }
   GJ_CHECK_LAUNCH("k_agent_forward");
   return 0;
 }
@@ -831,18 +908,23 @@ int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_b
   if (nets && (!io->w || !io->wq || !io->R || !io->cR || !io->tape_v || !io->S_unscaled || !io->beta))
     return bad("backward workspaces are NULL");
   if ((pp.phases & GJ_PHASE_SAMPLE) && !io->tape_y0) return bad("tape_y0 is NULL");
-  k_agent_backward<<<agent_grid(N), kBlock, 0, st>>>(*w, pp, *io, sc.red_part, sc.tickets);
+  {
+    ProfScope ps(K_AGENT_BWD, st);
+    k_agent_backward<<<agent_grid(N), kBlock, 0, st>>>(*w, pp, *io, sc.red_part, sc.tickets);
+  }
   GJ_CHECK_LAUNCH("k_agent_backward");
   if (nets) {
     if (int e = launch_group_pass<true>(w, &pp, ch, io->beta, io->leisure_prob, io->w, io->wq, io->cR, io->R, sc, st))
       return e;
     if (io->g_beta && pp.n_nets > 0) {
       dim3 grid(kRedBlocks / 8, pp.n_nets);
+      ProfScope ps(K_DBETA, st);
       k_dbeta<<<grid, kBlock, 0, st>>>(*w, pp, io->S_unscaled, io->R, sc.dbeta_part, sc.tickets, io->g_beta);
       GJ_CHECK_LAUNCH("k_dbeta");
     }
     if (io->g_T || io->g_inf || io->g_tinf) {
       if (!io->g_T && (!io->tinf || !io->inf || !io->maxinf || !io->k0)) return bad("state arrays are NULL");
+      ProfScope ps(K_AGENT_BWD_GATHER, st);
       k_agent_backward_gather<<<agent_grid(N), kBlock, 0, st>>>(*w, pp, *io);
       GJ_CHECK_LAUNCH("k_agent_backward_gather");
     }

@@ -141,6 +141,8 @@ def lib():
     L.gj_philox_fill.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gj_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.gj_philox4x32_10.restype = None
+    L.gj_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
+    L.gj_profile_kernel_name.restype = C.c_char_p
     cfg = (C.c_int64 * 7)()
     L.gj_config(cfg, 7)
     _config = {
@@ -168,5 +170,19 @@ def check(rc, what):
 EXPORTED_SYMBOLS = [
     "gj_abi_version", "gj_last_error", "gj_config", "gj_scratch_bytes", "gj_profile_prepare",
     "gj_transmission_forward", "gj_transmission_backward", "gj_step_forward", "gj_step_backward",
-    "gj_philox_fill", "gj_philox4x32_10",
+    "gj_philox_fill", "gj_philox4x32_10", "gj_profile_enable", "gj_profile_read", "gj_profile_kernel_name",
 ]
+
+
+def profile_enable(on=True):
+    check(lib().gj_profile_enable(1 if on else 0), "gj_profile_enable")
+
+
+def profile_read():
+    """{kernel name: (summed ms, timed launches, launches)} since profile_enable()."""
+    n = 16
+    ms, timed, launches = (C.c_double * n)(), (C.c_int64 * n)(), (C.c_int64 * n)()
+    k = lib().gj_profile_read(ms, timed, launches, n)
+    if k < 0:
+        check(k, "gj_profile_read")
+    return {lib().gj_profile_kernel_name(i).decode(): (ms[i], timed[i], launches[i]) for i in range(k)}

@@ -343,6 +343,9 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
 def get_device_world(data: HeteroData, device, small_group: Optional[int] = None, chunk: Optional[int] = None):
     """CSR layout of ``data`` on ``device``; cached on the world object and rebuilt when an edge list,
     ``people`` or the agent attributes are replaced (identity + version check)."""
+    cache = data.__dict__.setdefault("_gj_cache", {})
+    if cache.get("frozen") == str(device):
+        return cache["world"]
     types = data.venue_types()
     sig = [str(device)]
     for t in types:
@@ -351,7 +354,6 @@ def get_device_world(data: HeteroData, device, small_group: Optional[int] = None
         sig.append((t, id(ei), ei._version, tuple(ei.shape), id(pp), getattr(pp, "_version", 0), len(data[t]["id"])))
     sig.append((id(data["agent"].age), id(data["agent"].sex)))
     sig = tuple(sig)
-    cache = data.__dict__.setdefault("_gj_cache", {})
     if cache.get("sig") == sig:
         return cache["world"]
     if small_group is None or chunk is None:
@@ -370,6 +372,19 @@ def get_device_world(data: HeteroData, device, small_group: Optional[int] = None
     cache["sig"] = sig
     cache["world"] = world
     cache.pop("scratch", None)
+    return world
+
+
+def freeze_device_world(data: HeteroData, device, drop_edge_lists: bool = True):
+    """Build the CSR layout once and pin it: later calls return it without looking at the edge lists,
+    which can then be dropped (an England-scale world's int64 [2,E] lists are ~4 GB the kernels never read)."""
+    world = get_device_world(data, device)
+    data._gj_cache["frozen"] = str(device)
+    if drop_edge_lists:
+        for key in list(data._edge_store_dict):
+            store = data._edge_store_dict[key]
+            if "edge_index" in store:
+                store.edge_index = store.edge_index[:, :0]
     return world
 
 

@@ -234,6 +234,13 @@ int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fw
 /* reverse-mode derivative of gj_step_forward (replaces autograd's replay of the op tape) */
 int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_bwd_io* io, void* stream);
 
+/* ---- measurement (bench.py): CUDA events recorded on the launching stream around every kernel ---- */
+int gj_profile_enable(int on); /* also resets the counters */
+/* per kernel id: summed event time (ms), number of timed launches, number of launches since enable;
+ * synchronises on the recorded events; returns the number of kernel ids */
+int gj_profile_read(double* ms, int64_t* timed, int64_t* launches, int n);
+const char* gj_profile_kernel_name(int id);
+
 /* ---- noise ------------------------------------------------------------------------------- */
 /* the exact draws gj_step_forward makes for (seed, call_index): E[2][N], u[N], z[N] */
 int gj_philox_fill(uint64_t seed, uint32_t call_index, int64_t n, float* E, float* u, float* z, void* stream);
