@@ -69,7 +69,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                stdout=open(self.path, "w"), stderr=subprocess.STDOUT)
         except Exception:  # noqa: BLE001
             self.proc = None
         return self
@@ -100,7 +100,10 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            busy = [x for x in sm if x > 0.5 * max(sm)] or sm
+            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        else:
+            out["error"] = open(self.path).read()[:200]
         os.unlink(self.path)
         return out
 
@@ -278,10 +281,12 @@ def main():
     with ClockSampler(local_rank) as clocks:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.nvtx.range_push("timed")
         e0.record()
         for _ in range(n_windows):
             out = one_window(False)
         e1.record()
+        torch.cuda.nvtx.range_pop()
         barrier()
         ms = e0.elapsed_time(e1)
     prof = _lib.profile_read()
@@ -314,10 +319,12 @@ def main():
         # dominant kernel + its algorithmic bytes per launch (DESIGN.md "Roofline")
         e_bar = world.n_edges / N
         g_bar = world.n_groups / N
-        small = world.group_size <= _lib.config()["small_group"]
+        small = (world.group_size <= _lib.config()["small_group"]) & (world.group_size > 0)
         e_small = float(world.group_size[small].sum()) / N
         g_small = float(small.sum()) / N
-        alg = kernel_alg_bytes(e_bar, g_bar, e_small, g_small)
+        e_gen = world.n_generic_edges / N
+        g_gen = float((world.group_size > 0).sum()) / N
+        alg = kernel_alg_bytes(e_gen, g_gen, e_small, g_small)
         timed = {k: v for k, v in prof.items() if v[1] > 0}
         dom = max(timed, key=lambda k: timed[k][0]) if timed else None
         roof = None
@@ -338,6 +345,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(N), "agents_per_gpu": N, "edges_per_agent": round(e_bar, 3),
                        "groups_per_agent": round(g_bar, 3), "bptt_window": window, "networks": 11,
+                       "layout_tiers": dict(zip(world.types, world.type_tier)),
                        "parallelism": "ensemble shard (one beta sample per GPU, no data-path collective)" if world_size > 1 else "single GPU",
                        "l2": "inputs (>= 2 GB per pass) far larger than the 126 MB L2; no flush needed"},
             "clocks": clk,
@@ -355,25 +363,23 @@ def main():
         dist.destroy_process_group()
 
 
-def kernel_alg_bytes(e_bar, g_bar, e_small, g_small, c=1.2):
+def kernel_alg_bytes(e_gen, g_gen, e_small, g_small, c=1.0):
     """Algorithmic bytes per agent and launch of each kernel: every operand array touched once,
-    int32 indices, fp32 values (DESIGN.md lists the terms)."""
+    int32 indices, fp32 values (DESIGN.md "Roofline" lists the terms).  e_gen / g_gen: edges and groups per
+    agent of the GENERIC-tier types; e_small / g_small: the part of them in groups <= GJ_SMALL_GROUP."""
+    grp_small = 4 * e_small + 4 * min(e_small, 1.0) + 8 * g_small + 8 * c * g_small
+    grp_chunk = 4 * (e_gen - e_small) + 4 * min(e_gen - e_small, 1.0) + 8 * (g_gen - g_small) + 8 * c * (g_gen - g_small)
     return {
-        # tinf, inf, 4 profile + k0 reads (28) + T write (4)
-        "k_transmission": 32.0,
-        # member ids 4e + T gathers 4e + group ptr/pc 8g + two sums written 8cg
-        "k_group_small<fwd>": 4 * e_small + 4 * min(e_small, 1.0) + 8 * g_small + 8 * c * g_small,
-        "k_group_chunk<fwd>": 4 * (e_bar - e_small) + 4 * min(e_bar - e_small, 1.0) + 8 * (g_bar - g_small)
-        + 8 * c * (g_bar - g_small),
-        "k_group_small<bwd>": 4 * e_small + 4 * min(e_small, 1.0) + 8 * g_small + 8 * c * g_small,
-        "k_group_chunk<bwd>": 4 * (e_bar - e_small) + 4 * min(e_bar - e_small, 1.0) + 8 * (g_bar - g_small)
-        + 8 * c * (g_bar - g_small),
-        # state in 24 + cls 1 + row ptr 4 + entries 4e + group sums 4cg + state out 24 + tape 8
-        "k_agent_forward": 24 + 1 + 4 + 4 * e_bar + 4 * c * g_bar + 24 + 8,
-        # state in 24 + post is_infected 4 + tape 8 + cls 1 + cotangents in 8 (is_infected, stage) + out 20 + w 4
-        "k_agent_backward": 24 + 4 + 8 + 1 + 8 + 20 + 4,
-        # row ptr 4 + entries 4e + cR 4cg + profile/state 28 + cls/cur 5 + RMW of two cotangents 16
-        "k_agent_backward_gather": 4 + 4 * e_bar + 4 * c * g_bar + 28 + 5 + 16,
+        # is_infected, infection_time, 4 profile + k0 (28) + class byte + T write
+        "k_tile_transmission": 28 + 1 + 4,
+        "k_group_small<fwd>": grp_small, "k_group_chunk<fwd>": grp_chunk,
+        "k_group_small<bwd>": grp_small, "k_group_chunk<bwd>": grp_chunk,
+        # state in 24 + class 1 + household slot+pc 8 + T 4 + row ptr 4 + generic entries + group sums + state out 24 + tape 8
+        "k_tile_forward": 24 + 1 + 8 + 4 + 4 + 4 * e_gen + 4 * c * g_gen + 24 + 8,
+        # state in 24 + post is_infected 4 + tape 8 + class 1 + cotangents in (is_infected, stage) 8 + out 20 + w 4
+        "k_tile_backward": 24 + 4 + 8 + 1 + 8 + 20 + 4,
+        # class 1 + household slot+pc 8 + w 4 + T 4 + row ptr 4 + generic entries + cR + profile/state 28 + RMW of 2 cotangents 16
+        "k_tile_backward_gather": 1 + 8 + 4 + 4 + 4 + 4 * e_gen + 4 * c * g_gen + 28 + 16,
     }
 
 

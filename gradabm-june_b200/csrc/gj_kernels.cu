@@ -1,14 +1,14 @@
 // Kernels + C ABI of the B200-native infection step (see include/gradjune_b200.h).
 //
-// One timestep forward = 3 passes over HBM-resident arrays:
-//   F1  k_transmission      agent-major   state -> T (and quarantine-masked Tq)
-//   F2  k_group_small/chunk group-major   CSR-sorted members -> per-group sums S (deterministic order)
-//        (+ k_group_fix for groups that span several chunks)
-//   F3  k_agent_forward     agent-major   gather S over the agent's groups -> pressure -> q ->
-//                                         Gumbel-softmax draw -> state + symptoms update -> reductions
-// and backward mirrors it (B1 k_agent_backward, B2 the same group kernels on cotangents, B3
-// k_agent_backward_gather, k_dbeta).  No global atomics on data: group sums are segmented reductions
-// over the CSR member lists in a fixed order, so results are bit-reproducible run to run.
+// One timestep forward = passes over HBM-resident arrays (tile kernels in gj_tiled.cuh):
+//   K1  k_tile_transmission  agent tiles   state -> T (and quarantine-masked Tq); tile partials of CELL types
+//   K2  k_group_small/chunk  group-major   CSR-sorted members -> per-group sums S (GENERIC types only)
+//        (+ k_group_fix for groups that span several chunks); k_cell_groups/k_cell_gather for CELL types
+//   K3  k_tile_forward       agent tiles   pressure from RANGE / CELL / GENERIC tiers -> q -> Gumbel-softmax
+//                                          draw -> state + symptoms update -> reductions
+// and backward mirrors it (k_tile_backward, the same group/cell kernels on cotangents,
+// k_tile_backward_gather, k_dbeta).  No global atomics on data: every sum has a fixed order, so results
+// are bit-reproducible run to run.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include "gj_device.cuh"
+#include "gj_tiled.cuh"
 
 namespace gj {
 
@@ -38,12 +39,12 @@ static int bad(const char* what) {
 // ---- optional per-kernel timing with CUDA events on the launching stream (gj_profile_*) -------------
 enum KernelId {
   K_TRANSMISSION = 0, K_GROUP_SMALL_F, K_GROUP_CHUNK_F, K_GROUP_FIX_F, K_AGENT_FWD,
-  K_AGENT_BWD, K_GROUP_SMALL_B, K_GROUP_CHUNK_B, K_GROUP_FIX_B, K_DBETA, K_AGENT_BWD_GATHER, K_OTHER, K_COUNT
+  K_AGENT_BWD, K_GROUP_SMALL_B, K_GROUP_CHUNK_B, K_GROUP_FIX_B, K_DBETA, K_AGENT_BWD_GATHER, K_CELL, K_OTHER, K_COUNT
 };
 static const char* kKernelNames[K_COUNT] = {
-  "k_transmission", "k_group_small<fwd>", "k_group_chunk<fwd>", "k_group_fix<fwd>", "k_agent_forward",
-  "k_agent_backward", "k_group_small<bwd>", "k_group_chunk<bwd>", "k_group_fix<bwd>", "k_dbeta",
-  "k_agent_backward_gather", "other"};
+  "k_tile_transmission", "k_group_small<fwd>", "k_group_chunk<fwd>", "k_group_fix<fwd>", "k_tile_forward",
+  "k_tile_backward", "k_group_small<bwd>", "k_group_chunk<bwd>", "k_group_fix<bwd>", "k_dbeta",
+  "k_tile_backward_gather", "k_cell_groups+gather", "other"};
 constexpr int kMaxProfiled = 16384;
 struct Profiler {
   bool on = false;
@@ -80,35 +81,47 @@ static inline int agent_grid(int64_t n) {
   return (int)(b < 1 ? 1 : b);
 }
 
-// scratch layout (bytes): [0,128) tickets | red partials double[kRedBlocks][kMaxRed] |
-//                         dbeta partials double[GJ_MAX_NETS][kRedBlocks] | part_a float[n_parts*nets] | part_b ...
+// scratch layout: tickets | reduction partials | d/dbeta partials | chunk partial sums (generic tier) |
+//                 tile partial sums + per-cell values (cell tier) | per-tile d/dbeta partials (range tier)
 struct Scratch {
   unsigned int* tickets;
-  double* red_part;
-  double* dbeta_part;
-  float* part_a;  // [GJ_MAX_NETS][n_parts]
+  double* red_part;    // [max(n_tiles, kRedBlocks)][kMaxRed]
+  double* dbeta_part;  // [GJ_MAX_NETS][kRedBlocks]
+  float* part_a;       // [GJ_MAX_CHANNELS][n_parts]
   float* part_b;
+  float* tile_part;    // [n_tiles][GJ_MAX_CHANNELS]
+  float* cell_buf;     // [n_cells_total][GJ_MAX_CHANNELS]
+  double* dbeta_tile;  // [n_tiles][GJ_MAX_RANGE_NETS]
 };
-static inline int64_t scratch_bytes(const gj_world_desc* w) {
-  int64_t b = 128;
-  b += (int64_t)sizeof(double) * kRedBlocks * kMaxRed;
-  b += (int64_t)sizeof(double) * GJ_MAX_NETS * kRedBlocks;
-  b += 2 * (int64_t)sizeof(float) * GJ_MAX_NETS * (w->n_parts > 0 ? w->n_parts : 1);
-  return (b + 255) / 256 * 256;
-}
-static inline Scratch carve(const gj_world_desc* w, void* base) {
+static inline int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
+static inline Scratch carve(const gj_world_desc* w, void* base, int64_t* total) {
   Scratch s;
+  int64_t off = 0;
   char* p = (char*)base;
-  s.tickets = (unsigned int*)p;
-  p += 128;
-  s.red_part = (double*)p;
-  p += sizeof(double) * kRedBlocks * kMaxRed;
-  s.dbeta_part = (double*)p;
-  p += sizeof(double) * GJ_MAX_NETS * kRedBlocks;
-  s.part_a = (float*)p;
-  p += sizeof(float) * GJ_MAX_NETS * (w->n_parts > 0 ? w->n_parts : 1);
-  s.part_b = (float*)p;
+  const int64_t n_tiles = w->n_tiles > 0 ? w->n_tiles : 1;
+  const int64_t n_red = n_tiles > kRedBlocks ? n_tiles : kRedBlocks;
+  const int64_t n_parts = w->n_parts > 0 ? w->n_parts : 1;
+  const int64_t n_cells = w->n_cells_total > 0 ? w->n_cells_total : 1;
+  auto take = [&](int64_t bytes) {
+    char* r = p ? p + off : nullptr;
+    off += align256(bytes);
+    return r;
+  };
+  s.tickets = (unsigned int*)take(256);
+  s.red_part = (double*)take((int64_t)sizeof(double) * n_red * kMaxRed);
+  s.dbeta_part = (double*)take((int64_t)sizeof(double) * GJ_MAX_NETS * kRedBlocks);
+  s.part_a = (float*)take((int64_t)sizeof(float) * GJ_MAX_CHANNELS * n_parts);
+  s.part_b = (float*)take((int64_t)sizeof(float) * GJ_MAX_CHANNELS * n_parts);
+  s.tile_part = (float*)take((int64_t)sizeof(float) * GJ_MAX_CHANNELS * n_tiles);
+  s.cell_buf = (float*)take((int64_t)sizeof(float) * GJ_MAX_CHANNELS * n_cells);
+  s.dbeta_tile = (double*)take((int64_t)sizeof(double) * GJ_MAX_RANGE_NETS * n_tiles);
+  if (total) *total = off;
   return s;
+}
+static inline int64_t scratch_bytes(const gj_world_desc* w) {
+  int64_t total = 0;
+  carve(w, nullptr, &total);
+  return total;
 }
 
 // per-type channel table derived from the net list (host, passed by value)
@@ -126,24 +139,12 @@ __global__ void __launch_bounds__(kBlock) k_transmission(int64_t n, float now, c
                                                          const float* __restrict__ shape,
                                                          const float* __restrict__ rate,
                                                          const float* __restrict__ shift,
-                                                         const float* __restrict__ k0, float* __restrict__ T,
-                                                         // optional quarantine-masked copy
-                                                         gj_step_params p, const float* __restrict__ cur,
-                                                         float* __restrict__ Tq) {
+                                                         const float* __restrict__ k0, float* __restrict__ T) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += stride) {
     const TransTerms tt = transmission_terms<false>(now, tinf[a], maxinf[a], shape[a], rate[a], shift[a], k0[a]);
-    const float t = tt.coef * inf[a];
-    T[a] = t;
-    if (Tq != nullptr && Tq != T) Tq[a] = quarantine_mask(p, cur[a]) * t;
+    T[a] = tt.coef * inf[a];
   }
-}
-
-__global__ void __launch_bounds__(kBlock) k_mask_transmission(int64_t n, gj_step_params p, const float* __restrict__ cur,
-                                                              const float* __restrict__ T, float* __restrict__ Tq) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += stride)
-    Tq[a] = quarantine_mask(p, cur[a]) * T[a];
 }
 
 __global__ void __launch_bounds__(kBlock) k_transmission_bwd(int64_t n, float now, const float* __restrict__ tinf,
@@ -372,327 +373,81 @@ __device__ __forceinline__ void block_reduce_finish(double (&v)[kR], int nr, dou
 }
 
 // ================================================================================================
-// F3  agent-major forward
+// agent-major kernels for calls WITHOUT the networks phase (stand-alone sampler / infect / symptoms and the
+// seeding step): persistent grid-stride loop, reductions finished by the last CTA
 // ================================================================================================
-struct Masks {
-  float mT, mS, mS_age;  // mS_age: care-visit (age > 75) factor
-};
-
-__device__ __forceinline__ Masks net_masks(const gj_step_params& p, const gj_net& net, float mq, int cls,
-                                           const float* __restrict__ lprob) {
-  Masks m;
-  m.mS_age = 1.0f;
-  if (net.kind == GJ_KIND_HOUSEHOLD) {
-    m.mT = m.mS = 1.0f;
-  } else if (net.kind == GJ_KIND_PLAIN) {
-    m.mT = m.mS = mq;
-  } else {
-    const float lm = leisure_prob(lprob, net.prob_row, p.day_type, cls);
-    m.mT = m.mS = mq * lm;
-    if (net.kind == GJ_KIND_CARE_VISIT) m.mS_age = ((cls % 100) > 75) ? 1.0f : 0.0f;
-  }
-  return m;
-}
-
 __global__ void __launch_bounds__(kBlock) k_agent_forward(gj_world_desc w, gj_step_params p, gj_fwd_io io,
                                                           double* __restrict__ red_part,
                                                           unsigned int* __restrict__ ticket) {
   const int64_t N = w.n_agents;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int dead = p.n_stages - 1;
   double red[kMaxRed];
 #pragma unroll
   for (int r = 0; r < kMaxRed; ++r) red[r] = 0.0;
-
   for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < N; a += stride) {
     const int cls = w.cls ? w.cls[a] : 0;
-    const int age = cls % 100;
-    float s = io.s ? io.s[a] : 0.0f;
-    float inf = io.inf ? io.inf[a] : 0.0f;
-    float tinf = io.tinf ? io.tinf[a] : 0.0f;
-    float cur = io.cur ? io.cur[a] : 1.0f;
-    float nxt = io.nxt ? io.nxt[a] : 1.0f;
-    float ttn = io.ttn ? io.ttn[a] : 0.0f;
-
-    float q = 1.0f;
-    // ---- InfectionNetworks.forward: gather the group sums of every active network ----------------
-    if (p.phases & GJ_PHASE_NETWORKS) {
-      const float mq = (p.n_quar > 0) ? quarantine_mask(p, cur) : 1.0f;
-      float lam = 0.0f, X = 0.0f;
-      const uint32_t e0 = w.am_ptr[a], e1 = w.am_ptr[a + 1];
-      for (int k = 0; k < p.n_nets; ++k) {
-        const gj_net net = p.nets[k];
-        const Masks m = net_masks(p, net, mq, cls, io.leisure_prob);
-        float sp = m.mS * s;  // susceptibilities = mask * [leisure_mask *] susceptibility
-        float sx = m.mS;
-        if (net.kind == GJ_KIND_CARE_VISIT) {
-          sp = sp * m.mS_age;
-          sx = sx * m.mS_age;
-        }
-        float Pk = 0.0f, PXk = 0.0f;
-        for (uint32_t j = e0; j < e1; ++j) {
-          const uint32_t ent = w.am_ent[j];
-          if ((int)(ent >> 28) == net.type) {
-            const float Sg = io.S_scaled[(int64_t)net.s_off + (ent & 0x0FFFFFFFu)];
-            Pk += Sg * sp;  // message = cumulative_trans * susceptibility   base.py:80-87
-            PXk += Sg * sx;
-          }
-        }
-        lam += Pk;  // trans_susc += network(...)   base.py:133-135
-        X += PXk;
-      }
-      q = not_infected_prob(lam, p.dt);
-      if (io.tape_v) io.tape_v[a] = (s == 0.0f) ? X : lam;
-      if (io.q) io.q[a] = q;
-      if (io.lam) io.lam[a] = lam;
-    } else if (io.q_in) {
-      q = io.q_in[a];
-    }
-    if (p.mode == GJ_MODE_SEED) {
-      const float f = io.seed_fraction[0];
-      const float probs = f * 1.0f;
-      q = 1.0f - probs;  // infection.py:36-40
-    }
-
-    // ---- IsInfectedSampler.forward -----------------------------------------------------------------
-    float n = 0.0f;
-    StepNoise nz;
-    nz.E0 = nz.E1 = 1.0f;
-    nz.u = 0.0f;
-    const bool need_noise = (p.phases & (GJ_PHASE_SAMPLE | GJ_PHASE_SYMPTOMS)) != 0;
-    if (need_noise) {
-      if (io.inj_E == nullptr || io.inj_u == nullptr) nz = draw_step_noise(p.seed, p.call_index, a);
-      if (io.inj_E) {
-        nz.E0 = io.inj_E[a];
-        nz.E1 = io.inj_E[N + a];
-      }
-      if (io.inj_u) nz.u = io.inj_u[a];
-    }
-    if (p.phases & GJ_PHASE_SAMPLE) {
-      const Draw d = gumbel_draw(q, nz.E0, nz.E1, p.tau);
-      n = d.n;
-      if (io.tape_y0) io.tape_y0[a] = d.ty;
-    } else if (io.n_in) {
-      n = io.n_in[a];
-    }
-    if (io.n) io.n[a] = n;
-
-    // ---- infect_people ---------------------------------------------------------------------------
-    if (p.phases & GJ_PHASE_INFECT) {
-      s = fmaxf(0.0f, s - n);  // maximum(0, s - n) and clamp(s - n, min=0) agree in value
-      inf = inf + n;
-      tinf = tinf + n * (p.now - tinf);
-      if (io.s_o) io.s_o[a] = s;
-      if (io.inf_o) io.inf_o[a] = inf;
-      if (io.tinf_o) io.tinf_o[a] = tinf;
-    }
-
-    // ---- SymptomsUpdater.forward -----------------------------------------------------------------
-    if (p.phases & GJ_PHASE_SYMPTOMS) {
-      const float* inj_z = io.inj_z;
-      const uint64_t seed = p.seed;
-      const uint32_t call = p.call_index;
-      const SympOut so = symptoms_forward(p, io.stage_prob, cur, nxt, ttn, n, age, nz.u, [&](int row) {
-        return inj_z ? inj_z[(int64_t)row * N + a] : draw_step_normal(seed, call, a);
-      });
-      cur = so.cur;
-      nxt = so.nxt;
-      ttn = so.ttn;
-      if (io.cur_o) io.cur_o[a] = cur;
-      if (io.nxt_o) io.nxt_o[a] = nxt;
-      if (io.ttn_o) io.ttn_o[a] = ttn;
-    }
-
-    // ---- Runner.forward reductions (runner.py:167-171,198-224) ------------------------------------
-    if (io.red) {
-      red[0] += (double)inf;
-      red[1] += (cur == (float)dead) ? (double)(cur / (float)dead) : 0.0;
-      for (int b = 0; b < p.n_age_bins; ++b)
-        if (age > p.age_bins[b] && age < p.age_bins[b + 1]) red[2 + b] += (double)inf;
-    }
+    AgentState st;
+    st.s = io.s ? io.s[a] : 0.0f;
+    st.inf = io.inf ? io.inf[a] : 0.0f;
+    st.tinf = io.tinf ? io.tinf[a] : 0.0f;
+    st.cur = io.cur ? io.cur[a] : 1.0f;
+    st.nxt = io.nxt ? io.nxt[a] : 1.0f;
+    st.ttn = io.ttn ? io.ttn[a] : 0.0f;
+    const float q = io.q_in ? io.q_in[a] : 1.0f;
+    forward_tail(p, io, N, a, cls % 100, q, st, red);
   }
   if (io.red) block_reduce_finish<kMaxRed>(red, 2 + p.n_age_bins, red_part, ticket, io.red);
 }
 
-// ================================================================================================
-// B1  agent-major backward, part 1: symptoms^T, infect^T, sampler^T, pressure^T up to the group sums
-// ================================================================================================
 __global__ void __launch_bounds__(kBlock) k_agent_backward(gj_world_desc w, gj_step_params p, gj_bwd_io io,
                                                            double* __restrict__ red_part,
                                                            unsigned int* __restrict__ ticket) {
   const int64_t N = w.n_agents;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int dead = p.n_stages - 1;
   double gfrac[1] = {0.0};
   const bool seed_mode = p.mode == GJ_MODE_SEED;
-
   for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < N; a += stride) {
     const int cls = w.cls ? w.cls[a] : 0;
-    const int age = cls % 100;
-    const float s = io.s ? io.s[a] : 0.0f;
-    const float inf = io.inf ? io.inf[a] : 0.0f;
-    const float tinf = io.tinf ? io.tinf[a] : 0.0f;
-    const float cur = io.cur ? io.cur[a] : 1.0f;
-    const float nxt = io.nxt ? io.nxt[a] : 1.0f;
-    const float ttn = io.ttn ? io.ttn[a] : 0.0f;
-    float n = 0.0f;
-    if (io.inf_o) n = io.inf_o[a] - inf;  // exact: both are small integers
-    else if (io.n_in) n = io.n_in[a];
-
-    float gs_o = io.g_s_o ? io.g_s_o[a] : 0.0f;
-    float ginf_o = io.g_inf_o ? io.g_inf_o[a] : 0.0f;
-    float gtinf_o = io.g_tinf_o ? io.g_tinf_o[a] : 0.0f;
-    float gcur_o = io.g_cur_o ? io.g_cur_o[a] : 0.0f;
-    float gnxt_o = io.g_nxt_o ? io.g_nxt_o[a] : 0.0f;
-    float gttn_o = io.g_ttn_o ? io.g_ttn_o[a] : 0.0f;
-    float gn = io.g_n ? io.g_n[a] : 0.0f;
-
-    float gcur = gcur_o, gnxt = gnxt_o, gttn = gttn_o;
-    // ---- symptoms^T ------------------------------------------------------------------------------
-    if (p.phases & GJ_PHASE_SYMPTOMS) {
-      float u = 0.0f;
-      if (io.inj_u) u = io.inj_u[a];
-      else u = draw_step_noise(p.seed, p.call_index, a).u;
-      const float* inj_z = io.inj_z;
-      const uint64_t seed = p.seed;
-      const uint32_t call = p.call_index;
-      const SympOut so = symptoms_forward(p, io.stage_prob, cur, nxt, ttn, n, age, u, [&](int row) {
-        return inj_z ? inj_z[(int64_t)row * N + a] : draw_step_normal(seed, call, a);
-      });
-      // reductions fold in here: deaths = sum (cur' == dead) * cur' / dead   runner.py:204-209
-      if (io.g_red && so.cur == (float)dead) gcur_o += io.g_red[1] / (float)dead;
-      float gcur1 = gcur_o;
-      float gnxt1 = gnxt_o;
-      const float gttn1 = gttn_o;
-      if (so.branch == 1) {         // next += m ; ttn += dwell * m ; m = (cur==i)*cur/i * transition * symp
-        gcur1 += (gnxt_o + gttn_o * so.dwell) / (float)so.stage;
-      } else if (so.branch == 2) {  // next -= next * m ; ttn += dwell * m
-        gcur1 += (gttn_o * so.dwell - gnxt_o * so.nxt1) / (float)so.stage;
-        gnxt1 = 0.0f;               // d(next - next*m)/dnext = 1 - m = 0
-      }
-      gcur = gcur1 * (1.0f - so.tr);  // cur' = cur - (cur - next1) * transition
-      gnxt1 += gcur1 * so.tr;
-      gnxt = gnxt1 * (1.0f - n);      // next1 = next + n * (2 - next)
-      gn += gnxt1 * (2.0f - nxt);
-      gttn = gttn1 * (1.0f - n);      // ttn1 = ttn + n * (now - ttn)
-      gn += gttn1 * (p.now - ttn);
-    } else if (io.g_red && cur == (float)dead) {
-      gcur += io.g_red[1] / (float)dead;
-    }
-
-    // ---- infect^T -------------------------------------------------------------------------------
-    float gs = gs_o, ginf = ginf_o, gtinf = gtinf_o;
-    if (io.g_red) {
-      ginf_o += io.g_red[0];
-      for (int b = 0; b < p.n_age_bins; ++b)
-        if (age > p.age_bins[b] && age < p.age_bins[b + 1]) ginf_o += io.g_red[2 + b];
-      ginf = ginf_o;
-    }
-    if (p.phases & GJ_PHASE_INFECT) {
-      const float d = s - n;
-      float wgt;
-      if (seed_mode) wgt = (d >= 0.0f) ? 1.0f : 0.0f;            // clamp(min=0): gradient where x >= min
-      else wgt = (d > 0.0f) ? 1.0f : ((d == 0.0f) ? 0.5f : 0.0f);  // maximum(0, x): ties split 1/2
-      gs = gs_o * wgt;
-      gn += -(gs_o * wgt) + ginf_o + gtinf_o * (p.now - tinf);
-      ginf = ginf_o;
-      gtinf = gtinf_o * (1.0f - n);
-    }
-
-    // ---- sampler^T -------------------------------------------------------------------------------
-    float gq = io.g_q ? io.g_q[a] : 0.0f;
-    float lam = 0.0f, q = 1.0f, v = 0.0f;
-    if (p.phases & GJ_PHASE_NETWORKS) {
-      v = io.tape_v[a];
-      lam = (s == 0.0f) ? 0.0f : v;
-      q = not_infected_prob(lam, p.dt);
-    }
-    if (seed_mode) q = 1.0f - io.seed_fraction[0] * 1.0f;
-    if (p.phases & GJ_PHASE_SAMPLE) {
-      if (!(p.phases & GJ_PHASE_NETWORKS) && !seed_mode && io.q_in) q = io.q_in[a];  // stand-alone sampler
-      float y0, y1;
-      decode_soft(io.tape_y0[a], y0, y1);
-      const float gret0 = -gn;                        // new_infected = 1 - ret[0]
-      const float dot = gret0 * y0;                   // softmax^T: (g - sum(g*y)) * y with g = (gret0, 0)
-      const float gx0 = (gret0 - dot) * y0;
-      const float gx1 = (0.0f - dot) * y1;
-      const float gl0 = gx0 / p.tau, gl1 = gx1 / p.tau;
-      gq += gl0 / q - gl1 / (1.0f - q);               // logits = log([q, 1-q])
-    }
-    if (io.g_q_out) io.g_q_out[a] = gq;
-    if (io.g_n_out) io.g_n_out[a] = gn;
-    if (seed_mode) gfrac[0] += (double)(-gq);     // q = 1 - fraction
-
-    // ---- pressure^T, agent side ------------------------------------------------------------------
-    if (p.phases & GJ_PHASE_NETWORKS) {
-      // q = clamp(exp(-clamp(lam)*dt), 0, 1): clamp passes the gradient on its closed interval
-      float glam = 0.0f;
-      if (q >= 0.0f && q <= 1.0f) {
-        const float glc = gq * q * (-p.dt);
-        if (lam >= 1e-6f && lam <= 100.0f) glam = glc;
-      }
-      if (io.g_lam) glam += io.g_lam[a];
-      const float X = (s == 0.0f) ? v : v / s;
-      gs += glam * X;
-      const float mq = (p.n_quar > 0) ? quarantine_mask(p, cur) : 1.0f;
-      const float wv = glam * s;
-      io.w[a] = wv;
-      if (io.wq != io.w) io.wq[a] = glam * (mq * s);
-    }
-    if (io.g_s) io.g_s[a] = gs;
-    if (io.g_inf) io.g_inf[a] = ginf;
-    if (io.g_tinf) io.g_tinf[a] = gtinf;
-    if (io.g_cur) io.g_cur[a] = gcur;
-    if (io.g_nxt) io.g_nxt[a] = gnxt;
-    if (io.g_ttn) io.g_ttn[a] = gttn;
+    AgentState st;
+    st.s = io.s ? io.s[a] : 0.0f;
+    st.inf = io.inf ? io.inf[a] : 0.0f;
+    st.tinf = io.tinf ? io.tinf[a] : 0.0f;
+    st.cur = io.cur ? io.cur[a] : 1.0f;
+    st.nxt = io.nxt ? io.nxt[a] : 1.0f;
+    st.ttn = io.ttn ? io.ttn[a] : 0.0f;
+    const BackAgent r = backward_agent(p, io, N, a, cls % 100, st, false);
+    if (io.g_q_out) io.g_q_out[a] = r.gq;
+    if (io.g_n_out) io.g_n_out[a] = r.gn;
+    if (seed_mode) gfrac[0] += (double)(-r.gq);  // q = 1 - fraction
+    if (io.g_s) io.g_s[a] = r.gs;
+    if (io.g_inf) io.g_inf[a] = r.ginf;
+    if (io.g_tinf) io.g_tinf[a] = r.gtinf;
+    if (io.g_cur) io.g_cur[a] = r.gcur;
+    if (io.g_nxt) io.g_nxt[a] = r.gnxt;
+    if (io.g_ttn) io.g_ttn[a] = r.gttn;
   }
   if (seed_mode && io.g_seed_fraction) block_reduce_finish<1>(gfrac, 1, red_part, ticket, io.g_seed_fraction);
 }
 
-// ================================================================================================
-// B3  agent-major backward, part 2: gather c_g * R_g -> dL/dT -> (is_infected, infection_time)
-// ================================================================================================
-__global__ void __launch_bounds__(kBlock) k_agent_backward_gather(gj_world_desc w, gj_step_params p, gj_bwd_io io) {
-  const int64_t N = w.n_agents;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < N; a += stride) {
-    const int cls = w.cls[a];
-    const float cur = io.cur ? io.cur[a] : 1.0f;
-    const float mq = (p.n_quar > 0) ? quarantine_mask(p, cur) : 1.0f;
-    float gT = 0.0f;
-    const uint32_t e0 = w.am_ptr[a], e1 = w.am_ptr[a + 1];
-    for (int k = 0; k < p.n_nets; ++k) {
-      const gj_net net = p.nets[k];
-      const Masks m = net_masks(p, net, mq, cls, io.leisure_prob);
-      float acc = 0.0f;
-      for (uint32_t j = e0; j < e1; ++j) {
-        const uint32_t ent = w.am_ent[j];
-        if ((int)(ent >> 28) == net.type) acc += io.cR[(int64_t)net.s_off + (ent & 0x0FFFFFFFu)];
-      }
-      gT += m.mT * acc;
-    }
-    if (io.g_T) {
-      io.g_T[a] = gT;
-    } else {
-      const TransTerms tt =
-          transmission_terms<true>(p.now, io.tinf[a], io.maxinf[a], io.shape[a], io.rate[a], io.shift[a], io.k0[a]);
-      if (io.g_inf) io.g_inf[a] += gT * tt.coef;
-      if (io.g_tinf) io.g_tinf[a] += gT * (tt.dcoef * io.inf[a]);
-    }
-  }
-}
-
 // dL/dbeta_k = sum_g pc_g * S~_g * R_g   (fixed-order two-level sum in fp64)
-__global__ void __launch_bounds__(kBlock) k_dbeta(gj_world_desc w, gj_step_params p, const float* __restrict__ S_un,
-                                                  const float* __restrict__ R, double* __restrict__ partials,
+__global__ void __launch_bounds__(kBlock) k_dbeta(gj_world_desc w, gj_step_params p, Plan pl,
+                                                  const float* __restrict__ S_un, const float* __restrict__ R,
+                                                  const double* __restrict__ dbeta_tile, double* __restrict__ partials,
                                                   unsigned int* __restrict__ tickets, float* __restrict__ g_beta) {
   const int k = blockIdx.y;
   const gj_net net = p.nets[k];
-  const int64_t g0 = w.type_group_off[net.type];
-  const int64_t G = w.type_group_off[net.type + 1] - g0;
   double acc[1] = {0.0};
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < G; i += (int64_t)gridDim.x * blockDim.x)
-    acc[0] += (double)(w.pc[g0 + i] * S_un[(int64_t)net.s_off + i]) * (double)R[(int64_t)net.s_off + i];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (w.type_tier[net.type] == GJ_TIER_RANGE) {  // per-tile partials written by k_tile_backward_gather
+    const int i = pl.net_t1[k];
+    for (int64_t tl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tl < w.n_tiles; tl += stride)
+      acc[0] += dbeta_tile[tl * GJ_MAX_RANGE_NETS + i];
+  } else {
+    const int64_t g0 = w.type_group_off[net.type];
+    const int64_t G = w.type_group_off[net.type + 1] - g0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < G; i += stride)
+      acc[0] += (double)(w.pc[g0 + i] * S_un[(int64_t)net.s_off + i]) * (double)R[(int64_t)net.s_off + i];
+  }
   block_reduce_finish<1>(acc, 1, partials + (int64_t)k * kRedBlocks, tickets + 1 + k, g_beta + k);
 }
 
@@ -713,14 +468,35 @@ __global__ void k_philox_fill(uint64_t seed, uint32_t call, int64_t n, float* __
 // ================================================================================================
 // host side
 // ================================================================================================
-static int build_channels(const gj_world_desc* w, const gj_step_params* p, Channels* ch) {
+static int build_channels(const gj_world_desc* w, const gj_step_params* p, Channels* ch, Plan* pl) {
   memset(ch, 0, sizeof(*ch));
+  memset(pl, 0, sizeof(*pl));
   if (p->n_nets < 0 || p->n_nets > GJ_MAX_NETS) return bad("n_nets");
   for (int k = 0; k < p->n_nets; ++k) {
     const int t = p->nets[k].type;
     if (t < 0 || t >= w->n_types) return bad("net.type");
-    if (ch->nch[t] >= GJ_MAX_CHANNELS) return bad("too many networks share one edge type");
-    ch->net[t][ch->nch[t]++] = k;
+    pl->net_t1[k] = pl->net_t2[k] = pl->net_lei[k] = -1;
+    const int kind = p->nets[k].kind;
+    if (kind == GJ_KIND_LEISURE || kind == GJ_KIND_CARE_VISIT) {
+      if (pl->n_lei >= GJ_MAX_CHANNELS) return bad("too many networks with attendance tables");
+      if (p->nets[k].prob_row < 0) return bad("leisure network without a table row");
+      pl->net_lei[k] = pl->n_lei;
+      pl->lei_net[pl->n_lei++] = k;
+    }
+    const int tier = w->type_tier[t];
+    if (tier == GJ_TIER_RANGE) {
+      if (pl->n_t1 >= GJ_MAX_RANGE_NETS) return bad("too many networks on range-tier edge types");
+      pl->net_t1[k] = pl->n_t1;
+      pl->t1_net[pl->n_t1++] = k;
+    } else if (tier == GJ_TIER_CELL) {
+      if (pl->n_t2 >= GJ_MAX_CHANNELS) return bad("too many networks on cell-tier edge types");
+      pl->net_t2[k] = pl->n_t2;
+      pl->t2_net[pl->n_t2++] = k;
+    } else {
+      if (ch->nch[t] >= GJ_MAX_CHANNELS) return bad("too many networks share one edge type");
+      ch->net[t][ch->nch[t]++] = k;
+      pl->n_generic++;
+    }
   }
   return 0;
 }
@@ -759,6 +535,26 @@ static int launch_group_pass(const gj_world_desc* w, const gj_step_params* p, co
   return 0;
 }
 
+// cell tier: tile partials -> per-group sums (plain + beta*pc-scaled) -> per-cell sum of the scaled group sums
+static int launch_cell_pass(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const float* beta,
+                            float* out_scaled, float* out_plain, const Scratch& sc, cudaStream_t st) {
+  if (pl.n_t2 == 0) return 0;
+  int64_t maxG = 1, maxC = 1;
+  for (int j = 0; j < pl.n_t2; ++j) {
+    const int t = p->nets[pl.t2_net[j]].type;
+    const int64_t G = w->type_group_off[t + 1] - w->type_group_off[t];
+    if (G > maxG) maxG = G;
+    if (w->n_cells[t] > maxC) maxC = w->n_cells[t];
+  }
+  ProfScope ps(K_CELL, st);
+  k_cell_groups<<<dim3(blocks_for(maxG, kBlock), pl.n_t2), kBlock, 0, st>>>(*w, *p, pl, beta, sc.tile_part, out_scaled,
+                                                                           out_plain);
+  GJ_CHECK_LAUNCH("k_cell_groups");
+  k_cell_gather<<<dim3(blocks_for(maxC, kBlock), pl.n_t2), kBlock, 0, st>>>(*w, *p, pl, out_scaled, sc.cell_buf);
+  GJ_CHECK_LAUNCH("k_cell_gather");
+  return 0;
+}
+
 }  // namespace gj
 
 using namespace gj;
@@ -769,10 +565,10 @@ int gj_abi_version(void) { return GJ_ABI_VERSION; }
 const char* gj_last_error(void) { return g_err; }
 
 int gj_config(int64_t* out, int n) {
-  const int64_t v[7] = {GJ_SMALL_GROUP,      GJ_CHUNK,          (int64_t)sizeof(gj_world_desc), (int64_t)sizeof(gj_step_params),
-                        (int64_t)sizeof(gj_fwd_io), (int64_t)sizeof(gj_bwd_io), kRedBlocks};
-  for (int i = 0; i < n && i < 7; ++i) out[i] = v[i];
-  return 7;
+  const int64_t v[8] = {GJ_SMALL_GROUP,      GJ_CHUNK,          (int64_t)sizeof(gj_world_desc), (int64_t)sizeof(gj_step_params),
+                        (int64_t)sizeof(gj_fwd_io), (int64_t)sizeof(gj_bwd_io), kRedBlocks, GJ_TILE_AGENTS};
+  for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
+  return 8;
 }
 
 int64_t gj_scratch_bytes(const gj_world_desc* w) { return w ? scratch_bytes(w) : -1; }
@@ -824,10 +620,8 @@ int gj_transmission_forward(int64_t n, float now, const float* tinf, const float
                             void* stream) {
   if (n <= 0) return 0;
   if (!tinf || !inf || !maxinf || !shape || !rate || !shift || !k0 || !T) return bad("NULL array");
-  gj_step_params p;
-  memset(&p, 0, sizeof(p));
   k_transmission<<<agent_grid(n), kBlock, 0, (cudaStream_t)stream>>>(n, now, tinf, inf, maxinf, shape, rate, shift, k0,
-                                                                    T, p, nullptr, nullptr);
+                                                                    T);
   GJ_CHECK_LAUNCH("k_transmission");
   return 0;
 }
@@ -851,44 +645,48 @@ int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fw
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t N = w->n_agents;
   if (N == 0) return 0;
-  const Scratch sc = carve(w, io->scratch);
+  const Scratch sc = carve(w, io->scratch, nullptr);
   Channels ch;
-  if (int e = build_channels(w, p, &ch)) return e;
-  const bool nets = (p->phases & GJ_PHASE_NETWORKS) && p->mode == GJ_MODE_STEP;
+  Plan pl;
+  if (int e = build_channels(w, p, &ch, &pl)) return e;
   gj_step_params pp = *p;
   if (p->mode == GJ_MODE_SEED) {
     pp.phases &= ~GJ_PHASE_NETWORKS;
     if (!io->seed_fraction) return bad("seed_fraction is NULL");
   }
-  if (nets) {
-    if (!io->beta || !io->S_scaled || !io->S_unscaled) return bad("beta / S buffers are NULL");
-    const float* T = io->T_in;
-    const float* Tq = io->T_in;
-    if (!T) {  // fused: compute the transmissions from the state
-      if (!io->T || !io->tinf || !io->inf || !io->maxinf || !io->k0) return bad("state / T buffers are NULL");
-      float* tq = (p->n_quar > 0) ? io->Tq : io->T;
-      if (!tq) return bad("Tq is NULL with an active quarantine");
-      ProfScope ps(K_TRANSMISSION, st);
-      k_transmission<<<agent_grid(N), kBlock, 0, st>>>(N, p->now, io->tinf, io->inf, io->maxinf, io->shape, io->rate,
-                                                      io->shift, io->k0, io->T, *p, io->cur, tq);
-      GJ_CHECK_LAUNCH("k_transmission");
-      T = io->T;
-      Tq = tq;
-    } else if (p->n_quar > 0) {  // stand-alone InfectionNetworks under a quarantine: mask the given T
-      if (!io->Tq || !io->cur) return bad("Tq / cur are NULL with an active quarantine");
-      k_mask_transmission<<<agent_grid(N), kBlock, 0, st>>>(N, *p, io->cur, io->T_in, io->Tq);
-      GJ_CHECK_LAUNCH("k_mask_transmission");
-      Tq = io->Tq;
-    }
+  if (!(pp.phases & GJ_PHASE_NETWORKS)) {  // stand-alone sampler / infect / symptoms, seeding
+    ProfScope ps(K_AGENT_FWD, st);
+    k_agent_forward<<<agent_grid(N), kBlock, 0, st>>>(*w, pp, *io, sc.red_part, sc.tickets);
+    GJ_CHECK_LAUNCH("k_agent_forward");
+    return 0;
+  }
+  // ---- networks phase (fused step or stand-alone InfectionNetworks): tile kernels ----------------------
+  if (w->n_tiles <= 0 || !w->tile_begin) return bad("world has no tiles");
+  if (!io->beta || !io->S_scaled || !io->S_unscaled || !io->s || !io->tape_v) return bad("beta / S / state buffers are NULL");
+  if (!io->T_in && (!io->T || !io->tinf || !io->inf || !io->maxinf || !io->shape || !io->rate || !io->shift || !io->k0))
+    return bad("state / T buffers are NULL");
+  if (p->n_quar > 0 && (!io->Tq || !io->cur)) return bad("Tq / cur are NULL with an active quarantine");
+  if ((pp.phases & ~GJ_PHASE_NETWORKS) && (!io->inf || !io->tinf || !io->cur || !io->nxt || !io->ttn))
+    return bad("state arrays are NULL");
+  if (pl.n_lei > 0 && !io->leisure_prob) return bad("leisure_prob is NULL");
+  const int grid = (int)w->n_tiles;
+  {
+    ProfScope ps(K_TRANSMISSION, st);
+    k_tile_transmission<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.tile_part);
+    GJ_CHECK_LAUNCH("k_tile_transmission");
+  }
+  const float* T = io->T_in ? io->T_in : io->T;
+  const float* Tq = (p->n_quar > 0) ? io->Tq : T;
+  if (pl.n_generic > 0)
     if (int e = launch_group_pass<false>(w, &pp, ch, io->beta, io->leisure_prob, T, Tq, io->S_scaled, io->S_unscaled, sc,
                                          st))
       return e;
-  }
+  if (int e = launch_cell_pass(w, &pp, pl, io->beta, io->S_scaled, io->S_unscaled, sc, st)) return e;
   {
     ProfScope ps(K_AGENT_FWD, st);
-    k_agent_forward<<<agent_grid(N), kBlock, 0, st>>>(*w, pp, *io, sc.red_part, sc.tickets);
+    k_tile_forward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
+    GJ_CHECK_LAUNCH("k_tile_forward");
   }
-  GJ_CHECK_LAUNCH("k_agent_forward");
   return 0;
 }
 
@@ -899,35 +697,46 @@ int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_b
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t N = w->n_agents;
   if (N == 0) return 0;
-  const Scratch sc = carve(w, io->scratch);
+  const Scratch sc = carve(w, io->scratch, nullptr);
   Channels ch;
-  if (int e = build_channels(w, p, &ch)) return e;
+  Plan pl;
+  if (int e = build_channels(w, p, &ch, &pl)) return e;
   gj_step_params pp = *p;
   if (p->mode == GJ_MODE_SEED) pp.phases &= ~GJ_PHASE_NETWORKS;
-  const bool nets = (pp.phases & GJ_PHASE_NETWORKS) != 0;
-  if (nets && (!io->w || !io->wq || !io->R || !io->cR || !io->tape_v || !io->S_unscaled || !io->beta))
-    return bad("backward workspaces are NULL");
   if ((pp.phases & GJ_PHASE_SAMPLE) && !io->tape_y0) return bad("tape_y0 is NULL");
-  {
+  if (!(pp.phases & GJ_PHASE_NETWORKS)) {
     ProfScope ps(K_AGENT_BWD, st);
     k_agent_backward<<<agent_grid(N), kBlock, 0, st>>>(*w, pp, *io, sc.red_part, sc.tickets);
+    GJ_CHECK_LAUNCH("k_agent_backward");
+    return 0;
   }
-  GJ_CHECK_LAUNCH("k_agent_backward");
-  if (nets) {
+  if (w->n_tiles <= 0 || !w->tile_begin) return bad("world has no tiles");
+  if (!io->w || !io->wq || !io->R || !io->cR || !io->tape_v || !io->S_unscaled || !io->beta || !io->s || !io->T_in)
+    return bad("backward workspaces are NULL");
+  if (p->n_quar > 0 && !io->cur) return bad("cur is NULL with an active quarantine");
+  if (!io->g_T && (!io->tinf || !io->inf || !io->maxinf || !io->k0 || !io->g_inf || !io->g_tinf))
+    return bad("state arrays are NULL");
+  const int grid = (int)w->n_tiles;
+  {
+    ProfScope ps(K_AGENT_BWD, st);
+    k_tile_backward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.tile_part);
+    GJ_CHECK_LAUNCH("k_tile_backward");
+  }
+  if (pl.n_generic > 0)
     if (int e = launch_group_pass<true>(w, &pp, ch, io->beta, io->leisure_prob, io->w, io->wq, io->cR, io->R, sc, st))
       return e;
-    if (io->g_beta && pp.n_nets > 0) {
-      dim3 grid(kRedBlocks / 8, pp.n_nets);
-      ProfScope ps(K_DBETA, st);
-      k_dbeta<<<grid, kBlock, 0, st>>>(*w, pp, io->S_unscaled, io->R, sc.dbeta_part, sc.tickets, io->g_beta);
-      GJ_CHECK_LAUNCH("k_dbeta");
-    }
-    if (io->g_T || io->g_inf || io->g_tinf) {
-      if (!io->g_T && (!io->tinf || !io->inf || !io->maxinf || !io->k0)) return bad("state arrays are NULL");
-      ProfScope ps(K_AGENT_BWD_GATHER, st);
-      k_agent_backward_gather<<<agent_grid(N), kBlock, 0, st>>>(*w, pp, *io);
-      GJ_CHECK_LAUNCH("k_agent_backward_gather");
-    }
+  if (int e = launch_cell_pass(w, &pp, pl, io->beta, io->cR, io->R, sc, st)) return e;
+  {
+    ProfScope ps(K_AGENT_BWD_GATHER, st);
+    k_tile_backward_gather<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.dbeta_tile);
+    GJ_CHECK_LAUNCH("k_tile_backward_gather");
+  }
+  if (io->g_beta && pp.n_nets > 0) {
+    ProfScope ps(K_DBETA, st);
+    dim3 grid2(kRedBlocks / 8, pp.n_nets);
+    k_dbeta<<<grid2, kBlock, 0, st>>>(*w, pp, pl, io->S_unscaled, io->R, sc.dbeta_tile, sc.dbeta_part, sc.tickets,
+                                      io->g_beta);
+    GJ_CHECK_LAUNCH("k_dbeta");
   }
   return 0;
 }

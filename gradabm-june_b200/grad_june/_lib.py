@@ -38,6 +38,13 @@ class WorldDesc(C.Structure):
         ("chunk_group", _u32p), ("chunk_begin", _u32p), ("chunk_end", _u32p), ("chunk_part", C.c_void_p),
         ("n_chunks", C.c_int64),
         ("big_groups", _u32p), ("big_part_ptr", _u32p), ("n_big", C.c_int64), ("n_parts", C.c_int64),
+        ("type_tier", C.c_int32 * GJ_MAX_TYPES),
+        ("range_slot", C.c_void_p * GJ_MAX_TYPES), ("range_pc", C.c_void_p * GJ_MAX_TYPES),
+        ("n_tiles", C.c_int64), ("tile_begin", _u32p),
+        ("n_cells", C.c_int64 * GJ_MAX_TYPES), ("cell_off", C.c_int64 * GJ_MAX_TYPES), ("n_cells_total", C.c_int64),
+        ("tile_cell", C.c_void_p * GJ_MAX_TYPES), ("cell_tile_ptr", C.c_void_p * GJ_MAX_TYPES),
+        ("cell_grp_ptr", C.c_void_p * GJ_MAX_TYPES), ("cell_grp", C.c_void_p * GJ_MAX_TYPES),
+        ("grp_cell_ptr", C.c_void_p * GJ_MAX_TYPES), ("grp_cell", C.c_void_p * GJ_MAX_TYPES),
     ]
 
 
@@ -143,10 +150,10 @@ def lib():
     L.gj_philox4x32_10.restype = None
     L.gj_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
     L.gj_profile_kernel_name.restype = C.c_char_p
-    cfg = (C.c_int64 * 7)()
-    L.gj_config(cfg, 7)
+    cfg = (C.c_int64 * 8)()
+    L.gj_config(cfg, 8)
     _config = {
-        "small_group": cfg[0], "chunk": cfg[1], "red_blocks": cfg[6],
+        "small_group": cfg[0], "chunk": cfg[1], "red_blocks": cfg[6], "tile_agents": cfg[7],
     }
     sizes = {"gj_world_desc": (cfg[2], C.sizeof(WorldDesc)), "gj_step_params": (cfg[3], C.sizeof(StepParams)),
              "gj_fwd_io": (cfg[4], C.sizeof(FwdIO)), "gj_bwd_io": (cfg[5], C.sizeof(BwdIO))}

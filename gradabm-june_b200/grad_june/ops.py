@@ -358,8 +358,10 @@ class _Step(torch.autograd.Function):
 
         ctx.static, ctx.spec, ctx.noise_key = static, spec, (seed, call_index)
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(beta, st["s"], st["inf"], st["tinf"], st["cur"], st["nxt"], st["ttn"], T_in, q_in, n_in,
+        ctx.save_for_backward(beta, st["s"], st["inf"], st["tinf"], st["cur"], st["nxt"], st["ttn"],
+                              T_in if T_in is not None else T, q_in, n_in,
                               seed_fraction, out.get("inf_o"), tape_v, tape_y0, S_un, E, u, z, q, n)
+        ctx.fused_T = fused_T
         outs = (out.get("s_o"), out.get("inf_o"), out.get("tinf_o"), out.get("cur_o"), out.get("nxt_o"),
                 out.get("ttn_o"), T, q, n, red, lam)
         nd = [t for t in (T,) if t is not None]
@@ -398,7 +400,7 @@ class _Step(torch.autograd.Function):
         put("inj_E", E), put("inj_u", u), put("inj_z", z)
         for name, t in zip(_STATE, (s, inf, tinf, cur, nxt, ttn)):
             put(name, t)
-        fused_T = nets_on and T_in is None
+        fused_T = ctx.fused_T
         if fused_T:
             for name in ("maxinf", "shape", "rate", "shift", "k0"):
                 put(name, getattr(static, name))
@@ -434,7 +436,7 @@ class _Step(torch.autograd.Function):
             for name in ("inf", "tinf"):
                 if name not in grads:
                     grads[name] = new("g_" + name)
-        g_T_in = new("g_T") if (nets_on and T_in is not None and need[10]) else None
+        g_T_in = new("g_T") if (nets_on and not fused_T) else None
         g_q_in = new("g_q_out") if (q_in is not None and need[11]) else None
         g_n_in = new("g_n_out") if (n_in is not None and need[12]) else None
         g_beta = new("g_beta", max(p.n_nets, 1), zero=True) if nets_on else None
@@ -453,7 +455,7 @@ class _Step(torch.autograd.Function):
                 grads.get("s") if need[4] else None, grads.get("inf") if need[5] else None,
                 grads.get("tinf") if need[6] else None, grads.get("cur") if need[7] else None,
                 grads.get("nxt") if need[8] else None, grads.get("ttn") if need[9] else None,
-                g_T_in, g_q_in, g_n_in, g_frac if need[13] else None)
+                g_T_in if need[10] else None, g_q_in, g_n_in, g_frac if need[13] else None)
 
 
 def infection_step(static: StepStatic, spec: StepSpec, beta, state: dict, T_in=None, q_in=None, n_in=None,

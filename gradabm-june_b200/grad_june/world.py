@@ -224,8 +224,26 @@ def world_from_arrays(arrays: Dict[str, np.ndarray], types: List[str], device="c
 # --------------------------------------------------------------------------------------
 # CSR layout
 # --------------------------------------------------------------------------------------
+TIER_GENERIC, TIER_RANGE, TIER_CELL = 0, 1, 2
+TILE_AGENTS = 1024          # agents per CTA tile of the agent-major kernels (== GJ_TILE_AGENTS)
+RANGE_MAX_GROUP = 64        # range tier: every agent re-sums its (small) group from its neighbours
+CELL_MIN_MEAN_AGENTS = 256  # cell tier only pays when cells are much larger than a tile row
+CELL_MAX_GROUPS = 16
+
+
 class DeviceWorld:
-    """CSR-sorted device arrays + the ctypes descriptor handed to the library."""
+    """Device arrays of the world + the ctypes descriptor handed to the library.
+
+    Every edge type is stored in the cheapest of three layouts (``type_tier``):
+      * RANGE  — each group is a contiguous, ascending run of agent ids and every agent belongs to at most
+        one group (households after area-contiguous numbering): per agent one packed (offset, size) word and
+        the group's contact probability; group sums are re-formed in-stream from neighbouring agents, there
+        is no group-major pass and no per-group buffer;
+      * CELL   — consecutive agents share the same ordered list of groups (leisure: everybody of a super-area
+        attends the same k nearest venues): agents -> tile partial sums -> cells -> groups, so the per-edge
+        work of the 3 leisure edges per agent collapses to one streaming pass;
+      * GENERIC — CSR in both orientations (companies, schools, ...; any world that is not laid out as above).
+    """
 
     def __init__(self, **kw):
         self.__dict__.update(kw)
@@ -233,15 +251,34 @@ class DeviceWorld:
     def desc(self):
         from . import _lib
 
+        d = self.__dict__.get("_desc")
+        if d is not None:
+            return d
         d = _lib.WorldDesc()
         d.n_agents, d.n_groups, d.n_edges, d.n_types = self.n_agents, self.n_groups, self.n_edges, len(self.types)
         for i, off in enumerate(self.type_group_off):
             d.type_group_off[i] = off
         for name in ("am_ptr", "am_ent", "gm_ptr", "gm_agent", "pc", "cls", "small_groups", "chunk_group",
-                     "chunk_begin", "chunk_end", "chunk_part", "big_groups", "big_part_ptr"):
+                     "chunk_begin", "chunk_end", "chunk_part", "big_groups", "big_part_ptr", "tile_begin"):
             setattr(d, name, getattr(self, name).data_ptr())
         d.n_small, d.n_chunks = self.small_groups.numel(), self.chunk_group.numel()
         d.n_big, d.n_parts = self.big_groups.numel(), self.n_parts
+        d.n_tiles = self.tile_begin.numel() - 1
+        cell_off = 0
+        for ti in range(len(self.types)):
+            d.type_tier[ti] = self.type_tier[ti]
+            d.cell_off[ti] = cell_off
+            if self.type_tier[ti] == TIER_RANGE:
+                d.range_slot[ti] = self.range_slot[ti].data_ptr()
+                d.range_pc[ti] = self.range_pc[ti].data_ptr()
+            elif self.type_tier[ti] == TIER_CELL:
+                c = self.cells[ti]
+                d.n_cells[ti] = c["n_cells"]
+                for name in ("tile_cell", "cell_tile_ptr", "cell_grp_ptr", "cell_grp", "grp_cell_ptr", "grp_cell"):
+                    getattr(d, name)[ti] = c[name].data_ptr()
+                cell_off += c["n_cells"]
+        d.n_cells_total = cell_off
+        self.__dict__["_desc"] = d
         return d
 
 
@@ -252,9 +289,86 @@ def p_contact(people: torch.Tensor) -> torch.Tensor:
     return torch.maximum(torch.minimum(1.0 / (people - 1), one), zero).to(torch.float32)
 
 
+def _u32(t):
+    """uint32 values stored as int32 bit patterns (torch has no general uint32 support)."""
+    t = t.to(torch.int64)
+    return (((t + (1 << 31)) % (1 << 32)) - (1 << 31)).to(torch.int32).contiguous()
+
+
+def _ptr_from_counts(counts):
+    ptr = torch.zeros(counts.numel() + 1, dtype=torch.long, device=counts.device)
+    ptr[1:] = torch.cumsum(counts, 0)
+    return ptr
+
+
+def _try_range_tier(n_agents, src, dst, n_groups, pc_t):
+    """RANGE layout if every agent has <= 1 edge and every group is a contiguous ascending id run."""
+    E = src.numel()
+    dev = src.device
+    deg = torch.bincount(src, minlength=n_agents)
+    if E == 0 or int(deg.max()) > 1:
+        return None
+    size = torch.bincount(dst, minlength=n_groups)
+    if int(size.max()) > RANGE_MAX_GROUP:
+        return None
+    _, perm = torch.sort(dst, stable=True)
+    members = src[perm]
+    ptr = _ptr_from_counts(size)
+    gid = dst[perm]
+    first = members[ptr[:-1].clamp(max=E - 1)]          # first member of each group (garbage for empty groups)
+    offset = members - first[gid]
+    if not bool((offset == torch.arange(E, device=dev) - ptr[gid]).all()):
+        return None
+    slot = torch.full((n_agents,), 0xFFFFFFFF, dtype=torch.long, device=dev)
+    slot[members] = (offset << 16) | size[gid]
+    rpc = torch.zeros(n_agents, dtype=torch.float32, device=dev)
+    rpc[members] = pc_t[gid]
+    return {"range_slot": _u32(slot), "range_pc": rpc.contiguous()}
+
+
+def _try_cell_tier(n_agents, src, dst, n_groups):
+    """CELL layout if long runs of consecutive agents share the same ordered group list."""
+    E = src.numel()
+    dev = src.device
+    if E == 0:
+        return None
+    deg = torch.bincount(src, minlength=n_agents)
+    if int(deg.max()) > CELL_MAX_GROUPS:
+        return None
+    _, perm = torch.sort(src, stable=True)
+    s_sorted, d_sorted = src[perm], dst[perm]
+    aptr = _ptr_from_counts(deg)
+    pos = torch.arange(E, device=dev) - aptr[s_sorted]
+    # exact comparison of each agent's ordered list with its predecessor's
+    same_deg = torch.ones(n_agents, dtype=torch.bool, device=dev)
+    same_deg[1:] = deg[1:] == deg[:-1]
+    same_deg[0] = False
+    prev_idx = (aptr[(s_sorted - 1).clamp(min=0)] + pos).clamp(max=E - 1)
+    differs = (d_sorted != d_sorted[prev_idx]) & same_deg[s_sorted]
+    n_diff = torch.zeros(n_agents, dtype=torch.long, device=dev).index_add_(0, s_sorted, differs.long())
+    boundary = ~same_deg | (n_diff > 0)
+    n_cells = int(boundary.sum())
+    if n_cells * CELL_MIN_MEAN_AGENTS > n_agents:
+        return None
+    cell_start = torch.nonzero(boundary).flatten()
+    cell_of_agent = torch.cumsum(boundary.long(), 0) - 1
+    cdeg = deg[cell_start]
+    cell_grp_ptr = _ptr_from_counts(cdeg)
+    idx = torch.repeat_interleave(aptr[cell_start], cdeg) + (torch.arange(int(cdeg.sum()), device=dev)
+                                                             - torch.repeat_interleave(cell_grp_ptr[:-1], cdeg))
+    cell_grp = d_sorted[idx]
+    cell_ids = torch.repeat_interleave(torch.arange(n_cells, device=dev), cdeg)
+    _, gperm = torch.sort(cell_grp, stable=True)
+    grp_cell = cell_ids[gperm]
+    grp_cell_ptr = _ptr_from_counts(torch.bincount(cell_grp, minlength=n_groups))
+    return {"n_cells": n_cells, "cell_start": cell_start, "cell_of_agent": cell_of_agent,
+            "cell_grp_ptr": _u32(cell_grp_ptr), "cell_grp": _u32(cell_grp), "grp_cell_ptr": _u32(grp_cell_ptr),
+            "grp_cell": _u32(grp_cell)}
+
+
 def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], people: Dict[str, torch.Tensor],
               n_groups: Dict[str, int], age: torch.Tensor, sex: torch.Tensor, small_group: int, chunk: int,
-              device) -> DeviceWorld:
+              device, tiers: bool = True) -> DeviceWorld:
     if len(types) > MAX_TYPES:
         raise ValueError(f"at most {MAX_TYPES} edge types are supported")
     dev = torch.device(device)
@@ -262,7 +376,12 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
     for t in types:
         offs.append(offs[-1] + int(n_groups[t]))
     G = offs[-1]
+    pc = torch.cat([p_contact(torch.as_tensor(people[t]).to(dev)) for t in types]) if types else torch.zeros(0, device=dev)
+    if pc.numel() != G:
+        raise ValueError("people arrays do not match the number of groups")
+    type_tier, range_slot, range_pc, cells = [], {}, {}, {}
     srcs, gkeys, ents = [], [], []
+    n_edges_total = 0
     for ti, t in enumerate(types):
         ei = edges[t].to(dev)
         if ei.numel():
@@ -272,50 +391,58 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
                 raise ValueError(f"edge type {t}: group index out of range")
         if n_groups[t] >= (1 << 28):
             raise ValueError(f"edge type {t}: too many groups")
-        srcs.append(ei[0])
-        gkeys.append(ei[1] + offs[ti])
-        ents.append(ei[1] + (ti << 28))
+        n_edges_total += ei.shape[1]
+        tier = TIER_GENERIC
+        if tiers and n_agents > 0:
+            r = _try_range_tier(n_agents, ei[0], ei[1], int(n_groups[t]), pc[offs[ti]:offs[ti + 1]])
+            if r is not None:
+                tier, range_slot[ti], range_pc[ti] = TIER_RANGE, r["range_slot"], r["range_pc"]
+            else:
+                c = _try_cell_tier(n_agents, ei[0], ei[1], int(n_groups[t]))
+                if c is not None:
+                    tier, cells[ti] = TIER_CELL, c
+        type_tier.append(tier)
+        if tier == TIER_GENERIC:
+            srcs.append(ei[0])
+            gkeys.append(ei[1] + offs[ti])
+            ents.append(ei[1] + (ti << 28))
     if srcs:
-        src = torch.cat(srcs)
-        gkey = torch.cat(gkeys)
-        ent = torch.cat(ents)
+        src, gkey, ent = torch.cat(srcs), torch.cat(gkeys), torch.cat(ents)
     else:
         src = gkey = ent = torch.zeros(0, dtype=torch.long, device=dev)
     E = src.numel()
-    if E >= (1 << 32) or n_agents >= (1 << 32):
+    if n_edges_total >= (1 << 32) or n_agents >= (1 << 32):
         raise ValueError("world too large for 32-bit CSR offsets")
     # group-major: stable sort by global group id keeps the reference's edge order inside each group
     _, perm = torch.sort(gkey, stable=True)
     gm_agent = src[perm].to(torch.int32)
     size = torch.bincount(gkey, minlength=G) if E else torch.zeros(G, dtype=torch.long, device=dev)
-    gm_ptr = torch.zeros(G + 1, dtype=torch.long, device=dev)
-    gm_ptr[1:] = torch.cumsum(size, 0)
+    gm_ptr = _ptr_from_counts(size)
     del perm
     # agent-major: types were concatenated in order, so a stable sort by agent gives (type, edge order)
     _, perm = torch.sort(src, stable=True)
     am_ent = ent[perm].to(torch.int64)
     deg = torch.bincount(src, minlength=n_agents) if E else torch.zeros(n_agents, dtype=torch.long, device=dev)
-    am_ptr = torch.zeros(n_agents + 1, dtype=torch.long, device=dev)
-    am_ptr[1:] = torch.cumsum(deg, 0)
+    am_ptr = _ptr_from_counts(deg)
     del perm
-    pc = torch.cat([p_contact(people[t].to(dev)) for t in types]) if types else torch.zeros(0, device=dev)
-    if pc.numel() != G:
-        raise ValueError("people arrays do not match the number of groups")
     age = age.to(dev).long()
     sex = sex.to(dev).long()
     if age.numel() and (int(age.min()) < 0 or int(age.max()) > 99 or int(sex.min()) < 0 or int(sex.max()) > 1):
         raise ValueError("age must be in [0, 99] and sex in {0, 1}")
     cls = (sex * 100 + age).to(torch.uint8)
 
-    # work lists of the group-major passes
+    # work lists of the group-major passes (GENERIC types only: the other tiers have no group-major pass)
+    generic_group = torch.zeros(G, dtype=torch.bool, device=dev)
+    for ti in range(len(types)):
+        if type_tier[ti] == TIER_GENERIC:
+            generic_group[offs[ti]:offs[ti + 1]] = True
     gids = torch.arange(G, device=dev)
-    small = gids[size <= small_group]
-    big_mask = size > small_group
+    small = gids[(size <= small_group) & generic_group]
+    big_mask = (size > small_group) & generic_group
     bg = gids[big_mask]
     nchunk = (size[big_mask] + chunk - 1) // chunk
     chunk_group = torch.repeat_interleave(bg, nchunk)
-    first = torch.zeros(nchunk.numel() + 1, dtype=torch.long, device=dev)
-    first[1:] = torch.cumsum(nchunk, 0)
+    first = _ptr_from_counts(nchunk)
     within = torch.arange(chunk_group.numel(), device=dev) - torch.repeat_interleave(first[:-1], nchunk)
     chunk_begin = gm_ptr[chunk_group] + within * chunk
     chunk_end = torch.minimum(chunk_begin + chunk, gm_ptr[chunk_group + 1])
@@ -324,19 +451,33 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
     n_parts = int(multi.sum())
     chunk_part[multi] = torch.arange(n_parts, device=dev)
     big_groups = bg[nchunk > 1]
-    big_part_ptr = torch.zeros(big_groups.numel() + 1, dtype=torch.long, device=dev)
-    big_part_ptr[1:] = torch.cumsum(nchunk[nchunk > 1], 0)
+    big_part_ptr = _ptr_from_counts(nchunk[nchunk > 1])
 
-    def u32(t):  # uint32 values stored as int32 bit patterns (torch has no general uint32 support)
-        t = t.to(torch.int64)
-        return (((t + (1 << 31)) % (1 << 32)) - (1 << 31)).to(torch.int32).contiguous()
+    # CTA tiles of the agent-major kernels: <= TILE_AGENTS consecutive agents inside one cell of every CELL type
+    cuts = [torch.zeros(1, dtype=torch.long, device=dev)]
+    for c in cells.values():
+        cuts.append(c["cell_start"])
+    seg_start = torch.unique(torch.cat(cuts)) if n_agents > 0 else torch.zeros(0, dtype=torch.long, device=dev)
+    seg_end = torch.cat((seg_start[1:], torch.tensor([n_agents], device=dev))) if n_agents > 0 else seg_start
+    ntile = (seg_end - seg_start + TILE_AGENTS - 1) // TILE_AGENTS
+    tfirst = _ptr_from_counts(ntile)
+    tw = torch.arange(int(ntile.sum()), device=dev) - torch.repeat_interleave(tfirst[:-1], ntile)
+    tile_begin = torch.cat((torch.repeat_interleave(seg_start, ntile) + tw * TILE_AGENTS,
+                            torch.tensor([n_agents], device=dev)))
+    for ti, c in cells.items():
+        c["tile_cell"] = _u32(c["cell_of_agent"][tile_begin[:-1]])
+        c["cell_tile_ptr"] = _u32(torch.cat((torch.searchsorted(tile_begin[:-1].contiguous(), c["cell_start"]),
+                                             torch.tensor([tile_begin.numel() - 1], device=dev))))
+        del c["cell_of_agent"]
 
     return DeviceWorld(
-        n_agents=n_agents, n_groups=G, n_edges=E, types=list(types), type_group_off=offs,
-        group_size=size, am_ptr=u32(am_ptr), am_ent=u32(am_ent), gm_ptr=u32(gm_ptr), gm_agent=gm_agent.contiguous(),
-        pc=pc.contiguous(), cls=cls.contiguous(), small_groups=u32(small), chunk_group=u32(chunk_group),
-        chunk_begin=u32(chunk_begin), chunk_end=u32(chunk_end), chunk_part=chunk_part.to(torch.int32),
-        big_groups=u32(big_groups), big_part_ptr=u32(big_part_ptr), n_parts=n_parts, device=dev,
+        n_agents=n_agents, n_groups=G, n_edges=n_edges_total, n_generic_edges=E, types=list(types),
+        type_group_off=offs, type_tier=type_tier, range_slot=range_slot, range_pc=range_pc, cells=cells,
+        group_size=size, am_ptr=_u32(am_ptr), am_ent=_u32(am_ent), gm_ptr=_u32(gm_ptr),
+        gm_agent=gm_agent.contiguous(), pc=pc.contiguous(), cls=cls.contiguous(), small_groups=_u32(small),
+        chunk_group=_u32(chunk_group), chunk_begin=_u32(chunk_begin), chunk_end=_u32(chunk_end),
+        chunk_part=chunk_part.to(torch.int32), big_groups=_u32(big_groups), big_part_ptr=_u32(big_part_ptr),
+        n_parts=n_parts, tile_begin=_u32(tile_begin), device=dev,
     )
 
 

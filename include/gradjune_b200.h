@@ -38,6 +38,10 @@ extern "C" {
 #define GJ_SMALL_GROUP 16   /* <= this many members: one lane sums the group sequentially */
 #define GJ_CHUNK 1024       /* larger groups are cut into chunks of this many members, one warp each */
 
+enum { GJ_TIER_GENERIC = 0, GJ_TIER_RANGE = 1, GJ_TIER_CELL = 2 };
+#define GJ_TILE_AGENTS 1024
+#define GJ_MAX_RANGE_NETS 4 /* networks running on RANGE-tier types in one step */
+
 /* how a network masks transmissions / susceptibilities
  * (grad_june/infection_networks/base.py:47-59,144-149; leisure_network.py:61-85,107-120) */
 enum { GJ_KIND_PLAIN = 0, GJ_KIND_HOUSEHOLD = 1, GJ_KIND_LEISURE = 2, GJ_KIND_CARE_VISIT = 3 };
@@ -95,6 +99,28 @@ typedef struct gj_world_desc {
   const uint32_t* big_part_ptr; /* [n_big+1] their partial-sum ranges */
   int64_t n_big;
   int64_t n_parts; /* total partial sums (= big_part_ptr[n_big]) */
+
+  /* ---- layout tiers: each edge type is stored in the cheapest layout its structure allows; the CSR
+   *      arrays above hold the GENERIC types only ---- */
+  int32_t type_tier[GJ_MAX_TYPES]; /* GJ_TIER_* */
+  /* RANGE tier: [n_agents] (a - first_member) << 16 | group_size, 0xFFFFFFFF = not a member; and the
+   * contact probability of the agent's group */
+  const uint32_t* range_slot[GJ_MAX_TYPES];
+  const float* range_pc[GJ_MAX_TYPES];
+  /* CTA tiles of the agent-major kernels: tile i = agents [tile_begin[i], tile_begin[i+1]), at most
+   * GJ_TILE_AGENTS, never straddling a cell boundary of a CELL-tier type */
+  int64_t n_tiles;
+  const uint32_t* tile_begin;
+  /* CELL tier: runs of consecutive agents with the same ordered group list */
+  int64_t n_cells[GJ_MAX_TYPES];
+  int64_t cell_off[GJ_MAX_TYPES]; /* offset of the type's cells in per-cell buffers */
+  int64_t n_cells_total;
+  const uint32_t* tile_cell[GJ_MAX_TYPES];     /* [n_tiles] cell of each tile */
+  const uint32_t* cell_tile_ptr[GJ_MAX_TYPES]; /* [n_cells+1] consecutive tiles of each cell */
+  const uint32_t* cell_grp_ptr[GJ_MAX_TYPES];  /* [n_cells+1] */
+  const uint32_t* cell_grp[GJ_MAX_TYPES];      /* groups (ids local to the type) of each cell, agent edge order */
+  const uint32_t* grp_cell_ptr[GJ_MAX_TYPES];  /* [G_type+1] */
+  const uint32_t* grp_cell[GJ_MAX_TYPES];      /* cells of each group, ascending */
 } gj_world_desc;
 
 typedef struct gj_net {
@@ -180,7 +206,7 @@ typedef struct gj_bwd_io {
   const float *maxinf, *shape, *rate, *shift, *k0;
   const float* inf_o; /* post-step is_infected (new_infected = inf_o - inf) or NULL with n_in */
   const float* n_in;
-  const float* T_in;
+  const float* T_in; /* transmissions: the stand-alone input, or the T written by the fused forward */
   const float* q_in; /* stand-alone SAMPLE: the q it was given */
   const float* tape_v;
   const float* tape_y0;
