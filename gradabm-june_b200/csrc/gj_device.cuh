@@ -53,9 +53,9 @@ __device__ __forceinline__ StepNoise draw_step_noise(uint64_t seed, uint32_t cal
   uint32_t r[4];
   philox4x32_10((uint32_t)agent, (uint32_t)((uint64_t)agent >> 32), call, 0u, (uint32_t)seed,
                 (uint32_t)(seed >> 32), r);
-  StepNoise n;
-  n.E0 = -logf(u01_open(r[0]));
-  n.E1 = -logf(u01_open(r[1]));
+  StepNoise n;  // Exp(1) by inversion with the hardware log2 (this IS the definition of the stream: the
+  n.E0 = -__logf(u01_open(r[0]));  // forward, the backward and gj_philox_fill all come through here)
+  n.E1 = -__logf(u01_open(r[1]));
   n.u = u01_half(r[2]);
   return n;
 }
@@ -100,7 +100,7 @@ __device__ __forceinline__ TransTerms transmission_terms(float now, float tinf, 
   r.dcoef = 0.0f;
   if (kGrad) {
     // d/dt [k0 * b^e * exp((shift-t)*rate) * rate] = k0*rate*( e*b^(e-1)*rate*ex - b^e*rate*ex ), dt/dtinf = -1
-    const float dpw = (e == 0.0f) ? 0.0f : e * powf(b, e - 1.0f) * rate;  // torch pow backward: 0 where exponent == 0
+    const float dpw = (e == 0.0f) ? 0.0f : e * (pw / b) * rate;  // e*b^(e-1)*rate ; torch: 0 where exponent == 0
     const float daux = k0 * dpw;
     const float daux2 = -(ex * rate) * rate;
     const float dcoef_dt = head * (daux * aux2 + aux * daux2);
@@ -187,9 +187,9 @@ __device__ __forceinline__ float dwell_time(const gj_dist& d, float z) {
   return d.kind == 0 ? expf(x) : x;
 }
 
-template <typename ZF>
+template <typename UF, typename ZF>
 __device__ __forceinline__ SympOut symptoms_forward(const gj_step_params& p, const float* __restrict__ stage_prob,
-                                                    float cur, float nxt, float ttn, float n, int age, float u, ZF zf) {
+                                                    float cur, float nxt, float ttn, float n, int age, UF uf, ZF zf) {
   SympOut o;
   const float nxt1 = nxt + n * (2.0f - nxt);
   const float ttn1 = ttn + n * (p.now - ttn);
@@ -206,7 +206,7 @@ __device__ __forceinline__ SympOut symptoms_forward(const gj_step_params& p, con
   o.nxt1 = nxt1;
   if (tr != 0.0f && st >= 2 && st <= p.n_stages - 2 && cur1 == (float)st) {
     const float pr = __ldg(stage_prob + st * 100 + age);
-    const bool symp = u < pr;
+    const bool symp = uf() < pr;
     const gj_dist& d = symp ? p.trans_time[st] : p.rec_time[st];
     if (d.kind >= 0) {
       const float z = zf((st - 2) * 2 + (symp ? 0 : 1));

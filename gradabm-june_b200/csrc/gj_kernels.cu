@@ -394,7 +394,12 @@ __global__ void __launch_bounds__(kBlock) k_agent_forward(gj_world_desc w, gj_st
     st.nxt = io.nxt ? io.nxt[a] : 1.0f;
     st.ttn = io.ttn ? io.ttn[a] : 0.0f;
     const float q = io.q_in ? io.q_in[a] : 1.0f;
-    forward_tail(p, io, N, a, cls % 100, q, st, red);
+    float one[kMaxRed];
+#pragma unroll
+    for (int r = 0; r < kMaxRed; ++r) one[r] = 0.0f;
+    forward_tail<false>(p, io, N, a, cls % 100, q, st, one);
+#pragma unroll
+    for (int r = 0; r < kMaxRed; ++r) red[r] += (double)one[r];
   }
   if (io.red) block_reduce_finish<kMaxRed>(red, 2 + p.n_age_bins, red_part, ticket, io.red);
 }
@@ -484,7 +489,11 @@ static int build_channels(const gj_world_desc* w, const gj_step_params* p, Chann
       pl->lei_net[pl->n_lei++] = k;
     }
     const int tier = w->type_tier[t];
+    pl->tier[k] = tier;
+    pl->slot[k] = w->range_slot[t];
+    pl->rpc[k] = w->range_pc[t];
     if (tier == GJ_TIER_RANGE) {
+      if (!w->range_slot[t] || !w->range_pc[t]) return bad("range-tier type without slot arrays");
       if (pl->n_t1 >= GJ_MAX_RANGE_NETS) return bad("too many networks on range-tier edge types");
       pl->net_t1[k] = pl->n_t1;
       pl->t1_net[pl->n_t1++] = k;
@@ -684,7 +693,9 @@ int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fw
   if (int e = launch_cell_pass(w, &pp, pl, io->beta, io->S_scaled, io->S_unscaled, sc, st)) return e;
   {
     ProfScope ps(K_AGENT_FWD, st);
-    k_tile_forward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
+    const bool fast = !io->inj_E && !io->inj_u && !io->inj_z;  // in-kernel Philox: hardware log2/exp2 draw
+    if (fast) k_tile_forward<true><<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
+    else k_tile_forward<false><<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
     GJ_CHECK_LAUNCH("k_tile_forward");
   }
   return 0;

@@ -26,6 +26,9 @@ struct Plan {
   int lei_net[GJ_MAX_CHANNELS];
   int net_lei[GJ_MAX_NETS];
   int n_generic;                    // networks on GENERIC types
+  int tier[GJ_MAX_NETS];            // layout tier of each network's edge type
+  const uint32_t* slot[GJ_MAX_NETS];  // RANGE networks: the type's per-agent (offset, size) words
+  const float* rpc[GJ_MAX_NETS];      //                 and per-agent contact probability
 };
 
 // ---- shared-memory tables ---------------------------------------------------------------------------
@@ -202,8 +205,25 @@ struct AgentState {
   float s, inf, tinf, cur, nxt, ttn;
 };
 
+// Gumbel-softmax draw from Philox bits with hardware log2/exp2 (MUFU): used when the noise is generated
+// in-kernel.  Same distribution and the same decision rule as gumbel_draw (argmax of the softmax, ties ->
+// not infected); logs carry ~2^-22 absolute error in log2 instead of 1 ulp, which only matters for draws
+// that are near-ties to begin with.  Injected-noise calls (parity tests) use the IEEE path.
+__device__ __forceinline__ Draw gumbel_draw_fast(float q, float E0, float E1, float inv_tau) {
+  const float x0 = (__logf(q) - __logf(E0)) * inv_tau;
+  const float x1 = (__logf(1.0f - q) - __logf(E1)) * inv_tau;
+  const bool one_bigger = x1 > x0;
+  const float e = __expf(one_bigger ? (x0 - x1) : (x1 - x0));  // exp(small - big) <= 1 ; exp(big - big) = 1
+  const float ys = __fdividef(e, 1.0f + e);
+  Draw d;
+  d.n = (one_bigger && e < 1.0f) ? 1.0f : 0.0f;
+  d.ty = (one_bigger && e < 1.0f) ? -ys : ys;
+  return d;
+}
+
+template <bool kFast>
 __device__ __forceinline__ void forward_tail(const gj_step_params& p, const gj_fwd_io& io, int64_t N, int64_t a, int age,
-                                             float q, AgentState st, double* red) {
+                                             float q, AgentState st, float* red) {
   const int dead = p.n_stages - 1;
   if (p.mode == GJ_MODE_SEED) q = 1.0f - io.seed_fraction[0] * 1.0f;  // infection.py:36-40
   float n = 0.0f;
@@ -211,15 +231,17 @@ __device__ __forceinline__ void forward_tail(const gj_step_params& p, const gj_f
   nz.E0 = nz.E1 = 1.0f;
   nz.u = 0.0f;
   if (p.phases & (GJ_PHASE_SAMPLE | GJ_PHASE_SYMPTOMS)) {
-    if (io.inj_E == nullptr || io.inj_u == nullptr) nz = draw_step_noise(p.seed, p.call_index, a);
-    if (io.inj_E) {
-      nz.E0 = io.inj_E[a];
-      nz.E1 = io.inj_E[N + a];
+    if (kFast || io.inj_E == nullptr || io.inj_u == nullptr) nz = draw_step_noise(p.seed, p.call_index, a);
+    if (!kFast) {
+      if (io.inj_E) {
+        nz.E0 = io.inj_E[a];
+        nz.E1 = io.inj_E[N + a];
+      }
+      if (io.inj_u) nz.u = io.inj_u[a];
     }
-    if (io.inj_u) nz.u = io.inj_u[a];
   }
   if (p.phases & GJ_PHASE_SAMPLE) {
-    const Draw d = gumbel_draw(q, nz.E0, nz.E1, p.tau);
+    const Draw d = kFast ? gumbel_draw_fast(q, nz.E0, nz.E1, 1.0f / p.tau) : gumbel_draw(q, nz.E0, nz.E1, p.tau);
     n = d.n;
     if (io.tape_y0) io.tape_y0[a] = d.ty;
   } else if (io.n_in) {
@@ -235,10 +257,12 @@ __device__ __forceinline__ void forward_tail(const gj_step_params& p, const gj_f
     if (io.tinf_o) io.tinf_o[a] = st.tinf;
   }
   if (p.phases & GJ_PHASE_SYMPTOMS) {
-    const float* inj_z = io.inj_z;
+    const float* inj_z = kFast ? nullptr : io.inj_z;
     const uint64_t seed = p.seed;
     const uint32_t call = p.call_index;
-    const SympOut so = symptoms_forward(p, io.stage_prob, st.cur, st.nxt, st.ttn, n, age, nz.u, [&](int row) {
+    const float uu = nz.u;
+    const SympOut so = symptoms_forward(p, io.stage_prob, st.cur, st.nxt, st.ttn, n, age, [&]() { return uu; },
+                                        [&](int row) {
       return inj_z ? inj_z[(int64_t)row * N + a] : draw_step_normal(seed, call, a);
     });
     st.cur = so.cur;
@@ -248,11 +272,12 @@ __device__ __forceinline__ void forward_tail(const gj_step_params& p, const gj_f
     if (io.nxt_o) io.nxt_o[a] = st.nxt;
     if (io.ttn_o) io.ttn_o[a] = st.ttn;
   }
-  if (io.red) {  // runner.py:167-171,198-224
-    red[0] += (double)st.inf;
-    red[1] += (st.cur == (float)dead) ? (double)(st.cur / (float)dead) : 0.0;
-    for (int b = 0; b < p.n_age_bins; ++b)
-      if (age > p.age_bins[b] && age < p.age_bins[b + 1]) red[2 + b] += (double)st.inf;
+  if (io.red) {  // runner.py:167-171,198-224 ; per-thread partial sums of small integers: exact in fp32
+    red[0] += st.inf;
+    red[1] += (st.cur == (float)dead) ? (st.cur / (float)dead) : 0.0f;
+#pragma unroll
+    for (int b = 0; b < GJ_MAX_AGE_BINS; ++b)
+      if (b < p.n_age_bins && age > p.age_bins[b] && age < p.age_bins[b + 1]) red[2 + b] += st.inf;
   }
 }
 
@@ -280,10 +305,91 @@ __device__ __forceinline__ NetMask tile_net_mask(const TileTables& tb, const Pla
 // =====================================================================================================
 // F3'  forward: pressure from the three tiers -> q -> draw -> update -> symptoms -> reductions
 // =====================================================================================================
-__global__ void __launch_bounds__(kBlock) k_tile_forward(gj_world_desc w, gj_step_params p, Plan pl, gj_fwd_io io,
-                                                         const float* __restrict__ cell_buf,
-                                                         double* __restrict__ red_part,
-                                                         unsigned int* __restrict__ ticket) {
+// pressure of all active networks on agent `a` in the reference's accumulation order; the network loop is
+// fully unrolled so that every per-network parameter is a compile-time slot of the constant bank
+struct Pressure {
+  float lam, X;
+};
+
+__device__ __forceinline__ Pressure agent_pressure(const gj_world_desc& w, const gj_step_params& p, const Plan& pl,
+                                                   const TileTables& tb, const float* __restrict__ S_scaled,
+                                                   const float* __restrict__ Tsrc, const float* __restrict__ Tq,
+                                                   uint32_t a, int cls, float s, float mq) {
+  uint32_t e0 = 0, deg = 0, ent0 = 0, ent1 = 0;
+  if (pl.n_generic > 0) {
+    e0 = w.am_ptr[a];
+    deg = w.am_ptr[a + 1] - e0;
+    if (deg > 0) ent0 = w.am_ent[e0];
+    if (deg > 1) ent1 = w.am_ent[e0 + 1];
+  }
+  const float age_f = ((cls % 100) > 75) ? 1.0f : 0.0f;
+  Pressure out;
+  out.lam = 0.0f;
+  out.X = 0.0f;
+#pragma unroll
+  for (int k = 0; k < GJ_MAX_NETS; ++k) {
+    if (k < p.n_nets) {
+      const int kind = p.nets[k].kind;
+      const int type = p.nets[k].type;
+      const int tier = pl.tier[k];
+      float mS = (kind == GJ_KIND_HOUSEHOLD) ? 1.0f : mq;
+      if (kind >= GJ_KIND_LEISURE) mS = mq * tb.prob[pl.net_lei[k]][cls];
+      float sp = mS * s, sx = mS;  // susceptibilities = mask * [leisure_mask *] susceptibility
+      if (kind == GJ_KIND_CARE_VISIT) {
+        sp = sp * age_f;
+        sx = sx * age_f;
+      }
+      float Pk = 0.0f, PXk = 0.0f;
+      if (tier == GJ_TIER_RANGE) {
+        const uint32_t slot = pl.slot[k][a];
+        if (slot != kNoSlot) {
+          const uint32_t b0 = a - (slot >> 16), nb = slot & 0xFFFFu;
+          const float cg = tb.beta[k] * pl.rpc[k][a];
+          float Sg = 0.0f;
+          for (uint32_t b = b0; b < b0 + nb; ++b) {  // members in id order = the reference's edge order
+            const float v = member_value(tb, pl, k, kind, Tsrc[b], Tq[b], kind >= GJ_KIND_LEISURE ? w.cls[b] : 0);
+            Sg += v * cg;
+          }
+          Pk = Sg * sp;
+          PXk = Sg * sx;
+        }
+      } else if (tier == GJ_TIER_CELL) {
+        const float B = tb.cellv[pl.net_t2[k]];
+        Pk = B * sp;
+        PXk = B * sx;
+      } else {
+        const int64_t so = p.nets[k].s_off;
+        if (deg > 0 && (int)(ent0 >> 28) == type) {
+          const float Sg = S_scaled[so + (ent0 & 0x0FFFFFFFu)];
+          Pk += Sg * sp;  // message = cumulative_trans * susceptibility   base.py:80-87
+          PXk += Sg * sx;
+        }
+        if (deg > 1 && (int)(ent1 >> 28) == type) {
+          const float Sg = S_scaled[so + (ent1 & 0x0FFFFFFFu)];
+          Pk += Sg * sp;
+          PXk += Sg * sx;
+        }
+        for (uint32_t j = 2; j < deg; ++j) {
+          const uint32_t ent = w.am_ent[e0 + j];
+          if ((int)(ent >> 28) == type) {
+            const float Sg = S_scaled[so + (ent & 0x0FFFFFFFu)];
+            Pk += Sg * sp;
+            PXk += Sg * sx;
+          }
+        }
+      }
+      out.lam += Pk;  // trans_susc += network(...)   base.py:133-135
+      out.X += PXk;
+    }
+  }
+  return out;
+}
+
+template <bool kFast>
+__global__ void __launch_bounds__(kBlock, 4) k_tile_forward(gj_world_desc w, gj_step_params p, Plan pl, gj_fwd_io io,
+                                                            const float* __restrict__ cell_buf,
+                                                            double* __restrict__ red_part,
+                                                            unsigned int* __restrict__ ticket) {
   __shared__ TileTables tb;
   const int64_t N = w.n_agents;
   const int64_t tile = blockIdx.x;
@@ -291,9 +397,9 @@ __global__ void __launch_bounds__(kBlock) k_tile_forward(gj_world_desc w, gj_ste
   load_tables(tb, p, pl, io.leisure_prob, io.beta);
   load_cell_values(tb, w, p, pl, cell_buf, tile);
   __syncthreads();
-  double red[kMaxRed];
+  float red[kMaxRed];
 #pragma unroll
-  for (int r = 0; r < kMaxRed; ++r) red[r] = 0.0;
+  for (int r = 0; r < kMaxRed; ++r) red[r] = 0.0f;
   const float* __restrict__ Tsrc = io.T_in ? io.T_in : io.T;
   const float* __restrict__ Tq = (p.n_quar > 0) ? io.Tq : Tsrc;
 
@@ -307,60 +413,18 @@ __global__ void __launch_bounds__(kBlock) k_tile_forward(gj_world_desc w, gj_ste
     st.nxt = io.nxt ? io.nxt[a] : 1.0f;
     st.ttn = io.ttn ? io.ttn[a] : 0.0f;
     const float mq = (p.n_quar > 0) ? quarantine_mask(p, st.cur) : 1.0f;
-    uint32_t e0 = 0, e1 = 0;
-    if (pl.n_generic > 0) {
-      e0 = w.am_ptr[a];
-      e1 = w.am_ptr[a + 1];
-    }
-    float lam = 0.0f, X = 0.0f;
-    for (int k = 0; k < p.n_nets; ++k) {
-      const gj_net net = p.nets[k];
-      const int tier = w.type_tier[net.type];
-      const NetMask m = tile_net_mask(tb, pl, k, net.kind, mq, cls);
-      float sp = m.mS * st.s, sx = m.mS;  // susceptibilities = mask * [leisure_mask *] susceptibility
-      if (net.kind == GJ_KIND_CARE_VISIT) {
-        sp = sp * m.age_f;
-        sx = sx * m.age_f;
-      }
-      float Pk = 0.0f, PXk = 0.0f;
-      if (tier == GJ_TIER_RANGE) {
-        const uint32_t slot = w.range_slot[net.type][a];
-        if (slot != kNoSlot) {
-          const uint32_t b0 = a - (slot >> 16), nb = slot & 0xFFFFu;
-          const float cg = tb.beta[k] * w.range_pc[net.type][a];
-          float Sg = 0.0f;
-          for (uint32_t b = b0; b < b0 + nb; ++b) {  // members in id order = the reference's edge order
-            const float v = member_value(tb, pl, k, net.kind, Tsrc[b], Tq[b], net.kind >= GJ_KIND_LEISURE ? w.cls[b] : 0);
-            Sg += v * cg;
-          }
-          Pk += Sg * sp;
-          PXk += Sg * sx;
-        }
-      } else if (tier == GJ_TIER_CELL) {
-        const float B = tb.cellv[pl.net_t2[k]];
-        Pk += B * sp;
-        PXk += B * sx;
-      } else {
-        for (uint32_t j = e0; j < e1; ++j) {
-          const uint32_t ent = w.am_ent[j];
-          if ((int)(ent >> 28) == net.type) {
-            const float Sg = io.S_scaled[(int64_t)net.s_off + (ent & 0x0FFFFFFFu)];
-            Pk += Sg * sp;  // message = cumulative_trans * susceptibility   base.py:80-87
-            PXk += Sg * sx;
-          }
-        }
-      }
-      lam += Pk;  // trans_susc += network(...)   base.py:133-135
-      X += PXk;
-    }
-    const float q = not_infected_prob(lam, p.dt);
-    io.tape_v[a] = (st.s == 0.0f) ? X : lam;
+    const Pressure pr = agent_pressure(w, p, pl, tb, io.S_scaled, Tsrc, Tq, a, cls, st.s, mq);
+    const float q = not_infected_prob(pr.lam, p.dt);
+    io.tape_v[a] = (st.s == 0.0f) ? pr.X : pr.lam;
     if (io.q) io.q[a] = q;
-    if (io.lam) io.lam[a] = lam;
-    forward_tail(p, io, N, a, cls % 100, q, st, red);
+    if (io.lam) io.lam[a] = pr.lam;
+    forward_tail<kFast>(p, io, N, a, cls % 100, q, st, red);
   }
   if (io.red) {
-    block_sums<double, kMaxRed>(red, 2 + p.n_age_bins, red_part + tile * kMaxRed);
+    double redd[kMaxRed];
+#pragma unroll
+    for (int r = 0; r < kMaxRed; ++r) redd[r] = (double)red[r];
+    block_sums<double, kMaxRed>(redd, 2 + p.n_age_bins, red_part + tile * kMaxRed);
     finish_partials<kMaxRed>(2 + p.n_age_bins, red_part, gridDim.x, ticket, io.red);
   }
 }
@@ -394,11 +458,14 @@ __device__ __forceinline__ BackAgent backward_agent(const gj_step_params& p, con
   r.gnxt = gnxt_o;
   r.gttn = gttn_o;
   if (p.phases & GJ_PHASE_SYMPTOMS) {
-    const float u = io.inj_u ? io.inj_u[a] : draw_step_noise(p.seed, p.call_index, a).u;
+    const float* inj_u = io.inj_u;
     const float* inj_z = io.inj_z;
     const uint64_t seed = p.seed;
     const uint32_t call = p.call_index;
-    const SympOut so = symptoms_forward(p, io.stage_prob, st.cur, st.nxt, st.ttn, n, age, u, [&](int row) {
+    // the uniform / normal draws are regenerated only for the few agents whose stage actually updates
+    const SympOut so = symptoms_forward(p, io.stage_prob, st.cur, st.nxt, st.ttn, n, age,
+                                        [&]() { return inj_u ? inj_u[a] : draw_step_noise(seed, call, a).u; },
+                                        [&](int row) {
       return inj_z ? inj_z[(int64_t)row * N + a] : draw_step_normal(seed, call, a);
     });
     // reductions fold in here: deaths = sum (cur' == dead) * cur' / dead   runner.py:204-209
@@ -473,7 +540,7 @@ __device__ __forceinline__ BackAgent backward_agent(const gj_step_params& p, con
   return r;
 }
 
-__global__ void __launch_bounds__(kBlock) k_tile_backward(gj_world_desc w, gj_step_params p, Plan pl, gj_bwd_io io,
+__global__ void __launch_bounds__(kBlock, 3) k_tile_backward(gj_world_desc w, gj_step_params p, Plan pl, gj_bwd_io io,
                                                           float* __restrict__ tile_part) {
   __shared__ TileTables tb;
   const int64_t N = w.n_agents;
@@ -524,9 +591,9 @@ __global__ void __launch_bounds__(kBlock) k_tile_backward(gj_world_desc w, gj_st
 // =====================================================================================================
 // B3'  backward part 2: dL/dT from the three tiers -> (is_infected, infection_time); d/dbeta of RANGE nets
 // =====================================================================================================
-__global__ void __launch_bounds__(kBlock) k_tile_backward_gather(gj_world_desc w, gj_step_params p, Plan pl,
-                                                                 gj_bwd_io io, const float* __restrict__ cell_buf,
-                                                                 double* __restrict__ dbeta_tile) {
+__global__ void __launch_bounds__(kBlock, 4) k_tile_backward_gather(gj_world_desc w, gj_step_params p, Plan pl,
+                                                                    gj_bwd_io io, const float* __restrict__ cell_buf,
+                                                                    double* __restrict__ dbeta_tile) {
   __shared__ TileTables tb;
   const int64_t tile = blockIdx.x;
   const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];
@@ -542,49 +609,59 @@ __global__ void __launch_bounds__(kBlock) k_tile_backward_gather(gj_world_desc w
   for (uint32_t a = a0 + threadIdx.x; a < a1; a += kBlock) {
     const int cls = w.cls[a];
     const float mq = quar ? quarantine_mask(p, io.cur[a]) : 1.0f;
-    uint32_t e0 = 0, e1 = 0;
+    uint32_t e0 = 0, deg = 0, ent0 = 0, ent1 = 0;
     if (pl.n_generic > 0) {
       e0 = w.am_ptr[a];
-      e1 = w.am_ptr[a + 1];
+      deg = w.am_ptr[a + 1] - e0;
+      if (deg > 0) ent0 = w.am_ent[e0];
+      if (deg > 1) ent1 = w.am_ent[e0 + 1];
     }
     float gT = 0.0f;
-    for (int k = 0; k < p.n_nets; ++k) {
-      const gj_net net = p.nets[k];
-      const int tier = w.type_tier[net.type];
-      const NetMask m = tile_net_mask(tb, pl, k, net.kind, mq, cls);
-      float acc = 0.0f;
-      if (tier == GJ_TIER_RANGE) {
-        const uint32_t slot = w.range_slot[net.type][a];
-        if (slot != kNoSlot) {
-          const uint32_t b0 = a - (slot >> 16), nb = slot & 0xFFFFu;
-          const float pcg = w.range_pc[net.type][a];
-          float R = 0.0f;
-          for (uint32_t b = b0; b < b0 + nb; ++b) {
-            const int cb = (net.kind >= GJ_KIND_LEISURE) ? w.cls[b] : 0;
-            float v = member_value(tb, pl, k, net.kind, io.w[b], io.wq[b], cb);
-            if (net.kind == GJ_KIND_CARE_VISIT) v = v * (((cb % 100) > 75) ? 1.0f : 0.0f);
-            R += v;
-          }
-          acc = (tb.beta[k] * pcg) * R;
-          if (b0 == a && R != 0.0f) {  // first member: d/dbeta += pc_g * (sum of the group's transmissions) * R_g
-            float S = 0.0f;
+#pragma unroll
+    for (int k = 0; k < GJ_MAX_NETS; ++k) {
+      if (k < p.n_nets) {
+        const int kind = p.nets[k].kind;
+        const int type = p.nets[k].type;
+        const int tier = pl.tier[k];
+        float mT = (kind == GJ_KIND_HOUSEHOLD) ? 1.0f : mq;
+        if (kind >= GJ_KIND_LEISURE) mT = mq * tb.prob[pl.net_lei[k]][cls];
+        float acc = 0.0f;
+        if (tier == GJ_TIER_RANGE) {
+          const uint32_t slot = pl.slot[k][a];
+          if (slot != kNoSlot) {
+            const uint32_t b0 = a - (slot >> 16), nb = slot & 0xFFFFu;
+            const float pcg = pl.rpc[k][a];
+            float R = 0.0f;
             for (uint32_t b = b0; b < b0 + nb; ++b) {
-              const float Tb = T[b];
-              const float Tqb = quar ? quarantine_mask(p, io.cur[b]) * Tb : Tb;
-              S += member_value(tb, pl, k, net.kind, Tb, Tqb, net.kind >= GJ_KIND_LEISURE ? w.cls[b] : 0);
+              const int cb = (kind >= GJ_KIND_LEISURE) ? w.cls[b] : 0;
+              float v = member_value(tb, pl, k, kind, io.w[b], io.wq[b], cb);
+              if (kind == GJ_KIND_CARE_VISIT) v = v * (((cb % 100) > 75) ? 1.0f : 0.0f);
+              R += v;
             }
-            db[pl.net_t1[k]] += (double)(pcg * S) * (double)R;
+            acc = (tb.beta[k] * pcg) * R;
+            if (b0 == a && R != 0.0f) {  // first member: d/dbeta += pc_g * (sum of the group's transmissions) * R_g
+              float S = 0.0f;
+              for (uint32_t b = b0; b < b0 + nb; ++b) {
+                const float Tb = T[b];
+                const float Tqb = quar ? quarantine_mask(p, io.cur[b]) * Tb : Tb;
+                S += member_value(tb, pl, k, kind, Tb, Tqb, kind >= GJ_KIND_LEISURE ? w.cls[b] : 0);
+              }
+              db[pl.net_t1[k]] += (double)(pcg * S) * (double)R;
+            }
+          }
+        } else if (tier == GJ_TIER_CELL) {
+          acc = tb.cellv[pl.net_t2[k]];
+        } else {
+          const int64_t so = p.nets[k].s_off;
+          if (deg > 0 && (int)(ent0 >> 28) == type) acc += io.cR[so + (ent0 & 0x0FFFFFFFu)];
+          if (deg > 1 && (int)(ent1 >> 28) == type) acc += io.cR[so + (ent1 & 0x0FFFFFFFu)];
+          for (uint32_t j = 2; j < deg; ++j) {
+            const uint32_t ent = w.am_ent[e0 + j];
+            if ((int)(ent >> 28) == type) acc += io.cR[so + (ent & 0x0FFFFFFFu)];
           }
         }
-      } else if (tier == GJ_TIER_CELL) {
-        acc = tb.cellv[pl.net_t2[k]];
-      } else {
-        for (uint32_t j = e0; j < e1; ++j) {
-          const uint32_t ent = w.am_ent[j];
-          if ((int)(ent >> 28) == net.type) acc += io.cR[(int64_t)net.s_off + (ent & 0x0FFFFFFFu)];
-        }
+        gT += mT * acc;
       }
-      gT += m.mT * acc;
     }
     if (io.g_T) {
       io.g_T[a] = gT;

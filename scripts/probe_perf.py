@@ -50,3 +50,28 @@ for it in range(3):
     print(f"iter {it}: fwd {f:.1f} ms bwd {b:.1f} ms  -> {n*steps/((f+b)*1e-3)/1e9:.3f} G agent-steps/s "
           f"({(f+b)/steps:.2f} ms/step) cases {results['cases_per_timestep'][[0,-1]].tolist()} "
           f"mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB", flush=True)
+
+# host-side issue cost (no sync inside): how long Python needs to enqueue one step
+import time as _t
+torch.cuda.synchronize()
+runner.timer.reset(); runner.restore_initial_data(); runner.set_initial_cases()
+torch.cuda.synchronize()
+t0 = _t.perf_counter()
+reds = []
+with ops.philox_seed(1):
+    for _ in range(steps):
+        next(runner.timer)
+        _, red = model.step(runner.data, runner.timer, age_bins=(0, 18, 65, 100))
+        reds.append(red)
+t1 = _t.perf_counter()
+torch.cuda.synchronize()
+t2 = _t.perf_counter()
+loss = torch.stack(reds)[:, :2].sum()
+torch.cuda.synchronize()
+t3 = _t.perf_counter()
+loss.backward()
+t4 = _t.perf_counter()
+torch.cuda.synchronize()
+t5 = _t.perf_counter()
+print(f"host issue per fwd step {1e3*(t1-t0)/steps:.3f} ms (gpu drained after {1e3*(t2-t1):.2f} ms); "
+      f"host issue per bwd step {1e3*(t4-t3)/steps:.3f} ms (gpu drained after {1e3*(t5-t4):.2f} ms)")
