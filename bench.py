@@ -57,54 +57,61 @@ def bench_params(device, steps):
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons through NVML from a background thread while the timed region
+    runs (polling `nvidia-smi -lms` from a subprocess was measured to slow the timed kernels by 2-3x)."""
 
-    def __init__(self, index):
-        self.index, self.proc, self.path = index, None, None
+    def __init__(self, index, period=0.05):
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz, self.error = [], set(), None, None
+        self._stop = None
+        self._thread = None
 
     def __enter__(self):
+        import threading
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=open(self.path, "w"), stderr=subprocess.STDOUT)
-        except Exception:  # noqa: BLE001
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.error = repr(e)[:200]
+            return self
+        names = {"hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        self._stop = threading.Event()
+
+        def loop():
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    mask = int(get_reasons(h))
+                    for k, bit in names.items():
+                        if mask & bit:
+                            self.reasons.add(k)
+                except Exception as e:  # noqa: BLE001
+                    self.error = repr(e)[:200]
+                    return
+                self._stop.wait(self.period)
+
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
         return self
 
     def __exit__(self, *a):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except Exception:  # noqa: BLE001
-                self.proc.kill()
+        if self._stop is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
 
     def summary(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if not self.path or not os.path.exists(self.path):
-            return out
-        sm, mx, reasons = [], [], set()
-        for line in open(self.path):
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            busy = [x for x in sm if x > 0.5 * max(sm)] or sm
-            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
-        else:
-            out["error"] = open(self.path).read()[:200]
-        os.unlink(self.path)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        if self.samples:
+            out.update(sm_mhz=float(np.median(self.samples)), samples=len(self.samples))
+        if self.error:
+            out["error"] = self.error
         return out
 
 

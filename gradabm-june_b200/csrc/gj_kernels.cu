@@ -17,6 +17,7 @@
 
 #include "gj_device.cuh"
 #include "gj_tiled.cuh"
+#include "gj_fast.cuh"
 
 namespace gj {
 
@@ -693,8 +694,9 @@ int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fw
   if (int e = launch_cell_pass(w, &pp, pl, io->beta, io->S_scaled, io->S_unscaled, sc, st)) return e;
   {
     ProfScope ps(K_AGENT_FWD, st);
-    const bool fast = !io->inj_E && !io->inj_u && !io->inj_z;  // in-kernel Philox: hardware log2/exp2 draw
-    if (fast) k_tile_forward<true><<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
+    // in-kernel Philox noise -> throughput-mode kernel; injected noise (parity tests) -> reference-order kernel
+    const bool fast = !io->inj_E && !io->inj_u && !io->inj_z && !p->exact_order;
+    if (fast) k_fast_forward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
     else k_tile_forward<false><<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
     GJ_CHECK_LAUNCH("k_tile_forward");
   }
@@ -728,9 +730,11 @@ int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_b
   if (!io->g_T && (!io->tinf || !io->inf || !io->maxinf || !io->k0 || !io->g_inf || !io->g_tinf))
     return bad("state arrays are NULL");
   const int grid = (int)w->n_tiles;
+  const bool fast = !io->inj_E && !io->inj_u && !io->inj_z && !p->exact_order;
   {
     ProfScope ps(K_AGENT_BWD, st);
-    k_tile_backward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.tile_part);
+    if (fast) k_fast_backward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.tile_part);
+    else k_tile_backward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.tile_part);
     GJ_CHECK_LAUNCH("k_tile_backward");
   }
   if (pl.n_generic > 0)
@@ -739,7 +743,8 @@ int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_b
   if (int e = launch_cell_pass(w, &pp, pl, io->beta, io->cR, io->R, sc, st)) return e;
   {
     ProfScope ps(K_AGENT_BWD_GATHER, st);
-    k_tile_backward_gather<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.dbeta_tile);
+    if (fast) k_fast_backward_gather<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.dbeta_tile);
+    else k_tile_backward_gather<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.dbeta_tile);
     GJ_CHECK_LAUNCH("k_tile_backward_gather");
   }
   if (io->g_beta && pp.n_nets > 0) {

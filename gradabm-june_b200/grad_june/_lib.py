@@ -63,7 +63,7 @@ class StepParams(C.Structure):
         ("n_quar", C.c_int32), ("quar_thr", C.c_float * GJ_MAX_QUAR),
         ("n_stages", C.c_int32), ("trans_time", Dist * GJ_MAX_STAGES), ("rec_time", Dist * GJ_MAX_STAGES),
         ("n_age_bins", C.c_int32), ("age_bins", C.c_int32 * (GJ_MAX_AGE_BINS + 1)),
-        ("tau", C.c_float), ("seed", C.c_uint64), ("call_index", C.c_uint32), ("_pad1", C.c_uint32),
+        ("tau", C.c_float), ("seed", C.c_uint64), ("call_index", C.c_uint32), ("exact_order", C.c_uint32),
     ]
 
 

@@ -16,6 +16,7 @@ from ._lib import (KIND_CARE_VISIT, KIND_HOUSEHOLD, KIND_LEISURE, KIND_PLAIN, MO
 from .world import DeviceWorld
 
 TAU = 0.1
+EXACT_ORDER = False   # module-wide switch: run the reference-order kernels even in Philox mode
 
 
 def require_cuda(t: torch.Tensor, what: str):
@@ -146,6 +147,7 @@ class StepSpec:
     age_bins: Sequence[int] = ()
     want_reductions: bool = True
     want_lam: bool = False
+    exact_order: bool = False   # force the reference-order kernels even with in-kernel Philox noise
 
 
 def _scratch(world: DeviceWorld):
@@ -212,6 +214,7 @@ def _fill_params(world: DeviceWorld, spec: StepSpec, sym: Optional[SymptomsTable
         p.age_bins[i] = int(b)
     p.tau = TAU
     p.seed, p.call_index = int(seed), int(call_index)
+    p.exact_order = 1 if (spec.exact_order or EXACT_ORDER) else 0
     return p, off
 
 

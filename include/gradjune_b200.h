@@ -156,7 +156,10 @@ typedef struct gj_step_params {
    * injected array is given */
   uint64_t seed;
   uint32_t call_index;
-  uint32_t _pad1;
+  /* 0: with in-kernel Philox noise run the throughput-mode kernels (same arithmetic, re-associated sums and
+   * hardware log2/exp2 in the draw); 1: always run the reference-order kernels (they also run whenever noise
+   * is injected) */
+  uint32_t exact_order;
 } gj_step_params;
 
 /* device arrays of one forward call; unused ones may be NULL */
