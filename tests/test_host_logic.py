@@ -1,0 +1,218 @@
+"""CPU tests of the host-side logic: the C-ABI library loads and exports every symbol the header declares,
+Philox known answers, the default configuration equals the reference's, Timer/Policies reproduce the
+reference's schedule, the world container reads reference pickles' layout, and the CSR/tier builder."""
+import ctypes
+import json
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    from grad_june import _lib
+    header = (ROOT / "include" / "gradjune_b200.h").read_text()
+    declared = set(re.findall(r"\b(gj_[a-z0-9_]+)\s*\(", header))
+    declared -= {"gj_world_desc", "gj_step_params"}
+    assert {"gj_step_forward", "gj_step_backward", "gj_transmission_forward", "gj_philox_fill"} <= declared
+    raw = ctypes.CDLL(str(_lib.build()))
+    for sym in sorted(declared):
+        assert hasattr(raw, sym), f"{sym} is declared in include/gradjune_b200.h but not exported"
+    assert set(_lib.EXPORTED_SYMBOLS) <= declared
+    L = _lib.lib()                     # also checks struct sizes against the header's
+    assert L.gj_abi_version() == 1
+
+
+def test_philox_known_answers():
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors)."""
+    from grad_june import _lib
+    L = _lib.lib()
+
+    def philox(ctr, key):
+        c = (ctypes.c_uint32 * 4)(*ctr)
+        k = (ctypes.c_uint32 * 2)(*key)
+        out = (ctypes.c_uint32 * 4)()
+        L.gj_philox4x32_10(c, k, out)
+        return [int(x) for x in out]
+
+    assert philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_default_config_equals_reference(golden_dir):
+    from grad_june.default_config import default_parameters
+    ref = json.load(open(golden_dir / "reference_default_params.json"))
+    mine = json.loads(json.dumps(default_parameters(), default=str, sort_keys=True))
+    assert mine == ref
+
+
+def test_default_yaml_roundtrip(tmp_path):
+    import yaml
+    from grad_june.default_config import default_parameters, write_default_config
+    write_default_config(tmp_path / "default.yaml")
+    assert yaml.safe_load(open(tmp_path / "default.yaml")) == default_parameters()
+
+
+@pytest.mark.parametrize("tag", list(H.RUNS))
+def test_schedule_matches_reference(tag):
+    """Timer + Policies + network table give the reference's per-step (now, dt, day type, activity order,
+    beta_eff, active quarantine thresholds) — recorded from the reference by make_golden.py."""
+    from grad_june import Timer
+    from grad_june.infection_networks import InfectionNetworks
+    from grad_june.policies import Policies
+    params, schedule = H.load_params(tag)
+    nets = InfectionNetworks.from_parameters(params)
+    policies = Policies.from_parameters(params)
+    timer = Timer.from_parameters(params)
+    i = 0
+    while timer.date < timer.final_date:
+        next(timer)
+        ref = schedule[i]
+        assert timer.now == ref["now"] and timer.duration == ref["dt"] and timer.day_type == ref["day_type"]
+        assert timer.date.isoformat() == ref["date"]
+        active = nets.active_networks(timer, policies)
+        assert [n.name for n in active] == ref["order"]
+        for n in active:
+            assert float(n.beta_eff(policies, timer)) == pytest.approx(ref["beta"][n.name], rel=1e-7)
+        q = policies.quarantine_policies.active_thresholds(timer) if policies.quarantine_policies else None
+        assert q == ref["quarantine"]
+        i += 1
+    assert i == len(schedule)
+
+
+def test_timer_shifts_and_unknown_activity():
+    from grad_june import Timer
+    t = Timer(initial_day="2022-02-04", total_days=3, weekday_step_duration=(8, 8, 8), weekend_step_duration=(12, 12),
+              weekday_activities=(("company", "school", "household"), ("pub", "household"), ("household",)),
+              weekend_activities=(("pub",), ("household",)))
+    assert t.get_activity_order() == ["school", "company", "household"]      # hierarchy order, not config order
+    seen = []
+    while t.date < t.final_date:
+        seen.append((t.day_of_week, t.shift, t.duration))
+        next(t)
+    assert seen[:3] == [("Friday", 0, 8 / 24), ("Friday", 1, 8 / 24), ("Friday", 2, 8 / 24)]
+    assert seen[3:5] == [("Saturday", 0, 0.5), ("Saturday", 1, 0.5)]
+    bad = Timer(initial_day="2022-02-01", weekday_activities=(("leisure",),), weekday_step_duration=(24,))
+    with pytest.raises(ValueError):
+        bad.get_activity_order()
+
+
+def test_parse_age_probabilities_overlapping_bins():
+    from grad_june.utils import parse_age_probabilities
+    out = parse_age_probabilities({"0-75": 0.0, "75-85": 0.25, "75-100": 0.5})
+    assert len(out) == 100 and out[10] == 0.0 and out[74] == 0.0
+    assert out[75] in (0.25, 0.5) and out[99] in (0.0, 0.5)
+    simple = parse_age_probabilities({"20-40": 0.3, "0-20": 0.1})
+    assert simple[0] == 0.1 and simple[19] == 0.1 and simple[20] == 0.3 and simple[39] == 0.3 and simple[40] == 0
+
+
+def test_world_container_and_pickle_roundtrip(tmp_path, golden_dir):
+    import pickle
+    from grad_june.world import HeteroData, ToUndirected, load_world, world_from_arrays
+    arrays = np.load(golden_dir / "sample_world.npz")
+    data = world_from_arrays(arrays, H.SAMPLE_TYPES)
+    assert data["agent"].age.shape[0] == 769 and data["agent"]["age"] is data["agent"].age
+    assert data["attends_school"].edge_index.shape[0] == 2
+    assert torch.equal(data["rev_attends_school"].edge_index, data["attends_school"].edge_index.flip(0))
+    assert data["school"]["people"].shape[0] == len(data["school"]["id"])
+    data["results"] = {"x": 1}
+    assert data["results"]["x"] == 1 and data.results["x"] == 1
+    del data["rev_attends_school"]
+    assert "rev_attends_school" not in data
+    data = ToUndirected()(data)
+    with open(tmp_path / "w.pkl", "wb") as f:
+        pickle.dump(data, f)
+    again = load_world(tmp_path / "w.pkl")
+    assert torch.equal(again["attends_leisure"].edge_index, data["attends_leisure"].edge_index)
+    assert set(again.venue_types()) == set(H.SAMPLE_TYPES)
+
+
+def _group_sums_reference(ei, n_groups, values):
+    return torch.zeros(n_groups, dtype=torch.float64).index_add_(0, ei[1], values.double()[ei[0]])
+
+
+def test_world_tiers_reproduce_group_sums():
+    """Whatever layout tier a type lands in, the stored structure must describe the same agent<->group
+    incidence: recompute per-group sums of a random per-agent vector from each tier and compare."""
+    from grad_june import world as W
+    n = 40_000
+    data = W.make_synthetic_world(n, seed=4, agents_per_super_area=3000)
+    types = data.venue_types()
+    dw = W.build_csr(n, types, {t: data["attends_" + t].edge_index for t in types},
+                     {t: data[t]["people"] for t in types}, {t: len(data[t]["id"]) for t in types},
+                     data["agent"].age, data["agent"].sex, 16, 1024, "cpu")
+    tiers = dict(zip(types, dw.type_tier))
+    assert tiers["household"] == W.TIER_RANGE and tiers["leisure"] == W.TIER_CELL and tiers["company"] == W.TIER_GENERIC
+    x = torch.rand(n, dtype=torch.float64)
+    u32 = lambda t: t.long() & 0xFFFFFFFF
+    tile_begin = u32(dw.tile_begin)
+    assert tile_begin[0] == 0 and tile_begin[-1] == n and int((tile_begin[1:] - tile_begin[:-1]).max()) <= W.TILE_AGENTS
+    for ti, t in enumerate(types):
+        ei = data["attends_" + t].edge_index
+        G = len(data[t]["id"])
+        ref = _group_sums_reference(ei, G, x)
+        if dw.type_tier[ti] == W.TIER_RANGE:
+            slot = u32(dw.range_slot[ti])
+            member = slot != 0xFFFFFFFF
+            start = torch.arange(n)[member] - (slot[member] >> 16)
+            size = slot[member] & 0xFFFF
+            # every member sees the same (start, size); group sum = sum over the run
+            csum = torch.cat((torch.zeros(1, dtype=torch.float64), torch.cumsum(x, 0)))
+            mine = csum[start + size] - csum[start]
+            g_of = torch.zeros(n, dtype=torch.long)
+            g_of[ei[0]] = ei[1]
+            assert torch.allclose(mine, ref[g_of[member]], rtol=1e-9, atol=1e-9)
+            pc = W.p_contact(data[t]["people"])
+            assert torch.equal(dw.range_pc[ti][member], pc[g_of[member]])
+        elif dw.type_tier[ti] == W.TIER_CELL:
+            c = dw.cells[ti]
+            ctp, cgp, cg = u32(c["cell_tile_ptr"]), u32(c["cell_grp_ptr"]), u32(c["cell_grp"])
+            mine = torch.zeros(G, dtype=torch.float64)
+            csum = torch.cat((torch.zeros(1, dtype=torch.float64), torch.cumsum(x, 0)))
+            for cell in range(c["n_cells"]):
+                lo, hi = tile_begin[ctp[cell]], tile_begin[ctp[cell + 1]]
+                for g in cg[cgp[cell]:cgp[cell + 1]]:
+                    mine[g] += csum[hi] - csum[lo]
+            assert torch.allclose(mine, ref, rtol=1e-9, atol=1e-9)
+            # reverse map is consistent
+            gcp, gc = u32(c["grp_cell_ptr"]), u32(c["grp_cell"])
+            assert int(gcp[-1]) == cg.numel() == gc.numel()
+        else:
+            off = dw.type_group_off[ti]
+            gm_ptr, gm_agent = u32(dw.gm_ptr), u32(dw.gm_agent)
+            seg = torch.repeat_interleave(torch.arange(G), (gm_ptr[off + 1:off + G + 1] - gm_ptr[off:off + G]))
+            vals = x[gm_agent[gm_ptr[off]:gm_ptr[off + G]]]
+            mine = torch.zeros(G, dtype=torch.float64).index_add_(0, seg, vals)
+            assert torch.allclose(mine, ref, rtol=1e-9, atol=1e-9)
+    # work lists cover every generic group exactly once
+    small, chunks = u32(dw.small_groups), u32(dw.chunk_group)
+    generic = torch.cat([torch.arange(dw.type_group_off[i], dw.type_group_off[i + 1])
+                         for i in range(len(types)) if dw.type_tier[i] == W.TIER_GENERIC])
+    assert torch.equal(torch.sort(torch.cat((small, torch.unique(chunks))))[0], generic)
+
+
+def test_untiered_world_matches_tiered_incidence():
+    from grad_june import world as W
+    data = W.make_synthetic_world(5000, seed=2, agents_per_super_area=1000)
+    types = data.venue_types()
+    args = (5000, types, {t: data["attends_" + t].edge_index for t in types}, {t: data[t]["people"] for t in types},
+            {t: len(data[t]["id"]) for t in types}, data["agent"].age, data["agent"].sex, 16, 1024, "cpu")
+    flat = W.build_csr(*args, tiers=False)
+    assert set(flat.type_tier) == {W.TIER_GENERIC} and flat.n_generic_edges == flat.n_edges
+    tiered = W.build_csr(*args)
+    assert tiered.n_generic_edges < flat.n_edges and tiered.n_edges == flat.n_edges
+
+
+def test_cpu_tensors_fail_loudly():
+    """There is no CPU fallback: the modules refuse CPU tensors instead of silently computing elsewhere."""
+    from grad_june import IsInfectedSampler, _lib
+    with pytest.raises(_lib.GradJuneLibraryError):
+        IsInfectedSampler()(torch.full((8,), 0.5))
