@@ -14,6 +14,51 @@
 
 namespace gj {
 
+// ---- TMA bulk staging of a tile's contiguous per-agent arrays into shared memory ------------------------
+// cp.async.bulk (1-D, no tensor map) moves [a0, a1) of every state array into shared memory while the CTA's
+// threads are idle; with several CTAs per SM the copies of one tile overlap the arithmetic of another, and no
+// register is spent on loads in flight.  Arrays whose base pointer is not 16-byte aligned (views) fall back to
+// cooperative loads.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+constexpr int kStageElems = GJ_TILE_AGENTS + 8;  // room for the 16-byte alignment slack on both sides
+
+// Stage src[a0s .. a1e) (element size 4) into dst; a0s = a0 & ~3, a1e = (a1 + 3) & ~3.  Thread 0 issues the bulk
+// copy when the source is 16-byte aligned, otherwise all threads copy.  Returns the bytes the barrier must expect.
+__device__ __forceinline__ uint32_t stage4(void* dst, const void* src, uint32_t a0s, uint32_t a1e, uint64_t* bar) {
+  if (src == nullptr) return 0;
+  const char* g = (const char*)src + (size_t)a0s * 4;
+  const uint32_t bytes = (a1e - a0s) * 4;
+  if ((((uintptr_t)src) & 15) == 0) {
+    if (threadIdx.x == 0) bulk_g2s(dst, g, bytes, bar);
+    return bytes;
+  }
+  for (uint32_t i = threadIdx.x; i < a1e - a0s; i += blockDim.x) ((uint32_t*)dst)[i] = ((const uint32_t*)g)[i];
+  return 0;
+}
+
 struct FastTables {
   float L[200];        // CELL tier, attendance-table kinds: sum_k V_k * p_k(class) [* (age>75) for care visits on the S side]
   float c_house;       // CELL tier, HOUSEHOLD-kind networks: sum_k V_k
@@ -123,58 +168,83 @@ struct RangeSums {
 };
 
 template <bool kBwd>
-__device__ __forceinline__ RangeSums range_sums(const gj_world_desc& w, const FastTables& ft, const gj_step_params& p,
-                                                const Plan& pl, const float* __restrict__ in0,
-                                                const float* __restrict__ in1, uint32_t a, int cls) {
-  RangeSums r;
-  r.house = r.plain = 0.0f;
-#pragma unroll
-  for (int i = 0; i < GJ_MAX_RANGE_NETS; ++i) {
-    if (i < pl.n_t1) {
-      const int k = pl.t1_net[i];
-      const uint32_t slot = pl.slot[k][a];
-      if (slot != kNoSlot) {
-        const int kind = p.nets[k].kind;
-        const uint32_t b0 = a - (slot >> 16), nb = slot & 0xFFFFu;
-        const float cg = ft.beta[k] * pl.rpc[k][a];
-        float S = 0.0f;
-        if (kind == GJ_KIND_HOUSEHOLD) {
-          for (uint32_t b = b0; b < b0 + nb; ++b) S += in0[b];
-        } else if (kind == GJ_KIND_PLAIN) {
-          for (uint32_t b = b0; b < b0 + nb; ++b) S += in1[b];
-        } else {
-          for (uint32_t b = b0; b < b0 + nb; ++b) {
-            const int cb = w.cls[b];
-            float v = ft.prob[pl.net_lei[k]][cb] * in1[b];
-            if (kBwd && kind == GJ_KIND_CARE_VISIT) v = v * (((cb % 100) > 75) ? 1.0f : 0.0f);
-            S += v;
-          }
-        }
-        // the agent-side mask of a table kind is applied here so that the caller only distinguishes house / plain
-        float own = 1.0f;
-        if (kind >= GJ_KIND_LEISURE) {
-          own = ft.prob[pl.net_lei[k]][cls];
-          if (!kBwd && kind == GJ_KIND_CARE_VISIT) own = own * (((cls % 100) > 75) ? 1.0f : 0.0f);
-        }
-        if (kind == GJ_KIND_HOUSEHOLD) r.house += cg * S;
-        else r.plain += (cg * S) * own;
-      }
+__device__ __forceinline__ void range_one(RangeSums& r, int k, const gj_world_desc& w, const FastTables& ft,
+                                          const gj_step_params& p, const Plan& pl, const float* __restrict__ in0,
+                                          const float* __restrict__ in1, uint32_t a, int cls) {
+  const uint32_t slot = pl.slot[k][a];
+  if (slot == kNoSlot) return;
+  const int kind = p.nets[k].kind;
+  const uint32_t b0 = a - (slot >> 16), nb = slot & 0xFFFFu;
+  const float cg = ft.beta[k] * pl.rpc[k][a];
+  float S = 0.0f;
+  if (kind == GJ_KIND_HOUSEHOLD) {
+    for (uint32_t b = b0; b < b0 + nb; ++b) S += in0[b];
+  } else if (kind == GJ_KIND_PLAIN) {
+    for (uint32_t b = b0; b < b0 + nb; ++b) S += in1[b];
+  } else {
+    for (uint32_t b = b0; b < b0 + nb; ++b) {
+      const int cb = w.cls[b];
+      float v = ft.prob[pl.net_lei[k]][cb] * in1[b];
+      if (kBwd && kind == GJ_KIND_CARE_VISIT) v = v * (((cb % 100) > 75) ? 1.0f : 0.0f);
+      S += v;
     }
   }
+  // the agent-side mask of a table kind is applied here so that the caller only distinguishes house / plain
+  float own = 1.0f;
+  if (kind >= GJ_KIND_LEISURE) {
+    own = ft.prob[pl.net_lei[k]][cls];
+    if (!kBwd && kind == GJ_KIND_CARE_VISIT) own = own * (((cls % 100) > 75) ? 1.0f : 0.0f);
+  }
+  if (kind == GJ_KIND_HOUSEHOLD) r.house += cg * S;
+  else r.plain += (cg * S) * own;
+}
+
+template <bool kBwd>
+__device__ __forceinline__ RangeSums range_sums(const gj_world_desc& w, const FastTables& ft, const gj_step_params& p,
+                                                const Plan& pl, const float* __restrict__ in0,
+                                                const float* __restrict__ in1, uint32_t a, int cls, int first = 0) {
+  RangeSums r;
+  r.house = r.plain = 0.0f;
+  for (int i = first; i < pl.n_t1; ++i) range_one<kBwd>(r, pl.t1_net[i], w, ft, p, pl, in0, in1, a, cls);
   return r;
 }
 
 // =====================================================================================================
 // forward
 // =====================================================================================================
+struct FwdStage {
+  float s[kStageElems], inf[kStageElems], tinf[kStageElems], cur[kStageElems], nxt[kStageElems], ttn[kStageElems];
+  uint32_t ptr[kStageElems];  // am_ptr[a0s .. a1e] (one extra element is read directly)
+  alignas(16) uint64_t bar;
+};
+
 __global__ void __launch_bounds__(kBlock, 4) k_fast_forward(gj_world_desc w, gj_step_params p, Plan pl, gj_fwd_io io,
                                                             const float* __restrict__ cell_buf,
                                                             double* __restrict__ red_part,
                                                             unsigned int* __restrict__ ticket) {
   __shared__ FastTables ft;
+  __shared__ alignas(128) FwdStage sg;
   const int64_t N = w.n_agents;
   const int64_t tile = blockIdx.x;
   const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];
+  const uint32_t a0s = a0 & ~3u;
+  uint32_t a1e = (a1 + 3u) & ~3u;
+  if (threadIdx.x == 0) {
+    mbar_init(&sg.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  {
+    uint32_t bytes = 0;
+    bytes += stage4(sg.s, io.s, a0s, a1e, &sg.bar);
+    bytes += stage4(sg.inf, io.inf, a0s, a1e, &sg.bar);
+    bytes += stage4(sg.tinf, io.tinf, a0s, a1e, &sg.bar);
+    bytes += stage4(sg.cur, io.cur, a0s, a1e, &sg.bar);
+    bytes += stage4(sg.nxt, io.nxt, a0s, a1e, &sg.bar);
+    bytes += stage4(sg.ttn, io.ttn, a0s, a1e, &sg.bar);
+    if (pl.n_generic > 0) bytes += stage4(sg.ptr, w.am_ptr, a0s, a1e, &sg.bar);
+    if (threadIdx.x == 0) mbar_expect_tx(&sg.bar, bytes);
+  }
   build_fast_tables<true>(ft, w, p, pl, io.leisure_prob, io.beta, pl.n_t2 > 0 ? cell_buf : nullptr, tile);
   float red[kMaxRed];
 #pragma unroll
@@ -182,18 +252,27 @@ __global__ void __launch_bounds__(kBlock, 4) k_fast_forward(gj_world_desc w, gj_
   const float* __restrict__ Tsrc = io.T_in ? io.T_in : io.T;
   const float* __restrict__ Tq = (p.n_quar > 0) ? io.Tq : Tsrc;
   const bool has_cell = pl.n_t2 > 0;
+  mbar_wait(&sg.bar, 0);
+  __syncthreads();  // cooperative (unaligned) copies, if any, are visible too
 
   for (uint32_t a = a0 + threadIdx.x; a < a1; a += kBlock) {
+    const uint32_t i = a - a0s;
     const int cls = w.cls[a];
     AgentState st;
-    st.s = io.s[a];
-    st.inf = io.inf ? io.inf[a] : 0.0f;
-    st.tinf = io.tinf ? io.tinf[a] : 0.0f;
-    st.cur = io.cur ? io.cur[a] : 1.0f;
-    st.nxt = io.nxt ? io.nxt[a] : 1.0f;
-    st.ttn = io.ttn ? io.ttn[a] : 0.0f;
+    st.s = sg.s[i];
+    st.inf = io.inf ? sg.inf[i] : 0.0f;
+    st.tinf = io.tinf ? sg.tinf[i] : 0.0f;
+    st.cur = io.cur ? sg.cur[i] : 1.0f;
+    st.nxt = io.nxt ? sg.nxt[i] : 1.0f;
+    st.ttn = io.ttn ? sg.ttn[i] : 0.0f;
     const float mq = (p.n_quar > 0) ? quarantine_mask(p, st.cur) : 1.0f;
-    const GenericSums g = generic_sums(w, ft, p, pl, io.S_scaled, a, cls, true);
+    GenericSums g;
+    g.house = g.plain = 0.0f;
+    if (pl.n_generic > 0) {
+      const uint32_t e0 = sg.ptr[i];
+      const uint32_t e1 = (i + 1 < a1e - a0s) ? sg.ptr[i + 1] : w.am_ptr[a + 1];
+      for (uint32_t j = e0; j < e1; ++j) add_entry(g, ft, p, pl, io.S_scaled, w.am_ent[j], cls, true);
+    }
     const RangeSums r = range_sums<false>(w, ft, p, pl, Tsrc, Tq, a, cls);
     float house = g.house + r.house, plain = g.plain + r.plain;
     if (has_cell) {

@@ -18,6 +18,7 @@
 #include "gj_device.cuh"
 #include "gj_tiled.cuh"
 #include "gj_fast.cuh"
+#include "gj_pipe.cuh"
 
 namespace gj {
 
@@ -511,6 +512,23 @@ static int build_channels(const gj_world_desc* w, const gj_step_params* p, Chann
   return 0;
 }
 
+static bool all_aligned16(const void* const* ptrs, size_t n) {
+  for (size_t i = 0; i < n; ++i)
+    if (ptrs[i] && (((uintptr_t)ptrs[i]) & 15)) return false;
+  return true;
+}
+
+// persistent grid of the pipelined kernels: two CTAs per SM
+static int pipe_grid() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    n = 2 * sms;
+  }
+  return n;
+}
+
 static int check_world(const gj_world_desc* w) {
   if (!w) return bad("world is NULL");
   if (w->n_agents < 0 || w->n_types < 0 || w->n_types > GJ_MAX_TYPES) return bad("world sizes");
@@ -696,8 +714,24 @@ int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fw
     ProfScope ps(K_AGENT_FWD, st);
     // in-kernel Philox noise -> throughput-mode kernel; injected noise (parity tests) -> reference-order kernel
     const bool fast = !io->inj_E && !io->inj_u && !io->inj_z && !p->exact_order;
-    if (fast) k_fast_forward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
-    else k_tile_forward<false><<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
+    const void* staged[] = {io->s, io->inf, io->tinf, io->cur, io->nxt, io->ttn, w->am_ptr, w->cls, T, Tq,
+                            pl.n_t1 > 0 ? (const void*)pl.slot[pl.t1_net[0]] : nullptr,
+                            pl.n_t1 > 0 ? (const void*)pl.rpc[pl.t1_net[0]] : nullptr};
+    if (fast && all_aligned16(staged, sizeof(staged) / sizeof(staged[0]))) {
+      static bool configured = false;
+      const size_t smem = PipeLayout<FS_COUNT>::total_bytes;
+      if (!configured) {
+        if (cudaFuncSetAttribute(k_pipe_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+          return fail("cudaFuncSetAttribute(k_pipe_forward)", cudaGetLastError());
+        configured = true;
+      }
+      const int pgrid = grid < pipe_grid() ? grid : pipe_grid();
+      k_pipe_forward<<<pgrid, kPipeThreads, smem, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
+    } else if (fast) {
+      k_fast_forward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
+    } else {
+      k_tile_forward<false><<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
+    }
     GJ_CHECK_LAUNCH("k_tile_forward");
   }
   return 0;

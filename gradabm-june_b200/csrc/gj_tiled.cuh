@@ -92,7 +92,7 @@ template <int kR>
 __device__ __forceinline__ void finish_partials(int nr, const double* __restrict__ partials, int64_t n_part,
                                                 unsigned int* __restrict__ ticket, float* __restrict__ out) {
   __shared__ bool last;
-  __shared__ double sm[kBlock / 32];
+  __shared__ double sm[32];
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
@@ -107,7 +107,7 @@ __device__ __forceinline__ void finish_partials(int nr, const double* __restrict
     __syncthreads();
     if (threadIdx.x == 0) {
       double tsum = 0.0;
-      for (int k = 0; k < kBlock / 32; ++k) tsum += sm[k];
+      for (int k = 0; k < (int)(blockDim.x / 32); ++k) tsum += sm[k];
       out[r] = (float)tsum;
     }
     __syncthreads();

@@ -295,6 +295,14 @@ def _u32(t):
     return (((t + (1 << 31)) % (1 << 32)) - (1 << 31)).to(torch.int32).contiguous()
 
 
+def _padded(t, slack=32):
+    """Same tensor with `slack` readable elements behind it: the kernels fetch tiles with 16-byte-granular bulk
+    copies that may run a few elements past the logical end."""
+    buf = torch.zeros(t.numel() + slack, dtype=t.dtype, device=t.device)
+    buf[: t.numel()] = t
+    return buf[: t.numel()]
+
+
 def _ptr_from_counts(counts):
     ptr = torch.zeros(counts.numel() + 1, dtype=torch.long, device=counts.device)
     ptr[1:] = torch.cumsum(counts, 0)
@@ -323,7 +331,7 @@ def _try_range_tier(n_agents, src, dst, n_groups, pc_t):
     slot[members] = (offset << 16) | size[gid]
     rpc = torch.zeros(n_agents, dtype=torch.float32, device=dev)
     rpc[members] = pc_t[gid]
-    return {"range_slot": _u32(slot), "range_pc": rpc.contiguous()}
+    return {"range_slot": _padded(_u32(slot)), "range_pc": _padded(rpc.contiguous())}
 
 
 def _try_cell_tier(n_agents, src, dst, n_groups):
@@ -473,8 +481,8 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
     return DeviceWorld(
         n_agents=n_agents, n_groups=G, n_edges=n_edges_total, n_generic_edges=E, types=list(types),
         type_group_off=offs, type_tier=type_tier, range_slot=range_slot, range_pc=range_pc, cells=cells,
-        group_size=size, am_ptr=_u32(am_ptr), am_ent=_u32(am_ent), gm_ptr=_u32(gm_ptr),
-        gm_agent=gm_agent.contiguous(), pc=pc.contiguous(), cls=cls.contiguous(), small_groups=_u32(small),
+        group_size=size, am_ptr=_padded(_u32(am_ptr)), am_ent=_padded(_u32(am_ent)), gm_ptr=_u32(gm_ptr),
+        gm_agent=gm_agent.contiguous(), pc=pc.contiguous(), cls=_padded(cls.contiguous(), 64), small_groups=_u32(small),
         chunk_group=_u32(chunk_group), chunk_begin=_u32(chunk_begin), chunk_end=_u32(chunk_end),
         chunk_part=chunk_part.to(torch.int32), big_groups=_u32(big_groups), big_part_ptr=_u32(big_part_ptr),
         n_parts=n_parts, tile_begin=_u32(tile_begin), device=dev,
