@@ -370,23 +370,24 @@ def main():
         dist.destroy_process_group()
 
 
-def kernel_alg_bytes(e_gen, g_gen, e_small, g_small, c=1.0):
-    """Algorithmic bytes per agent and launch of each kernel: every operand array touched once,
-    int32 indices, fp32 values (DESIGN.md "Roofline" lists the terms).  e_gen / g_gen: edges and groups per
-    agent of the GENERIC-tier types; e_small / g_small: the part of them in groups <= GJ_SMALL_GROUP."""
-    grp_small = 4 * e_small + 4 * min(e_small, 1.0) + 8 * g_small + 8 * c * g_small
-    grp_chunk = 4 * (e_gen - e_small) + 4 * min(e_gen - e_small, 1.0) + 8 * (g_gen - g_small) + 8 * c * (g_gen - g_small)
+def kernel_alg_bytes(e_gen, g_gen, e_small, g_small):
+    """Algorithmic bytes per agent and launch of each throughput-mode kernel: every operand array touched once,
+    int32 indices, fp32 values (DESIGN.md "Kernels" lists the terms).  e_gen / g_gen: edges and groups per agent
+    of the GENERIC-tier types; e_small / g_small: the part of them in groups <= GJ_SMALL_GROUP."""
+    def grp(e, g):   # member index + member value per edge; per group: row pointer, pc, two outputs
+        return 8 * e + 16 * g
     return {
-        # is_infected, infection_time, 4 profile + k0 (28) + class byte + T write
-        "k_tile_transmission": 28 + 1 + 4,
-        "k_group_small<fwd>": grp_small, "k_group_chunk<fwd>": grp_chunk,
-        "k_group_small<bwd>": grp_small, "k_group_chunk<bwd>": grp_chunk,
-        # state in 24 + class 1 + household slot+pc 8 + T 4 + row ptr 4 + generic entries + group sums + state out 24 + tape 8
-        "k_tile_forward": 24 + 1 + 8 + 4 + 4 + 4 * e_gen + 4 * c * g_gen + 24 + 8,
-        # state in 24 + post is_infected 4 + tape 8 + class 1 + cotangents in (is_infected, stage) 8 + out 20 + w 4
-        "k_tile_backward": 24 + 4 + 8 + 1 + 8 + 20 + 4,
-        # class 1 + household slot+pc 8 + w 4 + T 4 + row ptr 4 + generic entries + cR + profile/state 28 + RMW of 2 cotangents 16
-        "k_tile_backward_gather": 1 + 8 + 4 + 4 + 4 + 4 * e_gen + 4 * c * g_gen + 28 + 16,
+        # is_infected in, T out; the profile (tinf 4 + packed 16) is read for infected agents only: not counted
+        "transmission": 4 + 4,
+        "group_small<fwd>": grp(e_small, g_small), "group_chunk<fwd>": grp(e_gen - e_small, g_gen - g_small),
+        "group_small<bwd>": grp(e_small, g_small), "group_chunk<bwd>": grp(e_gen - e_small, g_gen - g_small),
+        # state in 24 + class 1 + generic entry 4 + household slot+pc 8 + T 4 + group value + state out 24 + tape 8
+        "agent_forward": 24 + 1 + 4 + 8 + 4 + 4 * e_gen + 24 + 8,
+        # state in 20 + tape 8 + class 1 + cotangents in 24 + cotangents out 24 + w 4
+        "agent_backward": 20 + 8 + 1 + 24 + 24 + 4,
+        # class 1 + generic entry 4 + household slot+pc 8 + w 4 + group value + is_infected/infection_time 8 +
+        # packed profile 16 + read-modify-write of two cotangents 16
+        "backward_gather": 1 + 4 + 8 + 4 + 4 * e_gen + 8 + 16 + 16,
     }
 
 

@@ -1,14 +1,15 @@
 // Kernels + C ABI of the B200-native infection step (see include/gradjune_b200.h).
 //
-// One timestep forward = passes over HBM-resident arrays (tile kernels in gj_tiled.cuh):
-//   K1  k_tile_transmission  agent tiles   state -> T (and quarantine-masked Tq); tile partials of CELL types
-//   K2  k_group_small/chunk  group-major   CSR-sorted members -> per-group sums S (GENERIC types only)
-//        (+ k_group_fix for groups that span several chunks); k_cell_groups/k_cell_gather for CELL types
-//   K3  k_tile_forward       agent tiles   pressure from RANGE / CELL / GENERIC tiers -> q -> Gumbel-softmax
-//                                          draw -> state + symptoms update -> reductions
-// and backward mirrors it (k_tile_backward, the same group/cell kernels on cotangents,
-// k_tile_backward_gather, k_dbeta).  No global atomics on data: every sum has a fixed order, so results
-// are bit-reproducible run to run.
+// One timestep forward = passes over HBM-resident arrays:
+//   K1  transmission   agent tiles   state -> T (and quarantine-masked Tq); tile partials of CELL types
+//   K2  group sums     group-major   CSR-sorted members -> per-group sums S (GENERIC types only)
+//        (+ a fix-up for groups that span several chunks); k_cell_groups/k_cell_gather for CELL types
+//   K3  forward        agent tiles   pressure from RANGE / CELL / GENERIC tiers -> q -> Gumbel-softmax
+//                                    draw -> state + symptoms update -> reductions
+// and backward mirrors it (per-agent backward, the same group/cell kernels on cotangents, backward gather,
+// k_dbeta).  Two implementations of every pass: the reference-order kernels (gj_tiled.cuh: the reference's
+// summation order and IEEE libm, used with injected noise) and the throughput-mode kernels (gj_lean.cuh).
+// No global atomics on data: every sum has a fixed order, so results are bit-reproducible run to run.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -17,8 +18,7 @@
 
 #include "gj_device.cuh"
 #include "gj_tiled.cuh"
-#include "gj_fast.cuh"
-#include "gj_pipe.cuh"
+#include "gj_lean.cuh"
 
 namespace gj {
 
@@ -44,9 +44,9 @@ enum KernelId {
   K_AGENT_BWD, K_GROUP_SMALL_B, K_GROUP_CHUNK_B, K_GROUP_FIX_B, K_DBETA, K_AGENT_BWD_GATHER, K_CELL, K_OTHER, K_COUNT
 };
 static const char* kKernelNames[K_COUNT] = {
-  "k_tile_transmission", "k_group_small<fwd>", "k_group_chunk<fwd>", "k_group_fix<fwd>", "k_tile_forward",
-  "k_tile_backward", "k_group_small<bwd>", "k_group_chunk<bwd>", "k_group_fix<bwd>", "k_dbeta",
-  "k_tile_backward_gather", "k_cell_groups+gather", "other"};
+  "transmission", "group_small<fwd>", "group_chunk<fwd>", "group_fix<fwd>", "agent_forward",
+  "agent_backward", "group_small<bwd>", "group_chunk<bwd>", "group_fix<bwd>", "dbeta",
+  "backward_gather", "cell_groups+gather", "other"};
 constexpr int kMaxProfiled = 16384;
 struct Profiler {
   bool on = false;
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(kBlock) k_agent_forward(gj_world_desc w, gj_st
     float one[kMaxRed];
 #pragma unroll
     for (int r = 0; r < kMaxRed; ++r) one[r] = 0.0f;
-    forward_tail<false>(p, io, N, a, cls % 100, q, st, one);
+    forward_tail(p, io, N, a, cls % 100, q, st, one);
 #pragma unroll
     for (int r = 0; r < kMaxRed; ++r) red[r] += (double)one[r];
   }
@@ -437,7 +437,12 @@ __global__ void __launch_bounds__(kBlock) k_agent_backward(gj_world_desc w, gj_s
 }
 
 // dL/dbeta_k = sum_g pc_g * S~_g * R_g   (fixed-order two-level sum in fp64)
-__global__ void __launch_bounds__(kBlock) k_dbeta(gj_world_desc w, gj_step_params p, Plan pl,
+struct DbetaPlan {
+  int64_t soff[GJ_MAX_NETS];  // where network k's plain group sums / R live inside S_unscaled / R
+  int64_t n_range_parts;      // partials written by the backward gather (tiles, or CTAs of the persistent grid)
+};
+
+__global__ void __launch_bounds__(kBlock) k_dbeta(gj_world_desc w, gj_step_params p, Plan pl, DbetaPlan dp,
                                                   const float* __restrict__ S_un, const float* __restrict__ R,
                                                   const double* __restrict__ dbeta_tile, double* __restrict__ partials,
                                                   unsigned int* __restrict__ tickets, float* __restrict__ g_beta) {
@@ -445,15 +450,16 @@ __global__ void __launch_bounds__(kBlock) k_dbeta(gj_world_desc w, gj_step_param
   const gj_net net = p.nets[k];
   double acc[1] = {0.0};
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  if (w.type_tier[net.type] == GJ_TIER_RANGE) {  // per-tile partials written by k_tile_backward_gather
+  if (w.type_tier[net.type] == GJ_TIER_RANGE) {  // partials written by the backward gather
     const int i = pl.net_t1[k];
-    for (int64_t tl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tl < w.n_tiles; tl += stride)
+    for (int64_t tl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tl < dp.n_range_parts; tl += stride)
       acc[0] += dbeta_tile[tl * GJ_MAX_RANGE_NETS + i];
   } else {
     const int64_t g0 = w.type_group_off[net.type];
     const int64_t G = w.type_group_off[net.type + 1] - g0;
+    const int64_t so = dp.soff[k];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < G; i += stride)
-      acc[0] += (double)(w.pc[g0 + i] * S_un[(int64_t)net.s_off + i]) * (double)R[(int64_t)net.s_off + i];
+      acc[0] += (double)(w.pc[g0 + i] * S_un[so + i]) * (double)R[so + i];
   }
   block_reduce_finish<1>(acc, 1, partials + (int64_t)k * kRedBlocks, tickets + 1 + k, g_beta + k);
 }
@@ -512,21 +518,19 @@ static int build_channels(const gj_world_desc* w, const gj_step_params* p, Chann
   return 0;
 }
 
-static bool all_aligned16(const void* const* ptrs, size_t n) {
-  for (size_t i = 0; i < n; ++i)
-    if (ptrs[i] && (((uintptr_t)ptrs[i]) & 15)) return false;
-  return true;
-}
-
-// persistent grid of the pipelined kernels: two CTAs per SM
-static int pipe_grid() {
+// persistent grids of the throughput-mode kernels
+static int sm_count() {
   static int n = 0;
   if (n == 0) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    n = 2 * sms;
+    n = sms;
   }
   return n;
+}
+static int lean_grid(const gj_world_desc* w, int ctas_per_sm) {
+  const int64_t g = (int64_t)sm_count() * ctas_per_sm;
+  return (int)(w->n_tiles < g ? w->n_tiles : g);
 }
 
 static int check_world(const gj_world_desc* w) {
@@ -580,6 +584,132 @@ static int launch_cell_pass(const gj_world_desc* w, const gj_step_params* p, con
   GJ_CHECK_LAUNCH("k_cell_groups");
   k_cell_gather<<<dim3(blocks_for(maxC, kBlock), pl.n_t2), kBlock, 0, st>>>(*w, *p, pl, out_scaled, sc.cell_buf);
   GJ_CHECK_LAUNCH("k_cell_gather");
+  return 0;
+}
+
+// ---- throughput mode (gj_lean.cuh) ---------------------------------------------------------------------------
+// A step runs on the throughput-mode kernels when it is the whole fused step with in-kernel Philox noise and every
+// network is of the kind its layout tier handles in closed form; forward and backward take the same decision
+// from (world, params, prof4), so the group-sum buffers they exchange have the same layout.
+static bool lean_plan(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, LeanPlan* lp) {
+  memset(lp, 0, sizeof(*lp));
+  if (p->mode != GJ_MODE_STEP || p->phases != GJ_PHASE_ALL || p->exact_order) return false;
+  if (p->n_nets <= 0 || pl.n_t1 > 1) return false;
+  if (pl.n_generic > 0 && !w->ent1) return false;
+  int64_t total = 0;
+  for (int k = 0; k < p->n_nets; ++k) {
+    const int kind = p->nets[k].kind, t = p->nets[k].type;
+    total += w->type_group_off[t + 1] - w->type_group_off[t];
+    if (pl.tier[k] == GJ_TIER_RANGE) {
+      if (kind != GJ_KIND_HOUSEHOLD && kind != GJ_KIND_PLAIN) return false;
+      lp->n_range = 1;
+      lp->r_slot = w->range_slot[t];
+      lp->r_pc = w->range_pc[t];
+      lp->r_net = k;
+      lp->r_house = kind == GJ_KIND_HOUSEHOLD;
+    } else if (pl.tier[k] == GJ_TIER_CELL) {
+      if (kind != GJ_KIND_LEISURE && kind != GJ_KIND_CARE_VISIT) return false;
+      const int j = pl.net_t2[k];
+      lp->c_row[j] = p->nets[k].prob_row;
+      lp->c_care[j] = kind == GJ_KIND_CARE_VISIT;
+      lp->c_cell_off[j] = w->cell_off[t];
+      lp->c_tile_cell[j] = w->tile_cell[t];
+    } else if (kind != GJ_KIND_PLAIN) {
+      return false;
+    }
+  }
+  lp->n_cell = pl.n_t2;
+  lp->has_generic = pl.n_generic > 0;
+  lp->gen_base = total;
+  return true;
+}
+
+static int launch_lean_group_pass(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const float* beta,
+                                  const float* in, float* out_scaled, float* out_plain, const Scratch& sc, bool bwd,
+                                  cudaStream_t st) {
+  if (w->n_small > 0) {
+    ProfScope ps(bwd ? K_GROUP_SMALL_B : K_GROUP_SMALL_F, st);
+    k_lean_group_small<<<blocks_for(w->n_small, kBlock), kBlock, 0, st>>>(*w, *p, pl, beta, in, out_scaled, out_plain);
+    GJ_CHECK_LAUNCH("k_lean_group_small");
+  }
+  if (w->n_chunks > 0) {
+    ProfScope ps(bwd ? K_GROUP_CHUNK_B : K_GROUP_CHUNK_F, st);
+    k_lean_group_chunk<<<blocks_for(w->n_chunks * 32, kBlock), kBlock, 0, st>>>(*w, *p, pl, beta, in, out_scaled,
+                                                                              out_plain, sc.part_a);
+    GJ_CHECK_LAUNCH("k_lean_group_chunk");
+  }
+  if (w->n_big > 0) {
+    ProfScope ps(bwd ? K_GROUP_FIX_B : K_GROUP_FIX_F, st);
+    k_lean_group_fix<<<blocks_for(w->n_big, kBlock), kBlock, 0, st>>>(*w, *p, pl, beta, sc.part_a, out_scaled,
+                                                                    out_plain);
+    GJ_CHECK_LAUNCH("k_lean_group_fix");
+  }
+  return 0;
+}
+
+static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const LeanPlan& lp,
+                        const gj_fwd_io* io, const Scratch& sc, cudaStream_t st) {
+  const bool quar = p->n_quar > 0;
+  {
+    ProfScope ps(K_TRANSMISSION, st);
+    const int grid = lean_grid(w, 8);
+    if (quar) k_lean_transmission<true><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
+    else k_lean_transmission<false><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
+    GJ_CHECK_LAUNCH("k_lean_transmission");
+  }
+  if (lp.has_generic)
+    if (int e = launch_lean_group_pass(w, p, pl, io->beta, quar ? io->Tq : io->T, io->S_scaled + lp.gen_base,
+                                       io->S_unscaled + lp.gen_base, sc, false, st))
+      return e;
+  if (int e = launch_cell_pass(w, p, pl, io->beta, io->S_scaled, io->S_unscaled, sc, st)) return e;
+  {
+    ProfScope ps(K_AGENT_FWD, st);
+    const int grid = lean_grid(w, 4);
+    const bool diag = io->q || io->n;
+    if (quar && diag) k_lean_forward<true, true><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets);
+    else if (quar) k_lean_forward<true, false><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets);
+    else if (diag) k_lean_forward<false, true><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets);
+    else k_lean_forward<false, false><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets);
+    GJ_CHECK_LAUNCH("k_lean_forward");
+  }
+  return 0;
+}
+
+static int lean_backward(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, LeanPlan lp,
+                         const gj_bwd_io* io, const Scratch& sc, cudaStream_t st) {
+  const bool quar = p->n_quar > 0;
+  const int grid = lean_grid(w, 4);
+  {
+    ProfScope ps(K_AGENT_BWD, st);
+    if (quar) k_lean_backward<true><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
+    else k_lean_backward<false><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
+    GJ_CHECK_LAUNCH("k_lean_backward");
+  }
+  if (lp.has_generic)
+    if (int e = launch_lean_group_pass(w, p, pl, io->beta, quar ? io->wq : io->w, io->cR + lp.gen_base,
+                                       io->R + lp.gen_base, sc, true, st))
+      return e;
+  if (int e = launch_cell_pass(w, p, pl, io->beta, io->cR, io->R, sc, st)) return e;
+  {
+    ProfScope ps(K_AGENT_BWD_GATHER, st);
+    if (quar) k_lean_backward_gather<true><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.dbeta_tile);
+    else k_lean_backward_gather<false><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.dbeta_tile);
+    GJ_CHECK_LAUNCH("k_lean_backward_gather");
+  }
+  if (io->g_beta) {
+    ProfScope ps(K_DBETA, st);
+    DbetaPlan dp;
+    for (int k = 0; k < GJ_MAX_NETS; ++k) {
+      dp.soff[k] = 0;
+      if (k < p->n_nets)
+        dp.soff[k] = pl.tier[k] == GJ_TIER_GENERIC ? lp.gen_base + w->type_group_off[p->nets[k].type] : p->nets[k].s_off;
+    }
+    dp.n_range_parts = grid;
+    dim3 grid2(kRedBlocks / 8, p->n_nets);
+    k_dbeta<<<grid2, kBlock, 0, st>>>(*w, *p, pl, dp, io->S_unscaled, io->R, sc.dbeta_tile, sc.dbeta_part, sc.tickets,
+                                      io->g_beta);
+    GJ_CHECK_LAUNCH("k_dbeta");
+  }
   return 0;
 }
 
@@ -643,6 +773,17 @@ int gj_profile_prepare(int64_t n, const float* shape, float* k0, void* stream) {
   return 0;
 }
 
+int gj_profile_pack(int64_t n, const float* maxinf, const float* shape, const float* rate, const float* shift,
+                    const float* k0, float* prof4, void* stream) {
+  if (n <= 0) return 0;
+  if (!maxinf || !shape || !rate || !shift || !k0 || !prof4) return bad("NULL array");
+  if (((uintptr_t)prof4) & 15) return bad("prof4 must be 16-byte aligned");
+  k_profile_pack<<<agent_grid(n), kBlock, 0, (cudaStream_t)stream>>>(n, maxinf, shape, rate, shift, k0,
+                                                                    reinterpret_cast<float4*>(prof4));
+  GJ_CHECK_LAUNCH("k_profile_pack");
+  return 0;
+}
+
 int gj_transmission_forward(int64_t n, float now, const float* tinf, const float* inf, const float* maxinf,
                             const float* shape, const float* rate, const float* shift, const float* k0, float* T,
                             void* stream) {
@@ -697,6 +838,16 @@ int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fw
   if ((pp.phases & ~GJ_PHASE_NETWORKS) && (!io->inf || !io->tinf || !io->cur || !io->nxt || !io->ttn))
     return bad("state arrays are NULL");
   if (pl.n_lei > 0 && !io->leisure_prob) return bad("leisure_prob is NULL");
+  {
+    LeanPlan lp;
+    const bool no_injection = !io->inj_E && !io->inj_u && !io->inj_z;
+    if (no_injection && !io->T_in && !io->lam && io->prof4 && lean_plan(w, &pp, pl, &lp)) {
+      if (!io->inf || !io->tinf || !io->cur || !io->nxt || !io->ttn || !io->T || !io->tape_y0 || !io->stage_prob ||
+          !io->s_o || !io->inf_o || !io->tinf_o || !io->cur_o || !io->nxt_o || !io->ttn_o)
+        return bad("fused step: state / tape arrays are NULL");
+      return lean_forward(w, &pp, pl, lp, io, sc, st);
+    }
+  }
   const int grid = (int)w->n_tiles;
   {
     ProfScope ps(K_TRANSMISSION, st);
@@ -712,26 +863,7 @@ int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fw
   if (int e = launch_cell_pass(w, &pp, pl, io->beta, io->S_scaled, io->S_unscaled, sc, st)) return e;
   {
     ProfScope ps(K_AGENT_FWD, st);
-    // in-kernel Philox noise -> throughput-mode kernel; injected noise (parity tests) -> reference-order kernel
-    const bool fast = !io->inj_E && !io->inj_u && !io->inj_z && !p->exact_order;
-    const void* staged[] = {io->s, io->inf, io->tinf, io->cur, io->nxt, io->ttn, w->am_ptr, w->cls, T, Tq,
-                            pl.n_t1 > 0 ? (const void*)pl.slot[pl.t1_net[0]] : nullptr,
-                            pl.n_t1 > 0 ? (const void*)pl.rpc[pl.t1_net[0]] : nullptr};
-    if (fast && all_aligned16(staged, sizeof(staged) / sizeof(staged[0]))) {
-      static bool configured = false;
-      const size_t smem = PipeLayout<FS_COUNT>::total_bytes;
-      if (!configured) {
-        if (cudaFuncSetAttribute(k_pipe_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-          return fail("cudaFuncSetAttribute(k_pipe_forward)", cudaGetLastError());
-        configured = true;
-      }
-      const int pgrid = grid < pipe_grid() ? grid : pipe_grid();
-      k_pipe_forward<<<pgrid, kPipeThreads, smem, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
-    } else if (fast) {
-      k_fast_forward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
-    } else {
-      k_tile_forward<false><<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
-    }
+    k_tile_forward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
     GJ_CHECK_LAUNCH("k_tile_forward");
   }
   return 0;
@@ -763,12 +895,20 @@ int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_b
   if (p->n_quar > 0 && !io->cur) return bad("cur is NULL with an active quarantine");
   if (!io->g_T && (!io->tinf || !io->inf || !io->maxinf || !io->k0 || !io->g_inf || !io->g_tinf))
     return bad("state arrays are NULL");
+  {
+    LeanPlan lp;
+    const bool no_injection = !io->inj_E && !io->inj_u && !io->inj_z;
+    if (no_injection && !io->g_T && !io->g_lam && !io->g_q && !io->g_n && io->prof4 && lean_plan(w, &pp, pl, &lp)) {
+      if (!io->tinf || !io->inf || !io->cur || !io->nxt || !io->ttn || !io->tape_y0 || !io->stage_prob || !io->g_inf ||
+          !io->g_tinf)
+        return bad("fused step backward: state / tape arrays are NULL");
+      return lean_backward(w, &pp, pl, lp, io, sc, st);
+    }
+  }
   const int grid = (int)w->n_tiles;
-  const bool fast = !io->inj_E && !io->inj_u && !io->inj_z && !p->exact_order;
   {
     ProfScope ps(K_AGENT_BWD, st);
-    if (fast) k_fast_backward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.tile_part);
-    else k_tile_backward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.tile_part);
+    k_tile_backward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.tile_part);
     GJ_CHECK_LAUNCH("k_tile_backward");
   }
   if (pl.n_generic > 0)
@@ -777,14 +917,16 @@ int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_b
   if (int e = launch_cell_pass(w, &pp, pl, io->beta, io->cR, io->R, sc, st)) return e;
   {
     ProfScope ps(K_AGENT_BWD_GATHER, st);
-    if (fast) k_fast_backward_gather<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.dbeta_tile);
-    else k_tile_backward_gather<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.dbeta_tile);
+    k_tile_backward_gather<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.dbeta_tile);
     GJ_CHECK_LAUNCH("k_tile_backward_gather");
   }
   if (io->g_beta && pp.n_nets > 0) {
     ProfScope ps(K_DBETA, st);
+    DbetaPlan dp;
+    for (int k = 0; k < GJ_MAX_NETS; ++k) dp.soff[k] = k < pp.n_nets ? pp.nets[k].s_off : 0;
+    dp.n_range_parts = w->n_tiles;
     dim3 grid2(kRedBlocks / 8, pp.n_nets);
-    k_dbeta<<<grid2, kBlock, 0, st>>>(*w, pp, pl, io->S_unscaled, io->R, sc.dbeta_tile, sc.dbeta_part, sc.tickets,
+    k_dbeta<<<grid2, kBlock, 0, st>>>(*w, pp, pl, dp, io->S_unscaled, io->R, sc.dbeta_tile, sc.dbeta_part, sc.tickets,
                                       io->g_beta);
     GJ_CHECK_LAUNCH("k_dbeta");
   }

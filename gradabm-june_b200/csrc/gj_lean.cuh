@@ -1,0 +1,653 @@
+// Throughput-mode kernels of the fused step (included by gj_kernels.cu after gj_tiled.cuh).
+//
+// Same step as the reference-order kernels of gj_tiled.cuh, written for HBM throughput:
+//   * every kernel is a persistent grid (a few CTAs per SM) walking the agent tiles round-robin; tables are
+//     loaded once per CTA, reductions are carried across tiles and combined once per CTA;
+//   * the per-agent instruction count is small: the eleven-network loop collapses to
+//         pressure = s * (range + mq * (generic + L[class]))
+//     with ONE shared-memory lookup L[class] = sum_k V_k * p_k(class) per tile for all cell-tier (leisure)
+//     networks, ONE combined value per generic group (all generic networks of a type are PLAIN, so they share the
+//     group sum) fetched through the one-entry-per-agent ELL word `ent1`, and the household re-sum over
+//     neighbouring agents (L1 hits);
+//   * the infectiousness profile is read as one packed float4 per agent and evaluated with ex2/lg2;
+//   * the Gumbel-softmax decision uses six hardware log2 and one exp2; q itself stays the IEEE expf so that
+//     (1 - q) rounds like the reference's;
+//   * result reductions go through a shared-memory age histogram (small integers: exact in any order).
+// The kernels run when the noise is the in-kernel Philox stream and the step is "simple" (lean_supported() in
+// gj_kernels.cu): range-tier networks of HOUSEHOLD/PLAIN kind, cell-tier networks with an attendance table,
+// generic-tier networks of PLAIN kind.  Anything else, and every call with injected noise (parity tests), runs
+// the reference-order kernels.  Results agree with those to ~1e-6 on q (fp32 re-association) and differ in masks
+// only at near-ties (tests/test_gpu_scale.py::test_throughput_mode_matches_reference_order).
+#pragma once
+#include "gj_tiled.cuh"
+
+namespace gj {
+
+constexpr int kLeanThreads = 256;
+constexpr uint32_t kEntNone = 0xFFFFFFFFu;   // ent1: no generic edge
+constexpr uint32_t kEntMulti = 0xFFFFFFFEu;  // ent1: several generic edges -> agent-major CSR
+
+struct LeanPlan {
+  int n_range;                              // networks on RANGE-tier types: 0 or 1
+  const uint32_t* r_slot;                   // per agent (offset << 16) | size, kNoSlot = not a member
+  const float* r_pc;                        // per agent contact probability of its group
+  int r_net;                                // index of the network (beta)
+  int r_house;                              // 1: HOUSEHOLD kind (ignores quarantine), 0: PLAIN
+  int n_cell;                               // networks on CELL-tier types, same order as Plan::t2_net
+  int c_row[GJ_MAX_CHANNELS];               // attendance table row
+  int c_care[GJ_MAX_CHANNELS];              // CARE_VISIT: susceptible side masked by age > 75
+  int64_t c_cell_off[GJ_MAX_CHANNELS];
+  const uint32_t* c_tile_cell[GJ_MAX_CHANNELS];
+  int has_generic;
+  int64_t gen_base;                         // offset of the per-global-group buffers inside the S / R arrays
+  int n_range_parts;                        // grid of the gather kernel (d/dbeta partials of the range networks)
+};
+
+__device__ __forceinline__ float lg2_fast(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// packed profile {A = maxinf * k0 * rate, rate, e = shape - 1, shift}: T / is_infected and d/d infection_time
+// (transmission.py:38-51; same function as transmission_terms, evaluated as A * 2^(e*log2(x) - x*log2(e)))
+template <bool kGrad>
+__device__ __forceinline__ TransTerms lean_transmission(float now, float tinf, float4 pf) {
+  const float d = (now - tinf) - pf.w;
+  const float sg = d + 1e-10f;
+  const float sign01 = (sg > 0.0f) ? 1.0f : ((sg == 0.0f) ? 0.5f : 0.0f);
+  const float x = d * pf.y;
+  const float pe = ex2_fast(fmaf(pf.z, lg2_fast(x), -x * 1.4426950408889634f));
+  TransTerms r;
+  r.coef = (pf.x * sign01) * pe;
+  r.dcoef = 0.0f;
+  if (kGrad) r.dcoef = r.coef * pf.y * (1.0f - pf.z * rcp_fast(x));  // d/dtinf = -d/dt
+  return r;
+}
+
+__global__ void __launch_bounds__(kBlock) k_profile_pack(int64_t n, const float* __restrict__ maxinf,
+                                                         const float* __restrict__ shape,
+                                                         const float* __restrict__ rate,
+                                                         const float* __restrict__ shift, const float* __restrict__ k0,
+                                                         float4* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += stride)
+    out[a] = make_float4((maxinf[a] * k0[a]) * rate[a], rate[a], shape[a] - 1.0f, shift[a]);
+}
+
+// attendance tables of the cell-tier channels for today's day type; kCareSide folds the (age > 75) mask of
+// care visits into the table (susceptible side of the forward, member side of the backward)
+template <bool kCareSide>
+__device__ __forceinline__ void lean_load_prob(float (*prob)[200], const gj_step_params& p, const LeanPlan& lp,
+                                               const float* __restrict__ lprob) {
+  for (int i = threadIdx.x; i < lp.n_cell * 200; i += blockDim.x) {
+    const int j = i / 200, c = i - j * 200;
+    float v = lprob[(size_t)(lp.c_row[j] * 2 + p.day_type) * 200 + c];
+    if (kCareSide && lp.c_care[j] && (c % 100) <= 75) v = 0.0f;
+    prob[j][c] = v;
+  }
+}
+
+// L[class] = sum_j V_j * prob_j[class] from this tile's per-cell values
+__device__ __forceinline__ void lean_class_table(float* __restrict__ L, const float (*prob)[200], const LeanPlan& lp,
+                                                 const float* __restrict__ cell_buf, int64_t tile) {
+  if (threadIdx.x < 200) {
+    float acc = 0.0f;
+    for (int j = 0; j < lp.n_cell; ++j) {
+      const float v = cell_buf[(lp.c_cell_off[j] + lp.c_tile_cell[j][tile]) * GJ_MAX_CHANNELS + j];
+      acc = fmaf(v, prob[j][threadIdx.x], acc);
+    }
+    L[threadIdx.x] = acc;
+  }
+}
+
+// generic tier: combined value of the agent's group(s)
+__device__ __forceinline__ float lean_generic(const gj_world_desc& w, const float* __restrict__ buf, uint32_t ent,
+                                              uint32_t a) {
+  if (ent < kEntMulti) return buf[ent];
+  float v = 0.0f;
+  if (ent == kEntMulti) {
+    for (uint32_t j = w.am_ptr[a]; j < w.am_ptr[a + 1]; ++j) {
+      const uint32_t e = w.am_ent[j];
+      v += buf[w.type_group_off[e >> 28] + (e & 0x0FFFFFFFu)];
+    }
+  }
+  return v;
+}
+
+__device__ __forceinline__ float quar_mask(const gj_step_params& p, float cur) {
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < GJ_MAX_QUAR; ++i)
+    if (i < p.n_quar) ok = ok && (cur < p.quar_thr[i]);
+  return ok ? 1.0f : 0.0f;
+}
+
+// =====================================================================================================
+// K1  transmissions (+ quarantine-masked copy) and the tile partial sums of the cell channels
+// =====================================================================================================
+constexpr int kTileSlots = GJ_TILE_AGENTS / kLeanThreads;  // agents of one tile handled by one thread (4)
+
+template <bool kQuar>
+__global__ void __launch_bounds__(kLeanThreads) k_lean_transmission(gj_world_desc w, gj_step_params p, LeanPlan lp,
+                                                                    gj_fwd_io io, float* __restrict__ tile_part) {
+  __shared__ float prob[GJ_MAX_CHANNELS][200];
+  lean_load_prob<false>(prob, p, lp, io.leisure_prob);
+  __syncthreads();
+  const float4* __restrict__ prof = reinterpret_cast<const float4*>(io.prof4);
+  const float* __restrict__ g_inf = io.inf;
+  const float* __restrict__ g_cur = io.cur;
+  for (int64_t tile = blockIdx.x; tile < w.n_tiles; tile += gridDim.x) {
+    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];
+    float acc[GJ_MAX_CHANNELS];
+#pragma unroll
+    for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
+    float inf[kTileSlots], cur[kTileSlots];
+#pragma unroll
+    for (int h = 0; h < kTileSlots; ++h) {  // all of the tile's streaming loads first
+      const uint32_t a = a0 + threadIdx.x + h * kLeanThreads;
+      inf[h] = (a < a1) ? g_inf[a] : 0.0f;
+      cur[h] = (kQuar && a < a1) ? g_cur[a] : 0.0f;
+    }
+#pragma unroll
+    for (int h = 0; h < kTileSlots; ++h) {
+      const uint32_t a = a0 + threadIdx.x + h * kLeanThreads;
+      if (a >= a1) break;
+      float T = 0.0f;
+      if (inf[h] != 0.0f) T = lean_transmission<false>(p.now, io.tinf[a], prof[a]).coef * inf[h];
+      io.T[a] = T;
+      float Tq = T;
+      if (kQuar) {
+        Tq = quar_mask(p, cur[h]) * T;
+        io.Tq[a] = Tq;
+      }
+      if (Tq != 0.0f && lp.n_cell > 0) {
+        const int cls = w.cls[a];
+#pragma unroll
+        for (int j = 0; j < GJ_MAX_CHANNELS; ++j)
+          if (j < lp.n_cell) acc[j] = fmaf(prob[j][cls], Tq, acc[j]);
+      }
+    }
+    if (lp.n_cell > 0) block_sums<float, GJ_MAX_CHANNELS>(acc, lp.n_cell, tile_part + tile * GJ_MAX_CHANNELS);
+  }
+}
+
+// =====================================================================================================
+// K2  generic-tier group sums, one value per global group: plain = sum of member values,
+//     scaled = (sum of the betas of the type's networks) * pc_g * plain.  Forward: in = Tq; backward: in = wq.
+// =====================================================================================================
+__device__ __forceinline__ void lean_beta_sums(float* bsum, const gj_step_params& p, const Plan& pl,
+                                               const float* __restrict__ beta) {
+  if (threadIdx.x < GJ_MAX_TYPES) {
+    float b = 0.0f;
+    bool any = false;
+    for (int k = 0; k < p.n_nets; ++k)
+      if (pl.tier[k] == GJ_TIER_GENERIC && p.nets[k].type == (int)threadIdx.x) {
+        b += beta[k];
+        any = true;
+      }
+    bsum[threadIdx.x] = any ? b : nanf("");  // NaN marks "no active network on this type"
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kBlock) k_lean_group_small(gj_world_desc w, gj_step_params p, Plan pl,
+                                                             const float* __restrict__ beta,
+                                                             const float* __restrict__ in,
+                                                             float* __restrict__ out_scaled,
+                                                             float* __restrict__ out_plain) {
+  __shared__ float bsum[GJ_MAX_TYPES];
+  lean_beta_sums(bsum, p, pl, beta);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w.n_small) return;
+  const uint32_t g = w.small_groups[i];
+  const float b = bsum[type_of_group(w, g)];
+  float S = 0.0f;
+  if (b == b) {
+    const uint32_t j0 = w.gm_ptr[g], j1 = w.gm_ptr[g + 1];
+    for (uint32_t j = j0; j < j1; ++j) S += in[w.gm_agent[j]];
+  }
+  out_plain[g] = S;
+  out_scaled[g] = (b == b) ? (b * w.pc[g]) * S : 0.0f;
+}
+
+__global__ void __launch_bounds__(kBlock) k_lean_group_chunk(gj_world_desc w, gj_step_params p, Plan pl,
+                                                             const float* __restrict__ beta,
+                                                             const float* __restrict__ in,
+                                                             float* __restrict__ out_scaled,
+                                                             float* __restrict__ out_plain, float* __restrict__ part) {
+  __shared__ float bsum[GJ_MAX_TYPES];
+  lean_beta_sums(bsum, p, pl, beta);
+  const int lane = threadIdx.x & 31;
+  const int64_t ci = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (ci >= w.n_chunks) return;
+  const uint32_t g = w.chunk_group[ci];
+  const float b = bsum[type_of_group(w, g)];
+  float S = 0.0f;
+  if (b == b) {
+    const uint32_t j0 = w.chunk_begin[ci], j1 = w.chunk_end[ci];
+    for (uint32_t j = j0 + lane; j < j1; j += 32) S += in[w.gm_agent[j]];
+    S = warp_sum(S);
+  }
+  if (lane != 0) return;
+  const int pi = w.chunk_part[ci];
+  if (pi < 0) {
+    out_plain[g] = S;
+    out_scaled[g] = (b == b) ? (b * w.pc[g]) * S : 0.0f;
+  } else {
+    part[pi] = S;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_lean_group_fix(gj_world_desc w, gj_step_params p, Plan pl,
+                                                           const float* __restrict__ beta,
+                                                           const float* __restrict__ part,
+                                                           float* __restrict__ out_scaled,
+                                                           float* __restrict__ out_plain) {
+  __shared__ float bsum[GJ_MAX_TYPES];
+  lean_beta_sums(bsum, p, pl, beta);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w.n_big) return;
+  const uint32_t g = w.big_groups[i];
+  const float b = bsum[type_of_group(w, g)];
+  float S = 0.0f;
+  for (uint32_t j = w.big_part_ptr[i]; j < w.big_part_ptr[i + 1]; ++j) S += part[j];
+  out_plain[g] = S;
+  out_scaled[g] = (b == b) ? (b * w.pc[g]) * S : 0.0f;
+}
+
+// =====================================================================================================
+// K3  forward: pressure -> q -> draw -> state update -> symptoms -> reductions
+// =====================================================================================================
+struct LeanFwdShared {
+  float prob[GJ_MAX_CHANNELS][200];
+  float L[2][200];
+  float beta[GJ_MAX_NETS];
+  float hist[100];  // sum of post-step is_infected by age
+  float deaths;
+};
+
+// range-tier network: (offset, size) word -> sum of the group's member values (members = neighbouring agents)
+__device__ __forceinline__ float lean_range_sum(const float* __restrict__ v, uint32_t a, uint32_t slot) {
+  float S = 0.0f;
+  if (slot != kNoSlot) {
+    const uint32_t b0 = a - (slot >> 16), nb = slot & 0xFFFFu;
+    for (uint32_t b = b0; b < b0 + nb; ++b) S += v[b];
+  }
+  return S;
+}
+
+constexpr int kLeanBatch = 2;  // agents a thread keeps in flight: their loads are issued before any arithmetic
+
+template <bool kQuar, bool kDiag>
+__global__ void __launch_bounds__(kLeanThreads, 4) k_lean_forward(gj_world_desc w, gj_step_params p, LeanPlan lp,
+                                                                  gj_fwd_io io, const float* __restrict__ cell_buf,
+                                                                  double* __restrict__ red_part,
+                                                                  unsigned int* __restrict__ ticket) {
+  __shared__ LeanFwdShared sh;
+  lean_load_prob<true>(sh.prob, p, lp, io.leisure_prob);
+  if (threadIdx.x < p.n_nets) sh.beta[threadIdx.x] = io.beta[threadIdx.x];
+  if (threadIdx.x < 100) sh.hist[threadIdx.x] = 0.0f;
+  if (threadIdx.x == 0) sh.deaths = 0.0f;
+  __syncthreads();
+  const float* __restrict__ Tr = (kQuar && !lp.r_house) ? io.Tq : io.T;  // member values of the range network
+  const float* __restrict__ SP = io.S_scaled + lp.gen_base;
+  const float* __restrict__ i_s = io.s;
+  const float* __restrict__ i_inf = io.inf;
+  const float* __restrict__ i_tinf = io.tinf;
+  const float* __restrict__ i_cur = io.cur;
+  const float* __restrict__ i_nxt = io.nxt;
+  const float* __restrict__ i_ttn = io.ttn;
+  const float dead = (float)(p.n_stages - 1);
+  const float inv_tau = 1.0f / p.tau;
+  const uint32_t key0 = (uint32_t)p.seed, key1 = (uint32_t)(p.seed >> 32);
+  const float beta_r = lp.n_range > 0 ? sh.beta[lp.r_net] : 0.0f;
+
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < w.n_tiles; tile += gridDim.x, ++it) {
+    float* __restrict__ L = sh.L[it & 1];
+    if (lp.n_cell > 0) lean_class_table(L, sh.prob, lp, cell_buf, tile);
+    __syncthreads();  // one barrier per tile: the table of tile i+1 goes to the other buffer
+    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];
+    for (uint32_t base = a0 + threadIdx.x; base < a1; base += kLeanBatch * kLeanThreads) {
+      float s[kLeanBatch], inf[kLeanBatch], tinf[kLeanBatch], cur[kLeanBatch], nxt[kLeanBatch], ttn[kLeanBatch];
+      float rpc[kLeanBatch], gen[kLeanBatch], hs[kLeanBatch], Lc[kLeanBatch];
+      uint32_t ent[kLeanBatch], slot[kLeanBatch];
+      int cls[kLeanBatch];
+      // ---- stage 1: streaming loads of every agent in the batch ----------------------------------------
+#pragma unroll
+      for (int h = 0; h < kLeanBatch; ++h) {
+        const uint32_t a = base + h * kLeanThreads;
+        const bool live = a < a1;
+        const uint32_t al = live ? a : a0;  // dead slots re-read the tile's first agent (no branch around loads)
+        s[h] = i_s[al];
+        inf[h] = i_inf[al];
+        tinf[h] = i_tinf[al];
+        cur[h] = i_cur[al];
+        nxt[h] = i_nxt[al];
+        ttn[h] = i_ttn[al];
+        cls[h] = w.cls[al];
+        ent[h] = lp.has_generic ? w.ent1[al] : kEntNone;
+        slot[h] = lp.n_range > 0 ? lp.r_slot[al] : kNoSlot;
+        rpc[h] = lp.n_range > 0 ? lp.r_pc[al] : 0.0f;
+      }
+      // ---- stage 2: dependent gathers (group value from L2, household neighbours from L1) -------------
+#pragma unroll
+      for (int h = 0; h < kLeanBatch; ++h) {
+        const uint32_t a = base + h * kLeanThreads;
+        const uint32_t al = (a < a1) ? a : a0;
+        gen[h] = lean_generic(w, SP, ent[h], al);
+        hs[h] = lean_range_sum(Tr, al, slot[h]);
+        Lc[h] = lp.n_cell > 0 ? L[cls[h]] : 0.0f;
+      }
+      // ---- stage 3: arithmetic and stores -----------------------------------------------------------------
+#pragma unroll
+      for (int h = 0; h < kLeanBatch; ++h) {
+        const uint32_t a = base + h * kLeanThreads;
+        if (a >= a1) break;
+        const float rv = (beta_r * rpc[h]) * hs[h];
+        const float house = lp.r_house ? rv : 0.0f;
+        const float plain = (gen[h] + Lc[h]) + (lp.r_house ? 0.0f : rv);
+        const float mq = kQuar ? quar_mask(p, cur[h]) : 1.0f;
+        const float X = fmaf(mq, plain, house);  // pressure per unit susceptibility
+        const float lam = X * s[h];
+        const float q = not_infected_prob(lam, p.dt);
+        io.tape_v[a] = (s[h] == 0.0f) ? X : lam;
+        // Gumbel-softmax hard draw from Philox bits (same stream as draw_step_noise):
+        // x0 - x1 = (ln2 / tau) * d,  d = lg2 q - lg2(1-q) - lg2 E0 + lg2 E1, E = -ln u (the ln2 factors cancel)
+        uint32_t r[4];
+        philox4x32_10(a, 0u, p.call_index, 0u, key0, key1, r);
+        const float d = (lg2_fast(q) - lg2_fast(1.0f - q)) -
+                        (lg2_fast(-lg2_fast(u01_open(r[0]))) - lg2_fast(-lg2_fast(u01_open(r[1]))));
+        const float e = ex2_fast(-fabsf(d) * inv_tau);  // exp(x_small - x_big) <= 1
+        const float ys = e * rcp_fast(1.0f + e);        // the smaller soft probability
+        const bool hit = (d < 0.0f) && (e < 1.0f);      // argmax of the softmax; ties -> not infected
+        const float n = hit ? 1.0f : 0.0f;
+        io.tape_y0[a] = hit ? -ys : ys;
+        if (kDiag) {
+          if (io.q) io.q[a] = q;
+          if (io.lam) io.lam[a] = lam;
+          if (io.n) io.n[a] = n;
+        }
+        // infect (model.py:103-110)
+        const float inf_o = inf[h] + n;
+        io.s_o[a] = fmaxf(0.0f, s[h] - n);
+        io.inf_o[a] = inf_o;
+        io.tinf_o[a] = tinf[h] + n * (p.now - tinf[h]);
+        // symptoms (symptoms.py:204-247)
+        const uint64_t seed = p.seed;
+        const uint32_t call = p.call_index;
+        const float uu = u01_half(r[2]);
+        const int age = cls[h] % 100;
+        const SympOut so = symptoms_forward(p, io.stage_prob, cur[h], nxt[h], ttn[h], n, age, [&]() { return uu; },
+                                            [&](int) { return draw_step_normal(seed, call, a); });
+        io.cur_o[a] = so.cur;
+        io.nxt_o[a] = so.nxt;
+        io.ttn_o[a] = so.ttn;
+        // reductions (runner.py:167-171,198-224): small integers, exact in any order
+        if (inf_o != 0.0f) atomicAdd(&sh.hist[age], inf_o);
+        if (so.cur == dead) atomicAdd(&sh.deaths, so.cur / dead);
+      }
+    }
+  }
+  if (io.red) {
+    __syncthreads();
+    const int nr = 2 + p.n_age_bins;
+    if ((int)threadIdx.x < nr) {
+      double v = 0.0;
+      if (threadIdx.x == 0) {
+        for (int c = 0; c < 100; ++c) v += (double)sh.hist[c];
+      } else if (threadIdx.x == 1) {
+        v = (double)sh.deaths;
+      } else {
+        const int b = threadIdx.x - 2;
+        for (int c = max(p.age_bins[b] + 1, 0); c < p.age_bins[b + 1] && c < 100; ++c) v += (double)sh.hist[c];
+      }
+      red_part[(int64_t)blockIdx.x * kMaxRed + threadIdx.x] = v;
+    }
+    finish_partials<kMaxRed>(nr, red_part, gridDim.x, ticket, io.red);
+  }
+}
+
+// =====================================================================================================
+// B1  backward, per agent: symptoms^T, infect^T, sampler^T, clamp/exp chain -> cotangents of the state,
+//     w = dL/dLambda * s (and its quarantine-masked copy), tile partial sums of the cell channels
+// =====================================================================================================
+template <bool kQuar>
+__global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward(gj_world_desc w, gj_step_params p, LeanPlan lp,
+                                                                   gj_bwd_io io, float* __restrict__ tile_part) {
+  __shared__ float prob[GJ_MAX_CHANNELS][200];
+  __shared__ float gred_age[100];  // cotangent of is_infected from the cases / cases-by-age reductions
+  lean_load_prob<true>(prob, p, lp, io.leisure_prob);
+  if (threadIdx.x < 100) {
+    float g = 0.0f;
+    if (io.g_red) {
+      g = io.g_red[0];
+      const int age = threadIdx.x;
+      for (int b = 0; b < p.n_age_bins; ++b)
+        if (age > p.age_bins[b] && age < p.age_bins[b + 1]) g += io.g_red[2 + b];
+    }
+    gred_age[threadIdx.x] = g;
+  }
+  __syncthreads();
+  const float dead = (float)(p.n_stages - 1);
+  const float g_deaths = io.g_red ? io.g_red[1] / dead : 0.0f;
+  const float inv_tau = 1.0f / p.tau;
+  const float* __restrict__ i_s = io.s;
+  const float* __restrict__ i_tinf = io.tinf;
+  const float* __restrict__ i_cur = io.cur;
+  const float* __restrict__ i_nxt = io.nxt;
+  const float* __restrict__ i_ttn = io.ttn;
+  const float* __restrict__ i_ty = io.tape_y0;
+  const float* __restrict__ i_v = io.tape_v;
+  const float* __restrict__ c_s = io.g_s_o;
+  const float* __restrict__ c_inf = io.g_inf_o;
+  const float* __restrict__ c_tinf = io.g_tinf_o;
+  const float* __restrict__ c_cur = io.g_cur_o;
+  const float* __restrict__ c_nxt = io.g_nxt_o;
+  const float* __restrict__ c_ttn = io.g_ttn_o;
+
+  for (int64_t tile = blockIdx.x; tile < w.n_tiles; tile += gridDim.x) {
+    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];
+    float acc[GJ_MAX_CHANNELS];
+#pragma unroll
+    for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
+    for (uint32_t base = a0 + threadIdx.x; base < a1; base += kLeanBatch * kLeanThreads) {
+      float s[kLeanBatch], tinf[kLeanBatch], cur[kLeanBatch], nxt[kLeanBatch], ttn[kLeanBatch], ty[kLeanBatch],
+          v[kLeanBatch];
+      float gs_o[kLeanBatch], ginf_o[kLeanBatch], gtinf_o[kLeanBatch], gcur_o[kLeanBatch], gnxt_o[kLeanBatch],
+          gttn_o[kLeanBatch];
+      int cls[kLeanBatch];
+#pragma unroll
+      for (int h = 0; h < kLeanBatch; ++h) {
+        const uint32_t a = base + h * kLeanThreads;
+        const uint32_t al = (a < a1) ? a : a0;
+        s[h] = i_s[al];
+        tinf[h] = i_tinf[al];
+        cur[h] = i_cur[al];
+        nxt[h] = i_nxt[al];
+        ttn[h] = i_ttn[al];
+        ty[h] = i_ty[al];
+        v[h] = i_v[al];
+        cls[h] = w.cls[al];
+        gs_o[h] = c_s ? c_s[al] : 0.0f;
+        ginf_o[h] = c_inf ? c_inf[al] : 0.0f;
+        gtinf_o[h] = c_tinf ? c_tinf[al] : 0.0f;
+        gcur_o[h] = c_cur ? c_cur[al] : 0.0f;
+        gnxt_o[h] = c_nxt ? c_nxt[al] : 0.0f;
+        gttn_o[h] = c_ttn ? c_ttn[al] : 0.0f;
+      }
+#pragma unroll
+      for (int h = 0; h < kLeanBatch; ++h) {
+        const uint32_t a = base + h * kLeanThreads;
+        if (a >= a1) break;
+        const int age = cls[h] % 100;
+        const float n = signbit(ty[h]) ? 1.0f : 0.0f;  // the tape's sign bit is the draw
+        // symptoms^T: the draws are regenerated only for the few agents whose stage actually updates
+        const uint64_t seed = p.seed;
+        const uint32_t call = p.call_index;
+        const SympOut so = symptoms_forward(p, io.stage_prob, cur[h], nxt[h], ttn[h], n, age,
+                                            [&]() { return draw_step_noise(seed, call, a).u; },
+                                            [&](int) { return draw_step_normal(seed, call, a); });
+        float gc = gcur_o[h];
+        if (so.cur == dead) gc += g_deaths;
+        float gcur1 = gc, gnxt1 = gnxt_o[h];
+        if (so.branch == 1) {
+          gcur1 += (gnxt_o[h] + gttn_o[h] * so.dwell) / (float)so.stage;
+        } else if (so.branch == 2) {
+          gcur1 += (gttn_o[h] * so.dwell - gnxt_o[h] * so.nxt1) / (float)so.stage;
+          gnxt1 = 0.0f;
+        }
+        const float g_cur = gcur1 * (1.0f - so.tr);
+        gnxt1 += gcur1 * so.tr;
+        const float g_nxt = gnxt1 * (1.0f - n);
+        const float g_ttn = gttn_o[h] * (1.0f - n);
+        float gn = gnxt1 * (2.0f - nxt[h]) + gttn_o[h] * (p.now - ttn[h]);
+        // reductions and infect^T
+        const float gi = ginf_o[h] + gred_age[age];
+        const float dd = s[h] - n;
+        const float wgt = (dd > 0.0f) ? 1.0f : ((dd == 0.0f) ? 0.5f : 0.0f);  // maximum(0, x): ties split 1/2
+        float g_s = gs_o[h] * wgt;
+        gn += -(gs_o[h] * wgt) + gi + gtinf_o[h] * (p.now - tinf[h]);
+        const float g_tinf = gtinf_o[h] * (1.0f - n);
+        // sampler^T and the clamp / exp chain
+        const float lam = (s[h] == 0.0f) ? 0.0f : v[h];
+        const float q = not_infected_prob(lam, p.dt);
+        float y0, y1;
+        decode_soft(ty[h], y0, y1);
+        const float gret0 = -gn;
+        const float dot = gret0 * y0;
+        const float gl0 = ((gret0 - dot) * y0) * inv_tau, gl1 = ((0.0f - dot) * y1) * inv_tau;
+        const float gq = gl0 / q - gl1 / (1.0f - q);
+        float glam = 0.0f;
+        if (q >= 0.0f && q <= 1.0f && lam >= 1e-6f && lam <= 100.0f) glam = gq * q * (-p.dt);
+        const float X = (s[h] == 0.0f) ? v[h] : v[h] / s[h];
+        g_s += glam * X;
+        // outputs
+        const float wv = glam * s[h];
+        io.w[a] = wv;
+        float wqv = wv;
+        if (kQuar) {
+          wqv = glam * (quar_mask(p, cur[h]) * s[h]);
+          io.wq[a] = wqv;
+        }
+        if (wqv != 0.0f && lp.n_cell > 0) {
+#pragma unroll
+          for (int j = 0; j < GJ_MAX_CHANNELS; ++j)
+            if (j < lp.n_cell) acc[j] = fmaf(prob[j][cls[h]], wqv, acc[j]);
+        }
+        if (io.g_s) io.g_s[a] = g_s;
+        io.g_inf[a] = gi;
+        io.g_tinf[a] = g_tinf;
+        if (io.g_cur) io.g_cur[a] = g_cur;
+        if (io.g_nxt) io.g_nxt[a] = g_nxt;
+        if (io.g_ttn) io.g_ttn[a] = g_ttn;
+      }
+    }
+    if (lp.n_cell > 0) block_sums<float, GJ_MAX_CHANNELS>(acc, lp.n_cell, tile_part + tile * GJ_MAX_CHANNELS);
+  }
+}
+
+// =====================================================================================================
+// B3  backward gather: dL/dT from the three tiers -> (is_infected, infection_time); d/dbeta partial of the
+//     range-tier network (the group's first member adds pc_g * S_g * R_g)
+// =====================================================================================================
+template <bool kQuar>
+__global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward_gather(gj_world_desc w, gj_step_params p,
+                                                                          LeanPlan lp, gj_bwd_io io,
+                                                                          const float* __restrict__ cell_buf,
+                                                                          double* __restrict__ dbeta_part) {
+  __shared__ float prob[GJ_MAX_CHANNELS][200];
+  __shared__ float Ls[2][200];
+  __shared__ float beta_s[GJ_MAX_NETS];
+  lean_load_prob<false>(prob, p, lp, io.leisure_prob);
+  if (threadIdx.x < p.n_nets) beta_s[threadIdx.x] = io.beta[threadIdx.x];
+  __syncthreads();
+  const float* __restrict__ cRP = io.cR + lp.gen_base;
+  const float* __restrict__ wr = (kQuar && !lp.r_house) ? io.wq : io.w;  // member values of the range network
+  const float* __restrict__ T = io.T_in;
+  const float* __restrict__ i_cur = io.cur;
+  const float* __restrict__ i_inf = io.inf;
+  const float* __restrict__ i_tinf = io.tinf;
+  const float4* __restrict__ prof = reinterpret_cast<const float4*>(io.prof4);
+  const float beta_r = lp.n_range > 0 ? beta_s[lp.r_net] : 0.0f;
+  double db[1] = {0.0};
+
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < w.n_tiles; tile += gridDim.x, ++it) {
+    float* __restrict__ L = Ls[it & 1];
+    if (lp.n_cell > 0) lean_class_table(L, prob, lp, cell_buf, tile);
+    __syncthreads();
+    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];
+    for (uint32_t base = a0 + threadIdx.x; base < a1; base += kLeanBatch * kLeanThreads) {
+      float rpc[kLeanBatch], cur[kLeanBatch], inf[kLeanBatch], tinf[kLeanBatch], gen[kLeanBatch], R[kLeanBatch],
+          gi[kLeanBatch], gt[kLeanBatch];
+      float4 pf[kLeanBatch];
+      uint32_t ent[kLeanBatch], slot[kLeanBatch];
+      int cls[kLeanBatch];
+#pragma unroll
+      for (int h = 0; h < kLeanBatch; ++h) {
+        const uint32_t a = base + h * kLeanThreads;
+        const uint32_t al = (a < a1) ? a : a0;
+        cls[h] = w.cls[al];
+        ent[h] = lp.has_generic ? w.ent1[al] : kEntNone;
+        slot[h] = lp.n_range > 0 ? lp.r_slot[al] : kNoSlot;
+        rpc[h] = lp.n_range > 0 ? lp.r_pc[al] : 0.0f;
+        cur[h] = kQuar ? i_cur[al] : 0.0f;
+        inf[h] = i_inf[al];
+        tinf[h] = i_tinf[al];
+        pf[h] = prof[al];
+        gi[h] = io.g_inf[al];
+        gt[h] = io.g_tinf[al];
+      }
+#pragma unroll
+      for (int h = 0; h < kLeanBatch; ++h) {
+        const uint32_t a = base + h * kLeanThreads;
+        const uint32_t al = (a < a1) ? a : a0;
+        gen[h] = lean_generic(w, cRP, ent[h], al);
+        R[h] = lean_range_sum(wr, al, slot[h]);
+      }
+#pragma unroll
+      for (int h = 0; h < kLeanBatch; ++h) {
+        const uint32_t a = base + h * kLeanThreads;
+        if (a >= a1) break;
+        const float rv = (beta_r * rpc[h]) * R[h];
+        if (R[h] != 0.0f && (slot[h] >> 16) == 0) {  // first member: S_g = sum of the group's (masked) transmissions
+          const uint32_t nb = slot[h] & 0xFFFFu;
+          float S = 0.0f;
+          for (uint32_t b = a; b < a + nb; ++b) {
+            float Tb = T[b];
+            if (kQuar && !lp.r_house) Tb = quar_mask(p, i_cur[b]) * Tb;
+            S += Tb;
+          }
+          db[0] += (double)(rpc[h] * S) * (double)R[h];
+        }
+        const float house = lp.r_house ? rv : 0.0f;
+        const float plain = (gen[h] + (lp.n_cell > 0 ? L[cls[h]] : 0.0f)) + (lp.r_house ? 0.0f : rv);
+        const float mq = kQuar ? quar_mask(p, cur[h]) : 1.0f;
+        const float gT = fmaf(mq, plain, house);
+        if (gT != 0.0f) {
+          const TransTerms tt = lean_transmission<true>(p.now, tinf[h], pf[h]);
+          io.g_inf[a] = gi[h] + gT * tt.coef;
+          io.g_tinf[a] = gt[h] + gT * (tt.dcoef * inf[h]);
+        }
+      }
+    }
+  }
+  if (lp.n_range > 0) {
+    __syncthreads();
+    block_sums<double, 1>(db, 1, dbeta_part + (int64_t)blockIdx.x * GJ_MAX_RANGE_NETS);
+  }
+}
+
+}  // namespace gj

@@ -205,23 +205,6 @@ struct AgentState {
   float s, inf, tinf, cur, nxt, ttn;
 };
 
-// Gumbel-softmax draw from Philox bits with hardware log2/exp2 (MUFU): used when the noise is generated
-// in-kernel.  Same distribution and the same decision rule as gumbel_draw (argmax of the softmax, ties ->
-// not infected); logs carry ~2^-22 absolute error in log2 instead of 1 ulp, which only matters for draws
-// that are near-ties to begin with.  Injected-noise calls (parity tests) use the IEEE path.
-__device__ __forceinline__ Draw gumbel_draw_fast(float q, float E0, float E1, float inv_tau) {
-  const float x0 = (__logf(q) - __logf(E0)) * inv_tau;
-  const float x1 = (__logf(1.0f - q) - __logf(E1)) * inv_tau;
-  const bool one_bigger = x1 > x0;
-  const float e = __expf(one_bigger ? (x0 - x1) : (x1 - x0));  // exp(small - big) <= 1 ; exp(big - big) = 1
-  const float ys = __fdividef(e, 1.0f + e);
-  Draw d;
-  d.n = (one_bigger && e < 1.0f) ? 1.0f : 0.0f;
-  d.ty = (one_bigger && e < 1.0f) ? -ys : ys;
-  return d;
-}
-
-template <bool kFast>
 __device__ __forceinline__ void forward_tail(const gj_step_params& p, const gj_fwd_io& io, int64_t N, int64_t a, int age,
                                              float q, AgentState st, float* red) {
   const int dead = p.n_stages - 1;
@@ -231,17 +214,15 @@ __device__ __forceinline__ void forward_tail(const gj_step_params& p, const gj_f
   nz.E0 = nz.E1 = 1.0f;
   nz.u = 0.0f;
   if (p.phases & (GJ_PHASE_SAMPLE | GJ_PHASE_SYMPTOMS)) {
-    if (kFast || io.inj_E == nullptr || io.inj_u == nullptr) nz = draw_step_noise(p.seed, p.call_index, a);
-    if (!kFast) {
-      if (io.inj_E) {
-        nz.E0 = io.inj_E[a];
-        nz.E1 = io.inj_E[N + a];
-      }
-      if (io.inj_u) nz.u = io.inj_u[a];
+    if (io.inj_E == nullptr || io.inj_u == nullptr) nz = draw_step_noise(p.seed, p.call_index, a);
+    if (io.inj_E) {
+      nz.E0 = io.inj_E[a];
+      nz.E1 = io.inj_E[N + a];
     }
+    if (io.inj_u) nz.u = io.inj_u[a];
   }
   if (p.phases & GJ_PHASE_SAMPLE) {
-    const Draw d = kFast ? gumbel_draw_fast(q, nz.E0, nz.E1, 1.0f / p.tau) : gumbel_draw(q, nz.E0, nz.E1, p.tau);
+    const Draw d = gumbel_draw(q, nz.E0, nz.E1, p.tau);
     n = d.n;
     if (io.tape_y0) io.tape_y0[a] = d.ty;
   } else if (io.n_in) {
@@ -257,7 +238,7 @@ __device__ __forceinline__ void forward_tail(const gj_step_params& p, const gj_f
     if (io.tinf_o) io.tinf_o[a] = st.tinf;
   }
   if (p.phases & GJ_PHASE_SYMPTOMS) {
-    const float* inj_z = kFast ? nullptr : io.inj_z;
+    const float* inj_z = io.inj_z;
     const uint64_t seed = p.seed;
     const uint32_t call = p.call_index;
     const float uu = nz.u;
@@ -385,7 +366,6 @@ __device__ __forceinline__ Pressure agent_pressure(const gj_world_desc& w, const
   return out;
 }
 
-template <bool kFast>
 __global__ void __launch_bounds__(kBlock, 4) k_tile_forward(gj_world_desc w, gj_step_params p, Plan pl, gj_fwd_io io,
                                                             const float* __restrict__ cell_buf,
                                                             double* __restrict__ red_part,
@@ -418,7 +398,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_tile_forward(gj_world_desc w, gj_
     io.tape_v[a] = (st.s == 0.0f) ? pr.X : pr.lam;
     if (io.q) io.q[a] = q;
     if (io.lam) io.lam[a] = pr.lam;
-    forward_tail<kFast>(p, io, N, a, cls % 100, q, st, red);
+    forward_tail(p, io, N, a, cls % 100, q, st, red);
   }
   if (io.red) {
     double redd[kMaxRed];

@@ -18,6 +18,7 @@ GJ_MAX_STAGES = 16
 GJ_MAX_QUAR = 4
 GJ_MAX_AGE_BINS = 8
 GJ_MAX_CHANNELS = 8
+GJ_ABI_VERSION = 2
 
 KIND_PLAIN, KIND_HOUSEHOLD, KIND_LEISURE, KIND_CARE_VISIT = 0, 1, 2, 3
 PHASE_NETWORKS, PHASE_SAMPLE, PHASE_INFECT, PHASE_SYMPTOMS, PHASE_ALL = 1, 2, 4, 8, 15
@@ -45,6 +46,7 @@ class WorldDesc(C.Structure):
         ("tile_cell", C.c_void_p * GJ_MAX_TYPES), ("cell_tile_ptr", C.c_void_p * GJ_MAX_TYPES),
         ("cell_grp_ptr", C.c_void_p * GJ_MAX_TYPES), ("cell_grp", C.c_void_p * GJ_MAX_TYPES),
         ("grp_cell_ptr", C.c_void_p * GJ_MAX_TYPES), ("grp_cell", C.c_void_p * GJ_MAX_TYPES),
+        ("ent1", _u32p),
     ]
 
 
@@ -69,14 +71,14 @@ class StepParams(C.Structure):
 
 _FWD_FIELDS = [
     "beta", "leisure_prob", "stage_prob", "seed_fraction", "inj_E", "inj_u", "inj_z",
-    "s", "inf", "tinf", "cur", "nxt", "ttn", "maxinf", "shape", "rate", "shift", "k0",
+    "s", "inf", "tinf", "cur", "nxt", "ttn", "maxinf", "shape", "rate", "shift", "k0", "prof4",
     "T_in", "q_in", "n_in",
     "s_o", "inf_o", "tinf_o", "cur_o", "nxt_o", "ttn_o", "T", "Tq", "q", "lam", "n",
     "tape_v", "tape_y0", "S_scaled", "S_unscaled", "red", "scratch",
 ]
 _BWD_FIELDS = [
     "beta", "leisure_prob", "stage_prob", "seed_fraction", "inj_E", "inj_u", "inj_z",
-    "s", "inf", "tinf", "cur", "nxt", "ttn", "maxinf", "shape", "rate", "shift", "k0",
+    "s", "inf", "tinf", "cur", "nxt", "ttn", "maxinf", "shape", "rate", "shift", "k0", "prof4",
     "inf_o", "n_in", "T_in", "q_in", "tape_v", "tape_y0", "S_unscaled",
     "g_s_o", "g_inf_o", "g_tinf_o", "g_cur_o", "g_nxt_o", "g_ttn_o", "g_red", "g_q", "g_lam", "g_n",
     "g_s", "g_inf", "g_tinf", "g_cur", "g_nxt", "g_ttn", "g_T", "g_q_out", "g_n_out", "g_beta",
@@ -136,11 +138,15 @@ def lib():
         L = C.CDLL(str(LIB_PATH))
     except OSError as e:
         raise GradJuneLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    if L.gj_abi_version() != GJ_ABI_VERSION:
+        raise GradJuneLibraryError(f"{LIB_PATH} has ABI version {L.gj_abi_version()}, this binding needs "
+                                   f"{GJ_ABI_VERSION}: rebuild with `python __graft_entry__.py build`")
     L.gj_last_error.restype = C.c_char_p
     L.gj_scratch_bytes.restype = C.c_int64
     L.gj_scratch_bytes.argtypes = [C.POINTER(WorldDesc)]
     L.gj_config.argtypes = [C.POINTER(C.c_int64), C.c_int]
     L.gj_profile_prepare.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gj_profile_pack.argtypes = [C.c_int64] + [C.c_void_p] * 7
     L.gj_transmission_forward.argtypes = [C.c_int64, C.c_float] + [C.c_void_p] * 9
     L.gj_transmission_backward.argtypes = [C.c_int64, C.c_float] + [C.c_void_p] * 11
     L.gj_step_forward.argtypes = [C.POINTER(WorldDesc), C.POINTER(StepParams), C.POINTER(FwdIO), C.c_void_p]
@@ -175,7 +181,7 @@ def check(rc, what):
 
 
 EXPORTED_SYMBOLS = [
-    "gj_abi_version", "gj_last_error", "gj_config", "gj_scratch_bytes", "gj_profile_prepare",
+    "gj_abi_version", "gj_last_error", "gj_config", "gj_scratch_bytes", "gj_profile_prepare", "gj_profile_pack",
     "gj_transmission_forward", "gj_transmission_backward", "gj_step_forward", "gj_step_backward",
     "gj_philox_fill", "gj_philox4x32_10", "gj_profile_enable", "gj_profile_read", "gj_profile_kernel_name",
 ]

@@ -16,7 +16,7 @@ from .infection_networks.base import _quarantine_thresholds, beta_vector, leisur
 from .paths import ensure_default_config
 from .policies import Policies
 from .symptoms import SymptomsUpdater
-from .transmission import TransmissionUpdater, profile_tensors
+from .transmission import TransmissionUpdater, profile_packed, profile_tensors
 from .world import get_device_world
 
 
@@ -62,14 +62,15 @@ class GradJune(torch.nn.Module):
         hit = cache.get("static")
         if hit is None or hit[0] != key:
             static = ops.StepStatic(world=world, maxinf=maxinf, shape=shape, rate=rate, shift=shift, k0=k0,
-                                    leisure_prob=table,
+                                    prof4=profile_packed(data), leisure_prob=table,
                                     symptoms=self.symptoms_updater.symptoms_sampler.tables(device))
             cache["static"] = hit = (key, static, rows)
         return hit[1], hit[2]
 
-    def step(self, data, timer, age_bins=None, mode=ops.MODE_STEP, seed_fraction=None, noise=None):
+    def step(self, data, timer, age_bins=None, mode=ops.MODE_STEP, seed_fraction=None, noise=None, want_probs=True):
         """Fused step; returns (data, reductions) where reductions = [cases, deaths, cases by age bin...]
-        (None unless ``age_bins`` is given)."""
+        (None unless ``age_bins`` is given).  ``want_probs=False`` skips the two diagnostic per-agent outputs
+        (``not_infected_probs``, ``new_infected``) that the reference keeps only as locals of its forward."""
         agent = data["agent"]
         ops.require_cuda(agent.susceptibility, "data['agent'].susceptibility")
         dev = agent.susceptibility.device
@@ -84,7 +85,7 @@ class GradJune(torch.nn.Module):
             nets=[net.net_spec(rows.get(id(net), -1)) for net in nets],
             quarantine=_quarantine_thresholds(policies, timer), phases=phases, mode=mode,
             age_bins=tuple(int(b) for b in age_bins) if age_bins is not None else (),
-            want_reductions=age_bins is not None)
+            want_reductions=age_bins is not None, want_probs=want_probs)
         sym = agent["symptoms"]
         state = {"s": agent.susceptibility, "inf": agent.is_infected, "tinf": agent.infection_time,
                  "cur": sym["current_stage"], "nxt": sym["next_stage"], "ttn": sym["time_to_next_stage"]}
@@ -98,7 +99,8 @@ class GradJune(torch.nn.Module):
         sym["current_stage"] = out["cur"]
         sym["next_stage"] = out["nxt"]
         sym["time_to_next_stage"] = out["ttn"]
-        data["agent"]["new_infected"] = out["n"]
+        if out["n"] is not None:
+            data["agent"]["new_infected"] = out["n"]
         if out["q"] is not None:
             data["agent"]["not_infected_probs"] = out["q"]
         return data, out["red"]

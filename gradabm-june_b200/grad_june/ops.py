@@ -5,7 +5,7 @@ classes call the same entry point with a sub-set of phases.  All tensors must li
 there is no CPU fallback.
 """
 import ctypes as C
-from dataclasses import dataclass, field
+from dataclasses import dataclass, field, replace
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -147,6 +147,7 @@ class StepSpec:
     age_bins: Sequence[int] = ()
     want_reductions: bool = True
     want_lam: bool = False
+    want_probs: bool = True     # fused step: also return q (not_infected_probs) and n (new_infected)
     exact_order: bool = False   # force the reference-order kernels even with in-kernel Philox noise
 
 
@@ -214,7 +215,7 @@ def _fill_params(world: DeviceWorld, spec: StepSpec, sym: Optional[SymptomsTable
         p.age_bins[i] = int(b)
     p.tau = TAU
     p.seed, p.call_index = int(seed), int(call_index)
-    p.exact_order = 1 if (spec.exact_order or EXACT_ORDER) else 0
+    p.exact_order = 1 if spec.exact_order else 0
     return p, off
 
 
@@ -227,6 +228,7 @@ class StepStatic:
     rate: Optional[torch.Tensor] = None
     shift: Optional[torch.Tensor] = None
     k0: Optional[torch.Tensor] = None
+    prof4: Optional[torch.Tensor] = None          # [N, 4] packed profile (gj_profile_pack)
     leisure_prob: Optional[torch.Tensor] = None   # [n_tables, 2, 2, 100]
     symptoms: Optional[SymptomsTables] = None
 
@@ -238,6 +240,15 @@ def profile_k0(shape: torch.Tensor) -> torch.Tensor:
     _lib.check(_lib.lib().gj_profile_prepare(shape.numel(), shape.data_ptr(), k0.data_ptr(), _stream(shape.device)),
                "gj_profile_prepare")
     return k0
+
+
+def profile_pack(maxinf, shape, rate, shift, k0) -> torch.Tensor:
+    """[N, 4] = {maxinf*k0*rate, rate, shape-1, shift}: the profile as one 16-byte word per agent."""
+    out = torch.empty(shape.numel(), 4, dtype=torch.float32, device=shape.device)
+    _lib.check(_lib.lib().gj_profile_pack(shape.numel(), maxinf.data_ptr(), shape.data_ptr(), rate.data_ptr(),
+                                          shift.data_ptr(), k0.data_ptr(), out.data_ptr(), _stream(shape.device)),
+               "gj_profile_pack")
+    return out
 
 
 class _Transmission(torch.autograd.Function):
@@ -295,6 +306,8 @@ class _Step(torch.autograd.Function):
         N = world.n_agents
         L = _lib.lib()
         seed, call_index, E, u, z = noise
+        if EXACT_ORDER and not spec.exact_order:   # pin the choice: the backward must run the same kernel family
+            spec = replace(spec, exact_order=True)
         p, s_total = _fill_params(world, spec, static.symptoms, seed, call_index)
         io = _lib.FwdIO()
         keep = []
@@ -319,7 +332,7 @@ class _Step(torch.autograd.Function):
             st[name] = put(name, t)
         fused_T = nets_on and T_in is None
         if fused_T:
-            for name in ("maxinf", "shape", "rate", "shift", "k0"):
+            for name in ("maxinf", "shape", "rate", "shift", "k0", "prof4"):
                 put(name, getattr(static, name))
         T_in, q_in, n_in = put("T_in", T_in), put("q_in", q_in), put("n_in", n_in)
 
@@ -341,13 +354,16 @@ class _Step(torch.autograd.Function):
             io.Tq = _buffer(world, "Tq", N).data_ptr() if p.n_quar > 0 else T.data_ptr()
         elif nets_on and p.n_quar > 0:
             io.Tq = _buffer(world, "Tq", N).data_ptr()
-        q = new("q") if nets_on else None
+        fused_all = fused_T and phases == PHASE_ALL
+        probs = spec.want_probs or not fused_all   # the fused step needs neither q nor n for its own backward
+        q = new("q") if (nets_on and probs) else None
         lam = new("lam") if (nets_on and spec.want_lam) else None
-        n = new("n") if (phases & PHASE_SAMPLE) else None
+        n = new("n") if ((phases & PHASE_SAMPLE) and probs) else None
         tape_v = new("tape_v") if nets_on else None
         tape_y0 = new("tape_y0") if (phases & PHASE_SAMPLE) else None
         S_un = None
         if nets_on:
+            s_total += world.n_groups   # per-network sums, then one value per global group (throughput mode)
             io.S_scaled = _buffer(world, "S_scaled", s_total).data_ptr()
             S_un = torch.empty(max(s_total, 1), dtype=torch.float32, device=dev)
             io.S_unscaled = S_un.data_ptr()
@@ -405,7 +421,7 @@ class _Step(torch.autograd.Function):
             put(name, t)
         fused_T = ctx.fused_T
         if fused_T:
-            for name in ("maxinf", "shape", "rate", "shift", "k0"):
+            for name in ("maxinf", "shape", "rate", "shift", "k0", "prof4"):
                 put(name, getattr(static, name))
         put("inf_o", inf_o)
         if inf_o is None:
@@ -445,6 +461,7 @@ class _Step(torch.autograd.Function):
         g_beta = new("g_beta", max(p.n_nets, 1), zero=True) if nets_on else None
         g_frac = new("g_seed_fraction", 1, zero=True) if seed_mode else None
         if nets_on:
+            s_total += world.n_groups
             io.w = _buffer(world, "w", N).data_ptr()
             io.wq = _buffer(world, "wq", N).data_ptr() if p.n_quar > 0 else io.w
             io.R = _buffer(world, "R", s_total).data_ptr()

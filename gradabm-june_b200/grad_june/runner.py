@@ -117,7 +117,7 @@ class Runner(torch.nn.Module):
         dates = [timer.date]
         while timer.date < timer.final_date:
             next(timer)
-            data, red = model.step(data, timer, age_bins=self._age_bins_host)
+            data, red = model.step(data, timer, age_bins=self._age_bins_host, want_probs=False)
             reds.append(red)
             dates.append(timer.date)
         table = torch.stack(reds)                      # [T+1, 2 + n_bins]

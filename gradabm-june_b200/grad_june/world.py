@@ -259,7 +259,7 @@ class DeviceWorld:
         for i, off in enumerate(self.type_group_off):
             d.type_group_off[i] = off
         for name in ("am_ptr", "am_ent", "gm_ptr", "gm_agent", "pc", "cls", "small_groups", "chunk_group",
-                     "chunk_begin", "chunk_end", "chunk_part", "big_groups", "big_part_ptr", "tile_begin"):
+                     "chunk_begin", "chunk_end", "chunk_part", "big_groups", "big_part_ptr", "tile_begin", "ent1"):
             setattr(d, name, getattr(self, name).data_ptr())
         d.n_small, d.n_chunks = self.small_groups.numel(), self.chunk_group.numel()
         d.n_big, d.n_parts = self.big_groups.numel(), self.n_parts
@@ -433,6 +433,11 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
     deg = torch.bincount(src, minlength=n_agents) if E else torch.zeros(n_agents, dtype=torch.long, device=dev)
     am_ptr = _ptr_from_counts(deg)
     del perm
+    # one-entry-per-agent view for the throughput-mode kernels: global group id | none | "several: use the CSR"
+    ent1 = torch.full((n_agents,), 0xFFFFFFFF, dtype=torch.long, device=dev)
+    if E:
+        ent1[src] = gkey
+        ent1[deg > 1] = 0xFFFFFFFE
     age = age.to(dev).long()
     sex = sex.to(dev).long()
     if age.numel() and (int(age.min()) < 0 or int(age.max()) > 99 or int(sex.min()) < 0 or int(sex.max()) > 1):
@@ -485,7 +490,7 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
         gm_agent=gm_agent.contiguous(), pc=pc.contiguous(), cls=_padded(cls.contiguous(), 64), small_groups=_u32(small),
         chunk_group=_u32(chunk_group), chunk_begin=_u32(chunk_begin), chunk_end=_u32(chunk_end),
         chunk_part=chunk_part.to(torch.int32), big_groups=_u32(big_groups), big_part_ptr=_u32(big_part_ptr),
-        n_parts=n_parts, tile_begin=_u32(tile_begin), device=dev,
+        n_parts=n_parts, tile_begin=_u32(tile_begin), ent1=_padded(_u32(ent1)), device=dev,
     )
 
 

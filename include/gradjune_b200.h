@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GJ_ABI_VERSION 1
+#define GJ_ABI_VERSION 2
 
 #define GJ_MAX_TYPES 8      /* edge types (household, company, school, university, care_home, leisure, ...) */
 #define GJ_MAX_NETS 16      /* infection networks active in one step */
@@ -121,6 +121,9 @@ typedef struct gj_world_desc {
   const uint32_t* cell_grp[GJ_MAX_TYPES];      /* groups (ids local to the type) of each cell, agent edge order */
   const uint32_t* grp_cell_ptr[GJ_MAX_TYPES];  /* [G_type+1] */
   const uint32_t* grp_cell[GJ_MAX_TYPES];      /* cells of each group, ascending */
+  /* one-entry-per-agent view of the GENERIC types (throughput-mode kernels): the GLOBAL id of the agent's only
+   * generic group, 0xFFFFFFFF = none, 0xFFFFFFFE = several (walk am_ptr / am_ent); NULL = not built */
+  const uint32_t* ent1;
 } gj_world_desc;
 
 typedef struct gj_net {
@@ -156,9 +159,9 @@ typedef struct gj_step_params {
    * injected array is given */
   uint64_t seed;
   uint32_t call_index;
-  /* 0: with in-kernel Philox noise run the throughput-mode kernels (same arithmetic, re-associated sums and
-   * hardware log2/exp2 in the draw); 1: always run the reference-order kernels (they also run whenever noise
-   * is injected) */
+  /* 0: with in-kernel Philox noise run the throughput-mode kernels where the step allows it (same arithmetic,
+   * re-associated sums, hardware log2/exp2 in the draw and the infectiousness profile); 1: always run the
+   * reference-order kernels (they also run whenever noise is injected) */
   uint32_t exact_order;
 } gj_step_params;
 
@@ -176,6 +179,9 @@ typedef struct gj_fwd_io {
   const float *s, *inf, *tinf, *cur, *nxt, *ttn;
   /* per-agent infectiousness profile (transmission.py:8-35); k0 = exp(-lgamma(shape)) */
   const float *maxinf, *shape, *rate, *shift, *k0;
+  /* the same profile packed by gj_profile_pack: [N][4] = {maxinf*k0*rate, rate, shape-1, shift}; optional,
+   * enables the throughput-mode kernels */
+  const float* prof4;
   /* phase inputs when the producing phase is not run */
   const float* T_in; /* transmissions (NETWORKS phase without gj_transmission) */
   const float* q_in; /* not-infected probabilities (SAMPLE without NETWORKS) */
@@ -190,8 +196,10 @@ typedef struct gj_fwd_io {
   /* saved for backward */
   float* tape_v;  /* [N] pressure (s != 0) or pressure per unit susceptibility (s == 0) */
   float* tape_y0; /* [N] the smaller soft probability of the draw: +y1 (infected) or -y0 (not infected) */
-  float* S_scaled;   /* [sum_k G(type_k)] beta*pc-weighted group sums (forward operand) */
-  float* S_unscaled; /* [sum_k G(type_k)] plain group sums (saved: d/dbeta) */
+  /* group-sum buffers, [sum_k G(type_k) + n_groups] floats each: network k's sums at nets[k].s_off (reference-order
+   * kernels, cell tier), then one value per GLOBAL group id (throughput-mode kernels, generic tier) */
+  float* S_scaled;   /* beta*pc-weighted group sums (forward operand) */
+  float* S_unscaled; /* plain group sums (saved: d/dbeta) */
   float* red;        /* [2 + n_age_bins] cases, deaths, cases by age bin */
   void* scratch;     /* gj_scratch_bytes() bytes, zero-initialised once by the caller */
 } gj_fwd_io;
@@ -207,6 +215,7 @@ typedef struct gj_bwd_io {
   /* forward inputs and saved tensors */
   const float *s, *inf, *tinf, *cur, *nxt, *ttn;
   const float *maxinf, *shape, *rate, *shift, *k0;
+  const float* prof4;
   const float* inf_o; /* post-step is_infected (new_infected = inf_o - inf) or NULL with n_in */
   const float* n_in;
   const float* T_in; /* transmissions: the stand-alone input, or the T written by the fused forward */
@@ -230,8 +239,8 @@ typedef struct gj_bwd_io {
   /* workspaces */
   float* w;   /* [N] */
   float* wq;  /* [N], may alias w when n_quar <= 0 */
-  float* R;   /* [sum_k G(type_k)] */
-  float* cR;  /* [sum_k G(type_k)] */
+  float* R;   /* [sum_k G(type_k) + n_groups], laid out like S_unscaled */
+  float* cR;  /* [sum_k G(type_k) + n_groups] */
   void* scratch;
 } gj_bwd_io;
 
@@ -247,6 +256,9 @@ int64_t gj_scratch_bytes(const gj_world_desc* w);
 /* ---- TransmissionUpdater.forward (grad_june/transmission.py:38-51) ------------------------ */
 /* k0[i] = exp(-lgamma(shape[i])), the time-independent factor of the gamma profile */
 int gj_profile_prepare(int64_t n, const float* shape, float* k0, void* stream);
+/* prof4[i] = {maxinf*k0*rate, rate, shape-1, shift}: one 16-byte load per agent in the throughput-mode kernels */
+int gj_profile_pack(int64_t n, const float* maxinf, const float* shape, const float* rate, const float* shift,
+                    const float* k0, float* prof4, void* stream);
 int gj_transmission_forward(int64_t n, float now, const float* tinf, const float* inf, const float* maxinf,
                             const float* shape, const float* rate, const float* shift, const float* k0,
                             float* T, void* stream);

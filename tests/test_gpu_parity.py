@@ -28,7 +28,7 @@ def _need_gpu():
 
 def test_library_loaded():
     from grad_june import _lib
-    assert _lib.lib().gj_abi_version() == 1
+    assert _lib.lib().gj_abi_version() == _lib.GJ_ABI_VERSION
 
 
 def test_kat_through_module_api(golden_dir):

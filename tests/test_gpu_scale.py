@@ -260,3 +260,52 @@ def test_throughput_mode_matches_reference_order():
     assert np.allclose(e["red"], f["red"], atol=len(mism) + 0.5)
     if len(mism) == 0:
         assert np.allclose(e["grads"], f["grads"], rtol=2e-4, atol=1e-7 * np.abs(e["grads"]).max())
+
+
+def test_throughput_mode_bptt_window():
+    """Five timesteps of Runner() + backward (BPTT through the fused step) in throughput mode against the
+    reference-order kernels on the same Philox stream: identical trajectories (unless a near-tie flips an
+    agent) and matching log-beta gradients."""
+    from grad_june import GradJune, Timer, ops
+    from grad_june.default_config import default_parameters
+    from grad_june.runner import Runner
+    from grad_june.world import make_synthetic_world
+    n_agents = 200_000
+    params = default_parameters()
+    params["system"]["device"] = DEV
+    params["timer"]["total_days"] = 5
+    params["infection_seed"]["log_fraction_initial_cases"] = -1.5
+    params["policies"] = {}
+    torch.manual_seed(5)
+    data = Runner.get_data(params, data=make_synthetic_world(n_agents, seed=5, device=DEV))
+    model = GradJune.from_parameters(params)
+    keys = list(model.infection_networks.networks.keys())
+    runner = Runner(model=model, data=data, timer=Timer.from_parameters(params), log_fraction_initial_cases=-1.5,
+                    save_path="/tmp/gj_test", parameters=params)
+    outs = {}
+    for mode in ("exact", "fast"):
+        leaves = []
+        for k in keys:
+            leaf = torch.tensor(float(params["networks"][k]["log_beta"]) + 0.4, device=DEV, requires_grad=True)
+            model.infection_networks.networks[k].log_beta = leaf
+            leaves.append(leaf)
+        ops.EXACT_ORDER = mode == "exact"
+        try:
+            with ops.philox_seed(2024):
+                results, is_inf = runner()
+            loss = results["cases_per_timestep"].sum() + results["deaths_per_timestep"].sum() \
+                + 0.5 * results["cases_by_age_65"].sum()
+            loss.backward()
+        finally:
+            ops.EXACT_ORDER = False
+        outs[mode] = dict(cases=results["cases_per_timestep"].detach().cpu().numpy(), inf=is_inf.detach().cpu().numpy(),
+                          cur=data["agent"].symptoms["current_stage"].detach().cpu().numpy(),
+                          grads=torch.stack([l.grad for l in leaves]).cpu().numpy())
+    e, f = outs["exact"], outs["fast"]
+    assert e["cases"][-1] > e["cases"][0] > 0
+    flips = int((e["inf"] != f["inf"]).sum())
+    assert flips <= 20, flips
+    if flips == 0:
+        assert np.array_equal(e["cases"], f["cases"])
+        assert np.array_equal(e["cur"], f["cur"])
+        assert np.allclose(e["grads"], f["grads"], rtol=5e-5, atol=1e-6 * np.abs(e["grads"]).max()), (e["grads"], f["grads"])

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(raw, sym), f"{sym} is declared in include/gradjune_b200.h but not exported"
     assert set(_lib.EXPORTED_SYMBOLS) <= declared
     L = _lib.lib()                     # also checks struct sizes against the header's
-    assert L.gj_abi_version() == 1
+    assert L.gj_abi_version() == _lib.GJ_ABI_VERSION
 
 
 def test_philox_known_answers():
