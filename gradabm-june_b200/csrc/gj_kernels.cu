@@ -614,6 +614,9 @@ static bool lean_plan(const gj_world_desc* w, const gj_step_params* p, const Pla
       lp->c_care[j] = kind == GJ_KIND_CARE_VISIT;
       lp->c_cell_off[j] = w->cell_off[t];
       lp->c_tile_cell[j] = w->tile_cell[t];
+      bool seen = false;
+      for (int i = 0; i < lp->n_tc; ++i) seen = seen || lp->tc[i] == w->tile_cell[t];
+      if (!seen) lp->tc[lp->n_tc++] = w->tile_cell[t];
     } else if (kind != GJ_KIND_PLAIN) {
       return false;
     }

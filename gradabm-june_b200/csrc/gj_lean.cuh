@@ -1,23 +1,25 @@
 // Throughput-mode kernels of the fused step (included by gj_kernels.cu after gj_tiled.cuh).
 //
 // Same step as the reference-order kernels of gj_tiled.cuh, written for HBM throughput:
-//   * every kernel is a persistent grid (a few CTAs per SM) walking the agent tiles round-robin; tables are
-//     loaded once per CTA, reductions are carried across tiles and combined once per CTA;
+//   * every kernel is a persistent grid (a few CTAs per SM); each CTA walks a contiguous run of agent tiles, so
+//     tables are loaded once per CTA, per-cell work (class table, partial sums of the cell channels) is redone only
+//     when the run enters a new cell, and reductions are combined once per CTA;
+//   * a thread keeps a batch of agents in flight: all their streaming loads are issued first, then the dependent
+//     gathers (group value from L2, household neighbours from L1 with predicated, unrolled loads), then arithmetic;
 //   * the per-agent instruction count is small: the eleven-network loop collapses to
 //         pressure = s * (range + mq * (generic + L[class]))
-//     with ONE shared-memory lookup L[class] = sum_k V_k * p_k(class) per tile for all cell-tier (leisure)
-//     networks, ONE combined value per generic group (all generic networks of a type are PLAIN, so they share the
-//     group sum) fetched through the one-entry-per-agent ELL word `ent1`, and the household re-sum over
-//     neighbouring agents (L1 hits);
+//     with ONE shared-memory lookup L[class] = sum_k V_k * p_k(class) for all cell-tier (leisure) networks, ONE
+//     combined value per generic group (all generic networks of a type are PLAIN, so they share the group sum)
+//     fetched through the one-entry-per-agent ELL word `ent1`, and the household re-sum over neighbouring agents;
 //   * the infectiousness profile is read as one packed float4 per agent and evaluated with ex2/lg2;
 //   * the Gumbel-softmax decision uses six hardware log2 and one exp2; q itself stays the IEEE expf so that
 //     (1 - q) rounds like the reference's;
 //   * result reductions go through a shared-memory age histogram (small integers: exact in any order).
-// The kernels run when the noise is the in-kernel Philox stream and the step is "simple" (lean_supported() in
-// gj_kernels.cu): range-tier networks of HOUSEHOLD/PLAIN kind, cell-tier networks with an attendance table,
-// generic-tier networks of PLAIN kind.  Anything else, and every call with injected noise (parity tests), runs
-// the reference-order kernels.  Results agree with those to ~1e-6 on q (fp32 re-association) and differ in masks
-// only at near-ties (tests/test_gpu_scale.py::test_throughput_mode_matches_reference_order).
+// The kernels run when the noise is the in-kernel Philox stream and the step is "simple" (lean_plan() in
+// gj_kernels.cu): at most one range-tier network (HOUSEHOLD or PLAIN kind), cell-tier networks with an
+// attendance table, generic-tier networks of PLAIN kind.  Anything else, and every call with injected noise
+// (parity tests), runs the reference-order kernels.  Results agree with those to ~1e-6 on q (fp32 re-association)
+// and differ in masks only at near-ties (tests/test_gpu_scale.py::test_throughput_mode_*).
 #pragma once
 #include "gj_tiled.cuh"
 
@@ -38,9 +40,10 @@ struct LeanPlan {
   int c_care[GJ_MAX_CHANNELS];              // CARE_VISIT: susceptible side masked by age > 75
   int64_t c_cell_off[GJ_MAX_CHANNELS];
   const uint32_t* c_tile_cell[GJ_MAX_CHANNELS];
+  int n_tc;                                 // distinct tile -> cell maps among the channels
+  const uint32_t* tc[GJ_MAX_CHANNELS];
   int has_generic;
   int64_t gen_base;                         // offset of the per-global-group buffers inside the S / R arrays
-  int n_range_parts;                        // grid of the gather kernel (d/dbeta partials of the range networks)
 };
 
 __device__ __forceinline__ float lg2_fast(float x) {
@@ -58,6 +61,7 @@ __device__ __forceinline__ float rcp_fast(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ int age_of(int cls) { return cls >= 100 ? cls - 100 : cls; }  // cls = sex * 100 + age
 
 // packed profile {A = maxinf * k0 * rate, rate, e = shape - 1, shift}: T / is_infected and d/d infection_time
 // (transmission.py:38-51; same function as transmission_terms, evaluated as A * 2^(e*log2(x) - x*log2(e)))
@@ -85,30 +89,76 @@ __global__ void __launch_bounds__(kBlock) k_profile_pack(int64_t n, const float*
     out[a] = make_float4((maxinf[a] * k0[a]) * rate[a], rate[a], shape[a] - 1.0f, shift[a]);
 }
 
-// attendance tables of the cell-tier channels for today's day type; kCareSide folds the (age > 75) mask of
-// care visits into the table (susceptible side of the forward, member side of the backward)
+// ---- the CTA's run of tiles -------------------------------------------------------------------------------
+struct TileRun {
+  int64_t t0, t1;
+};
+__device__ __forceinline__ TileRun lean_tiles(const gj_world_desc& w) {
+  TileRun r;
+  r.t0 = w.n_tiles * (int64_t)blockIdx.x / gridDim.x;
+  r.t1 = w.n_tiles * ((int64_t)blockIdx.x + 1) / gridDim.x;
+  return r;
+}
+// does tile b lie in another cell (of any cell-tier type) than tile a?  (CTA-uniform)
+__device__ __forceinline__ bool lean_new_cell(const LeanPlan& lp, int64_t a, int64_t b) {
+  bool changed = false;
+  for (int i = 0; i < lp.n_tc; ++i) changed = changed || (lp.tc[i][a] != lp.tc[i][b]);
+  return changed;
+}
+
+// attendance tables of the cell-tier channels for today's day type, one row of GJ_MAX_CHANNELS per class;
+// kCareSide folds the (age > 75) mask of care visits into the table (susceptible side of the forward, member side
+// of the backward)
+struct alignas(16) ProbRow {
+  float v[GJ_MAX_CHANNELS];
+};
 template <bool kCareSide>
-__device__ __forceinline__ void lean_load_prob(float (*prob)[200], const gj_step_params& p, const LeanPlan& lp,
+__device__ __forceinline__ void lean_load_prob(ProbRow* prob, const gj_step_params& p, const LeanPlan& lp,
                                                const float* __restrict__ lprob) {
-  for (int i = threadIdx.x; i < lp.n_cell * 200; i += blockDim.x) {
+  for (int i = threadIdx.x; i < GJ_MAX_CHANNELS * 200; i += blockDim.x) {
     const int j = i / 200, c = i - j * 200;
-    float v = lprob[(size_t)(lp.c_row[j] * 2 + p.day_type) * 200 + c];
-    if (kCareSide && lp.c_care[j] && (c % 100) <= 75) v = 0.0f;
-    prob[j][c] = v;
+    float v = 0.0f;
+    if (j < lp.n_cell) {
+      v = lprob[(size_t)(lp.c_row[j] * 2 + p.day_type) * 200 + c];
+      if (kCareSide && lp.c_care[j] && age_of(c) <= 75) v = 0.0f;
+    }
+    prob[c].v[j] = v;
   }
 }
 
-// L[class] = sum_j V_j * prob_j[class] from this tile's per-cell values
-__device__ __forceinline__ void lean_class_table(float* __restrict__ L, const float (*prob)[200], const LeanPlan& lp,
-                                                 const float* __restrict__ cell_buf, int64_t tile) {
-  if (threadIdx.x < 200) {
-    float acc = 0.0f;
-    for (int j = 0; j < lp.n_cell; ++j) {
-      const float v = cell_buf[(lp.c_cell_off[j] + lp.c_tile_cell[j][tile]) * GJ_MAX_CHANNELS + j];
-      acc = fmaf(v, prob[j][threadIdx.x], acc);
-    }
-    L[threadIdx.x] = acc;
+// acc[j] += prob[cls][j] * x for the cell channels (two 16-byte shared loads)
+__device__ __forceinline__ void lean_channel_fma(float (&acc)[GJ_MAX_CHANNELS], const ProbRow* prob, int cls, float x,
+                                                 int n_cell) {
+  const float4 lo = *reinterpret_cast<const float4*>(&prob[cls].v[0]);
+  acc[0] = fmaf(lo.x, x, acc[0]);
+  acc[1] = fmaf(lo.y, x, acc[1]);
+  acc[2] = fmaf(lo.z, x, acc[2]);
+  acc[3] = fmaf(lo.w, x, acc[3]);
+  if (n_cell > 4) {
+    const float4 hi = *reinterpret_cast<const float4*>(&prob[cls].v[4]);
+    acc[4] = fmaf(hi.x, x, acc[4]);
+    acc[5] = fmaf(hi.y, x, acc[5]);
+    acc[6] = fmaf(hi.z, x, acc[6]);
+    acc[7] = fmaf(hi.w, x, acc[7]);
   }
+}
+
+// L[class] = sum_j V_j * prob[class][j] from the per-cell values of `tile`'s cell: lane j of every warp fetches
+// V_j, the warp shares it by shuffles
+__device__ __forceinline__ void lean_class_table(float* __restrict__ L, const ProbRow* prob, const LeanPlan& lp,
+                                                 const float* __restrict__ cell_buf, int64_t tile) {
+  const int lane = threadIdx.x & 31;
+  float mine = 0.0f;
+  if (lane < lp.n_cell)
+    mine = cell_buf[(lp.c_cell_off[lane] + lp.c_tile_cell[lane][tile]) * GJ_MAX_CHANNELS + lane];
+  float acc = 0.0f;
+  const int c = threadIdx.x < 200 ? threadIdx.x : 0;
+#pragma unroll
+  for (int j = 0; j < GJ_MAX_CHANNELS; ++j) {
+    const float v = __shfl_sync(0xffffffffu, mine, j);
+    acc = fmaf(v, prob[c].v[j], acc);  // channels >= n_cell hold zeros
+  }
+  if (threadIdx.x < 200) L[threadIdx.x] = acc;
 }
 
 // generic tier: combined value of the agent's group(s)
@@ -125,6 +175,19 @@ __device__ __forceinline__ float lean_generic(const gj_world_desc& w, const floa
   return v;
 }
 
+// range-tier network: (offset, size) word -> sum of the group's member values (members = neighbouring agents).
+// Up to eight members are fetched with predicated loads that are all in flight together (households).
+__device__ __forceinline__ float lean_range_sum(const float* __restrict__ v, uint32_t a, uint32_t slot) {
+  if (slot == kNoSlot) return 0.0f;
+  const uint32_t b0 = a - (slot >> 16), nb = slot & 0xFFFFu;
+  float x[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] = (j < (int)nb) ? v[b0 + j] : 0.0f;
+  float S = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+  for (uint32_t b = b0 + 8; b < b0 + nb; ++b) S += v[b];
+  return S;
+}
+
 __device__ __forceinline__ float quar_mask(const gj_step_params& p, float cur) {
   bool ok = true;
 #pragma unroll
@@ -134,24 +197,29 @@ __device__ __forceinline__ float quar_mask(const gj_step_params& p, float cur) {
 }
 
 // =====================================================================================================
-// K1  transmissions (+ quarantine-masked copy) and the tile partial sums of the cell channels
+// K1  transmissions (+ quarantine-masked copy) and the partial sums of the cell channels.  The sums of a run of
+//     tiles inside one cell are kept in registers and written once, to the run's last tile (the other tiles of the
+//     run get zeros): k_cell_groups adds a cell's tiles, so the per-cell totals are unchanged.
 // =====================================================================================================
 constexpr int kTileSlots = GJ_TILE_AGENTS / kLeanThreads;  // agents of one tile handled by one thread (4)
 
 template <bool kQuar>
 __global__ void __launch_bounds__(kLeanThreads) k_lean_transmission(gj_world_desc w, gj_step_params p, LeanPlan lp,
                                                                     gj_fwd_io io, float* __restrict__ tile_part) {
-  __shared__ float prob[GJ_MAX_CHANNELS][200];
+  __shared__ ProbRow prob[200];
   lean_load_prob<false>(prob, p, lp, io.leisure_prob);
   __syncthreads();
   const float4* __restrict__ prof = reinterpret_cast<const float4*>(io.prof4);
   const float* __restrict__ g_inf = io.inf;
   const float* __restrict__ g_cur = io.cur;
-  for (int64_t tile = blockIdx.x; tile < w.n_tiles; tile += gridDim.x) {
-    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];
-    float acc[GJ_MAX_CHANNELS];
+  const TileRun run = lean_tiles(w);
+  float acc[GJ_MAX_CHANNELS];
 #pragma unroll
-    for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
+  for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
+  uint32_t a1 = run.t0 < run.t1 ? w.tile_begin[run.t0] : 0;
+  for (int64_t tile = run.t0; tile < run.t1; ++tile) {
+    const uint32_t a0 = a1;
+    a1 = w.tile_begin[tile + 1];
     float inf[kTileSlots], cur[kTileSlots];
 #pragma unroll
     for (int h = 0; h < kTileSlots; ++h) {  // all of the tile's streaming loads first
@@ -171,14 +239,18 @@ __global__ void __launch_bounds__(kLeanThreads) k_lean_transmission(gj_world_des
         Tq = quar_mask(p, cur[h]) * T;
         io.Tq[a] = Tq;
       }
-      if (Tq != 0.0f && lp.n_cell > 0) {
-        const int cls = w.cls[a];
+      if (Tq != 0.0f && lp.n_cell > 0) lean_channel_fma(acc, prob, w.cls[a], Tq, lp.n_cell);
+    }
+    if (lp.n_cell > 0) {
+      const bool flush = (tile + 1 == run.t1) || lean_new_cell(lp, tile, tile + 1);
+      if (flush) {
+        block_sums<float, GJ_MAX_CHANNELS>(acc, lp.n_cell, tile_part + tile * GJ_MAX_CHANNELS);
 #pragma unroll
-        for (int j = 0; j < GJ_MAX_CHANNELS; ++j)
-          if (j < lp.n_cell) acc[j] = fmaf(prob[j][cls], Tq, acc[j]);
+        for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
+      } else if ((int)threadIdx.x < lp.n_cell) {
+        tile_part[tile * GJ_MAX_CHANNELS + threadIdx.x] = 0.0f;
       }
     }
-    if (lp.n_cell > 0) block_sums<float, GJ_MAX_CHANNELS>(acc, lp.n_cell, tile_part + tile * GJ_MAX_CHANNELS);
   }
 }
 
@@ -270,22 +342,12 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_fix(gj_world_desc w, gj_s
 // K3  forward: pressure -> q -> draw -> state update -> symptoms -> reductions
 // =====================================================================================================
 struct LeanFwdShared {
-  float prob[GJ_MAX_CHANNELS][200];
+  ProbRow prob[200];
   float L[2][200];
   float beta[GJ_MAX_NETS];
   float hist[100];  // sum of post-step is_infected by age
   float deaths;
 };
-
-// range-tier network: (offset, size) word -> sum of the group's member values (members = neighbouring agents)
-__device__ __forceinline__ float lean_range_sum(const float* __restrict__ v, uint32_t a, uint32_t slot) {
-  float S = 0.0f;
-  if (slot != kNoSlot) {
-    const uint32_t b0 = a - (slot >> 16), nb = slot & 0xFFFFu;
-    for (uint32_t b = b0; b < b0 + nb; ++b) S += v[b];
-  }
-  return S;
-}
 
 constexpr int kLeanBatch = 2;  // agents a thread keeps in flight: their loads are issued before any arithmetic
 
@@ -313,12 +375,22 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_forward(gj_world_desc 
   const uint32_t key0 = (uint32_t)p.seed, key1 = (uint32_t)(p.seed >> 32);
   const float beta_r = lp.n_range > 0 ? sh.beta[lp.r_net] : 0.0f;
 
-  int it = 0;
-  for (int64_t tile = blockIdx.x; tile < w.n_tiles; tile += gridDim.x, ++it) {
-    float* __restrict__ L = sh.L[it & 1];
-    if (lp.n_cell > 0) lean_class_table(L, sh.prob, lp, cell_buf, tile);
-    __syncthreads();  // one barrier per tile: the table of tile i+1 goes to the other buffer
-    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];
+  const TileRun run = lean_tiles(w);
+  int nbuild = 0;
+  const float* __restrict__ L = sh.L[0];
+  uint32_t a1 = run.t0 < run.t1 ? w.tile_begin[run.t0] : 0;
+  for (int64_t tile = run.t0; tile < run.t1; ++tile) {
+    const uint32_t a0 = a1;
+    a1 = w.tile_begin[tile + 1];
+    if (lp.n_cell > 0 && (tile == run.t0 || lean_new_cell(lp, tile - 1, tile))) {
+      // new cell: rebuild the class table in the other buffer (one barrier per rebuild is enough: a buffer is
+      // rewritten only two rebuilds later, after every warp has passed the barrier in between)
+      float* __restrict__ Lw = sh.L[nbuild & 1];
+      ++nbuild;
+      lean_class_table(Lw, sh.prob, lp, cell_buf, tile);
+      __syncthreads();
+      L = Lw;
+    }
     for (uint32_t base = a0 + threadIdx.x; base < a1; base += kLeanBatch * kLeanThreads) {
       float s[kLeanBatch], inf[kLeanBatch], tinf[kLeanBatch], cur[kLeanBatch], nxt[kLeanBatch], ttn[kLeanBatch];
       float rpc[kLeanBatch], gen[kLeanBatch], hs[kLeanBatch], Lc[kLeanBatch];
@@ -328,8 +400,7 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_forward(gj_world_desc 
 #pragma unroll
       for (int h = 0; h < kLeanBatch; ++h) {
         const uint32_t a = base + h * kLeanThreads;
-        const bool live = a < a1;
-        const uint32_t al = live ? a : a0;  // dead slots re-read the tile's first agent (no branch around loads)
+        const uint32_t al = (a < a1) ? a : a0;  // dead slots re-read the tile's first agent (no branch around loads)
         s[h] = i_s[al];
         inf[h] = i_inf[al];
         tinf[h] = i_tinf[al];
@@ -388,7 +459,7 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_forward(gj_world_desc 
         const uint64_t seed = p.seed;
         const uint32_t call = p.call_index;
         const float uu = u01_half(r[2]);
-        const int age = cls[h] % 100;
+        const int age = age_of(cls[h]);
         const SympOut so = symptoms_forward(p, io.stage_prob, cur[h], nxt[h], ttn[h], n, age, [&]() { return uu; },
                                             [&](int) { return draw_step_normal(seed, call, a); });
         io.cur_o[a] = so.cur;
@@ -421,12 +492,12 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_forward(gj_world_desc 
 
 // =====================================================================================================
 // B1  backward, per agent: symptoms^T, infect^T, sampler^T, clamp/exp chain -> cotangents of the state,
-//     w = dL/dLambda * s (and its quarantine-masked copy), tile partial sums of the cell channels
+//     w = dL/dLambda * s (and its quarantine-masked copy), partial sums of the cell channels (as in K1)
 // =====================================================================================================
 template <bool kQuar>
 __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward(gj_world_desc w, gj_step_params p, LeanPlan lp,
                                                                    gj_bwd_io io, float* __restrict__ tile_part) {
-  __shared__ float prob[GJ_MAX_CHANNELS][200];
+  __shared__ ProbRow prob[200];
   __shared__ float gred_age[100];  // cotangent of is_infected from the cases / cases-by-age reductions
   lean_load_prob<true>(prob, p, lp, io.leisure_prob);
   if (threadIdx.x < 100) {
@@ -457,11 +528,14 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward(gj_world_desc
   const float* __restrict__ c_nxt = io.g_nxt_o;
   const float* __restrict__ c_ttn = io.g_ttn_o;
 
-  for (int64_t tile = blockIdx.x; tile < w.n_tiles; tile += gridDim.x) {
-    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];
-    float acc[GJ_MAX_CHANNELS];
+  const TileRun run = lean_tiles(w);
+  float acc[GJ_MAX_CHANNELS];
 #pragma unroll
-    for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
+  for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
+  uint32_t a1 = run.t0 < run.t1 ? w.tile_begin[run.t0] : 0;
+  for (int64_t tile = run.t0; tile < run.t1; ++tile) {
+    const uint32_t a0 = a1;
+    a1 = w.tile_begin[tile + 1];
     for (uint32_t base = a0 + threadIdx.x; base < a1; base += kLeanBatch * kLeanThreads) {
       float s[kLeanBatch], tinf[kLeanBatch], cur[kLeanBatch], nxt[kLeanBatch], ttn[kLeanBatch], ty[kLeanBatch],
           v[kLeanBatch];
@@ -491,7 +565,7 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward(gj_world_desc
       for (int h = 0; h < kLeanBatch; ++h) {
         const uint32_t a = base + h * kLeanThreads;
         if (a >= a1) break;
-        const int age = cls[h] % 100;
+        const int age = age_of(cls[h]);
         const float n = signbit(ty[h]) ? 1.0f : 0.0f;  // the tape's sign bit is the draw
         // symptoms^T: the draws are regenerated only for the few agents whose stage actually updates
         const uint64_t seed = p.seed;
@@ -520,7 +594,8 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward(gj_world_desc
         float g_s = gs_o[h] * wgt;
         gn += -(gs_o[h] * wgt) + gi + gtinf_o[h] * (p.now - tinf[h]);
         const float g_tinf = gtinf_o[h] * (1.0f - n);
-        // sampler^T and the clamp / exp chain
+        // sampler^T and the clamp / exp chain: dL/dq = gl0/q - gl1/(1-q), dL/dLambda = dL/dq * q * (-dt)
+        // evaluated as (gl1 * q/(1-q) - gl0) * dt
         const float lam = (s[h] == 0.0f) ? 0.0f : v[h];
         const float q = not_infected_prob(lam, p.dt);
         float y0, y1;
@@ -528,10 +603,9 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward(gj_world_desc
         const float gret0 = -gn;
         const float dot = gret0 * y0;
         const float gl0 = ((gret0 - dot) * y0) * inv_tau, gl1 = ((0.0f - dot) * y1) * inv_tau;
-        const float gq = gl0 / q - gl1 / (1.0f - q);
         float glam = 0.0f;
-        if (q >= 0.0f && q <= 1.0f && lam >= 1e-6f && lam <= 100.0f) glam = gq * q * (-p.dt);
-        const float X = (s[h] == 0.0f) ? v[h] : v[h] / s[h];
+        if (lam >= 1e-6f && lam <= 100.0f) glam = (gl1 * (q * rcp_fast(1.0f - q)) - gl0) * p.dt;
+        const float X = (s[h] == 0.0f) ? v[h] : ((s[h] == 1.0f) ? v[h] : v[h] * rcp_fast(s[h]));
         g_s += glam * X;
         // outputs
         const float wv = glam * s[h];
@@ -541,11 +615,7 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward(gj_world_desc
           wqv = glam * (quar_mask(p, cur[h]) * s[h]);
           io.wq[a] = wqv;
         }
-        if (wqv != 0.0f && lp.n_cell > 0) {
-#pragma unroll
-          for (int j = 0; j < GJ_MAX_CHANNELS; ++j)
-            if (j < lp.n_cell) acc[j] = fmaf(prob[j][cls[h]], wqv, acc[j]);
-        }
+        if (wqv != 0.0f && lp.n_cell > 0) lean_channel_fma(acc, prob, cls[h], wqv, lp.n_cell);
         if (io.g_s) io.g_s[a] = g_s;
         io.g_inf[a] = gi;
         io.g_tinf[a] = g_tinf;
@@ -554,20 +624,29 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward(gj_world_desc
         if (io.g_ttn) io.g_ttn[a] = g_ttn;
       }
     }
-    if (lp.n_cell > 0) block_sums<float, GJ_MAX_CHANNELS>(acc, lp.n_cell, tile_part + tile * GJ_MAX_CHANNELS);
+    if (lp.n_cell > 0) {
+      const bool flush = (tile + 1 == run.t1) || lean_new_cell(lp, tile, tile + 1);
+      if (flush) {
+        block_sums<float, GJ_MAX_CHANNELS>(acc, lp.n_cell, tile_part + tile * GJ_MAX_CHANNELS);
+#pragma unroll
+        for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
+      } else if ((int)threadIdx.x < lp.n_cell) {
+        tile_part[tile * GJ_MAX_CHANNELS + threadIdx.x] = 0.0f;
+      }
+    }
   }
 }
 
 // =====================================================================================================
 // B3  backward gather: dL/dT from the three tiers -> (is_infected, infection_time); d/dbeta partial of the
-//     range-tier network (the group's first member adds pc_g * S_g * R_g)
+//     range-tier network: sum_g pc_g S_g R_g = sum over agents of T_a * pc_g(a) * R_g(a)
 // =====================================================================================================
 template <bool kQuar>
 __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward_gather(gj_world_desc w, gj_step_params p,
                                                                           LeanPlan lp, gj_bwd_io io,
                                                                           const float* __restrict__ cell_buf,
                                                                           double* __restrict__ dbeta_part) {
-  __shared__ float prob[GJ_MAX_CHANNELS][200];
+  __shared__ ProbRow prob[200];
   __shared__ float Ls[2][200];
   __shared__ float beta_s[GJ_MAX_NETS];
   lean_load_prob<false>(prob, p, lp, io.leisure_prob);
@@ -583,15 +662,23 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward_gather(gj_wor
   const float beta_r = lp.n_range > 0 ? beta_s[lp.r_net] : 0.0f;
   double db[1] = {0.0};
 
-  int it = 0;
-  for (int64_t tile = blockIdx.x; tile < w.n_tiles; tile += gridDim.x, ++it) {
-    float* __restrict__ L = Ls[it & 1];
-    if (lp.n_cell > 0) lean_class_table(L, prob, lp, cell_buf, tile);
-    __syncthreads();
-    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];
+  const TileRun run = lean_tiles(w);
+  int nbuild = 0;
+  const float* __restrict__ L = Ls[0];
+  uint32_t a1 = run.t0 < run.t1 ? w.tile_begin[run.t0] : 0;
+  for (int64_t tile = run.t0; tile < run.t1; ++tile) {
+    const uint32_t a0 = a1;
+    a1 = w.tile_begin[tile + 1];
+    if (lp.n_cell > 0 && (tile == run.t0 || lean_new_cell(lp, tile - 1, tile))) {
+      float* __restrict__ Lw = Ls[nbuild & 1];
+      ++nbuild;
+      lean_class_table(Lw, prob, lp, cell_buf, tile);
+      __syncthreads();
+      L = Lw;
+    }
     for (uint32_t base = a0 + threadIdx.x; base < a1; base += kLeanBatch * kLeanThreads) {
       float rpc[kLeanBatch], cur[kLeanBatch], inf[kLeanBatch], tinf[kLeanBatch], gen[kLeanBatch], R[kLeanBatch],
-          gi[kLeanBatch], gt[kLeanBatch];
+          gi[kLeanBatch], gt[kLeanBatch], Tm[kLeanBatch];
       float4 pf[kLeanBatch];
       uint32_t ent[kLeanBatch], slot[kLeanBatch];
       int cls[kLeanBatch];
@@ -603,6 +690,7 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward_gather(gj_wor
         ent[h] = lp.has_generic ? w.ent1[al] : kEntNone;
         slot[h] = lp.n_range > 0 ? lp.r_slot[al] : kNoSlot;
         rpc[h] = lp.n_range > 0 ? lp.r_pc[al] : 0.0f;
+        Tm[h] = lp.n_range > 0 ? T[al] : 0.0f;
         cur[h] = kQuar ? i_cur[al] : 0.0f;
         inf[h] = i_inf[al];
         tinf[h] = i_tinf[al];
@@ -621,20 +709,12 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward_gather(gj_wor
       for (int h = 0; h < kLeanBatch; ++h) {
         const uint32_t a = base + h * kLeanThreads;
         if (a >= a1) break;
-        const float rv = (beta_r * rpc[h]) * R[h];
-        if (R[h] != 0.0f && (slot[h] >> 16) == 0) {  // first member: S_g = sum of the group's (masked) transmissions
-          const uint32_t nb = slot[h] & 0xFFFFu;
-          float S = 0.0f;
-          for (uint32_t b = a; b < a + nb; ++b) {
-            float Tb = T[b];
-            if (kQuar && !lp.r_house) Tb = quar_mask(p, i_cur[b]) * Tb;
-            S += Tb;
-          }
-          db[0] += (double)(rpc[h] * S) * (double)R[h];
-        }
+        const float mq = kQuar ? quar_mask(p, cur[h]) : 1.0f;
+        const float pr = rpc[h] * R[h];
+        if (pr != 0.0f) db[0] += (double)((kQuar && !lp.r_house) ? mq * Tm[h] : Tm[h]) * (double)pr;
+        const float rv = beta_r * pr;
         const float house = lp.r_house ? rv : 0.0f;
         const float plain = (gen[h] + (lp.n_cell > 0 ? L[cls[h]] : 0.0f)) + (lp.r_house ? 0.0f : rv);
-        const float mq = kQuar ? quar_mask(p, cur[h]) : 1.0f;
         const float gT = fmaf(mq, plain, house);
         if (gT != 0.0f) {
           const TransTerms tt = lean_transmission<true>(p.now, tinf[h], pf[h]);
@@ -644,10 +724,7 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward_gather(gj_wor
       }
     }
   }
-  if (lp.n_range > 0) {
-    __syncthreads();
-    block_sums<double, 1>(db, 1, dbeta_part + (int64_t)blockIdx.x * GJ_MAX_RANGE_NETS);
-  }
+  if (lp.n_range > 0) block_sums<double, 1>(db, 1, dbeta_part + (int64_t)blockIdx.x * GJ_MAX_RANGE_NETS);
 }
 
 }  // namespace gj

@@ -103,9 +103,23 @@ def leisure_table(networks, device):
     return (torch.stack(tabs).contiguous() if tabs else None), rows
 
 
+def _interaction_active(policies, timer):
+    ip = None if policies is None else policies.interaction_policies
+    return bool(ip) and any(pol.is_active(timer.date) for pol in ip.policies)
+
+
 def beta_vector(networks, policies, timer, device):
+    """[K] vector of beta_eff = 10**log_beta * policy factors (base.py:36-42), differentiable wrt every
+    log_beta / factor tensor."""
     if not networks:
         return torch.zeros(0, device=device)
+    device = torch.device(device)
+    lbs = [net.log_beta for net in networks]
+    if (not _interaction_active(policies, timer)
+            and all(torch.is_tensor(lb) and lb.device == device and lb.dtype == torch.float32 for lb in lbs)):
+        # every log_beta already lives on the step's device: one stack + one pow instead of K of each
+        # (same elementwise powf as the per-scalar evaluation)
+        return 10.0 ** torch.stack([lb.reshape(()) for lb in lbs])
     # log_beta usually lives on the CPU while policy factors follow system.device: move each scalar first
     return torch.stack([net.beta_eff(policies, timer).reshape(()).to(device=device, dtype=torch.float32)
                         for net in networks])

@@ -54,13 +54,20 @@ class GradJune(torch.nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _static(self, data, device):
+        """Per-world constants of the step, rebuilt only when the world, the profile parameters, a leisure
+        table or the symptoms tables are replaced."""
         world = get_device_world(data, device)
-        maxinf, shape, rate, shift, k0 = profile_tensors(data)
-        table, rows = leisure_table(list(self.infection_networks.networks.values()), device)
+        prof = profile_tensors(data)
+        nets = list(self.infection_networks.networks.values())
+        tables = tuple((id(t), t._version) for t in (getattr(net, "leisure_probabilities", None) for net in nets)
+                       if t is not None)
+        key = (id(world), id(prof[4]), tables, tuple(id(net) for net in nets),
+               id(self.symptoms_updater.symptoms_sampler.stage_transition_probabilities))
         cache = data.__dict__.setdefault("_gj_cache", {})
-        key = ("static", id(world), id(k0), id(self.symptoms_updater.symptoms_sampler.stage_transition_probabilities))
         hit = cache.get("static")
         if hit is None or hit[0] != key:
+            maxinf, shape, rate, shift, k0 = prof
+            table, rows = leisure_table(nets, device)
             static = ops.StepStatic(world=world, maxinf=maxinf, shape=shape, rate=rate, shift=shift, k0=k0,
                                     prof4=profile_packed(data), leisure_prob=table,
                                     symptoms=self.symptoms_updater.symptoms_sampler.tables(device))

@@ -170,10 +170,31 @@ def _buffer(world: DeviceWorld, name: str, n: int):
     return t
 
 
+_PARAMS_CACHE: dict = {}
+
+
 def _fill_params(world: DeviceWorld, spec: StepSpec, sym: Optional[SymptomsTables], seed: int, call_index: int):
+    """gj_step_params of this call.  Everything but (now, dt, seed, call_index) depends only on the step's
+    structure, so the filled struct is cached per structure and copied."""
+    key = (id(world), tuple((n.edge_type, n.kind, n.prob_row) for n in spec.nets),
+           None if spec.quarantine is None else tuple(float(t) for t in spec.quarantine), id(sym),
+           tuple(spec.age_bins), spec.mode, spec.phases, int(spec.day_type), bool(spec.exact_order))
+    hit = _PARAMS_CACHE.get(key)
+    if hit is None or hit[2] is not world or hit[3] is not sym:
+        if len(_PARAMS_CACHE) > 256:
+            _PARAMS_CACHE.clear()
+        p0, off = _build_params(world, spec, sym)
+        _PARAMS_CACHE[key] = hit = (bytes(p0), off, world, sym)
+    p = _lib.StepParams.from_buffer_copy(hit[0])
+    p.now, p.dt = float(spec.now), float(spec.dt)
+    p.seed, p.call_index = int(seed), int(call_index)
+    return p, hit[1]
+
+
+def _build_params(world: DeviceWorld, spec: StepSpec, sym: Optional[SymptomsTables]):
     p = _lib.StepParams()
     p.mode, p.phases = spec.mode, spec.phases
-    p.now, p.dt, p.day_type = float(spec.now), float(spec.dt), int(spec.day_type)
+    p.day_type = int(spec.day_type)
     if len(spec.nets) > _lib.GJ_MAX_NETS:
         raise ValueError(f"at most {_lib.GJ_MAX_NETS} networks per step")
     p.n_nets = len(spec.nets)
@@ -214,7 +235,6 @@ def _fill_params(world: DeviceWorld, spec: StepSpec, sym: Optional[SymptomsTable
     for i, b in enumerate(bins):
         p.age_bins[i] = int(b)
     p.tau = TAU
-    p.seed, p.call_index = int(seed), int(call_index)
     p.exact_order = 1 if spec.exact_order else 0
     return p, off
 
