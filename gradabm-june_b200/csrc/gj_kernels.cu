@@ -528,8 +528,16 @@ static int sm_count() {
   }
   return n;
 }
-static int lean_grid(const gj_world_desc* w, int ctas_per_sm) {
-  const int64_t g = (int64_t)sm_count() * ctas_per_sm;
+// one resident wave: SMs x (CTAs of this kernel that fit on an SM), at most one CTA per tile
+template <typename K>
+static int lean_grid(const gj_world_desc* w, K kernel, int* cache) {
+  if (*cache == 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kLeanThreads, 0) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    *cache = per_sm;
+  }
+  const int64_t g = (int64_t)sm_count() * *cache;
   return (int)(w->n_tiles < g ? w->n_tiles : g);
 }
 
@@ -616,7 +624,10 @@ static bool lean_plan(const gj_world_desc* w, const gj_step_params* p, const Pla
       lp->c_tile_cell[j] = w->tile_cell[t];
       bool seen = false;
       for (int i = 0; i < lp->n_tc; ++i) seen = seen || lp->tc[i] == w->tile_cell[t];
-      if (!seen) lp->tc[lp->n_tc++] = w->tile_cell[t];
+      if (!seen) {
+        lp->ctp[lp->n_tc] = w->cell_tile_ptr[t];
+        lp->tc[lp->n_tc++] = w->tile_cell[t];
+      }
     } else if (kind != GJ_KIND_PLAIN) {
       return false;
     }
@@ -655,9 +666,9 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
   const bool quar = p->n_quar > 0;
   {
     ProfScope ps(K_TRANSMISSION, st);
-    const int grid = lean_grid(w, 8);
-    if (quar) k_lean_transmission<true><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
-    else k_lean_transmission<false><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
+    static int occ[2] = {0, 0};
+    if (quar) k_lean_transmission<true><<<lean_grid(w, k_lean_transmission<true>, &occ[1]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
+    else k_lean_transmission<false><<<lean_grid(w, k_lean_transmission<false>, &occ[0]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
     GJ_CHECK_LAUNCH("k_lean_transmission");
   }
   if (lp.has_generic)
@@ -667,12 +678,12 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
   if (int e = launch_cell_pass(w, p, pl, io->beta, io->S_scaled, io->S_unscaled, sc, st)) return e;
   {
     ProfScope ps(K_AGENT_FWD, st);
-    const int grid = lean_grid(w, 4);
+    static int occ[4] = {0, 0, 0, 0};
     const bool diag = io->q || io->n;
-    if (quar && diag) k_lean_forward<true, true><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets);
-    else if (quar) k_lean_forward<true, false><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets);
-    else if (diag) k_lean_forward<false, true><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets);
-    else k_lean_forward<false, false><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets);
+    if (quar && diag) k_lean_forward<true, true><<<lean_grid(w, k_lean_forward<true, true>, &occ[3]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets);
+    else if (quar) k_lean_forward<true, false><<<lean_grid(w, k_lean_forward<true, false>, &occ[2]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets);
+    else if (diag) k_lean_forward<false, true><<<lean_grid(w, k_lean_forward<false, true>, &occ[1]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets);
+    else k_lean_forward<false, false><<<lean_grid(w, k_lean_forward<false, false>, &occ[0]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets);
     GJ_CHECK_LAUNCH("k_lean_forward");
   }
   return 0;
@@ -681,11 +692,12 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
 static int lean_backward(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, LeanPlan lp,
                          const gj_bwd_io* io, const Scratch& sc, cudaStream_t st) {
   const bool quar = p->n_quar > 0;
-  const int grid = lean_grid(w, 4);
+  static int occ_b[2] = {0, 0}, occ_g[2] = {0, 0};
+  int gather_grid = 1;
   {
     ProfScope ps(K_AGENT_BWD, st);
-    if (quar) k_lean_backward<true><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
-    else k_lean_backward<false><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
+    if (quar) k_lean_backward<true><<<lean_grid(w, k_lean_backward<true>, &occ_b[1]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
+    else k_lean_backward<false><<<lean_grid(w, k_lean_backward<false>, &occ_b[0]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
     GJ_CHECK_LAUNCH("k_lean_backward");
   }
   if (lp.has_generic)
@@ -695,8 +707,8 @@ static int lean_backward(const gj_world_desc* w, const gj_step_params* p, const 
   if (int e = launch_cell_pass(w, p, pl, io->beta, io->cR, io->R, sc, st)) return e;
   {
     ProfScope ps(K_AGENT_BWD_GATHER, st);
-    if (quar) k_lean_backward_gather<true><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.dbeta_tile);
-    else k_lean_backward_gather<false><<<grid, kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.dbeta_tile);
+    if (quar) k_lean_backward_gather<true><<<(gather_grid = lean_grid(w, k_lean_backward_gather<true>, &occ_g[1])), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.dbeta_tile);
+    else k_lean_backward_gather<false><<<(gather_grid = lean_grid(w, k_lean_backward_gather<false>, &occ_g[0])), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.dbeta_tile);
     GJ_CHECK_LAUNCH("k_lean_backward_gather");
   }
   if (io->g_beta) {
@@ -707,7 +719,7 @@ static int lean_backward(const gj_world_desc* w, const gj_step_params* p, const 
       if (k < p->n_nets)
         dp.soff[k] = pl.tier[k] == GJ_TIER_GENERIC ? lp.gen_base + w->type_group_off[p->nets[k].type] : p->nets[k].s_off;
     }
-    dp.n_range_parts = grid;
+    dp.n_range_parts = gather_grid;
     dim3 grid2(kRedBlocks / 8, p->n_nets);
     k_dbeta<<<grid2, kBlock, 0, st>>>(*w, *p, pl, dp, io->S_unscaled, io->R, sc.dbeta_tile, sc.dbeta_part, sc.tickets,
                                       io->g_beta);

@@ -26,6 +26,16 @@
 namespace gj {
 
 constexpr int kLeanThreads = 256;
+// resident CTAs per SM the agent kernels are compiled for (register budget): measured best on B200
+#ifndef GJ_LEAN_MINB_FWD
+#define GJ_LEAN_MINB_FWD 3
+#endif
+#ifndef GJ_LEAN_MINB_BWD
+#define GJ_LEAN_MINB_BWD 4
+#endif
+#ifndef GJ_LEAN_MINB_GATHER
+#define GJ_LEAN_MINB_GATHER 3
+#endif
 constexpr uint32_t kEntNone = 0xFFFFFFFFu;   // ent1: no generic edge
 constexpr uint32_t kEntMulti = 0xFFFFFFFEu;  // ent1: several generic edges -> agent-major CSR
 
@@ -42,6 +52,7 @@ struct LeanPlan {
   const uint32_t* c_tile_cell[GJ_MAX_CHANNELS];
   int n_tc;                                 // distinct tile -> cell maps among the channels
   const uint32_t* tc[GJ_MAX_CHANNELS];
+  const uint32_t* ctp[GJ_MAX_CHANNELS];     // their cell -> first tile maps (cell_tile_ptr)
   int has_generic;
   int64_t gen_base;                         // offset of the per-global-group buffers inside the S / R arrays
 };
@@ -98,6 +109,15 @@ __device__ __forceinline__ TileRun lean_tiles(const gj_world_desc& w) {
   r.t0 = w.n_tiles * (int64_t)blockIdx.x / gridDim.x;
   r.t1 = w.n_tiles * ((int64_t)blockIdx.x + 1) / gridDim.x;
   return r;
+}
+// first tile after `tile` that lies in another cell (of any cell-tier type), clipped to the run  (CTA-uniform)
+__device__ __forceinline__ int64_t lean_segment_end(const LeanPlan& lp, int64_t tile, int64_t t1) {
+  int64_t e = t1;
+  for (int i = 0; i < lp.n_tc; ++i) {
+    const int64_t c = lp.ctp[i][lp.tc[i][tile] + 1];
+    e = c < e ? c : e;
+  }
+  return e;
 }
 // does tile b lie in another cell (of any cell-tier type) than tile a?  (CTA-uniform)
 __device__ __forceinline__ bool lean_new_cell(const LeanPlan& lp, int64_t a, int64_t b) {
@@ -161,11 +181,13 @@ __device__ __forceinline__ void lean_class_table(float* __restrict__ L, const Pr
   if (threadIdx.x < 200) L[threadIdx.x] = acc;
 }
 
-// generic tier: combined value of the agent's group(s)
-__device__ __forceinline__ float lean_generic(const gj_world_desc& w, const float* __restrict__ buf, uint32_t ent,
-                                              uint32_t a) {
-  if (ent < kEntMulti) return buf[ent];
-  float v = 0.0f;
+// generic tier: combined value of the agent's group(s): the single-entry gather is issued early, the (rare)
+// several-entries case walks the agent-major CSR afterwards
+__device__ __forceinline__ float lean_generic_issue(const float* __restrict__ buf, uint32_t ent) {
+  return (ent < kEntMulti) ? buf[ent] : 0.0f;
+}
+__device__ __forceinline__ float lean_generic_finish(const gj_world_desc& w, const float* __restrict__ buf, uint32_t ent,
+                                                     uint32_t a, float v) {
   if (ent == kEntMulti) {
     for (uint32_t j = w.am_ptr[a]; j < w.am_ptr[a + 1]; ++j) {
       const uint32_t e = w.am_ent[j];
@@ -175,16 +197,27 @@ __device__ __forceinline__ float lean_generic(const gj_world_desc& w, const floa
   return v;
 }
 
-// range-tier network: (offset, size) word -> sum of the group's member values (members = neighbouring agents).
-// Up to eight members are fetched with predicated loads that are all in flight together (households).
-__device__ __forceinline__ float lean_range_sum(const float* __restrict__ v, uint32_t a, uint32_t slot) {
-  if (slot == kNoSlot) return 0.0f;
-  const uint32_t b0 = a - (slot >> 16), nb = slot & 0xFFFFu;
+// range-tier network: (offset, size) word -> the group's member values (members = neighbouring agents).  The
+// first eight members are fetched with predicated loads that are all in flight together (households); the sum is
+// formed later, after the other loads of the batch have been issued.
+struct RangeLoads {
   float x[8];
+};
+__device__ __forceinline__ RangeLoads lean_range_issue(const float* __restrict__ v, uint32_t a, uint32_t slot) {
+  RangeLoads r;
+  const uint32_t b0 = a - (slot >> 16);
+  const int nb = (slot == kNoSlot) ? 0 : (int)(slot & 0xFFFFu);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) x[j] = (j < (int)nb) ? v[b0 + j] : 0.0f;
-  float S = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
-  for (uint32_t b = b0 + 8; b < b0 + nb; ++b) S += v[b];
+  for (int j = 0; j < 8; ++j) r.x[j] = (j < nb) ? v[b0 + j] : 0.0f;
+  return r;
+}
+__device__ __forceinline__ float lean_range_finish(const RangeLoads& r, const float* __restrict__ v, uint32_t a,
+                                                   uint32_t slot) {
+  float S = ((r.x[0] + r.x[1]) + (r.x[2] + r.x[3])) + ((r.x[4] + r.x[5]) + (r.x[6] + r.x[7]));
+  if (slot != kNoSlot && (slot & 0xFFFFu) > 8u) {
+    const uint32_t b0 = a - (slot >> 16), nb = slot & 0xFFFFu;
+    for (uint32_t b = b0 + 8; b < b0 + nb; ++b) S += v[b];
+  }
   return S;
 }
 
@@ -197,14 +230,14 @@ __device__ __forceinline__ float quar_mask(const gj_step_params& p, float cur) {
 }
 
 // =====================================================================================================
-// K1  transmissions (+ quarantine-masked copy) and the partial sums of the cell channels.  The sums of a run of
-//     tiles inside one cell are kept in registers and written once, to the run's last tile (the other tiles of the
-//     run get zeros): k_cell_groups adds a cell's tiles, so the per-cell totals are unchanged.
+// K1  transmissions (+ quarantine-masked copy) and the partial sums of the cell channels.  A CTA's run of tiles
+//     is walked cell by cell ("segments"); a segment's partial sums are written to its first tile and zeros to its
+//     other tiles: k_cell_groups adds a cell's tiles, so the per-cell totals are unchanged.
 // =====================================================================================================
-constexpr int kTileSlots = GJ_TILE_AGENTS / kLeanThreads;  // agents of one tile handled by one thread (4)
+constexpr int kK1Batch = 8;
 
 template <bool kQuar>
-__global__ void __launch_bounds__(kLeanThreads) k_lean_transmission(gj_world_desc w, gj_step_params p, LeanPlan lp,
+__global__ void __launch_bounds__(kLeanThreads, 6) k_lean_transmission(gj_world_desc w, gj_step_params p, LeanPlan lp,
                                                                     gj_fwd_io io, float* __restrict__ tile_part) {
   __shared__ ProbRow prob[200];
   lean_load_prob<false>(prob, p, lp, io.leisure_prob);
@@ -213,44 +246,41 @@ __global__ void __launch_bounds__(kLeanThreads) k_lean_transmission(gj_world_des
   const float* __restrict__ g_inf = io.inf;
   const float* __restrict__ g_cur = io.cur;
   const TileRun run = lean_tiles(w);
-  float acc[GJ_MAX_CHANNELS];
+  for (int64_t tile = run.t0; tile < run.t1;) {
+    const int64_t tend = lp.n_cell > 0 ? lean_segment_end(lp, tile, run.t1) : run.t1;
+    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tend];
+    float acc[GJ_MAX_CHANNELS];
 #pragma unroll
-  for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
-  uint32_t a1 = run.t0 < run.t1 ? w.tile_begin[run.t0] : 0;
-  for (int64_t tile = run.t0; tile < run.t1; ++tile) {
-    const uint32_t a0 = a1;
-    a1 = w.tile_begin[tile + 1];
-    float inf[kTileSlots], cur[kTileSlots];
+    for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
+    for (uint32_t base = a0 + threadIdx.x; base < a1; base += kK1Batch * kLeanThreads) {
+      float inf[kK1Batch], cur[kK1Batch];
 #pragma unroll
-    for (int h = 0; h < kTileSlots; ++h) {  // all of the tile's streaming loads first
-      const uint32_t a = a0 + threadIdx.x + h * kLeanThreads;
-      inf[h] = (a < a1) ? g_inf[a] : 0.0f;
-      cur[h] = (kQuar && a < a1) ? g_cur[a] : 0.0f;
-    }
-#pragma unroll
-    for (int h = 0; h < kTileSlots; ++h) {
-      const uint32_t a = a0 + threadIdx.x + h * kLeanThreads;
-      if (a >= a1) break;
-      float T = 0.0f;
-      if (inf[h] != 0.0f) T = lean_transmission<false>(p.now, io.tinf[a], prof[a]).coef * inf[h];
-      io.T[a] = T;
-      float Tq = T;
-      if (kQuar) {
-        Tq = quar_mask(p, cur[h]) * T;
-        io.Tq[a] = Tq;
+      for (int h = 0; h < kK1Batch; ++h) {  // the batch's streaming loads first
+        const uint32_t a = base + h * kLeanThreads;
+        inf[h] = (a < a1) ? g_inf[a] : 0.0f;
+        cur[h] = (kQuar && a < a1) ? g_cur[a] : 0.0f;
       }
-      if (Tq != 0.0f && lp.n_cell > 0) lean_channel_fma(acc, prob, w.cls[a], Tq, lp.n_cell);
+#pragma unroll
+      for (int h = 0; h < kK1Batch; ++h) {
+        const uint32_t a = base + h * kLeanThreads;
+        if (a >= a1) break;
+        float T = 0.0f;
+        if (inf[h] != 0.0f) T = lean_transmission<false>(p.now, io.tinf[a], prof[a]).coef * inf[h];
+        io.T[a] = T;
+        float Tq = T;
+        if (kQuar) {
+          Tq = quar_mask(p, cur[h]) * T;
+          io.Tq[a] = Tq;
+        }
+        if (Tq != 0.0f && lp.n_cell > 0) lean_channel_fma(acc, prob, w.cls[a], Tq, lp.n_cell);
+      }
     }
     if (lp.n_cell > 0) {
-      const bool flush = (tile + 1 == run.t1) || lean_new_cell(lp, tile, tile + 1);
-      if (flush) {
-        block_sums<float, GJ_MAX_CHANNELS>(acc, lp.n_cell, tile_part + tile * GJ_MAX_CHANNELS);
-#pragma unroll
-        for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
-      } else if ((int)threadIdx.x < lp.n_cell) {
-        tile_part[tile * GJ_MAX_CHANNELS + threadIdx.x] = 0.0f;
-      }
+      block_sums<float, GJ_MAX_CHANNELS>(acc, lp.n_cell, tile_part + tile * GJ_MAX_CHANNELS);
+      for (int64_t i = threadIdx.x; i < (tend - tile - 1) * GJ_MAX_CHANNELS; i += kLeanThreads)
+        tile_part[(tile + 1) * GJ_MAX_CHANNELS + i] = 0.0f;
     }
+    tile = tend;
   }
 }
 
@@ -287,7 +317,16 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_small(gj_world_desc w, gj
   float S = 0.0f;
   if (b == b) {
     const uint32_t j0 = w.gm_ptr[g], j1 = w.gm_ptr[g + 1];
-    for (uint32_t j = j0; j < j1; ++j) S += in[w.gm_agent[j]];
+    for (uint32_t j = j0; j < j1; j += 4) {  // four member gathers in flight (same summation order)
+      uint32_t m[4];
+      float x[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) m[k] = (j + k < j1) ? w.gm_agent[j + k] : 0u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[k] = (j + k < j1) ? in[m[k]] : 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) S += x[k];
+    }
   }
   out_plain[g] = S;
   out_scaled[g] = (b == b) ? (b * w.pc[g]) * S : 0.0f;
@@ -308,7 +347,16 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_chunk(gj_world_desc w, gj
   float S = 0.0f;
   if (b == b) {
     const uint32_t j0 = w.chunk_begin[ci], j1 = w.chunk_end[ci];
-    for (uint32_t j = j0 + lane; j < j1; j += 32) S += in[w.gm_agent[j]];
+    for (uint32_t j = j0 + lane; j < j1; j += 128) {  // four member gathers per lane in flight
+      uint32_t m[4];
+      float x[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) m[k] = (j + 32 * k < j1) ? w.gm_agent[j + 32 * k] : 0u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[k] = (j + 32 * k < j1) ? in[m[k]] : 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) S += x[k];
+    }
     S = warp_sum(S);
   }
   if (lane != 0) return;
@@ -352,7 +400,7 @@ struct LeanFwdShared {
 constexpr int kLeanBatch = 2;  // agents a thread keeps in flight: their loads are issued before any arithmetic
 
 template <bool kQuar, bool kDiag>
-__global__ void __launch_bounds__(kLeanThreads, 4) k_lean_forward(gj_world_desc w, gj_step_params p, LeanPlan lp,
+__global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_FWD) k_lean_forward(gj_world_desc w, gj_step_params p, LeanPlan lp,
                                                                   gj_fwd_io io, const float* __restrict__ cell_buf,
                                                                   double* __restrict__ red_part,
                                                                   unsigned int* __restrict__ ticket) {
@@ -370,37 +418,54 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_forward(gj_world_desc 
   const float* __restrict__ i_cur = io.cur;
   const float* __restrict__ i_nxt = io.nxt;
   const float* __restrict__ i_ttn = io.ttn;
+  const uint32_t* __restrict__ i_ent = w.ent1;
+  const uint32_t* __restrict__ i_slot = lp.r_slot;
   const float dead = (float)(p.n_stages - 1);
   const float inv_tau = 1.0f / p.tau;
   const uint32_t key0 = (uint32_t)p.seed, key1 = (uint32_t)(p.seed >> 32);
   const float beta_r = lp.n_range > 0 ? sh.beta[lp.r_net] : 0.0f;
+  const bool has_gen = lp.has_generic != 0, has_range = lp.n_range > 0;
 
   const TileRun run = lean_tiles(w);
   int nbuild = 0;
-  const float* __restrict__ L = sh.L[0];
-  uint32_t a1 = run.t0 < run.t1 ? w.tile_begin[run.t0] : 0;
-  for (int64_t tile = run.t0; tile < run.t1; ++tile) {
-    const uint32_t a0 = a1;
-    a1 = w.tile_begin[tile + 1];
-    if (lp.n_cell > 0 && (tile == run.t0 || lean_new_cell(lp, tile - 1, tile))) {
-      // new cell: rebuild the class table in the other buffer (one barrier per rebuild is enough: a buffer is
-      // rewritten only two rebuilds later, after every warp has passed the barrier in between)
-      float* __restrict__ Lw = sh.L[nbuild & 1];
+  for (int64_t tile = run.t0; tile < run.t1;) {
+    // ---- one segment = the part of the CTA's run that lies in one cell: one class table -----------------
+    const int64_t tend = lp.n_cell > 0 ? lean_segment_end(lp, tile, run.t1) : run.t1;
+    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tend];
+    const float* __restrict__ L = sh.L[nbuild & 1];
+    if (lp.n_cell > 0) {
+      // rebuilt in the other buffer; one barrier per rebuild is enough: a buffer is rewritten only two rebuilds
+      // later, after every warp has passed the barrier in between
+      lean_class_table(sh.L[nbuild & 1], sh.prob, lp, cell_buf, tile);
       ++nbuild;
-      lean_class_table(Lw, sh.prob, lp, cell_buf, tile);
       __syncthreads();
-      L = Lw;
+    }
+    // index words (generic entry, household slot) are fetched one batch ahead, so that the gathers they
+    // address are issued together with the batch's streaming loads
+    uint32_t ent_n[kLeanBatch], slot_n[kLeanBatch];
+#pragma unroll
+    for (int h = 0; h < kLeanBatch; ++h) {
+      const uint32_t a = a0 + threadIdx.x + h * kLeanThreads;
+      const uint32_t al = (a < a1) ? a : a0;
+      ent_n[h] = has_gen ? i_ent[al] : kEntNone;
+      slot_n[h] = has_range ? i_slot[al] : kNoSlot;
     }
     for (uint32_t base = a0 + threadIdx.x; base < a1; base += kLeanBatch * kLeanThreads) {
       float s[kLeanBatch], inf[kLeanBatch], tinf[kLeanBatch], cur[kLeanBatch], nxt[kLeanBatch], ttn[kLeanBatch];
-      float rpc[kLeanBatch], gen[kLeanBatch], hs[kLeanBatch], Lc[kLeanBatch];
+      float rpc[kLeanBatch], gen[kLeanBatch];
+      RangeLoads rl[kLeanBatch];
       uint32_t ent[kLeanBatch], slot[kLeanBatch];
       int cls[kLeanBatch];
-      // ---- stage 1: streaming loads of every agent in the batch ----------------------------------------
+      // ---- issue every load of the batch: gathers (addresses known from the previous iteration), streaming
+      //      loads, and the next batch's index words --------------------------------------------------------
 #pragma unroll
       for (int h = 0; h < kLeanBatch; ++h) {
         const uint32_t a = base + h * kLeanThreads;
-        const uint32_t al = (a < a1) ? a : a0;  // dead slots re-read the tile's first agent (no branch around loads)
+        const uint32_t al = (a < a1) ? a : a0;  // dead slots re-read the segment's first agent (no branches)
+        ent[h] = ent_n[h];
+        slot[h] = slot_n[h];
+        gen[h] = lean_generic_issue(SP, ent[h]);
+        rl[h] = lean_range_issue(Tr, al, slot[h]);
         s[h] = i_s[al];
         inf[h] = i_inf[al];
         tinf[h] = i_tinf[al];
@@ -408,27 +473,23 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_forward(gj_world_desc 
         nxt[h] = i_nxt[al];
         ttn[h] = i_ttn[al];
         cls[h] = w.cls[al];
-        ent[h] = lp.has_generic ? w.ent1[al] : kEntNone;
-        slot[h] = lp.n_range > 0 ? lp.r_slot[al] : kNoSlot;
-        rpc[h] = lp.n_range > 0 ? lp.r_pc[al] : 0.0f;
+        rpc[h] = has_range ? lp.r_pc[al] : 0.0f;
+        const uint32_t an = a + kLeanBatch * kLeanThreads;
+        const uint32_t anl = (an < a1) ? an : a0;
+        ent_n[h] = has_gen ? i_ent[anl] : kEntNone;
+        slot_n[h] = has_range ? i_slot[anl] : kNoSlot;
       }
-      // ---- stage 2: dependent gathers (group value from L2, household neighbours from L1) -------------
-#pragma unroll
-      for (int h = 0; h < kLeanBatch; ++h) {
-        const uint32_t a = base + h * kLeanThreads;
-        const uint32_t al = (a < a1) ? a : a0;
-        gen[h] = lean_generic(w, SP, ent[h], al);
-        hs[h] = lean_range_sum(Tr, al, slot[h]);
-        Lc[h] = lp.n_cell > 0 ? L[cls[h]] : 0.0f;
-      }
-      // ---- stage 3: arithmetic and stores -----------------------------------------------------------------
+      // ---- arithmetic and stores ------------------------------------------------------------------------------
 #pragma unroll
       for (int h = 0; h < kLeanBatch; ++h) {
         const uint32_t a = base + h * kLeanThreads;
         if (a >= a1) break;
-        const float rv = (beta_r * rpc[h]) * hs[h];
+        const float hs = lean_range_finish(rl[h], Tr, a, slot[h]);
+        const float gv = lean_generic_finish(w, SP, ent[h], a, gen[h]);
+        const float Lc = lp.n_cell > 0 ? L[cls[h]] : 0.0f;
+        const float rv = (beta_r * rpc[h]) * hs;
         const float house = lp.r_house ? rv : 0.0f;
-        const float plain = (gen[h] + Lc[h]) + (lp.r_house ? 0.0f : rv);
+        const float plain = (gv + Lc) + (lp.r_house ? 0.0f : rv);
         const float mq = kQuar ? quar_mask(p, cur[h]) : 1.0f;
         const float X = fmaf(mq, plain, house);  // pressure per unit susceptibility
         const float lam = X * s[h];
@@ -470,6 +531,7 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_forward(gj_world_desc 
         if (so.cur == dead) atomicAdd(&sh.deaths, so.cur / dead);
       }
     }
+    tile = tend;
   }
   if (io.red) {
     __syncthreads();
@@ -495,7 +557,7 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_forward(gj_world_desc 
 //     w = dL/dLambda * s (and its quarantine-masked copy), partial sums of the cell channels (as in K1)
 // =====================================================================================================
 template <bool kQuar>
-__global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward(gj_world_desc w, gj_step_params p, LeanPlan lp,
+__global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_BWD) k_lean_backward(gj_world_desc w, gj_step_params p, LeanPlan lp,
                                                                    gj_bwd_io io, float* __restrict__ tile_part) {
   __shared__ ProbRow prob[200];
   __shared__ float gred_age[100];  // cotangent of is_infected from the cases / cases-by-age reductions
@@ -642,7 +704,7 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward(gj_world_desc
 //     range-tier network: sum_g pc_g S_g R_g = sum over agents of T_a * pc_g(a) * R_g(a)
 // =====================================================================================================
 template <bool kQuar>
-__global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward_gather(gj_world_desc w, gj_step_params p,
+__global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_GATHER) k_lean_backward_gather(gj_world_desc w, gj_step_params p,
                                                                           LeanPlan lp, gj_bwd_io io,
                                                                           const float* __restrict__ cell_buf,
                                                                           double* __restrict__ dbeta_part) {
@@ -658,27 +720,36 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward_gather(gj_wor
   const float* __restrict__ i_cur = io.cur;
   const float* __restrict__ i_inf = io.inf;
   const float* __restrict__ i_tinf = io.tinf;
+  const uint32_t* __restrict__ i_ent = w.ent1;
+  const uint32_t* __restrict__ i_slot = lp.r_slot;
   const float4* __restrict__ prof = reinterpret_cast<const float4*>(io.prof4);
   const float beta_r = lp.n_range > 0 ? beta_s[lp.r_net] : 0.0f;
+  const bool has_gen = lp.has_generic != 0, has_range = lp.n_range > 0;
   double db[1] = {0.0};
 
   const TileRun run = lean_tiles(w);
   int nbuild = 0;
-  const float* __restrict__ L = Ls[0];
-  uint32_t a1 = run.t0 < run.t1 ? w.tile_begin[run.t0] : 0;
-  for (int64_t tile = run.t0; tile < run.t1; ++tile) {
-    const uint32_t a0 = a1;
-    a1 = w.tile_begin[tile + 1];
-    if (lp.n_cell > 0 && (tile == run.t0 || lean_new_cell(lp, tile - 1, tile))) {
-      float* __restrict__ Lw = Ls[nbuild & 1];
+  for (int64_t tile = run.t0; tile < run.t1;) {
+    const int64_t tend = lp.n_cell > 0 ? lean_segment_end(lp, tile, run.t1) : run.t1;
+    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tend];
+    const float* __restrict__ L = Ls[nbuild & 1];
+    if (lp.n_cell > 0) {
+      lean_class_table(Ls[nbuild & 1], prob, lp, cell_buf, tile);
       ++nbuild;
-      lean_class_table(Lw, prob, lp, cell_buf, tile);
       __syncthreads();
-      L = Lw;
+    }
+    uint32_t ent_n[kLeanBatch], slot_n[kLeanBatch];
+#pragma unroll
+    for (int h = 0; h < kLeanBatch; ++h) {
+      const uint32_t a = a0 + threadIdx.x + h * kLeanThreads;
+      const uint32_t al = (a < a1) ? a : a0;
+      ent_n[h] = has_gen ? i_ent[al] : kEntNone;
+      slot_n[h] = has_range ? i_slot[al] : kNoSlot;
     }
     for (uint32_t base = a0 + threadIdx.x; base < a1; base += kLeanBatch * kLeanThreads) {
-      float rpc[kLeanBatch], cur[kLeanBatch], inf[kLeanBatch], tinf[kLeanBatch], gen[kLeanBatch], R[kLeanBatch],
-          gi[kLeanBatch], gt[kLeanBatch], Tm[kLeanBatch];
+      float rpc[kLeanBatch], cur[kLeanBatch], inf[kLeanBatch], tinf[kLeanBatch], gen[kLeanBatch], gi[kLeanBatch],
+          gt[kLeanBatch], Tm[kLeanBatch];
+      RangeLoads rl[kLeanBatch];
       float4 pf[kLeanBatch];
       uint32_t ent[kLeanBatch], slot[kLeanBatch];
       int cls[kLeanBatch];
@@ -686,35 +757,36 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward_gather(gj_wor
       for (int h = 0; h < kLeanBatch; ++h) {
         const uint32_t a = base + h * kLeanThreads;
         const uint32_t al = (a < a1) ? a : a0;
+        ent[h] = ent_n[h];
+        slot[h] = slot_n[h];
+        gen[h] = lean_generic_issue(cRP, ent[h]);
+        rl[h] = lean_range_issue(wr, al, slot[h]);
         cls[h] = w.cls[al];
-        ent[h] = lp.has_generic ? w.ent1[al] : kEntNone;
-        slot[h] = lp.n_range > 0 ? lp.r_slot[al] : kNoSlot;
-        rpc[h] = lp.n_range > 0 ? lp.r_pc[al] : 0.0f;
-        Tm[h] = lp.n_range > 0 ? T[al] : 0.0f;
+        rpc[h] = has_range ? lp.r_pc[al] : 0.0f;
+        Tm[h] = has_range ? T[al] : 0.0f;
         cur[h] = kQuar ? i_cur[al] : 0.0f;
         inf[h] = i_inf[al];
         tinf[h] = i_tinf[al];
         pf[h] = prof[al];
         gi[h] = io.g_inf[al];
         gt[h] = io.g_tinf[al];
-      }
-#pragma unroll
-      for (int h = 0; h < kLeanBatch; ++h) {
-        const uint32_t a = base + h * kLeanThreads;
-        const uint32_t al = (a < a1) ? a : a0;
-        gen[h] = lean_generic(w, cRP, ent[h], al);
-        R[h] = lean_range_sum(wr, al, slot[h]);
+        const uint32_t an = a + kLeanBatch * kLeanThreads;
+        const uint32_t anl = (an < a1) ? an : a0;
+        ent_n[h] = has_gen ? i_ent[anl] : kEntNone;
+        slot_n[h] = has_range ? i_slot[anl] : kNoSlot;
       }
 #pragma unroll
       for (int h = 0; h < kLeanBatch; ++h) {
         const uint32_t a = base + h * kLeanThreads;
         if (a >= a1) break;
+        const float R = lean_range_finish(rl[h], wr, a, slot[h]);
+        const float gv = lean_generic_finish(w, cRP, ent[h], a, gen[h]);
         const float mq = kQuar ? quar_mask(p, cur[h]) : 1.0f;
-        const float pr = rpc[h] * R[h];
+        const float pr = rpc[h] * R;
         if (pr != 0.0f) db[0] += (double)((kQuar && !lp.r_house) ? mq * Tm[h] : Tm[h]) * (double)pr;
         const float rv = beta_r * pr;
         const float house = lp.r_house ? rv : 0.0f;
-        const float plain = (gen[h] + (lp.n_cell > 0 ? L[cls[h]] : 0.0f)) + (lp.r_house ? 0.0f : rv);
+        const float plain = (gv + (lp.n_cell > 0 ? L[cls[h]] : 0.0f)) + (lp.r_house ? 0.0f : rv);
         const float gT = fmaf(mq, plain, house);
         if (gT != 0.0f) {
           const TransTerms tt = lean_transmission<true>(p.now, tinf[h], pf[h]);
@@ -723,6 +795,7 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_backward_gather(gj_wor
         }
       }
     }
+    tile = tend;
   }
   if (lp.n_range > 0) block_sums<double, 1>(db, 1, dbeta_part + (int64_t)blockIdx.x * GJ_MAX_RANGE_NETS);
 }

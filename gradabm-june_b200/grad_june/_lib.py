@@ -10,7 +10,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC_DIR = PKG_DIR.parent / "csrc"
 INCLUDE_DIR = PKG_DIR.parent.parent / "include"
-LIB_PATH = PKG_DIR / "libgradjune_b200.so"
+LIB_PATH = Path(os.environ.get("GJ_LIB_PATH") or PKG_DIR / "libgradjune_b200.so")   # override: kernel experiments
 
 GJ_MAX_TYPES = 8
 GJ_MAX_NETS = 16

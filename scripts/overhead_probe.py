@@ -38,6 +38,16 @@ def window():
 for _ in range(3):
     window()
 torch.cuda.synchronize()
+for _ in range(3):   # one window at a time from an empty queue: host time of forward / backward, then the drain
+    s0 = time.perf_counter(); t1 = window(); t2 = time.perf_counter(); torch.cuda.synchronize(); t3 = time.perf_counter()
+    print(f"  window from empty queue: fwd host {(t1 - s0) / steps * 1e3:.3f}  bwd host {(t2 - t1) / steps * 1e3:.3f}  "
+          f"drain {(t3 - t2) / steps * 1e3:.3f} ms/step")
+import gc
+gc.callbacks.append(lambda phase, info: print(f"    [gc {phase} gen{info['generation']} collected={info.get('collected')}] t={time.perf_counter():.4f}") if info['generation'] >= 1 else None)
+for i in range(8):
+    s0 = time.perf_counter(); t1 = window(); t2 = time.perf_counter(); torch.cuda.synchronize(); t3 = time.perf_counter()
+    print(f"  w{i}: fwd host {(t1 - s0) / steps * 1e3:.3f}  bwd host {(t2 - t1) / steps * 1e3:.3f} ms/step  t={s0:.4f}")
+gc.callbacks.clear()
 t0 = time.perf_counter(); tf = 0.0
 for _ in range(5):
     s = time.perf_counter(); t1 = window(); tf += t1 - s
