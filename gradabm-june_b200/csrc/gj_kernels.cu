@@ -458,23 +458,25 @@ __global__ void __launch_bounds__(kBlock) k_dbeta(gj_world_desc w, gj_step_param
     const int64_t g0 = w.type_group_off[net.type];
     const int64_t G = w.type_group_off[net.type + 1] - g0;
     const int64_t so = dp.soff[k];
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < G; i += stride)
-      acc[0] += (double)(w.pc[g0 + i] * S_un[so + i]) * (double)R[so + i];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < G; i += stride) {
+      const float own = w.dbeta_w ? w.dbeta_w[g0 + i] : 1.0f;  // partitioned worlds: every group counted by one rank
+      acc[0] += (double)((own * w.pc[g0 + i]) * S_un[so + i]) * (double)R[so + i];
+    }
   }
   block_reduce_finish<1>(acc, 1, partials + (int64_t)k * kRedBlocks, tickets + 1 + k, g_beta + k);
 }
 
-__global__ void k_philox_fill(uint64_t seed, uint32_t call, int64_t n, float* __restrict__ E, float* __restrict__ u,
-                              float* __restrict__ z) {
+__global__ void k_philox_fill(uint64_t seed, uint32_t call, int64_t first, int64_t n, float* __restrict__ E,
+                              float* __restrict__ u, float* __restrict__ z) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n; a += stride) {
-    const StepNoise nz = draw_step_noise(seed, call, a);
+    const StepNoise nz = draw_step_noise(seed, call, first + a);
     if (E) {
       E[a] = nz.E0;
       E[n + a] = nz.E1;
     }
     if (u) u[a] = nz.u;
-    if (z) z[a] = draw_step_normal(seed, call, a);
+    if (z) z[a] = draw_step_normal(seed, call, first + a);
   }
 }
 
@@ -575,22 +577,34 @@ static int launch_group_pass(const gj_world_desc* w, const gj_step_params* p, co
   return 0;
 }
 
-// cell tier: tile partials -> per-group sums (plain + beta*pc-scaled) -> per-cell sum of the scaled group sums
-static int launch_cell_pass(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const float* beta,
-                            float* out_scaled, float* out_plain, const Scratch& sc, cudaStream_t st) {
+// cell tier, part 1: tile partials -> per-group sums (plain + beta*pc-scaled)
+static int launch_cell_groups(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const float* beta,
+                              float* out_scaled, float* out_plain, const Scratch& sc, cudaStream_t st) {
   if (pl.n_t2 == 0) return 0;
-  int64_t maxG = 1, maxC = 1;
+  int64_t maxG = 1;
   for (int j = 0; j < pl.n_t2; ++j) {
     const int t = p->nets[pl.t2_net[j]].type;
     const int64_t G = w->type_group_off[t + 1] - w->type_group_off[t];
     if (G > maxG) maxG = G;
-    if (w->n_cells[t] > maxC) maxC = w->n_cells[t];
   }
   ProfScope ps(K_CELL, st);
   k_cell_groups<<<dim3(blocks_for(maxG, kBlock), pl.n_t2), kBlock, 0, st>>>(*w, *p, pl, beta, sc.tile_part, out_scaled,
                                                                            out_plain);
   GJ_CHECK_LAUNCH("k_cell_groups");
-  k_cell_gather<<<dim3(blocks_for(maxC, kBlock), pl.n_t2), kBlock, 0, st>>>(*w, *p, pl, out_scaled, sc.cell_buf);
+  return 0;
+}
+
+// cell tier, part 2: per-cell sum of the scaled group sums (after the sums of straddling groups were exchanged)
+static int launch_cell_gather(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const float* in_scaled,
+                              const Scratch& sc, cudaStream_t st) {
+  if (pl.n_t2 == 0) return 0;
+  int64_t maxC = 1;
+  for (int j = 0; j < pl.n_t2; ++j) {
+    const int t = p->nets[pl.t2_net[j]].type;
+    if (w->n_cells[t] > maxC) maxC = w->n_cells[t];
+  }
+  ProfScope ps(K_CELL, st);
+  k_cell_gather<<<dim3(blocks_for(maxC, kBlock), pl.n_t2), kBlock, 0, st>>>(*w, *p, pl, in_scaled, sc.cell_buf);
   GJ_CHECK_LAUNCH("k_cell_gather");
   return 0;
 }
@@ -664,18 +678,22 @@ static int launch_lean_group_pass(const gj_world_desc* w, const gj_step_params* 
 static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const LeanPlan& lp,
                         const gj_fwd_io* io, const Scratch& sc, cudaStream_t st) {
   const bool quar = p->n_quar > 0;
-  {
-    ProfScope ps(K_TRANSMISSION, st);
-    static int occ[2] = {0, 0};
-    if (quar) k_lean_transmission<true><<<lean_grid(w, k_lean_transmission<true>, &occ[1]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
-    else k_lean_transmission<false><<<lean_grid(w, k_lean_transmission<false>, &occ[0]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
-    GJ_CHECK_LAUNCH("k_lean_transmission");
+  if (p->stage != GJ_STAGE_REST) {
+    {
+      ProfScope ps(K_TRANSMISSION, st);
+      static int occ[2] = {0, 0};
+      if (quar) k_lean_transmission<true><<<lean_grid(w, k_lean_transmission<true>, &occ[1]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
+      else k_lean_transmission<false><<<lean_grid(w, k_lean_transmission<false>, &occ[0]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
+      GJ_CHECK_LAUNCH("k_lean_transmission");
+    }
+    if (lp.has_generic)
+      if (int e = launch_lean_group_pass(w, p, pl, io->beta, quar ? io->Tq : io->T, io->S_scaled + lp.gen_base,
+                                         io->S_unscaled + lp.gen_base, sc, false, st))
+        return e;
+    if (int e = launch_cell_groups(w, p, pl, io->beta, io->S_scaled, io->S_unscaled, sc, st)) return e;
   }
-  if (lp.has_generic)
-    if (int e = launch_lean_group_pass(w, p, pl, io->beta, quar ? io->Tq : io->T, io->S_scaled + lp.gen_base,
-                                       io->S_unscaled + lp.gen_base, sc, false, st))
-      return e;
-  if (int e = launch_cell_pass(w, p, pl, io->beta, io->S_scaled, io->S_unscaled, sc, st)) return e;
+  if (p->stage == GJ_STAGE_SUMS) return 0;
+  if (int e = launch_cell_gather(w, p, pl, io->S_scaled, sc, st)) return e;
   {
     ProfScope ps(K_AGENT_FWD, st);
     static int occ[4] = {0, 0, 0, 0};
@@ -694,17 +712,21 @@ static int lean_backward(const gj_world_desc* w, const gj_step_params* p, const 
   const bool quar = p->n_quar > 0;
   static int occ_b[2] = {0, 0}, occ_g[2] = {0, 0};
   int gather_grid = 1;
-  {
-    ProfScope ps(K_AGENT_BWD, st);
+  if (p->stage != GJ_STAGE_REST) {
+    {
+      ProfScope ps(K_AGENT_BWD, st);
     if (quar) k_lean_backward<true><<<lean_grid(w, k_lean_backward<true>, &occ_b[1]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
     else k_lean_backward<false><<<lean_grid(w, k_lean_backward<false>, &occ_b[0]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
-    GJ_CHECK_LAUNCH("k_lean_backward");
+      GJ_CHECK_LAUNCH("k_lean_backward");
+    }
+    if (lp.has_generic)
+      if (int e = launch_lean_group_pass(w, p, pl, io->beta, quar ? io->wq : io->w, io->cR + lp.gen_base,
+                                         io->R + lp.gen_base, sc, true, st))
+        return e;
+    if (int e = launch_cell_groups(w, p, pl, io->beta, io->cR, io->R, sc, st)) return e;
   }
-  if (lp.has_generic)
-    if (int e = launch_lean_group_pass(w, p, pl, io->beta, quar ? io->wq : io->w, io->cR + lp.gen_base,
-                                       io->R + lp.gen_base, sc, true, st))
-      return e;
-  if (int e = launch_cell_pass(w, p, pl, io->beta, io->cR, io->R, sc, st)) return e;
+  if (p->stage == GJ_STAGE_SUMS) return 0;
+  if (int e = launch_cell_gather(w, p, pl, io->cR, sc, st)) return e;
   {
     ProfScope ps(K_AGENT_BWD_GATHER, st);
     if (quar) k_lean_backward_gather<true><<<(gather_grid = lean_grid(w, k_lean_backward_gather<true>, &occ_g[1])), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.dbeta_tile);
@@ -864,18 +886,22 @@ int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fw
     }
   }
   const int grid = (int)w->n_tiles;
-  {
-    ProfScope ps(K_TRANSMISSION, st);
-    k_tile_transmission<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.tile_part);
-    GJ_CHECK_LAUNCH("k_tile_transmission");
+  if (pp.stage != GJ_STAGE_REST) {
+    {
+      ProfScope ps(K_TRANSMISSION, st);
+      k_tile_transmission<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.tile_part);
+      GJ_CHECK_LAUNCH("k_tile_transmission");
+    }
+    const float* T = io->T_in ? io->T_in : io->T;
+    const float* Tq = (p->n_quar > 0) ? io->Tq : T;
+    if (pl.n_generic > 0)
+      if (int e = launch_group_pass<false>(w, &pp, ch, io->beta, io->leisure_prob, T, Tq, io->S_scaled, io->S_unscaled,
+                                           sc, st))
+        return e;
+    if (int e = launch_cell_groups(w, &pp, pl, io->beta, io->S_scaled, io->S_unscaled, sc, st)) return e;
   }
-  const float* T = io->T_in ? io->T_in : io->T;
-  const float* Tq = (p->n_quar > 0) ? io->Tq : T;
-  if (pl.n_generic > 0)
-    if (int e = launch_group_pass<false>(w, &pp, ch, io->beta, io->leisure_prob, T, Tq, io->S_scaled, io->S_unscaled, sc,
-                                         st))
-      return e;
-  if (int e = launch_cell_pass(w, &pp, pl, io->beta, io->S_scaled, io->S_unscaled, sc, st)) return e;
+  if (pp.stage == GJ_STAGE_SUMS) return 0;
+  if (int e = launch_cell_gather(w, &pp, pl, io->S_scaled, sc, st)) return e;
   {
     ProfScope ps(K_AGENT_FWD, st);
     k_tile_forward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.red_part, sc.tickets);
@@ -921,15 +947,19 @@ int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_b
     }
   }
   const int grid = (int)w->n_tiles;
-  {
-    ProfScope ps(K_AGENT_BWD, st);
-    k_tile_backward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.tile_part);
-    GJ_CHECK_LAUNCH("k_tile_backward");
+  if (pp.stage != GJ_STAGE_REST) {
+    {
+      ProfScope ps(K_AGENT_BWD, st);
+      k_tile_backward<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.tile_part);
+      GJ_CHECK_LAUNCH("k_tile_backward");
+    }
+    if (pl.n_generic > 0)
+      if (int e = launch_group_pass<true>(w, &pp, ch, io->beta, io->leisure_prob, io->w, io->wq, io->cR, io->R, sc, st))
+        return e;
+    if (int e = launch_cell_groups(w, &pp, pl, io->beta, io->cR, io->R, sc, st)) return e;
   }
-  if (pl.n_generic > 0)
-    if (int e = launch_group_pass<true>(w, &pp, ch, io->beta, io->leisure_prob, io->w, io->wq, io->cR, io->R, sc, st))
-      return e;
-  if (int e = launch_cell_pass(w, &pp, pl, io->beta, io->cR, io->R, sc, st)) return e;
+  if (pp.stage == GJ_STAGE_SUMS) return 0;
+  if (int e = launch_cell_gather(w, &pp, pl, io->cR, sc, st)) return e;
   {
     ProfScope ps(K_AGENT_BWD_GATHER, st);
     k_tile_backward_gather<<<grid, kBlock, 0, st>>>(*w, pp, pl, *io, sc.cell_buf, sc.dbeta_tile);
@@ -948,11 +978,28 @@ int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_b
   return 0;
 }
 
-int gj_philox_fill(uint64_t seed, uint32_t call_index, int64_t n, float* E, float* u, float* z, void* stream) {
+int gj_philox_fill_at(uint64_t seed, uint32_t call_index, uint64_t first_agent, int64_t n, float* E, float* u, float* z,
+                      void* stream) {
   if (n <= 0) return 0;
-  k_philox_fill<<<agent_grid(n), kBlock, 0, (cudaStream_t)stream>>>(seed, call_index, n, E, u, z);
+  k_philox_fill<<<agent_grid(n), kBlock, 0, (cudaStream_t)stream>>>(seed, call_index, (int64_t)first_agent, n, E, u, z);
   GJ_CHECK_LAUNCH("k_philox_fill");
   return 0;
+}
+
+int gj_philox_fill(uint64_t seed, uint32_t call_index, int64_t n, float* E, float* u, float* z, void* stream) {
+  return gj_philox_fill_at(seed, call_index, 0, n, E, u, z, stream);
+}
+
+int gj_step_plan(const gj_world_desc* w, const gj_step_params* p, int64_t* out, int n) {
+  if (int e = check_world(w)) return e;
+  if (!p) return bad("params is NULL");
+  Channels ch;
+  Plan pl;
+  if (int e = build_channels(w, p, &ch, &pl)) return e;
+  LeanPlan lp;
+  const bool lean = lean_plan(w, p, pl, &lp);
+  if (out && n > 0) out[0] = lean ? lp.gen_base : 0;
+  return lean ? 1 : 0;
 }
 
 void gj_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {

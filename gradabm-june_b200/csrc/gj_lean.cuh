@@ -498,7 +498,8 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_FWD) k_lean_forward
         // Gumbel-softmax hard draw from Philox bits (same stream as draw_step_noise):
         // x0 - x1 = (ln2 / tau) * d,  d = lg2 q - lg2(1-q) - lg2 E0 + lg2 E1, E = -ln u (the ln2 factors cancel)
         uint32_t r[4];
-        philox4x32_10(a, 0u, p.call_index, 0u, key0, key1, r);
+        const uint64_t ga = p.agent_offset + a;  // global agent id = Philox counter
+        philox4x32_10((uint32_t)ga, (uint32_t)(ga >> 32), p.call_index, 0u, key0, key1, r);
         const float d = (lg2_fast(q) - lg2_fast(1.0f - q)) -
                         (lg2_fast(-lg2_fast(u01_open(r[0]))) - lg2_fast(-lg2_fast(u01_open(r[1]))));
         const float e = ex2_fast(-fabsf(d) * inv_tau);  // exp(x_small - x_big) <= 1
@@ -522,7 +523,7 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_FWD) k_lean_forward
         const float uu = u01_half(r[2]);
         const int age = age_of(cls[h]);
         const SympOut so = symptoms_forward(p, io.stage_prob, cur[h], nxt[h], ttn[h], n, age, [&]() { return uu; },
-                                            [&](int) { return draw_step_normal(seed, call, a); });
+                                            [&](int) { return draw_step_normal(seed, call, (int64_t)ga); });
         io.cur_o[a] = so.cur;
         io.nxt_o[a] = so.nxt;
         io.ttn_o[a] = so.ttn;
@@ -632,9 +633,10 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_BWD) k_lean_backwar
         // symptoms^T: the draws are regenerated only for the few agents whose stage actually updates
         const uint64_t seed = p.seed;
         const uint32_t call = p.call_index;
+        const int64_t ga = (int64_t)p.agent_offset + a;
         const SympOut so = symptoms_forward(p, io.stage_prob, cur[h], nxt[h], ttn[h], n, age,
-                                            [&]() { return draw_step_noise(seed, call, a).u; },
-                                            [&](int) { return draw_step_normal(seed, call, a); });
+                                            [&]() { return draw_step_noise(seed, call, ga).u; },
+                                            [&](int) { return draw_step_normal(seed, call, ga); });
         float gc = gcur_o[h];
         if (so.cur == dead) gc += g_deaths;
         float gcur1 = gc, gnxt1 = gnxt_o[h];

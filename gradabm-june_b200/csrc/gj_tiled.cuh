@@ -214,7 +214,7 @@ __device__ __forceinline__ void forward_tail(const gj_step_params& p, const gj_f
   nz.E0 = nz.E1 = 1.0f;
   nz.u = 0.0f;
   if (p.phases & (GJ_PHASE_SAMPLE | GJ_PHASE_SYMPTOMS)) {
-    if (io.inj_E == nullptr || io.inj_u == nullptr) nz = draw_step_noise(p.seed, p.call_index, a);
+    if (io.inj_E == nullptr || io.inj_u == nullptr) nz = draw_step_noise(p.seed, p.call_index, (int64_t)p.agent_offset + a);
     if (io.inj_E) {
       nz.E0 = io.inj_E[a];
       nz.E1 = io.inj_E[N + a];
@@ -241,10 +241,11 @@ __device__ __forceinline__ void forward_tail(const gj_step_params& p, const gj_f
     const float* inj_z = io.inj_z;
     const uint64_t seed = p.seed;
     const uint32_t call = p.call_index;
+    const int64_t ga = (int64_t)p.agent_offset + a;
     const float uu = nz.u;
     const SympOut so = symptoms_forward(p, io.stage_prob, st.cur, st.nxt, st.ttn, n, age, [&]() { return uu; },
                                         [&](int row) {
-      return inj_z ? inj_z[(int64_t)row * N + a] : draw_step_normal(seed, call, a);
+      return inj_z ? inj_z[(int64_t)row * N + a] : draw_step_normal(seed, call, ga);
     });
     st.cur = so.cur;
     st.nxt = so.nxt;
@@ -442,11 +443,12 @@ __device__ __forceinline__ BackAgent backward_agent(const gj_step_params& p, con
     const float* inj_z = io.inj_z;
     const uint64_t seed = p.seed;
     const uint32_t call = p.call_index;
+    const int64_t ga = (int64_t)p.agent_offset + a;
     // the uniform / normal draws are regenerated only for the few agents whose stage actually updates
     const SympOut so = symptoms_forward(p, io.stage_prob, st.cur, st.nxt, st.ttn, n, age,
-                                        [&]() { return inj_u ? inj_u[a] : draw_step_noise(seed, call, a).u; },
+                                        [&]() { return inj_u ? inj_u[a] : draw_step_noise(seed, call, ga).u; },
                                         [&](int row) {
-      return inj_z ? inj_z[(int64_t)row * N + a] : draw_step_normal(seed, call, a);
+      return inj_z ? inj_z[(int64_t)row * N + a] : draw_step_normal(seed, call, ga);
     });
     // reductions fold in here: deaths = sum (cur' == dead) * cur' / dead   runner.py:204-209
     if (io.g_red && so.cur == (float)dead) gcur_o += io.g_red[1] / (float)dead;

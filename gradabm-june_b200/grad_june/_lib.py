@@ -18,11 +18,12 @@ GJ_MAX_STAGES = 16
 GJ_MAX_QUAR = 4
 GJ_MAX_AGE_BINS = 8
 GJ_MAX_CHANNELS = 8
-GJ_ABI_VERSION = 2
+GJ_ABI_VERSION = 3
 
 KIND_PLAIN, KIND_HOUSEHOLD, KIND_LEISURE, KIND_CARE_VISIT = 0, 1, 2, 3
 PHASE_NETWORKS, PHASE_SAMPLE, PHASE_INFECT, PHASE_SYMPTOMS, PHASE_ALL = 1, 2, 4, 8, 15
 MODE_STEP, MODE_SEED = 0, 1
+STAGE_ALL, STAGE_SUMS, STAGE_REST = 0, 1, 2
 
 _u32p = C.c_void_p
 _f32p = C.c_void_p
@@ -46,7 +47,7 @@ class WorldDesc(C.Structure):
         ("tile_cell", C.c_void_p * GJ_MAX_TYPES), ("cell_tile_ptr", C.c_void_p * GJ_MAX_TYPES),
         ("cell_grp_ptr", C.c_void_p * GJ_MAX_TYPES), ("cell_grp", C.c_void_p * GJ_MAX_TYPES),
         ("grp_cell_ptr", C.c_void_p * GJ_MAX_TYPES), ("grp_cell", C.c_void_p * GJ_MAX_TYPES),
-        ("ent1", _u32p),
+        ("ent1", _u32p), ("dbeta_w", _f32p),
     ]
 
 
@@ -66,6 +67,7 @@ class StepParams(C.Structure):
         ("n_stages", C.c_int32), ("trans_time", Dist * GJ_MAX_STAGES), ("rec_time", Dist * GJ_MAX_STAGES),
         ("n_age_bins", C.c_int32), ("age_bins", C.c_int32 * (GJ_MAX_AGE_BINS + 1)),
         ("tau", C.c_float), ("seed", C.c_uint64), ("call_index", C.c_uint32), ("exact_order", C.c_uint32),
+        ("stage", C.c_uint32), ("_pad1", C.c_uint32), ("agent_offset", C.c_uint64),
     ]
 
 
@@ -151,6 +153,9 @@ def lib():
     L.gj_transmission_backward.argtypes = [C.c_int64, C.c_float] + [C.c_void_p] * 11
     L.gj_step_forward.argtypes = [C.POINTER(WorldDesc), C.POINTER(StepParams), C.POINTER(FwdIO), C.c_void_p]
     L.gj_step_backward.argtypes = [C.POINTER(WorldDesc), C.POINTER(StepParams), C.POINTER(BwdIO), C.c_void_p]
+    L.gj_philox_fill_at.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]
+    L.gj_step_plan.argtypes = [C.POINTER(WorldDesc), C.POINTER(StepParams), C.POINTER(C.c_int64), C.c_int]
     L.gj_philox_fill.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gj_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.gj_philox4x32_10.restype = None
@@ -183,7 +188,7 @@ def check(rc, what):
 EXPORTED_SYMBOLS = [
     "gj_abi_version", "gj_last_error", "gj_config", "gj_scratch_bytes", "gj_profile_prepare", "gj_profile_pack",
     "gj_transmission_forward", "gj_transmission_backward", "gj_step_forward", "gj_step_backward",
-    "gj_philox_fill", "gj_philox4x32_10", "gj_profile_enable", "gj_profile_read", "gj_profile_kernel_name",
+    "gj_philox_fill", "gj_philox_fill_at", "gj_step_plan", "gj_philox4x32_10", "gj_profile_enable", "gj_profile_read", "gj_profile_kernel_name",
 ]
 
 

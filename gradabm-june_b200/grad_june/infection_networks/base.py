@@ -139,7 +139,9 @@ def _run_networks(networks, data, timer, policies, device, want_lam=False):
     state = {"s": agent.susceptibility}
     if spec.quarantine:
         state["cur"] = agent["symptoms"]["current_stage"]
-    static = ops.StepStatic(world=world, leisure_prob=table)
+    from ..partition import exchange_for
+
+    static = ops.StepStatic(world=world, leisure_prob=table, exchange=exchange_for(data, world))
     return ops.infection_step(static, spec, beta_vector(networks, policies, timer, dev), state,
                               T_in=agent.transmission)
 

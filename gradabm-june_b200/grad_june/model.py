@@ -17,6 +17,7 @@ from .paths import ensure_default_config
 from .policies import Policies
 from .symptoms import SymptomsUpdater
 from .transmission import TransmissionUpdater, profile_packed, profile_tensors
+from .partition import exchange_for
 from .world import get_device_world
 
 
@@ -70,7 +71,8 @@ class GradJune(torch.nn.Module):
             table, rows = leisure_table(nets, device)
             static = ops.StepStatic(world=world, maxinf=maxinf, shape=shape, rate=rate, shift=shift, k0=k0,
                                     prof4=profile_packed(data), leisure_prob=table,
-                                    symptoms=self.symptoms_updater.symptoms_sampler.tables(device))
+                                    symptoms=self.symptoms_updater.symptoms_sampler.tables(device),
+                                    exchange=exchange_for(data, world))
             cache["static"] = hit = (key, static, rows)
         return hit[1], hit[2]
 

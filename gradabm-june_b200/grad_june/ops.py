@@ -106,13 +106,14 @@ class philox_seed:
         NOISE.fixed_seed, NOISE.calls = self._saved
 
 
-def philox_fill(seed: int, call_index: int, n: int, device):
-    """The exact (E[2,N], u[N], z[N]) draws the kernels make for (seed, call_index)."""
+def philox_fill(seed: int, call_index: int, n: int, device, first_agent: int = 0):
+    """The exact (E[2,N], u[N], z[N]) draws the kernels make for (seed, call_index) and the agents
+    first_agent .. first_agent + n - 1 (global ids)."""
     E = torch.empty(2, n, device=device)
     u = torch.empty(n, device=device)
     z = torch.empty(n, device=device)
-    _lib.check(_lib.lib().gj_philox_fill(seed, call_index, n, E.data_ptr(), u.data_ptr(), z.data_ptr(), _stream(E.device)),
-               "gj_philox_fill")
+    _lib.check(_lib.lib().gj_philox_fill_at(seed, call_index, first_agent, n, E.data_ptr(), u.data_ptr(), z.data_ptr(),
+                                            _stream(E.device)), "gj_philox_fill_at")
     return E, u, z
 
 
@@ -251,6 +252,7 @@ class StepStatic:
     prof4: Optional[torch.Tensor] = None          # [N, 4] packed profile (gj_profile_pack)
     leisure_prob: Optional[torch.Tensor] = None   # [n_tables, 2, 2, 100]
     symptoms: Optional[SymptomsTables] = None
+    exchange: object = None                       # partition.BoundaryExchange of a partitioned world
 
 
 def profile_k0(shape: torch.Tensor) -> torch.Tensor:
@@ -309,6 +311,27 @@ def transmission(now, tinf, inf, maxinf, shape, rate, shift, k0=None):
 
 
 _STATE = ("s", "inf", "tinf", "cur", "nxt", "ttn")
+
+
+def _staged_call(fn, what, static: "StepStatic", desc, p, io, stream, sum_buffers, lean_inputs: bool):
+    """One library call, or — for a partitioned world — the two stages of it with the all-reduce of the boundary
+    groups' sums (``sum_buffers``: the two group-sum tensors of this call) in between."""
+    ex = static.exchange
+    if ex is None or sum_buffers is None:
+        _lib.check(fn(C.byref(desc), C.byref(p), C.byref(io), stream), what)
+        return
+    out = (C.c_int64 * 1)()
+    lean = _lib.lib().gj_step_plan(C.byref(desc), C.byref(p), out, 1)
+    if lean < 0:
+        _lib.check(lean, "gj_step_plan")
+    lean = bool(lean) and lean_inputs
+    region = ex.regions(lean, int(out[0]), [(p.nets[k].type, p.nets[k].s_off) for k in range(p.n_nets)])
+    p.stage = _lib.STAGE_SUMS
+    _lib.check(fn(C.byref(desc), C.byref(p), C.byref(io), stream), what)
+    ex.exchange(sum_buffers, region)
+    p.stage = _lib.STAGE_REST
+    _lib.check(fn(C.byref(desc), C.byref(p), C.byref(io), stream), what)
+    p.stage = _lib.STAGE_ALL
 
 
 class _Step(torch.autograd.Function):
@@ -381,10 +404,11 @@ class _Step(torch.autograd.Function):
         n = new("n") if ((phases & PHASE_SAMPLE) and probs) else None
         tape_v = new("tape_v") if nets_on else None
         tape_y0 = new("tape_y0") if (phases & PHASE_SAMPLE) else None
-        S_un = None
+        S_un = S_sc = None
         if nets_on:
             s_total += world.n_groups   # per-network sums, then one value per global group (throughput mode)
-            io.S_scaled = _buffer(world, "S_scaled", s_total).data_ptr()
+            S_sc = _buffer(world, "S_scaled", s_total)
+            io.S_scaled = S_sc.data_ptr()
             S_un = torch.empty(max(s_total, 1), dtype=torch.float32, device=dev)
             io.S_unscaled = S_un.data_ptr()
         red = None
@@ -393,7 +417,11 @@ class _Step(torch.autograd.Function):
             io.red = red.data_ptr()
         io.scratch = _scratch(world).data_ptr()
         desc = world.desc()
-        _lib.check(L.gj_step_forward(C.byref(desc), C.byref(p), C.byref(io), _stream(dev)), "gj_step_forward")
+        if static.exchange is not None:
+            p.agent_offset = static.exchange.part.agent_lo
+        lean_inputs = E is None and u is None and z is None and T_in is None and lam is None and static.prof4 is not None
+        _staged_call(L.gj_step_forward, "gj_step_forward", static, desc, p, io, _stream(dev),
+                     (S_sc, S_un) if nets_on else None, lean_inputs)
 
         ctx.static, ctx.spec, ctx.noise_key = static, spec, (seed, call_index)
         ctx.set_materialize_grads(False)
@@ -480,15 +508,21 @@ class _Step(torch.autograd.Function):
         g_n_in = new("g_n_out") if (n_in is not None and need[12]) else None
         g_beta = new("g_beta", max(p.n_nets, 1), zero=True) if nets_on else None
         g_frac = new("g_seed_fraction", 1, zero=True) if seed_mode else None
+        R_buf = cR_buf = None
         if nets_on:
             s_total += world.n_groups
             io.w = _buffer(world, "w", N).data_ptr()
             io.wq = _buffer(world, "wq", N).data_ptr() if p.n_quar > 0 else io.w
-            io.R = _buffer(world, "R", s_total).data_ptr()
-            io.cR = _buffer(world, "cR", s_total).data_ptr()
+            R_buf, cR_buf = _buffer(world, "R", s_total), _buffer(world, "cR", s_total)
+            io.R, io.cR = R_buf.data_ptr(), cR_buf.data_ptr()
         io.scratch = _scratch(world).data_ptr()
         desc = world.desc()
-        _lib.check(_lib.lib().gj_step_backward(C.byref(desc), C.byref(p), C.byref(io), _stream(dev)), "gj_step_backward")
+        if static.exchange is not None:
+            p.agent_offset = static.exchange.part.agent_lo
+        lean_inputs = (E is None and u is None and z is None and g_T_in is None and g_lam is None
+                       and static.prof4 is not None and io.g_q is None and io.g_n is None)
+        _staged_call(_lib.lib().gj_step_backward, "gj_step_backward", static, desc, p, io, _stream(dev),
+                     (cR_buf, R_buf) if nets_on else None, lean_inputs)
         if g_beta is not None:
             g_beta = g_beta[: p.n_nets]
         return (None, None, None, g_beta if need[3] else None,

@@ -1,0 +1,225 @@
+"""Geographic partition of a world across the GPUs of one box (one process per GPU).
+
+The reference has no multi-GPU code; this is the domain decomposition BASELINE.json's north
+star asks for.  Agents are numbered area-contiguously, so rank r owns a contiguous agent range (cut where no
+household-like group is split) and the groups its agents attend.  A step then runs in two stages
+(``gj_step_params.stage``): every rank forms the partial sums of its groups from its own members, the sums of the
+groups that straddle partitions ("boundary groups": commuter companies, schools, universities, leisure venues at
+partition borders) are all-reduced over NCCL/NVLink in one packed buffer, and everything after that (gather,
+exp, Gumbel-softmax draw, state update, symptoms) is rank-local.  The backward mirrors it with the cotangent
+sums.  Each boundary group is *owned* by the lowest rank attending it, which alone adds its term to d/dbeta
+(``gj_world_desc.dbeta_w``); summing the ranks' log-beta gradients gives the gradient of the whole world.
+The Philox counter is the global agent id (``agent_offset``), so a partitioned run draws the same noise as the
+unpartitioned one.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .world import HeteroData, RANGE_MAX_GROUP, TIER_CELL, TIER_GENERIC, TIER_RANGE, ToUndirected
+
+
+@dataclass
+class Partition:
+    rank: int
+    world_size: int
+    bounds: List[int]                      # world_size + 1 global agent cut points
+    n_global_agents: int
+    types: List[str]
+    local_groups: Dict[str, torch.Tensor]  # type -> global ids of this rank's groups (ascending) = local id order
+    n_boundary: Dict[str, int]             # type -> number of groups attended by >= 2 ranks (same on every rank)
+    touch_pos: Dict[str, torch.Tensor]     # type -> positions of this rank's boundary groups in the global boundary list
+    touch_lid: Dict[str, torch.Tensor]     # type -> their local group ids
+    owned: Dict[str, torch.Tensor]         # type -> [G_local] bool: this rank is the lowest one attending the group
+    process_group: object = None
+
+    @property
+    def agent_lo(self):
+        return self.bounds[self.rank]
+
+    @property
+    def agent_hi(self):
+        return self.bounds[self.rank + 1]
+
+
+def _slice_agents(v, lo, hi, n):
+    if torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == n:
+        return v[lo:hi].clone()
+    if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == n:
+        return v[lo:hi].copy()
+    if isinstance(v, dict):
+        return {k: _slice_agents(x, lo, hi, n) for k, x in v.items()}
+    return v
+
+
+def partition_bounds(data: HeteroData, world_size: int) -> List[int]:
+    """Equal-size agent ranges, each cut moved forward to the next agent at which no household-like group (every
+    agent in at most one group, groups = short runs of consecutive agents) is split."""
+    n = len(data["agent"].id)
+    dev = data["agent"].age.device if torch.is_tensor(data["agent"].age) else "cpu"
+    ok = torch.ones(n + 1, dtype=torch.bool, device=dev)
+    for t in data.venue_types():
+        ei = data["attends_" + t].edge_index
+        if ei.shape[1] == 0:
+            continue
+        src, dst = ei[0], ei[1]
+        if int(torch.bincount(src, minlength=n).max()) > 1:
+            continue
+        if int(torch.bincount(dst).max()) > RANGE_MAX_GROUP:
+            continue
+        gid = torch.full((n,), -1, dtype=torch.long, device=src.device)
+        gid[src] = dst
+        same = (gid[1:] == gid[:-1]) & (gid[1:] >= 0)      # agent a and a-1 share a group: no cut at a
+        ok[1:n] &= ~same.to(ok.device)
+    valid = torch.nonzero(ok).flatten()
+    bounds = [0]
+    for r in range(1, world_size):
+        c = (n * r) // world_size
+        j = int(torch.searchsorted(valid, torch.tensor([c], device=valid.device))[0])
+        bounds.append(max(int(valid[min(j, valid.numel() - 1)]), bounds[-1]))
+    bounds.append(n)
+    return bounds
+
+
+def partition_world(data: HeteroData, rank: int, world_size: int, bounds: Optional[List[int]] = None,
+                    process_group=None) -> HeteroData:
+    """This rank's part of ``data`` (a complete world, identical on every rank): its agents (every per-agent
+    attribute sliced), the edges of its agents with group ids renumbered to the groups it attends, and the global
+    ``people`` counts of those groups.  The partition record is attached as ``local._gj_partition``."""
+    n = len(data["agent"].id)
+    bounds = partition_bounds(data, world_size) if bounds is None else list(bounds)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    types = data.venue_types()
+    local = HeteroData()
+    for key, v in data["agent"].items():
+        local["agent"][key] = _slice_agents(v, lo, hi, n)
+    cuts = None
+    part = Partition(rank=rank, world_size=world_size, bounds=bounds, n_global_agents=n, types=types, local_groups={},
+                     n_boundary={}, touch_pos={}, touch_lid={}, owned={}, process_group=process_group)
+    for t in types:
+        ei = data["attends_" + t].edge_index
+        src, dst = ei[0], ei[1]
+        dev = src.device
+        G = len(data[t]["id"])
+        if cuts is None or cuts.device != dev:
+            cuts = torch.tensor(bounds[1:-1], dtype=torch.long, device=dev)
+        # which ranks attend each group (from the complete edge list: the same answer on every rank)
+        r_of = torch.bucketize(src, cuts, right=True)
+        pairs = torch.unique(dst * world_size + r_of)
+        pg, pr = pairs // world_size, pairs % world_size
+        n_ranks = torch.bincount(pg, minlength=G)
+        owner = torch.full((G,), world_size, dtype=torch.long, device=dev).scatter_reduce(0, pg, pr, reduce="amin")
+        boundary_ids = torch.nonzero(n_ranks >= 2).flatten()                  # ascending global ids
+        mine = pg[pr == rank]                                                 # ascending global ids of my groups
+        sel = (src >= lo) & (src < hi)
+        lsrc = src[sel] - lo
+        ldst = torch.searchsorted(mine, dst[sel])
+        local[t].id = torch.arange(mine.numel(), device=dev)
+        people = torch.as_tensor(data[t]["people"])
+        local[t].people = people.to(dev)[mine]
+        local["agent", "attends_" + t, t].edge_index = torch.stack((lsrc, ldst))
+        is_b = n_ranks[mine] >= 2
+        lid = torch.nonzero(is_b).flatten()
+        part.local_groups[t] = mine
+        part.n_boundary[t] = int(boundary_ids.numel())
+        part.touch_lid[t] = lid
+        part.touch_pos[t] = torch.searchsorted(boundary_ids, mine[lid])
+        part.owned[t] = owner[mine] == rank
+    if any(k[1].startswith("rev_") for k in data._edge_store_dict):
+        local = ToUndirected()(local)
+    local.__dict__["_gj_partition"] = part
+    return local
+
+
+class BoundaryExchange:
+    """Packs the sums of this rank's boundary groups, all-reduces them, and writes the totals back."""
+
+    def __init__(self, part: Partition, world):
+        self.part = part
+        self.world = world
+        self._regions = {}
+        dev = world.device
+        w = torch.zeros(world.n_groups, dtype=torch.float32, device=dev)
+        for ti, t in enumerate(world.types):
+            w[world.type_group_off[ti]:world.type_group_off[ti + 1]] = part.owned[t].to(dev, torch.float32)
+        world.dbeta_w = w
+        world.__dict__.pop("_desc", None)   # the descriptor carries the pointer
+
+    def regions(self, lean: bool, gen_base: int, nets):
+        """(index into the group-sum buffers, index into the packed buffer, packed length) for this step:
+        ``nets`` = [(type index, s_off)] in network order."""
+        key = (lean, gen_base, tuple(nets))
+        hit = self._regions.get(key)
+        if hit is not None:
+            return hit
+        world, part = self.world, self.part
+        dev = world.device
+        offsets = []                                  # (type index, offset of the type's groups in the buffers)
+        if lean:
+            for ti in range(len(world.types)):
+                if world.type_tier[ti] == TIER_GENERIC:
+                    offsets.append((ti, gen_base + world.type_group_off[ti]))
+            offsets += [(ti, off) for ti, off in nets if world.type_tier[ti] == TIER_CELL]
+        else:
+            offsets += [(ti, off) for ti, off in nets if world.type_tier[ti] != TIER_RANGE]
+        src, dst, base = [], [], 0
+        for ti, off in offsets:
+            t = world.types[ti]
+            src.append(part.touch_lid[t].to(dev) + off)
+            dst.append(part.touch_pos[t].to(dev) + base)
+            base += part.n_boundary[t]
+        cat = lambda xs: torch.cat(xs) if xs else torch.zeros(0, dtype=torch.long, device=dev)  # noqa: E731
+        hit = (cat(src), cat(dst), base)
+        self._regions[key] = hit
+        return hit
+
+    def exchange(self, buffers, region):
+        """In place: every buffer's boundary entries become the sum over ranks."""
+        import torch.distributed as dist
+
+        src, dst, n = region
+        if n == 0 or self.part.world_size == 1:
+            return
+        pack = torch.zeros(len(buffers), n, dtype=torch.float32, device=buffers[0].device)
+        for i, b in enumerate(buffers):
+            pack[i, dst] = b[src]
+        dist.all_reduce(pack, group=self.part.process_group)
+        for i, b in enumerate(buffers):
+            b[src] = pack[i, dst]
+
+
+class _AllReduceSum(torch.autograd.Function):
+    """Sum over ranks of a tensor every rank then uses in the same loss: the cotangent passes through."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        import torch.distributed as dist
+
+        y = x.clone()
+        dist.all_reduce(y, group=group)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def all_reduce_sum(x, part: Optional[Partition]):
+    if part is None or part.world_size == 1:
+        return x
+    return _AllReduceSum.apply(x, part.process_group)
+
+
+def exchange_for(data, world):
+    """The BoundaryExchange of a partitioned world (cached on the data object), or None."""
+    part = data.__dict__.get("_gj_partition")
+    if part is None:
+        return None
+    cache = data.__dict__.setdefault("_gj_cache", {})
+    hit = cache.get("exchange")
+    if hit is None or hit.world is not world:
+        hit = BoundaryExchange(part, world)
+        cache["exchange"] = hit
+    return hit

@@ -15,6 +15,7 @@ import yaml
 
 from . import ops
 from .model import GradJune
+from .partition import all_reduce_sum
 from .paths import ensure_default_config
 from .timer import Timer
 from .transmission import PROFILE_KEYS, TransmissionSampler
@@ -121,6 +122,7 @@ class Runner(torch.nn.Module):
             reds.append(red)
             dates.append(timer.date)
         table = torch.stack(reds)                      # [T+1, 2 + n_bins]
+        table = all_reduce_sum(table, data.__dict__.get("_gj_partition"))   # partitioned world: sum over ranks
         cases_per_timestep = table[:, 0]
         data["results"]["deaths_per_timestep"] = table[:, 1]
         results = {

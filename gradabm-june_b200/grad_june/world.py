@@ -278,6 +278,8 @@ class DeviceWorld:
                     getattr(d, name)[ti] = c[name].data_ptr()
                 cell_off += c["n_cells"]
         d.n_cells_total = cell_off
+        if self.__dict__.get("dbeta_w") is not None:
+            d.dbeta_w = self.dbeta_w.data_ptr()
         self.__dict__["_desc"] = d
         return d
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GJ_ABI_VERSION 2
+#define GJ_ABI_VERSION 3
 
 #define GJ_MAX_TYPES 8      /* edge types (household, company, school, university, care_home, leisure, ...) */
 #define GJ_MAX_NETS 16      /* infection networks active in one step */
@@ -55,6 +55,8 @@ enum {
   GJ_PHASE_SYMPTOMS = 8, /* SymptomsUpdater.forward              symptoms.py:204-247        */
   GJ_PHASE_ALL = 15
 };
+
+enum { GJ_STAGE_ALL = 0, GJ_STAGE_SUMS = 1, GJ_STAGE_REST = 2 };
 
 /* mode flags */
 enum {
@@ -124,6 +126,10 @@ typedef struct gj_world_desc {
   /* one-entry-per-agent view of the GENERIC types (throughput-mode kernels): the GLOBAL id of the agent's only
    * generic group, 0xFFFFFFFF = none, 0xFFFFFFFE = several (walk am_ptr / am_ent); NULL = not built */
   const uint32_t* ent1;
+  /* geographic partition (one process per GPU, each owning an agent range and the groups its agents attend):
+   * [n_groups] weight of each group in d/dbeta, 1 for groups this rank owns and 0 for groups owned by another
+   * rank (their sums are exchanged between the two stages of a step); NULL = all ones */
+  const float* dbeta_w;
 } gj_world_desc;
 
 typedef struct gj_net {
@@ -163,6 +169,14 @@ typedef struct gj_step_params {
    * re-associated sums, hardware log2/exp2 in the draw and the infectiousness profile); 1: always run the
    * reference-order kernels (they also run whenever noise is injected) */
   uint32_t exact_order;
+  /* two-stage execution for partitioned worlds: GJ_STAGE_ALL runs the whole step; GJ_STAGE_SUMS stops after the
+   * per-group sums (forward: S_scaled / S_unscaled, backward: cR / R) are written, so that the caller can
+   * all-reduce the sums of groups that straddle partitions; GJ_STAGE_REST continues from the (summed) buffers */
+  uint32_t stage;
+  uint32_t _pad1;
+  /* global id of this rank's first agent: the Philox counter is (agent_offset + local agent index), so a
+   * partitioned world draws exactly the noise of the unpartitioned one */
+  uint64_t agent_offset;
 } gj_step_params;
 
 /* device arrays of one forward call; unused ones may be NULL */
@@ -282,9 +296,18 @@ int gj_profile_enable(int on); /* also resets the counters */
 int gj_profile_read(double* ms, int64_t* timed, int64_t* launches, int n);
 const char* gj_profile_kernel_name(int id);
 
+/* which kernel family gj_step_forward / gj_step_backward run for this (world, params) when no noise is injected and
+ * the packed profile is given: returns 1 = throughput mode, 0 = reference order, < 0 = error; out[0] = offset of
+ * the per-global-group region inside the group-sum buffers (throughput mode).  Host-only; used by partitioned
+ * callers to locate the sums they exchange. */
+int gj_step_plan(const gj_world_desc* w, const gj_step_params* p, int64_t* out, int n);
+
 /* ---- noise ------------------------------------------------------------------------------- */
-/* the exact draws gj_step_forward makes for (seed, call_index): E[2][N], u[N], z[N] */
+/* the exact draws gj_step_forward makes for (seed, call_index) and agents first_agent .. first_agent+n-1:
+ * E[2][N], u[N], z[N] */
 int gj_philox_fill(uint64_t seed, uint32_t call_index, int64_t n, float* E, float* u, float* z, void* stream);
+int gj_philox_fill_at(uint64_t seed, uint32_t call_index, uint64_t first_agent, int64_t n, float* E, float* u, float* z,
+                      void* stream);
 /* raw Philox4x32-10 block for known-answer tests: out[4] = philox(ctr[4], key[2]) (host function) */
 void gj_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
