@@ -42,11 +42,20 @@ def measured_peak_gbs():
     return 6650.0, "fallback"
 
 
-def bench_params(device, steps):
+def bench_params(device, steps, policies=False):
     from grad_june.default_config import default_parameters
     p = default_parameters()
     p["system"]["device"] = device
     p["policies"] = {}
+    if policies:   # BASELINE config 4: everything active from day 15 of the run (start 2022-02-01)
+        span = {"start_date": "2022-02-16", "end_date": "2030-01-01"}
+        leisure = ("pub", "cinema", "gym", "grocery", "visit", "care_visit")
+        p["policies"] = {
+            "interaction": {"social_distancing": {1: dict(span, beta_factors=dict(
+                {"school": 0.5, "company": 0.5}, **{k: 0.5 for k in leisure}))}},
+            "close_venue": {"close_venue": {1: dict(span, names=["school", "pub", "cinema", "gym"])}},
+            "quarantine": {"quarantine": {1: dict(span, stage_threshold=4)}},
+        }
     p["timer"]["total_days"] = steps
     p["infection_seed"]["log_fraction_initial_cases"] = -2.0
     p["save_path"] = tempfile.gettempdir() + "/gj_bench"
@@ -118,7 +127,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU baseline = the oracle port of the reference's path, on the host cores
 # ------------------------------------------------------------------------------------------
-def cpu_reference_run(n_agents, steps, repeats=1):
+def cpu_reference_run(n_agents, steps, repeats=1, policies=False):
     """Oracle (torch CPU restatement of the reference) fwd+bwd on a bounded sample of the workload:
     the same synthetic world generator at n_agents, default 11 networks, `steps` timesteps.
     Returns (agent-timesteps/s, seconds per fwd+bwd pass, cores)."""
@@ -130,7 +139,7 @@ def cpu_reference_run(n_agents, steps, repeats=1):
     from grad_june.world import make_synthetic_world
     from oracle import gj_oracle as O
 
-    params = bench_params("cpu", steps)
+    params = bench_params("cpu", steps, policies)
     torch.manual_seed(0)
     data = make_synthetic_world(n_agents, seed=0, device="cpu")
     w = O.OracleWorld(n_agents=n_agents, age=data["agent"].age, sex=data["agent"].sex)
@@ -167,7 +176,7 @@ def run_reference_arm(args, rank, world_size):
     for _ in range(max(args.warmup, 0) and 1):
         cpu_reference_run(min(n_sample, 100_000), 1)
     t0 = time.perf_counter()
-    thr, secs, cores = cpu_reference_run(n_sample, args.steps)
+    thr, secs, cores = cpu_reference_run(n_sample, args.steps, policies=args.policies)
     line = {
         "impl": "reference", "metric": METRIC, "value": thr, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": secs * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -182,20 +191,31 @@ def run_reference_arm(args, rank, world_size):
     print(json.dumps(line), flush=True)
 
 
-def workload_name(n_agents):
+def workload_name(n_agents, policies=False):
     return (f"synthetic England-scale world ({n_agents / 1e6:.0f}M agents, ~4.6 edges/agent over household/company/school/"
-            "university/care_home/leisure), 11 default networks, symptoms on, fwd+bwd wrt log_beta")
+            "university/care_home/leisure), 11 default networks, symptoms on, fwd+bwd wrt log_beta"
+            + (", social distancing + school/pub/cinema/gym closure + quarantine(stage 4) from day 15" if policies else ""))
 
 
 # ------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=120)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--agents", type=int, default=56_000_000, help="agents per GPU")
-    ap.add_argument("--window", type=int, default=0, help="BPTT window (0 = as many steps as memory allows)")
+    ap.add_argument("--agents", type=int, default=56_000_000,
+                    help="agents per GPU (weak scaling) / of the whole world (strong scaling)")
+    ap.add_argument("--parallelism", default="geo", choices=["geo", "ensemble"],
+                    help="N > 1: geographic partition of ONE world with the boundary-group all-reduce (default), or one "
+                         "beta sample per GPU on replicas of the world (no data-path collective)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="geo: every GPU owns --agents agents of a world of N x --agents (weak), or the --agents world "
+                         "is cut into N parts (strong)")
+    ap.add_argument("--policies", action="store_true",
+                    help="BASELINE config 4: social distancing, school/leisure closures and quarantine from day 15")
+    ap.add_argument("--window", type=int, default=0,
+                    help="BPTT window (0 = 60 timesteps as in BASELINE.json, fewer if memory does not allow)")
     ap.add_argument("--cpu-agents", type=int, default=1_000_000, help="agents of the CPU-baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -218,26 +238,51 @@ def main():
     if world_size > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
-    N = args.agents
+    geo = world_size > 1 and args.parallelism == "geo"
+    strong = geo and args.scaling == "strong"
+    N = args.agents // world_size if strong else args.agents      # agents this rank owns (about, for strong)
     free, total = torch.cuda.mem_get_info()
     # bytes retained per agent per step until backward (pre-state 24 + tape 8 + group sums ~3) + margin
     per_step = 40.0 * N
     resident = 120.0 * N           # world CSR + static arrays + transient workspaces + initial state backup
     max_window = int(max(1, (free * 0.85 - resident) // per_step))
-    window = min(args.steps, args.window or max_window, max_window)
+    window = min(args.steps, args.window or min(max_window, 60), max_window)
+    if world_size > 1:     # the ranks of a partitioned world step together
+        wt = torch.tensor([window], device=dev)
+        dist.all_reduce(wt, op=dist.ReduceOp.MIN)
+        window = int(wt.item())
 
-    params = bench_params(dev, window)
+    params = bench_params(dev, window, args.policies)
     torch.manual_seed(1234 + rank)
-    data = make_synthetic_world(N, seed=0, device=dev)
+    part = None
+    if geo:
+        from grad_june.partition import partition_from_blocks, partition_world
+        if strong:      # the whole world fits every GPU: build it, keep this rank's part
+            whole = make_synthetic_world(args.agents, seed=0, device=dev)
+            data = partition_world(whole, rank, world_size)
+            del whole
+        else:           # no rank ever holds the whole world: each generates its own block
+            data = partition_from_blocks(make_synthetic_world(N, seed=0, device=dev, block=(rank, world_size)))
+        part = data._gj_partition
+        N = part.agent_hi - part.agent_lo
+        torch.cuda.empty_cache()
+    else:
+        data = make_synthetic_world(N, seed=0, device=dev)
     data = Runner.get_data(params, data=data)
     world = freeze_device_world(data, dev)   # the int64 edge lists are not needed once the CSR exists
     model = GradJune.from_parameters(params)
     keys = list(model.infection_networks.networks.keys())
-    # ensemble axis: every rank evaluates its own beta sample on the world (config 5 style sharding)
     gen = torch.Generator().manual_seed(99)
     offsets = 0.05 * torch.randn(max(world_size, 1), len(keys), generator=gen)
-    host_log_beta = torch.tensor([float(model.infection_networks.networks[k].log_beta) for k in keys]) + offsets[rank]
+    # geo: one parameter vector for the one world; ensemble: every rank evaluates its own beta sample (config 5)
+    host_log_beta = torch.tensor([float(model.infection_networks.networks[k].log_beta) for k in keys]) \
+        + offsets[0 if geo else rank]
     host_log_beta = host_log_beta.pin_memory()
+    n_total = N
+    if geo:
+        n_total = part.n_global_agents
+    elif world_size > 1:
+        n_total = N * world_size
 
     def fresh_runner():
         r = Runner(model=model, data=data, timer=Timer.from_parameters(params), log_fraction_initial_cases=-2.0,
@@ -262,6 +307,8 @@ def main():
         loss = results["cases_per_timestep"].sum() + results["deaths_per_timestep"].sum()
         loss.backward()
         grads = torch.stack([l.grad for l in leaves])
+        if geo:      # every rank holds the terms of the groups it owns: the world's gradient is their sum
+            dist.all_reduce(grads)
         out = torch.cat([results["cases_per_timestep"], results["deaths_per_timestep"], grads])
         if e2e:
             return out.to("cpu")                                     # D2H of the window's results
@@ -284,7 +331,7 @@ def main():
     barrier()
 
     # ---- timed region 1: device-resident inputs --------------------------------------------------
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank, period=0.02) as clocks:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.nvtx.range_push("timed")
@@ -323,12 +370,21 @@ def main():
         t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
-        gathered = [torch.zeros_like(out) for _ in range(world_size)]
-        dist.all_gather(gathered, out)      # the ensemble's only exchange: losses + gradients
+        if not geo:
+            gathered = [torch.zeros_like(out) for _ in range(world_size)]
+            dist.all_gather(gathered, out)      # the ensemble's only exchange: losses + gradients
 
+    parallelism = "single GPU"
+    if geo:
+        nb = {t: part.n_boundary[t] for t in part.types if part.n_boundary[t]}
+        parallelism = (f"geographic partition over {world_size} GPUs ({args.scaling} scaling), NCCL all-reduce of the "
+                       f"boundary-group sums once per step forward and once backward; boundary groups {nb} "
+                       f"of {world.n_groups} local groups")
+    elif world_size > 1:
+        parallelism = "ensemble shard (one beta sample per GPU on replicas of the world, no data-path collective)"
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
-        total_units = N * steps_done * world_size
+        total_units = n_total * steps_done
         value = total_units / (ms * 1e-3)
         # dominant kernel + its algorithmic bytes per launch (DESIGN.md "Roofline")
         e_bar = world.n_edges / N
@@ -358,12 +414,14 @@ def main():
         launches = int(sum(v[2] for v in prof.values()))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": steps_done,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / steps_done, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / steps_done, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(N), "agents_per_gpu": N, "edges_per_agent": round(e_bar, 3),
+            "config": {"workload": workload_name(n_total if geo else N, args.policies), "agents_per_gpu": N,
+                       "agents_total": n_total, "edges_per_agent": round(e_bar, 3),
                        "groups_per_agent": round(g_bar, 3), "bptt_window": window, "networks": 11,
                        "layout_tiers": dict(zip(world.types, world.type_tier)),
-                       "parallelism": "ensemble shard (one beta sample per GPU, no data-path collective)" if world_size > 1 else "single GPU",
+                       "parallelism": parallelism,
                        "l2": "inputs (>= 2 GB per pass) far larger than the 126 MB L2; no flush needed"},
             "clocks": clk,
             "e2e": {"value": total_units / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -371,7 +429,7 @@ def main():
             "roofline": roof,
         }
         if not args.no_cpu_baseline and world_size == 1:
-            thr, secs, cores = cpu_reference_run(args.cpu_agents, args.cpu_steps)
+            thr, secs, cores = cpu_reference_run(args.cpu_agents, args.cpu_steps, policies=args.policies)
             line["cpu_baseline"] = {"value": thr, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_agents} agents of the same synthetic world x {args.cpu_steps} "
                                               f"timesteps fwd+bwd ({secs:.1f} s)"}

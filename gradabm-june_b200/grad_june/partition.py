@@ -133,6 +133,69 @@ def partition_world(data: HeteroData, rank: int, world_size: int, bounds: Option
     return local
 
 
+def partition_from_blocks(block: HeteroData, process_group=None) -> HeteroData:
+    """The rank's local world from ONE block of a world generated block-wise
+    (``make_synthetic_world(..., block=(rank, world_size))``: local agent indices, global group ids) — the
+    distributed counterpart of :func:`partition_world` for worlds no single GPU could hold.  Collectives (NCCL on
+    GPUs, gloo on CPU): the block sizes (agent cut points), per group type the member counts of every rank's
+    groups (``people`` = sum over ranks) and the attendance bitmaps (which ranks attend a group -> boundary list
+    and owner).  The result is identical to ``partition_world(whole_world, rank, world_size, bounds)``."""
+    import torch.distributed as dist
+
+    rank, world_size, n_local = block.__dict__["_gj_block"]
+    if dist.is_initialized():
+        assert dist.get_world_size(process_group) == world_size and dist.get_rank(process_group) == rank
+    elif world_size != 1:
+        raise RuntimeError("partition_from_blocks needs an initialised process group")
+    dev = block["agent"].age.device
+    sizes = torch.zeros(world_size, dtype=torch.long, device=dev)
+    sizes[rank] = n_local
+    if world_size > 1:
+        dist.all_reduce(sizes, group=process_group)
+    bounds = [0] + [int(x) for x in torch.cumsum(sizes, 0).tolist()]
+    types = block.venue_types()
+    local = HeteroData()
+    for key, v in block["agent"].items():
+        local["agent"][key] = v
+    part = Partition(rank=rank, world_size=world_size, bounds=bounds, n_global_agents=bounds[-1], types=types,
+                     local_groups={}, n_boundary={}, touch_pos={}, touch_lid={}, owned={}, process_group=process_group)
+    for t in types:
+        ei = block["attends_" + t].edge_index
+        src, gid = ei[0], ei[1]
+        G = int(block[t].n_global)
+        cnt = torch.bincount(gid, minlength=G)
+        if block[t].scope == "local" or world_size == 1:
+            mine = torch.nonzero(cnt > 0).flatten() if block[t].scope != "local" else torch.arange(G, device=dev)
+            people = cnt[mine]
+            n_ranks_mine = torch.ones(mine.numel(), dtype=torch.long, device=dev)
+            owner_mine = torch.full((mine.numel(),), rank, dtype=torch.long, device=dev)
+            boundary_ids = torch.zeros(0, dtype=torch.long, device=dev)
+        else:
+            mask = (cnt > 0).to(torch.uint8)
+            masks = [torch.empty_like(mask) for _ in range(world_size)]
+            dist.all_gather(masks, mask, group=process_group)
+            masks = torch.stack(masks)                                   # [R, G]
+            n_ranks = masks.sum(0, dtype=torch.long)
+            owner = torch.argmax(masks, dim=0)                           # first (lowest) rank attending the group
+            dist.all_reduce(cnt, group=process_group)                    # people = members over the whole world
+            mine = torch.nonzero(mask).flatten()
+            people = cnt[mine]
+            n_ranks_mine, owner_mine = n_ranks[mine], owner[mine]
+            boundary_ids = torch.nonzero(n_ranks >= 2).flatten()
+            del masks, n_ranks, owner
+        local[t].id = torch.arange(mine.numel(), device=dev)
+        local[t].people = people
+        local["agent", "attends_" + t, t].edge_index = torch.stack((src, torch.searchsorted(mine, gid)))
+        lid = torch.nonzero(n_ranks_mine >= 2).flatten()
+        part.local_groups[t] = mine
+        part.n_boundary[t] = int(boundary_ids.numel())
+        part.touch_lid[t] = lid
+        part.touch_pos[t] = torch.searchsorted(boundary_ids, mine[lid])
+        part.owned[t] = owner_mine == rank
+    local.__dict__["_gj_partition"] = part
+    return local
+
+
 class BoundaryExchange:
     """Packs the sums of this rank's boundary groups, all-reduces them, and writes the totals back."""
 

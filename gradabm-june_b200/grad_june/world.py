@@ -585,21 +585,42 @@ _HOUSEHOLD_SIZES = torch.tensor([1, 2, 3, 4, 5, 6, 8])
 _HOUSEHOLD_PROBS = torch.tensor([0.41, 0.33, 0.11, 0.09, 0.03, 0.025, 0.005])
 
 
+def _company_table(n_agents, n_sa, seed, block, device):
+    """Companies of one block of the synthetic world: log-normal sizes (clipped to [1, 5000]), home super-area
+    uniform inside the block and sorted.  A function of (seed, block) alone, so every rank of a partitioned
+    world can rebuild the tables of its neighbours."""
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed) * 1_000_003 + 7919 * int(block) + 17)
+    n_comp = max(n_agents // 25, 1)
+    csize = torch.exp(1.5 + 1.3 * torch.randn(n_comp, generator=g, device=device)).clamp(1, 5000)
+    chome = torch.sort(torch.randint(0, n_sa, (n_comp,), generator=g, device=device))[0]
+    return csize, chome
+
+
 def make_synthetic_world(n_agents: int, seed: int = 0, device="cpu", agents_per_super_area: int = 7500,
-                         with_reverse: bool = False) -> HeteroData:
+                         with_reverse: bool = False, block=None, super_areas_per_region: int = 1000) -> HeteroData:
     """England-like synthetic world: area-contiguous agents, contiguous
     households (1-8 members), schools (ages 5-17, two per super-area), universities (18-22),
-    companies (19-64, log-normal sizes, 80 % local), care homes (over 75 + staff) and three leisure
-    groups per agent (own super-area and the two neighbouring ones).  ``people`` = member count.
-    Generated with torch ops on ``device`` so the 56 M-agent world builds on the GPU in seconds."""
+    companies (19-64, log-normal sizes, 80 % in the home super-area, 20 % uniform over the home region of
+    ``super_areas_per_region`` super-areas), care homes (over 75 + staff) and three leisure groups per agent (own
+    super-area and the two neighbouring ones).  ``people`` = member count.
+    Generated with torch ops on ``device`` so the 56 M-agent world builds on the GPU in seconds.
+
+    ``block=(b, B)``: generate only block ``b`` of a world made of ``B`` such blocks of ``n_agents`` agents each
+    (one block per GPU of a geographically partitioned run; no rank ever holds the whole world).  Agent indices are
+    local to the block, group ids are GLOBAL (``data[t].n_global`` groups; ``data[t].scope`` says whether other
+    blocks can attend them), ``people`` counts only this block's members:
+    :func:`grad_june.partition.partition_from_blocks` turns this into the rank's local world."""
     dev = torch.device(device)
+    b, B = (0, 1) if block is None else (int(block[0]), int(block[1]))
     g = torch.Generator(device=dev)
-    g.manual_seed(seed)
+    g.manual_seed(seed + 7919 * b)
     N = int(n_agents)
     SA = agents_per_super_area
     ids = torch.arange(N, device=dev)
-    sa = ids // SA
-    n_sa = int((N + SA - 1) // SA)
+    n_sa = int((N + SA - 1) // SA)           # super-areas per block
+    n_sa_g = n_sa * B                        # ... of the whole world
+    sa = ids // SA + b * n_sa                # global super-area of each agent
 
     def rand(n):
         return torch.rand(n, generator=g, device=dev)
@@ -615,18 +636,21 @@ def make_synthetic_world(n_agents: int, seed: int = 0, device="cpu", agents_per_
     data["agent"].age = age
     data["agent"].sex = sex
 
-    def add(name, agents, groups, n_groups):
-        data[name].id = torch.arange(n_groups, device=dev)
-        data[name].people = torch.bincount(groups, minlength=n_groups)
+    def add(name, agents, groups, n_groups, scope="global"):
+        data[name].id = torch.arange(n_groups, device=dev) if block is None else torch.zeros(0, device=dev)
+        if block is None:
+            data[name].people = torch.bincount(groups, minlength=n_groups)
+        else:
+            data[name].n_global, data[name].scope = int(n_groups), scope
         data["agent", "attends_" + name, name].edge_index = torch.stack((agents, groups))
 
-    # households: contiguous runs of agents
+    # households: contiguous runs of agents, never shared between blocks (ids local to the block)
     m = max(N // 2, 1) + 16
     hs = _HOUSEHOLD_SIZES.to(dev)[torch.multinomial(_HOUSEHOLD_PROBS.to(dev), m, replacement=True, generator=g)]
     ends = torch.cumsum(hs, 0)
     n_hh = int(torch.searchsorted(ends, torch.tensor([N], device=dev), right=False)[0]) + 1
     hh = torch.searchsorted(ends[:n_hh].contiguous(), ids, right=True)
-    add("household", ids, hh, n_hh)
+    add("household", ids, hh, n_hh, scope="local")
 
     r = rand(N)
     is_school = (age >= 5) & (age <= 17)
@@ -637,39 +661,48 @@ def make_synthetic_world(n_agents: int, seed: int = 0, device="cpu", agents_per_
     is_resident = (age > 75) & (r < 0.04)
 
     a = ids[is_school]
-    add("school", a, sa[a] * 2 + (rand(a.numel()) < 0.5).long(), n_sa * 2)
+    add("school", a, sa[a] * 2 + (rand(a.numel()) < 0.5).long(), n_sa_g * 2)
     a = ids[is_uni]
-    n_uni = max(n_sa // 111, 1)
+    n_uni = max(n_sa_g // 111, 1)
     add("university", a, torch.clamp(sa[a] // 111, max=n_uni - 1), n_uni)
 
-    # companies: log-normal sizes, home super-area uniform; workers pick proportionally to size
+    # companies: log-normal sizes, home super-area uniform; workers pick proportionally to size, 80 % among the
+    # companies of their own super-area, 20 % among those of their region
     a = ids[is_worker]
-    n_comp = max(int(a.numel() / 10.4), 1)
-    csize = torch.exp(1.5 + 1.3 * torch.randn(n_comp, generator=g, device=dev)).clamp(1, 5000)
-    chome = torch.sort(torch.randint(0, n_sa, (n_comp,), generator=g, device=dev))[0]
+    tables = [_company_table(N, n_sa, seed, j, dev) for j in range(B)]
+    csize = torch.cat([t[0] for t in tables])
+    chome = torch.cat([t[1] + j * n_sa for j, t in enumerate(tables)])     # ascending: blocks are in order
+    n_comp = csize.numel()
     cum = torch.cumsum(csize.double(), 0)
-    first = torch.searchsorted(chome, torch.arange(n_sa + 1, device=dev))      # companies of each super-area
-    lo = torch.where(first[:-1] > 0, cum[(first[:-1] - 1).clamp(min=0)], torch.zeros(n_sa, dtype=cum.dtype, device=dev))
-    hi = torch.where(first[1:] > 0, cum[(first[1:] - 1).clamp(min=0)], torch.zeros(n_sa, dtype=cum.dtype, device=dev))
+    cum0 = torch.cat((torch.zeros(1, dtype=cum.dtype, device=dev), cum))
+    first = torch.searchsorted(chome, torch.arange(n_sa_g + 1, device=dev))   # companies of each super-area
+    RS = max(int(super_areas_per_region), 1)
+    sa_a = sa[a]
+    lo, hi = cum0[first[sa_a]], cum0[first[sa_a + 1]]
+    reg_lo = (sa_a // RS) * RS
+    reg_hi = torch.clamp(reg_lo + RS, max=n_sa_g)
+    rlo, rhi = cum0[first[reg_lo]], cum0[first[reg_hi]]
     u = rand(a.numel()).double()
-    local = (rand(a.numel()) < 0.8) & (hi[sa[a]] > lo[sa[a]])
-    target = torch.where(local, lo[sa[a]] + u * (hi[sa[a]] - lo[sa[a]]), u * cum[-1])
+    local = (rand(a.numel()) < 0.8) & (hi > lo)
+    target = torch.where(local, lo + u * (hi - lo), rlo + u * (rhi - rlo))
     comp = torch.searchsorted(cum, target, right=True).clamp(max=n_comp - 1)
     add("company", a, comp, n_comp)
 
     a = torch.cat((ids[is_resident], ids[is_care_worker]))
-    add("care_home", a, sa[a], n_sa)
+    add("care_home", a, sa[a], n_sa_g)
 
     # leisure: own super-area and its two neighbours (k = 3 nearest, graph_loader.py:12)
-    left = torch.where(sa == 0, torch.full_like(sa, min(2, n_sa - 1)), sa - 1)
-    right = torch.where(sa == n_sa - 1, torch.full_like(sa, max(n_sa - 3, 0)), sa + 1)
-    if n_sa >= 3:
+    left = torch.where(sa == 0, torch.full_like(sa, min(2, n_sa_g - 1)), sa - 1)
+    right = torch.where(sa == n_sa_g - 1, torch.full_like(sa, max(n_sa_g - 3, 0)), sa + 1)
+    if n_sa_g >= 3:
         la = torch.cat((ids, ids, ids))
         lg = torch.cat((sa, left, right))
     else:
         la, lg = ids, sa
-    add("leisure", la, lg, n_sa)
+    add("leisure", la, lg, n_sa_g)
     data["agent"].ethnicity = np.array(["A"])  # one label; per-agent strings are not needed by the step
-    if with_reverse:
+    if block is not None:
+        data.__dict__["_gj_block"] = (b, B, N)
+    elif with_reverse:
         data = ToUndirected()(data)
     return data

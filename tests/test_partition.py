@@ -110,3 +110,70 @@ def test_partition_bounds_cover_all_agents():
         assert b[0] == 0 and b[-1] == 20_000 and all(b[i] <= b[i + 1] for i in range(p))
         sizes = [b[i + 1] - b[i] for i in range(p)]
         assert max(sizes) - min(sizes) <= 16
+
+
+# ---- block-wise worlds: every rank generates only its own block (weak-scaling runs) -----------------------
+N_BLOCK = 24_000
+
+
+def _assemble(blocks):
+    """The complete world of a list of blocks: agents concatenated, households renumbered consecutively."""
+    from grad_june.world import HeteroData
+    whole = HeteroData()
+    n0 = [0]
+    for b in blocks:
+        n0.append(n0[-1] + len(b["agent"].id))
+    whole["agent"].id = torch.arange(n0[-1])
+    for k in ("age", "sex"):
+        whole["agent"][k] = torch.cat([b["agent"][k] for b in blocks])
+    whole["agent"].ethnicity = blocks[0]["agent"].ethnicity
+    for t in blocks[0].venue_types():
+        srcs, dsts, g0 = [], [], 0
+        for i, b in enumerate(blocks):
+            ei = b["attends_" + t].edge_index
+            srcs.append(ei[0] + n0[i])
+            dsts.append(ei[1] + (g0 if b[t].scope == "local" else 0))
+            if b[t].scope == "local":
+                g0 += b[t].n_global
+        G = g0 if blocks[0][t].scope == "local" else blocks[0][t].n_global
+        dst = torch.cat(dsts)
+        whole[t].id = torch.arange(G)
+        whole[t].people = torch.bincount(dst, minlength=G)
+        whole["agent", "attends_" + t, t].edge_index = torch.stack((torch.cat(srcs), dst))
+    return whole, n0
+
+
+def _block_worker(rank, world_size, port, out):
+    from grad_june.partition import partition_from_blocks
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        kw = dict(seed=9, device="cpu", agents_per_super_area=2000, super_areas_per_region=5)
+        mine = make_synthetic_world(N_BLOCK, block=(rank, world_size), **kw)
+        local = partition_from_blocks(mine)
+        part = local._gj_partition
+        whole, n0 = _assemble([make_synthetic_world(N_BLOCK, block=(j, world_size), **kw) for j in range(world_size)])
+        assert part.bounds == n0
+        ref = partition_world(whole, rank, world_size, bounds=n0)
+        rp = ref._gj_partition
+        assert sum(part.n_boundary.values()) > 0
+        for t in part.types:
+            assert torch.equal(local["attends_" + t].edge_index, ref["attends_" + t].edge_index), t
+            assert torch.equal(local[t]["people"], ref[t]["people"]), t
+            assert part.n_boundary[t] == rp.n_boundary[t], t
+            assert torch.equal(part.touch_lid[t], rp.touch_lid[t]) and torch.equal(part.touch_pos[t], rp.touch_pos[t]), t
+            assert torch.equal(part.owned[t], rp.owned[t]), t
+        assert part.n_boundary["household"] == 0 and part.n_boundary["company"] > 0 and part.n_boundary["leisure"] > 0
+        # commuting stays inside the home region: only companies of the regions cut by a block border are shared
+        assert part.n_boundary["company"] < 0.5 * int(mine["company"].n_global)
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world_size", [2, 3])
+def test_blockwise_world_matches_partition_of_the_whole(world_size):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_block_worker, args=(world_size, _free_port(), out), nprocs=world_size, join=True)
+    assert sorted(out.keys()) == list(range(world_size))
