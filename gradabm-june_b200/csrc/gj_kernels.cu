@@ -14,11 +14,13 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "gj_device.cuh"
 #include "gj_tiled.cuh"
 #include "gj_lean.cuh"
+#include "gj_pipe.cuh"
 
 namespace gj {
 
@@ -543,6 +545,43 @@ static int lean_grid(const gj_world_desc* w, K kernel, int* cache) {
   return (int)(w->n_tiles < g ? w->n_tiles : g);
 }
 
+// bulk-copy pipelined kernels (gj_pipe.cuh): on unless GJ_PIPE=0; they need 16-byte aligned per-agent arrays
+static int g_pipe_on = -1;
+static bool pipe_enabled() {
+  if (g_pipe_on < 0) {
+    const char* e = getenv("GJ_PIPE");
+    g_pipe_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pipe_on == 1;
+}
+static bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+static bool pipe_aligned_fwd(const gj_world_desc* w, const LeanPlan& lp, const gj_fwd_io* io) {
+  return aligned16(io->s) && aligned16(io->inf) && aligned16(io->tinf) && aligned16(io->cur) && aligned16(io->nxt) &&
+         aligned16(io->ttn) && aligned16(io->T) && aligned16(io->Tq) && aligned16(w->ent1) && aligned16(w->cls) &&
+         aligned16(lp.r_slot) && aligned16(lp.r_pc);
+}
+static bool pipe_aligned_bwd(const gj_world_desc* w, const LeanPlan& lp, const gj_bwd_io* io) {
+  const void* ptrs[] = {io->s, io->inf, io->tinf, io->cur, io->nxt, io->ttn, io->tape_y0, io->tape_v, io->g_s_o,
+                        io->g_inf_o, io->g_tinf_o, io->g_cur_o, io->g_nxt_o, io->g_ttn_o, io->prof4, io->g_inf,
+                        io->g_tinf, io->T_in, io->w, io->wq, w->ent1, w->cls, lp.r_slot, lp.r_pc};
+  for (const void* q : ptrs)
+    if (!aligned16(q)) return false;   // NULL counts as aligned
+  return true;
+}
+// one resident wave of a kernel with dynamic shared memory
+template <typename K>
+static int pipe_grid(const gj_world_desc* w, K kernel, int threads, size_t smem, int* cache) {
+  if (*cache == 0) {
+    int per_sm = 0;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    *cache = per_sm;
+  }
+  const int64_t g = (int64_t)sm_count() * *cache;
+  return (int)(w->n_tiles < g ? w->n_tiles : g);
+}
+
 static int check_world(const gj_world_desc* w) {
   if (!w) return bad("world is NULL");
   if (w->n_agents < 0 || w->n_types < 0 || w->n_types > GJ_MAX_TYPES) return bad("world sizes");
@@ -694,6 +733,22 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
   }
   if (p->stage == GJ_STAGE_SUMS) return 0;
   if (int e = launch_cell_gather(w, p, pl, io->S_scaled, sc, st)) return e;
+  if (pipe_enabled() && pipe_aligned_fwd(w, lp, io)) {
+    ProfScope ps(K_AGENT_FWD, st);
+    static int occ[4] = {0, 0, 0, 0};
+    const bool diag = io->q || io->n;
+    const size_t smem = sizeof(PipeFwdShared);
+#define GJ_PIPE_FWD(Q, D, I)                                                                                         \
+  k_pipe_forward<Q, D><<<pipe_grid(w, k_pipe_forward<Q, D>, kPipeThreads, smem, &occ[I]), kPipeThreads, smem, st>>>(  \
+      *w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets)
+    if (quar && diag) GJ_PIPE_FWD(true, true, 3);
+    else if (quar) GJ_PIPE_FWD(true, false, 2);
+    else if (diag) GJ_PIPE_FWD(false, true, 1);
+    else GJ_PIPE_FWD(false, false, 0);
+#undef GJ_PIPE_FWD
+    GJ_CHECK_LAUNCH("k_pipe_forward");
+    return 0;
+  }
   {
     ProfScope ps(K_AGENT_FWD, st);
     static int occ[4] = {0, 0, 0, 0};
@@ -712,8 +767,16 @@ static int lean_backward(const gj_world_desc* w, const gj_step_params* p, const 
   const bool quar = p->n_quar > 0;
   static int occ_b[2] = {0, 0}, occ_g[2] = {0, 0};
   int gather_grid = 1;
+  const bool pipe = pipe_enabled() && pipe_aligned_bwd(w, lp, io);
   if (p->stage != GJ_STAGE_REST) {
-    {
+    if (pipe) {
+      ProfScope ps(K_AGENT_BWD, st);
+      static int occ[2] = {0, 0};
+      const size_t smem = sizeof(PipeBwdShared);
+      if (quar) k_pipe_backward<true><<<pipe_grid(w, k_pipe_backward<true>, kPipeThreads, smem, &occ[1]), kPipeThreads, smem, st>>>(*w, *p, lp, *io, sc.tile_part);
+      else k_pipe_backward<false><<<pipe_grid(w, k_pipe_backward<false>, kPipeThreads, smem, &occ[0]), kPipeThreads, smem, st>>>(*w, *p, lp, *io, sc.tile_part);
+      GJ_CHECK_LAUNCH("k_pipe_backward");
+    } else {
       ProfScope ps(K_AGENT_BWD, st);
     if (quar) k_lean_backward<true><<<lean_grid(w, k_lean_backward<true>, &occ_b[1]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
     else k_lean_backward<false><<<lean_grid(w, k_lean_backward<false>, &occ_b[0]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
@@ -727,7 +790,14 @@ static int lean_backward(const gj_world_desc* w, const gj_step_params* p, const 
   }
   if (p->stage == GJ_STAGE_SUMS) return 0;
   if (int e = launch_cell_gather(w, p, pl, io->cR, sc, st)) return e;
-  {
+  if (pipe) {
+    ProfScope ps(K_AGENT_BWD_GATHER, st);
+    static int occ[2] = {0, 0};
+    const size_t smem = sizeof(PipeGatShared);
+    if (quar) k_pipe_backward_gather<true><<<(gather_grid = pipe_grid(w, k_pipe_backward_gather<true>, kPipeThreads, smem, &occ[1])), kPipeThreads, smem, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.dbeta_tile);
+    else k_pipe_backward_gather<false><<<(gather_grid = pipe_grid(w, k_pipe_backward_gather<false>, kPipeThreads, smem, &occ[0])), kPipeThreads, smem, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.dbeta_tile);
+    GJ_CHECK_LAUNCH("k_pipe_backward_gather");
+  } else {
     ProfScope ps(K_AGENT_BWD_GATHER, st);
     if (quar) k_lean_backward_gather<true><<<(gather_grid = lean_grid(w, k_lean_backward_gather<true>, &occ_g[1])), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.dbeta_tile);
     else k_lean_backward_gather<false><<<(gather_grid = lean_grid(w, k_lean_backward_gather<false>, &occ_g[0])), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.dbeta_tile);
@@ -767,6 +837,12 @@ int gj_config(int64_t* out, int n) {
 }
 
 int64_t gj_scratch_bytes(const gj_world_desc* w) { return w ? scratch_bytes(w) : -1; }
+
+int gj_pipeline_enable(int on) {
+  const int prev = pipe_enabled() ? 1 : 0;
+  if (on >= 0) g_pipe_on = on ? 1 : 0;
+  return prev;
+}
 
 int gj_profile_enable(int on) {
   if (on && !g_prof.created) {

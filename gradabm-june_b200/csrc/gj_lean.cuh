@@ -386,6 +386,61 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_fix(gj_world_desc w, gj_s
   out_scaled[g] = (b == b) ? (b * w.pc[g]) * S : 0.0f;
 }
 
+// per-agent arithmetic of the forward pass, shared by the register-batched kernel below and the bulk-copy pipelined
+// kernel of gj_pipe.cuh (identical results): pressure -> q -> Gumbel-softmax draw -> infect -> symptoms -> reductions.
+// hs = sum of the member values of the agent's range-tier group, gv = combined value of its generic groups,
+// Lc = class-table value of the cell channels
+template <bool kQuar, bool kDiag>
+__device__ __forceinline__ void lean_forward_agent(const gj_step_params& p, const LeanPlan& lp, const gj_fwd_io& io,
+                                                   uint32_t a, float hs, float gv, float Lc, float beta_r, float rpc,
+                                                   float s, float inf, float tinf, float cur, float nxt, float ttn,
+                                                   int cls, float inv_tau, float dead, uint32_t key0, uint32_t key1,
+                                                   float* __restrict__ hist, float* __restrict__ deaths) {
+    const float rv = (beta_r * rpc) * hs;
+    const float house = lp.r_house ? rv : 0.0f;
+    const float plain = (gv + Lc) + (lp.r_house ? 0.0f : rv);
+    const float mq = kQuar ? quar_mask(p, cur) : 1.0f;
+    const float X = fmaf(mq, plain, house);  // pressure per unit susceptibility
+    const float lam = X * s;
+    const float q = not_infected_prob(lam, p.dt);
+    io.tape_v[a] = (s == 0.0f) ? X : lam;
+    // Gumbel-softmax hard draw from Philox bits (same stream as draw_step_noise):
+    // x0 - x1 = (ln2 / tau) * d,  d = lg2 q - lg2(1-q) - lg2 E0 + lg2 E1, E = -ln u (the ln2 factors cancel)
+    uint32_t r[4];
+    const uint64_t ga = p.agent_offset + a;  // global agent id = Philox counter
+    philox4x32_10((uint32_t)ga, (uint32_t)(ga >> 32), p.call_index, 0u, key0, key1, r);
+    const float d = (lg2_fast(q) - lg2_fast(1.0f - q)) -
+                    (lg2_fast(-lg2_fast(u01_open(r[0]))) - lg2_fast(-lg2_fast(u01_open(r[1]))));
+    const float e = ex2_fast(-fabsf(d) * inv_tau);  // exp(x_small - x_big) <= 1
+    const float ys = e * rcp_fast(1.0f + e);        // the smaller soft probability
+    const bool hit = (d < 0.0f) && (e < 1.0f);      // argmax of the softmax; ties -> not infected
+    const float n = hit ? 1.0f : 0.0f;
+    io.tape_y0[a] = hit ? -ys : ys;
+    if (kDiag) {
+      if (io.q) io.q[a] = q;
+      if (io.lam) io.lam[a] = lam;
+      if (io.n) io.n[a] = n;
+    }
+    // infect (model.py:103-110)
+    const float inf_o = inf + n;
+    io.s_o[a] = fmaxf(0.0f, s - n);
+    io.inf_o[a] = inf_o;
+    io.tinf_o[a] = tinf + n * (p.now - tinf);
+    // symptoms (symptoms.py:204-247)
+    const uint64_t seed = p.seed;
+    const uint32_t call = p.call_index;
+    const float uu = u01_half(r[2]);
+    const int age = age_of(cls);
+    const SympOut so = symptoms_forward(p, io.stage_prob, cur, nxt, ttn, n, age, [&]() { return uu; },
+                                        [&](int) { return draw_step_normal(seed, call, (int64_t)ga); });
+    io.cur_o[a] = so.cur;
+    io.nxt_o[a] = so.nxt;
+    io.ttn_o[a] = so.ttn;
+    // reductions (runner.py:167-171,198-224): small integers, exact in any order
+    if (inf_o != 0.0f) atomicAdd(&hist[age], inf_o);
+    if (so.cur == dead) atomicAdd(deaths, so.cur / dead);
+}
+
 // =====================================================================================================
 // K3  forward: pressure -> q -> draw -> state update -> symptoms -> reductions
 // =====================================================================================================
@@ -487,49 +542,8 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_FWD) k_lean_forward
         const float hs = lean_range_finish(rl[h], Tr, a, slot[h]);
         const float gv = lean_generic_finish(w, SP, ent[h], a, gen[h]);
         const float Lc = lp.n_cell > 0 ? L[cls[h]] : 0.0f;
-        const float rv = (beta_r * rpc[h]) * hs;
-        const float house = lp.r_house ? rv : 0.0f;
-        const float plain = (gv + Lc) + (lp.r_house ? 0.0f : rv);
-        const float mq = kQuar ? quar_mask(p, cur[h]) : 1.0f;
-        const float X = fmaf(mq, plain, house);  // pressure per unit susceptibility
-        const float lam = X * s[h];
-        const float q = not_infected_prob(lam, p.dt);
-        io.tape_v[a] = (s[h] == 0.0f) ? X : lam;
-        // Gumbel-softmax hard draw from Philox bits (same stream as draw_step_noise):
-        // x0 - x1 = (ln2 / tau) * d,  d = lg2 q - lg2(1-q) - lg2 E0 + lg2 E1, E = -ln u (the ln2 factors cancel)
-        uint32_t r[4];
-        const uint64_t ga = p.agent_offset + a;  // global agent id = Philox counter
-        philox4x32_10((uint32_t)ga, (uint32_t)(ga >> 32), p.call_index, 0u, key0, key1, r);
-        const float d = (lg2_fast(q) - lg2_fast(1.0f - q)) -
-                        (lg2_fast(-lg2_fast(u01_open(r[0]))) - lg2_fast(-lg2_fast(u01_open(r[1]))));
-        const float e = ex2_fast(-fabsf(d) * inv_tau);  // exp(x_small - x_big) <= 1
-        const float ys = e * rcp_fast(1.0f + e);        // the smaller soft probability
-        const bool hit = (d < 0.0f) && (e < 1.0f);      // argmax of the softmax; ties -> not infected
-        const float n = hit ? 1.0f : 0.0f;
-        io.tape_y0[a] = hit ? -ys : ys;
-        if (kDiag) {
-          if (io.q) io.q[a] = q;
-          if (io.lam) io.lam[a] = lam;
-          if (io.n) io.n[a] = n;
-        }
-        // infect (model.py:103-110)
-        const float inf_o = inf[h] + n;
-        io.s_o[a] = fmaxf(0.0f, s[h] - n);
-        io.inf_o[a] = inf_o;
-        io.tinf_o[a] = tinf[h] + n * (p.now - tinf[h]);
-        // symptoms (symptoms.py:204-247)
-        const uint64_t seed = p.seed;
-        const uint32_t call = p.call_index;
-        const float uu = u01_half(r[2]);
-        const int age = age_of(cls[h]);
-        const SympOut so = symptoms_forward(p, io.stage_prob, cur[h], nxt[h], ttn[h], n, age, [&]() { return uu; },
-                                            [&](int) { return draw_step_normal(seed, call, (int64_t)ga); });
-        io.cur_o[a] = so.cur;
-        io.nxt_o[a] = so.nxt;
-        io.ttn_o[a] = so.ttn;
-        // reductions (runner.py:167-171,198-224): small integers, exact in any order
-        if (inf_o != 0.0f) atomicAdd(&sh.hist[age], inf_o);
-        if (so.cur == dead) atomicAdd(&sh.deaths, so.cur / dead);
+        lean_forward_agent<kQuar, kDiag>(p, lp, io, a, hs, gv, Lc, beta_r, rpc[h], s[h], inf[h], tinf[h], cur[h], nxt[h],
+                                         ttn[h], cls[h], inv_tau, dead, key0, key1, sh.hist, &sh.deaths);
       }
     }
     tile = tend;
@@ -551,6 +565,75 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_FWD) k_lean_forward
     }
     finish_partials<kMaxRed>(nr, red_part, gridDim.x, ticket, io.red);
   }
+}
+
+// per-agent arithmetic of the backward pass (shared with gj_pipe.cuh): symptoms^T, infect^T, sampler^T, clamp/exp
+// chain -> cotangents of the state, w = dL/dLambda * s (and its quarantine-masked copy), cell-channel sums in acc
+template <bool kQuar>
+__device__ __forceinline__ void lean_backward_agent(const gj_step_params& p, const LeanPlan& lp, const gj_bwd_io& io,
+                                                    uint32_t a, float s, float tinf, float cur, float nxt, float ttn,
+                                                    float ty, float v, int cls, float gs_o, float ginf_o, float gtinf_o,
+                                                    float gcur_o, float gnxt_o, float gttn_o, float inv_tau, float dead,
+                                                    float g_deaths, const float* __restrict__ gred_age,
+                                                    const ProbRow* __restrict__ prob, float (&acc)[GJ_MAX_CHANNELS]) {
+    const int age = age_of(cls);
+    const float n = signbit(ty) ? 1.0f : 0.0f;  // the tape's sign bit is the draw
+    // symptoms^T: the draws are regenerated only for the few agents whose stage actually updates
+    const uint64_t seed = p.seed;
+    const uint32_t call = p.call_index;
+    const int64_t ga = (int64_t)p.agent_offset + a;
+    const SympOut so = symptoms_forward(p, io.stage_prob, cur, nxt, ttn, n, age,
+                                        [&]() { return draw_step_noise(seed, call, ga).u; },
+                                        [&](int) { return draw_step_normal(seed, call, ga); });
+    float gc = gcur_o;
+    if (so.cur == dead) gc += g_deaths;
+    float gcur1 = gc, gnxt1 = gnxt_o;
+    if (so.branch == 1) {
+      gcur1 += (gnxt_o + gttn_o * so.dwell) / (float)so.stage;
+    } else if (so.branch == 2) {
+      gcur1 += (gttn_o * so.dwell - gnxt_o * so.nxt1) / (float)so.stage;
+      gnxt1 = 0.0f;
+    }
+    const float g_cur = gcur1 * (1.0f - so.tr);
+    gnxt1 += gcur1 * so.tr;
+    const float g_nxt = gnxt1 * (1.0f - n);
+    const float g_ttn = gttn_o * (1.0f - n);
+    float gn = gnxt1 * (2.0f - nxt) + gttn_o * (p.now - ttn);
+    // reductions and infect^T
+    const float gi = ginf_o + gred_age[age];
+    const float dd = s - n;
+    const float wgt = (dd > 0.0f) ? 1.0f : ((dd == 0.0f) ? 0.5f : 0.0f);  // maximum(0, x): ties split 1/2
+    float g_s = gs_o * wgt;
+    gn += -(gs_o * wgt) + gi + gtinf_o * (p.now - tinf);
+    const float g_tinf = gtinf_o * (1.0f - n);
+    // sampler^T and the clamp / exp chain: dL/dq = gl0/q - gl1/(1-q), dL/dLambda = dL/dq * q * (-dt)
+    // evaluated as (gl1 * q/(1-q) - gl0) * dt
+    const float lam = (s == 0.0f) ? 0.0f : v;
+    const float q = not_infected_prob(lam, p.dt);
+    float y0, y1;
+    decode_soft(ty, y0, y1);
+    const float gret0 = -gn;
+    const float dot = gret0 * y0;
+    const float gl0 = ((gret0 - dot) * y0) * inv_tau, gl1 = ((0.0f - dot) * y1) * inv_tau;
+    float glam = 0.0f;
+    if (lam >= 1e-6f && lam <= 100.0f) glam = (gl1 * (q * rcp_fast(1.0f - q)) - gl0) * p.dt;
+    const float X = (s == 0.0f) ? v : ((s == 1.0f) ? v : v * rcp_fast(s));
+    g_s += glam * X;
+    // outputs
+    const float wv = glam * s;
+    io.w[a] = wv;
+    float wqv = wv;
+    if (kQuar) {
+      wqv = glam * (quar_mask(p, cur) * s);
+      io.wq[a] = wqv;
+    }
+    if (wqv != 0.0f && lp.n_cell > 0) lean_channel_fma(acc, prob, cls, wqv, lp.n_cell);
+    if (io.g_s) io.g_s[a] = g_s;
+    io.g_inf[a] = gi;
+    io.g_tinf[a] = g_tinf;
+    if (io.g_cur) io.g_cur[a] = g_cur;
+    if (io.g_nxt) io.g_nxt[a] = g_nxt;
+    if (io.g_ttn) io.g_ttn[a] = g_ttn;
 }
 
 // =====================================================================================================
@@ -628,64 +711,9 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_BWD) k_lean_backwar
       for (int h = 0; h < kLeanBatch; ++h) {
         const uint32_t a = base + h * kLeanThreads;
         if (a >= a1) break;
-        const int age = age_of(cls[h]);
-        const float n = signbit(ty[h]) ? 1.0f : 0.0f;  // the tape's sign bit is the draw
-        // symptoms^T: the draws are regenerated only for the few agents whose stage actually updates
-        const uint64_t seed = p.seed;
-        const uint32_t call = p.call_index;
-        const int64_t ga = (int64_t)p.agent_offset + a;
-        const SympOut so = symptoms_forward(p, io.stage_prob, cur[h], nxt[h], ttn[h], n, age,
-                                            [&]() { return draw_step_noise(seed, call, ga).u; },
-                                            [&](int) { return draw_step_normal(seed, call, ga); });
-        float gc = gcur_o[h];
-        if (so.cur == dead) gc += g_deaths;
-        float gcur1 = gc, gnxt1 = gnxt_o[h];
-        if (so.branch == 1) {
-          gcur1 += (gnxt_o[h] + gttn_o[h] * so.dwell) / (float)so.stage;
-        } else if (so.branch == 2) {
-          gcur1 += (gttn_o[h] * so.dwell - gnxt_o[h] * so.nxt1) / (float)so.stage;
-          gnxt1 = 0.0f;
-        }
-        const float g_cur = gcur1 * (1.0f - so.tr);
-        gnxt1 += gcur1 * so.tr;
-        const float g_nxt = gnxt1 * (1.0f - n);
-        const float g_ttn = gttn_o[h] * (1.0f - n);
-        float gn = gnxt1 * (2.0f - nxt[h]) + gttn_o[h] * (p.now - ttn[h]);
-        // reductions and infect^T
-        const float gi = ginf_o[h] + gred_age[age];
-        const float dd = s[h] - n;
-        const float wgt = (dd > 0.0f) ? 1.0f : ((dd == 0.0f) ? 0.5f : 0.0f);  // maximum(0, x): ties split 1/2
-        float g_s = gs_o[h] * wgt;
-        gn += -(gs_o[h] * wgt) + gi + gtinf_o[h] * (p.now - tinf[h]);
-        const float g_tinf = gtinf_o[h] * (1.0f - n);
-        // sampler^T and the clamp / exp chain: dL/dq = gl0/q - gl1/(1-q), dL/dLambda = dL/dq * q * (-dt)
-        // evaluated as (gl1 * q/(1-q) - gl0) * dt
-        const float lam = (s[h] == 0.0f) ? 0.0f : v[h];
-        const float q = not_infected_prob(lam, p.dt);
-        float y0, y1;
-        decode_soft(ty[h], y0, y1);
-        const float gret0 = -gn;
-        const float dot = gret0 * y0;
-        const float gl0 = ((gret0 - dot) * y0) * inv_tau, gl1 = ((0.0f - dot) * y1) * inv_tau;
-        float glam = 0.0f;
-        if (lam >= 1e-6f && lam <= 100.0f) glam = (gl1 * (q * rcp_fast(1.0f - q)) - gl0) * p.dt;
-        const float X = (s[h] == 0.0f) ? v[h] : ((s[h] == 1.0f) ? v[h] : v[h] * rcp_fast(s[h]));
-        g_s += glam * X;
-        // outputs
-        const float wv = glam * s[h];
-        io.w[a] = wv;
-        float wqv = wv;
-        if (kQuar) {
-          wqv = glam * (quar_mask(p, cur[h]) * s[h]);
-          io.wq[a] = wqv;
-        }
-        if (wqv != 0.0f && lp.n_cell > 0) lean_channel_fma(acc, prob, cls[h], wqv, lp.n_cell);
-        if (io.g_s) io.g_s[a] = g_s;
-        io.g_inf[a] = gi;
-        io.g_tinf[a] = g_tinf;
-        if (io.g_cur) io.g_cur[a] = g_cur;
-        if (io.g_nxt) io.g_nxt[a] = g_nxt;
-        if (io.g_ttn) io.g_ttn[a] = g_ttn;
+        lean_backward_agent<kQuar>(p, lp, io, a, s[h], tinf[h], cur[h], nxt[h], ttn[h], ty[h], v[h], cls[h], gs_o[h],
+                                   ginf_o[h], gtinf_o[h], gcur_o[h], gnxt_o[h], gttn_o[h], inv_tau, dead, g_deaths,
+                                   gred_age, prob, acc);
       }
     }
     if (lp.n_cell > 0) {
@@ -699,6 +727,28 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_BWD) k_lean_backwar
       }
     }
   }
+}
+
+// per-agent arithmetic of the backward gather (shared with gj_pipe.cuh): dL/dT from the three tiers ->
+// cotangents of (is_infected, infection_time); db accumulates the range-tier network's d/dbeta terms.
+// R = sum of w over the agent's range-tier group, gv = combined cR of its generic groups, Lc = class-table value
+template <bool kQuar>
+__device__ __forceinline__ void lean_gather_agent(const gj_step_params& p, const LeanPlan& lp, const gj_bwd_io& io,
+                                                  uint32_t a, float R, float gv, float Lc, float beta_r, float rpc,
+                                                  float Tm, float cur, float inf, float tinf, float4 pf, float gi,
+                                                  float gt, double& db) {
+    const float mq = kQuar ? quar_mask(p, cur) : 1.0f;
+    const float pr = rpc * R;
+    if (pr != 0.0f) db += (double)((kQuar && !lp.r_house) ? mq * Tm : Tm) * (double)pr;
+    const float rv = beta_r * pr;
+    const float house = lp.r_house ? rv : 0.0f;
+    const float plain = (gv + Lc) + (lp.r_house ? 0.0f : rv);
+    const float gT = fmaf(mq, plain, house);
+    if (gT != 0.0f) {
+      const TransTerms tt = lean_transmission<true>(p.now, tinf, pf);
+      io.g_inf[a] = gi + gT * tt.coef;
+      io.g_tinf[a] = gt + gT * (tt.dcoef * inf);
+    }
 }
 
 // =====================================================================================================
@@ -783,18 +833,8 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_GATHER) k_lean_back
         if (a >= a1) break;
         const float R = lean_range_finish(rl[h], wr, a, slot[h]);
         const float gv = lean_generic_finish(w, cRP, ent[h], a, gen[h]);
-        const float mq = kQuar ? quar_mask(p, cur[h]) : 1.0f;
-        const float pr = rpc[h] * R;
-        if (pr != 0.0f) db[0] += (double)((kQuar && !lp.r_house) ? mq * Tm[h] : Tm[h]) * (double)pr;
-        const float rv = beta_r * pr;
-        const float house = lp.r_house ? rv : 0.0f;
-        const float plain = (gv + (lp.n_cell > 0 ? L[cls[h]] : 0.0f)) + (lp.r_house ? 0.0f : rv);
-        const float gT = fmaf(mq, plain, house);
-        if (gT != 0.0f) {
-          const TransTerms tt = lean_transmission<true>(p.now, tinf[h], pf[h]);
-          io.g_inf[a] = gi[h] + gT * tt.coef;
-          io.g_tinf[a] = gt[h] + gT * (tt.dcoef * inf[h]);
-        }
+        lean_gather_agent<kQuar>(p, lp, io, a, R, gv, lp.n_cell > 0 ? L[cls[h]] : 0.0f, beta_r, rpc[h], Tm[h], cur[h],
+                                 inf[h], tinf[h], pf[h], gi[h], gt[h], db[0]);
       }
     }
     tile = tend;

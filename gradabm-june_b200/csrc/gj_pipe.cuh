@@ -1,0 +1,477 @@
+// Bulk-copy pipelined variants of the throughput-mode agent kernels (included by gj_kernels.cu after gj_lean.cuh).
+//
+// The register-batched kernels of gj_lean.cuh are latency-bound: every streaming operand is an LDG whose latency a
+// thread has to sit out with at most two agents in flight (ncu, profiles/r1_lean_v3_56M_*: 40-65 % of the stall
+// samples are long-scoreboard waits at the first use of a loaded value, 35-47 % occupancy).  Here a persistent
+// CTA of 512 threads walks its run of agent tiles (<= 1024 agents each) with a two-stage shared-memory pipeline:
+// one elected thread issues, per tile, one `cp.async.bulk` (TMA 1-D bulk copy, completion counted in bytes on an
+// mbarrier) for each per-agent array of the tile — state, tapes, cotangents, index words, class bytes, packed
+// profile, and the member values of the range-tier (household) network with a halo for the neighbours — while all
+// warps compute the previous tile out of shared memory, two agents per thread.  Memory-level parallelism is then set
+// by the bytes in flight per SM (2 CTAs x 2-3 tiles x 21-30 KB), not by registers x occupancy, and the only global
+// loads left in the agent loop are the L2-resident gathers of the generic groups' sums.  The arithmetic is
+// lean_forward_agent() / lean_backward_agent() / lean_gather_agent() of gj_lean.cuh: results are bit-identical to
+// the register-batched kernels (tests/test_gpu_scale.py::test_pipelined_kernels_are_bit_identical).
+//
+// Requirements checked by the launcher (else the gj_lean.cuh kernels run): every per-agent array 16-byte aligned.
+// Bulk copies move 16-byte granules, so a tile's copy starts at the preceding and ends at the following multiple of
+// four agents (sixteen for the class bytes); at the end of an array this reads up to 12 bytes past its last
+// element — inside the allocation granule of every allocator we are called with (documented in the header).
+#pragma once
+#include "gj_lean.cuh"
+
+namespace gj {
+
+constexpr int kPipeThreads = 512;
+constexpr int kPipeTile = GJ_TILE_AGENTS;  // agents per stage (a world tile)
+constexpr int kPipeHalo = 64;              // >= RANGE_MAX_GROUP - 1 of the world builder
+constexpr int kPipeStages = 2;
+constexpr int kPipeWarps = kPipeThreads / 32;
+constexpr int kPipePer = kPipeTile / kPipeThreads;  // agents per thread and tile, processed interleaved (ILP)
+static_assert(kPipePer * kPipeThreads == kPipeTile, "tile = whole agents per thread");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16; both addresses 16-byte aligned), completion on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- the copies of one tile ---------------------------------------------------------------------------------
+// 4-byte arrays: agents [lo4, hi4) (multiples of four around [a0, a1)); element a sits at index a - lo4
+struct TileSpan {
+  uint32_t a0, a1, lo4, hi4, n4;   // n4 = bytes of a 4-byte array's copy
+  uint32_t tlo, thi;               // window of the range-tier member values (halo on both sides)
+  uint32_t lo16, hi16;             // class bytes
+};
+__device__ __forceinline__ TileSpan tile_span(const gj_world_desc& w, int64_t tile) {
+  TileSpan t;
+  t.a0 = w.tile_begin[tile];
+  t.a1 = w.tile_begin[tile + 1];
+  t.lo4 = t.a0 & ~3u;
+  t.hi4 = (t.a1 + 3u) & ~3u;
+  t.n4 = (t.hi4 - t.lo4) * 4u;
+  const uint32_t nmax = (uint32_t)((w.n_agents + 3) & ~(int64_t)3);
+  t.tlo = (t.a0 > (uint32_t)kPipeHalo ? t.a0 - kPipeHalo : 0u) & ~3u;
+  t.thi = (t.a1 + kPipeHalo + 3u) & ~3u;
+  if (t.thi > nmax) t.thi = nmax;
+  t.lo16 = t.a0 & ~15u;
+  t.hi16 = (t.a1 + 15u) & ~15u;
+  return t;
+}
+__device__ __forceinline__ uint32_t halo_lo(uint32_t a0) { return (a0 > (uint32_t)kPipeHalo ? a0 - kPipeHalo : 0u) & ~3u; }
+
+struct Copier {   // one elected thread: sums the bytes first (expect_tx must precede the copies' completion)
+  uint64_t* bar;
+  __device__ __forceinline__ void f4(void* dst, const void* base, const TileSpan& t) const {
+    bulk_g2s(dst, reinterpret_cast<const char*>(base) + (size_t)t.lo4 * 4u, t.n4, bar);
+  }
+};
+
+// sum of the member values of agent a's range-tier group out of the staged window (same order as
+// lean_range_issue / lean_range_finish)
+__device__ __forceinline__ float pipe_range_sum(const float* __restrict__ Ts, uint32_t tlo, uint32_t a, uint32_t slot) {
+  if (slot == kNoSlot) return 0.0f;
+  const uint32_t b0 = a - (slot >> 16) - tlo;
+  const int nb = (int)(slot & 0xFFFFu);
+  float x[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] = (j < nb) ? Ts[b0 + j] : 0.0f;
+  float S = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+  for (int j = 8; j < nb; ++j) S += Ts[b0 + j];
+  return S;
+}
+
+constexpr int kPipeF = kPipeTile + 8;                     // floats of a staged 4-byte array
+constexpr int kPipeH = kPipeTile + 2 * kPipeHalo + 8;     // ... with the halo
+
+__device__ __forceinline__ void pipe_init_barriers(uint64_t* full) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kPipeStages; ++i) mbar_init(&full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+}
+
+// =====================================================================================================
+// K3p  forward
+// =====================================================================================================
+struct alignas(16) PipeFwdStage {
+  float s[kPipeF], inf[kPipeF], tinf[kPipeF], cur[kPipeF], nxt[kPipeF], ttn[kPipeF], rpc[kPipeF];
+  uint32_t ent[kPipeF], slot[kPipeF];
+  float T[kPipeH];
+  uint8_t cls[kPipeTile + 32];
+};
+struct PipeFwdShared {
+  PipeFwdStage st[kPipeStages];
+  ProbRow prob[200];
+  float L[2][200];
+  float beta[GJ_MAX_NETS];
+  float hist[100];
+  float deaths;
+  alignas(8) uint64_t full[kPipeStages];
+};
+
+__device__ __forceinline__ void pipe_fwd_issue(PipeFwdStage& sg, uint64_t* bar, const gj_world_desc& w,
+                                               const LeanPlan& lp, const gj_fwd_io& io, const float* Tr, int64_t tile,
+                                               bool has_gen, bool has_range) {
+  const TileSpan t = tile_span(w, tile);
+  uint32_t total = 6u * t.n4 + (t.hi16 - t.lo16);
+  if (has_gen) total += t.n4;
+  if (has_range) total += 2u * t.n4 + (t.thi - t.tlo) * 4u;
+  mbar_expect_tx(bar, total);
+  const Copier c{bar};
+  c.f4(sg.s, io.s, t);
+  c.f4(sg.inf, io.inf, t);
+  c.f4(sg.tinf, io.tinf, t);
+  c.f4(sg.cur, io.cur, t);
+  c.f4(sg.nxt, io.nxt, t);
+  c.f4(sg.ttn, io.ttn, t);
+  if (has_gen) c.f4(sg.ent, w.ent1, t);
+  if (has_range) {
+    c.f4(sg.slot, lp.r_slot, t);
+    c.f4(sg.rpc, lp.r_pc, t);
+    bulk_g2s(sg.T, Tr + t.tlo, (t.thi - t.tlo) * 4u, bar);
+  }
+  bulk_g2s(sg.cls, w.cls + t.lo16, t.hi16 - t.lo16, bar);
+}
+
+template <bool kQuar, bool kDiag>
+__global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc w, gj_step_params p, LeanPlan lp,
+                                                                 gj_fwd_io io, const float* __restrict__ cell_buf,
+                                                                 double* __restrict__ red_part,
+                                                                 unsigned int* __restrict__ ticket) {
+  extern __shared__ __align__(128) unsigned char pipe_smem[];
+  PipeFwdShared& sh = *reinterpret_cast<PipeFwdShared*>(pipe_smem);
+  const TileRun run = lean_tiles(w);
+  const float* __restrict__ Tr = (kQuar && !lp.r_house) ? io.Tq : io.T;
+  const bool has_gen = lp.has_generic != 0, has_range = lp.n_range > 0;
+  pipe_init_barriers(sh.full);
+  lean_load_prob<true>(sh.prob, p, lp, io.leisure_prob);
+  if (threadIdx.x < p.n_nets) sh.beta[threadIdx.x] = io.beta[threadIdx.x];
+  if (threadIdx.x < 100) sh.hist[threadIdx.x] = 0.0f;
+  if (threadIdx.x == 0) sh.deaths = 0.0f;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kPipeStages; ++i)
+      if (run.t0 + i < run.t1) pipe_fwd_issue(sh.st[i], &sh.full[i], w, lp, io, Tr, run.t0 + i, has_gen, has_range);
+  }
+  const float* __restrict__ SP = io.S_scaled + lp.gen_base;
+  const float dead = (float)(p.n_stages - 1);
+  const float inv_tau = 1.0f / p.tau;
+  const uint32_t key0 = (uint32_t)p.seed, key1 = (uint32_t)(p.seed >> 32);
+  const float beta_r = lp.n_range > 0 ? sh.beta[lp.r_net] : 0.0f;
+
+  int nbuild = 0, stg = 0;
+  uint32_t parity = 0;
+  const float* L = sh.L[0];
+  for (int64_t tile = run.t0; tile < run.t1; ++tile) {
+    PipeFwdStage& sg = sh.st[stg];
+    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];
+    if (lp.n_cell > 0 && (tile == run.t0 || lean_new_cell(lp, tile - 1, tile))) {
+      // rebuilt in the other buffer: a buffer is rewritten two rebuilds later, after the barriers in between
+      lean_class_table(sh.L[nbuild & 1], sh.prob, lp, cell_buf, tile);
+      L = sh.L[nbuild & 1];
+      ++nbuild;
+      __syncthreads();
+    }
+    mbar_wait(&sh.full[stg], parity);
+    const uint32_t sk = a0 & 3u, sk16 = a0 & 15u, tlo = halo_lo(a0);
+    uint32_t ent[kPipePer];
+    float gen[kPipePer];
+#pragma unroll
+    for (int h = 0; h < kPipePer; ++h) {   // the L2 gathers first, for all of this thread's agents
+      const uint32_t j = threadIdx.x + h * kPipeThreads;
+      ent[h] = (has_gen && a0 + j < a1) ? sg.ent[j + sk] : kEntNone;
+      gen[h] = lean_generic_issue(SP, ent[h]);
+    }
+#pragma unroll
+    for (int h = 0; h < kPipePer; ++h) {
+      const uint32_t j = threadIdx.x + h * kPipeThreads;
+      const uint32_t a = a0 + j, i = j + sk;
+      if (a >= a1) break;
+      const float hs = has_range ? pipe_range_sum(sg.T, tlo, a, sg.slot[i]) : 0.0f;
+      const int cls = sg.cls[j + sk16];
+      const float Lc = lp.n_cell > 0 ? L[cls] : 0.0f;
+      const float gv = lean_generic_finish(w, SP, ent[h], a, gen[h]);
+      lean_forward_agent<kQuar, kDiag>(p, lp, io, a, hs, gv, Lc, beta_r, has_range ? sg.rpc[i] : 0.0f, sg.s[i], sg.inf[i],
+                                       sg.tinf[i], sg.cur[i], sg.nxt[i], sg.ttn[i], cls, inv_tau, dead, key0, key1,
+                                       sh.hist, &sh.deaths);
+    }
+    __syncthreads();  // every warp is done with this stage: refill it with the tile kPipeStages ahead
+    if (threadIdx.x == 0 && tile + kPipeStages < run.t1)
+      pipe_fwd_issue(sg, &sh.full[stg], w, lp, io, Tr, tile + kPipeStages, has_gen, has_range);
+    if (++stg == kPipeStages) {
+      stg = 0;
+      parity ^= 1u;
+    }
+  }
+  if (io.red) {
+    __syncthreads();
+    const int nr = 2 + p.n_age_bins;
+    if ((int)threadIdx.x < nr) {
+      double v = 0.0;
+      if (threadIdx.x == 0) {
+        for (int c = 0; c < 100; ++c) v += (double)sh.hist[c];
+      } else if (threadIdx.x == 1) {
+        v = (double)sh.deaths;
+      } else {
+        const int b = threadIdx.x - 2;
+        for (int c = max(p.age_bins[b] + 1, 0); c < p.age_bins[b + 1] && c < 100; ++c) v += (double)sh.hist[c];
+      }
+      red_part[(int64_t)blockIdx.x * kMaxRed + threadIdx.x] = v;
+    }
+    finish_partials<kMaxRed>(nr, red_part, gridDim.x, ticket, io.red);
+  }
+}
+
+// =====================================================================================================
+// B1p  backward, per agent
+// =====================================================================================================
+struct alignas(16) PipeBwdStage {
+  float s[kPipeF], tinf[kPipeF], cur[kPipeF], nxt[kPipeF], ttn[kPipeF], ty[kPipeF], v[kPipeF];
+  uint8_t cls[kPipeTile + 32];
+};
+struct PipeBwdShared {
+  PipeBwdStage st[kPipeStages];
+  ProbRow prob[200];
+  float gred_age[100];
+  alignas(8) uint64_t full[kPipeStages];
+};
+struct BwdCot {
+  const float* p[6];
+};
+
+__device__ __forceinline__ void pipe_bwd_issue(PipeBwdStage& sg, uint64_t* bar, const gj_world_desc& w,
+                                               const gj_bwd_io& io, int64_t tile) {
+  const TileSpan t = tile_span(w, tile);
+  const uint32_t total = 7u * t.n4 + (t.hi16 - t.lo16);
+  mbar_expect_tx(bar, total);
+  const Copier c{bar};
+  c.f4(sg.s, io.s, t);
+  c.f4(sg.tinf, io.tinf, t);
+  c.f4(sg.cur, io.cur, t);
+  c.f4(sg.nxt, io.nxt, t);
+  c.f4(sg.ttn, io.ttn, t);
+  c.f4(sg.ty, io.tape_y0, t);
+  c.f4(sg.v, io.tape_v, t);
+  bulk_g2s(sg.cls, w.cls + t.lo16, t.hi16 - t.lo16, bar);
+}
+
+template <bool kQuar>
+__global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward(gj_world_desc w, gj_step_params p, LeanPlan lp,
+                                                                  gj_bwd_io io, float* __restrict__ tile_part) {
+  extern __shared__ __align__(128) unsigned char pipe_smem[];
+  PipeBwdShared& sh = *reinterpret_cast<PipeBwdShared*>(pipe_smem);
+  const TileRun run = lean_tiles(w);
+  const BwdCot cot{{io.g_s_o, io.g_inf_o, io.g_tinf_o, io.g_cur_o, io.g_nxt_o, io.g_ttn_o}};
+  pipe_init_barriers(sh.full);
+  lean_load_prob<true>(sh.prob, p, lp, io.leisure_prob);
+  if (threadIdx.x < 100) {
+    float g = 0.0f;
+    if (io.g_red) {
+      g = io.g_red[0];
+      const int age = threadIdx.x;
+      for (int b = 0; b < p.n_age_bins; ++b)
+        if (age > p.age_bins[b] && age < p.age_bins[b + 1]) g += io.g_red[2 + b];
+    }
+    sh.gred_age[threadIdx.x] = g;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kPipeStages; ++i)
+      if (run.t0 + i < run.t1) pipe_bwd_issue(sh.st[i], &sh.full[i], w, io, run.t0 + i);
+  }
+  const float dead = (float)(p.n_stages - 1);
+  const float g_deaths = io.g_red ? io.g_red[1] / dead : 0.0f;
+  const float inv_tau = 1.0f / p.tau;
+  float acc[GJ_MAX_CHANNELS];
+#pragma unroll
+  for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
+  int stg = 0;
+  uint32_t parity = 0;
+  for (int64_t tile = run.t0; tile < run.t1; ++tile) {
+    PipeBwdStage& sg = sh.st[stg];
+    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];
+    // the cotangents of the state outputs stream through registers (issued before the wait on the staged tile)
+    float c[kPipePer][6];
+#pragma unroll
+    for (int h = 0; h < kPipePer; ++h) {
+      const uint32_t a = a0 + threadIdx.x + h * kPipeThreads;
+      const uint32_t al = a < a1 ? a : a0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) c[h][k] = cot.p[k] ? cot.p[k][al] : 0.0f;
+    }
+    mbar_wait(&sh.full[stg], parity);
+    const uint32_t sk = a0 & 3u, sk16 = a0 & 15u;
+#pragma unroll
+    for (int h = 0; h < kPipePer; ++h) {
+      const uint32_t j = threadIdx.x + h * kPipeThreads;
+      const uint32_t a = a0 + j, i = j + sk;
+      if (a >= a1) break;
+      lean_backward_agent<kQuar>(p, lp, io, a, sg.s[i], sg.tinf[i], sg.cur[i], sg.nxt[i], sg.ttn[i], sg.ty[i], sg.v[i],
+                                 sg.cls[j + sk16], c[h][0], c[h][1], c[h][2], c[h][3], c[h][4], c[h][5], inv_tau, dead,
+                                 g_deaths, sh.gred_age, sh.prob, acc);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && tile + kPipeStages < run.t1)
+      pipe_bwd_issue(sg, &sh.full[stg], w, io, tile + kPipeStages);
+    if (++stg == kPipeStages) {
+      stg = 0;
+      parity ^= 1u;
+    }
+    if (lp.n_cell > 0) {   // partial sums of the cell channels: written at the last tile of a cell run (see K1)
+      const bool flush = (tile + 1 == run.t1) || lean_new_cell(lp, tile, tile + 1);
+      if (flush) {
+        block_sums<float, GJ_MAX_CHANNELS, kPipeWarps>(acc, lp.n_cell, tile_part + tile * GJ_MAX_CHANNELS);
+#pragma unroll
+        for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
+      } else if ((int)threadIdx.x < lp.n_cell) {
+        tile_part[tile * GJ_MAX_CHANNELS + threadIdx.x] = 0.0f;
+      }
+    }
+  }
+}
+
+// =====================================================================================================
+// B3p  backward gather
+// =====================================================================================================
+struct alignas(16) PipeGatStage {
+  float rpc[kPipeF], Tm[kPipeF], cur[kPipeF], inf[kPipeF], tinf[kPipeF];
+  uint32_t ent[kPipeF], slot[kPipeF];
+  float wr[kPipeH];
+  uint8_t cls[kPipeTile + 32];
+};
+struct PipeGatShared {
+  PipeGatStage st[kPipeStages];
+  ProbRow prob[200];
+  float L[2][200];
+  float beta[GJ_MAX_NETS];
+  alignas(8) uint64_t full[kPipeStages];
+};
+
+template <bool kQuar>
+__device__ __forceinline__ void pipe_gat_issue(PipeGatStage& sg, uint64_t* bar, const gj_world_desc& w,
+                                               const LeanPlan& lp, const gj_bwd_io& io, const float* wr, int64_t tile,
+                                               bool has_gen, bool has_range) {
+  const TileSpan t = tile_span(w, tile);
+  uint32_t total = 2u * t.n4 + (t.hi16 - t.lo16);
+  if (kQuar) total += t.n4;
+  if (has_gen) total += t.n4;
+  if (has_range) total += 3u * t.n4 + (t.thi - t.tlo) * 4u;
+  mbar_expect_tx(bar, total);
+  const Copier c{bar};
+  c.f4(sg.inf, io.inf, t);
+  c.f4(sg.tinf, io.tinf, t);
+  if (kQuar) c.f4(sg.cur, io.cur, t);
+  if (has_gen) c.f4(sg.ent, w.ent1, t);
+  if (has_range) {
+    c.f4(sg.slot, lp.r_slot, t);
+    c.f4(sg.rpc, lp.r_pc, t);
+    c.f4(sg.Tm, io.T_in, t);
+    bulk_g2s(sg.wr, wr + t.tlo, (t.thi - t.tlo) * 4u, bar);
+  }
+  bulk_g2s(sg.cls, w.cls + t.lo16, t.hi16 - t.lo16, bar);
+}
+
+template <bool kQuar>
+__global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward_gather(gj_world_desc w, gj_step_params p,
+                                                                         LeanPlan lp, gj_bwd_io io,
+                                                                         const float* __restrict__ cell_buf,
+                                                                         double* __restrict__ dbeta_part) {
+  extern __shared__ __align__(128) unsigned char pipe_smem[];
+  PipeGatShared& sh = *reinterpret_cast<PipeGatShared*>(pipe_smem);
+  const TileRun run = lean_tiles(w);
+  const float* __restrict__ wr = (kQuar && !lp.r_house) ? io.wq : io.w;  // member values of the range network
+  const bool has_gen = lp.has_generic != 0, has_range = lp.n_range > 0;
+  pipe_init_barriers(sh.full);
+  lean_load_prob<false>(sh.prob, p, lp, io.leisure_prob);
+  if (threadIdx.x < p.n_nets) sh.beta[threadIdx.x] = io.beta[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kPipeStages; ++i)
+      if (run.t0 + i < run.t1) pipe_gat_issue<kQuar>(sh.st[i], &sh.full[i], w, lp, io, wr, run.t0 + i, has_gen, has_range);
+  }
+  const float* __restrict__ cRP = io.cR + lp.gen_base;
+  const float4* __restrict__ prof = reinterpret_cast<const float4*>(io.prof4);
+  const float beta_r = lp.n_range > 0 ? sh.beta[lp.r_net] : 0.0f;
+  double db[1] = {0.0};
+  int nbuild = 0, stg = 0;
+  uint32_t parity = 0;
+  const float* L = sh.L[0];
+  for (int64_t tile = run.t0; tile < run.t1; ++tile) {
+    PipeGatStage& sg = sh.st[stg];
+    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];
+    if (lp.n_cell > 0 && (tile == run.t0 || lean_new_cell(lp, tile - 1, tile))) {
+      lean_class_table(sh.L[nbuild & 1], sh.prob, lp, cell_buf, tile);
+      L = sh.L[nbuild & 1];
+      ++nbuild;
+      __syncthreads();
+    }
+    // the packed profile and the two read-modify-write cotangents stream through registers
+    float4 pf[kPipePer];
+    float gi[kPipePer], gt[kPipePer];
+#pragma unroll
+    for (int h = 0; h < kPipePer; ++h) {
+      const uint32_t a = a0 + threadIdx.x + h * kPipeThreads;
+      const uint32_t al = a < a1 ? a : a0;
+      pf[h] = prof[al];
+      gi[h] = io.g_inf[al];
+      gt[h] = io.g_tinf[al];
+    }
+    mbar_wait(&sh.full[stg], parity);
+    const uint32_t sk = a0 & 3u, sk16 = a0 & 15u, tlo = halo_lo(a0);
+    uint32_t ent[kPipePer];
+    float gen[kPipePer];
+#pragma unroll
+    for (int h = 0; h < kPipePer; ++h) {
+      const uint32_t j = threadIdx.x + h * kPipeThreads;
+      ent[h] = (has_gen && a0 + j < a1) ? sg.ent[j + sk] : kEntNone;
+      gen[h] = lean_generic_issue(cRP, ent[h]);
+    }
+#pragma unroll
+    for (int h = 0; h < kPipePer; ++h) {
+      const uint32_t j = threadIdx.x + h * kPipeThreads;
+      const uint32_t a = a0 + j, i = j + sk;
+      if (a >= a1) break;
+      const float R = has_range ? pipe_range_sum(sg.wr, tlo, a, sg.slot[i]) : 0.0f;
+      const int cls = sg.cls[j + sk16];
+      const float Lc = lp.n_cell > 0 ? L[cls] : 0.0f;
+      const float gv = lean_generic_finish(w, cRP, ent[h], a, gen[h]);
+      lean_gather_agent<kQuar>(p, lp, io, a, R, gv, Lc, beta_r, has_range ? sg.rpc[i] : 0.0f,
+                               has_range ? sg.Tm[i] : 0.0f, kQuar ? sg.cur[i] : 0.0f, sg.inf[i], sg.tinf[i], pf[h],
+                               gi[h], gt[h], db[0]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && tile + kPipeStages < run.t1)
+      pipe_gat_issue<kQuar>(sg, &sh.full[stg], w, lp, io, wr, tile + kPipeStages, has_gen, has_range);
+    if (++stg == kPipeStages) {
+      stg = 0;
+      parity ^= 1u;
+    }
+  }
+  if (lp.n_range > 0)
+    block_sums<double, 1, kPipeWarps>(db, 1, dbeta_part + (int64_t)blockIdx.x * GJ_MAX_RANGE_NETS);
+}
+
+}  // namespace gj

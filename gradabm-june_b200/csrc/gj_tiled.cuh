@@ -65,9 +65,9 @@ __device__ __forceinline__ float member_value(const TileTables& tb, const Plan& 
 }
 
 // block-wide sums of up to kR values; result valid in threads [0, nr) of warp 0 ... written by the caller's lambda
-template <typename T, int kR>
+template <typename T, int kR, int kWarps = kBlock / 32>
 __device__ __forceinline__ void block_sums(T (&v)[kR], int nr, T* __restrict__ out /* [nr] global */) {
-  __shared__ T sm[kBlock / 32][kR];
+  __shared__ T sm[kWarps][kR];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int r = 0; r < kR; ++r)
@@ -81,7 +81,7 @@ __device__ __forceinline__ void block_sums(T (&v)[kR], int nr, T* __restrict__ o
   if (threadIdx.x < nr) {
     T s = (T)0;
 #pragma unroll
-    for (int k = 0; k < kBlock / 32; ++k) s += sm[k][threadIdx.x];
+    for (int k = 0; k < kWarps; ++k) s += sm[k][threadIdx.x];
     out[threadIdx.x] = s;
   }
   __syncthreads();

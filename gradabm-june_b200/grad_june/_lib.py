@@ -188,8 +188,14 @@ def check(rc, what):
 EXPORTED_SYMBOLS = [
     "gj_abi_version", "gj_last_error", "gj_config", "gj_scratch_bytes", "gj_profile_prepare", "gj_profile_pack",
     "gj_transmission_forward", "gj_transmission_backward", "gj_step_forward", "gj_step_backward",
-    "gj_philox_fill", "gj_philox_fill_at", "gj_step_plan", "gj_philox4x32_10", "gj_profile_enable", "gj_profile_read", "gj_profile_kernel_name",
+    "gj_philox_fill", "gj_philox_fill_at", "gj_step_plan", "gj_philox4x32_10", "gj_profile_enable", "gj_profile_read",
+    "gj_profile_kernel_name", "gj_pipeline_enable",
 ]
+
+
+def pipeline_enable(on=True):
+    """Bulk-copy pipelined agent kernels on/off (bit-identical results); returns the previous setting."""
+    return bool(lib().gj_pipeline_enable(-1 if on is None else (1 if on else 0)))
 
 
 def profile_enable(on=True):

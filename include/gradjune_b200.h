@@ -289,6 +289,13 @@ int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fw
 /* reverse-mode derivative of gj_step_forward (replaces autograd's replay of the op tape) */
 int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_bwd_io* io, void* stream);
 
+/* ---- kernel family of the throughput mode -------------------------------------------------------
+ * 1 (default; GJ_PIPE=0 in the environment turns it off): the agent kernels stage every per-agent array of a tile
+ * in shared memory with TMA bulk copies (two-stage mbarrier pipeline) — needs every per-agent array 16-byte aligned
+ * and readable up to the next multiple of 16 bytes past its end (true of any allocator with >= 16-byte granules);
+ * 0: register-batched loads.  Results are bit-identical.  on < 0 only queries.  Returns the previous setting. */
+int gj_pipeline_enable(int on);
+
 /* ---- measurement (bench.py): CUDA events recorded on the launching stream around every kernel ---- */
 int gj_profile_enable(int on); /* also resets the counters */
 /* per kernel id: summed event time (ms), number of timed launches, number of launches since enable;

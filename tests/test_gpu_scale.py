@@ -309,3 +309,57 @@ def test_throughput_mode_bptt_window():
         assert np.array_equal(e["cases"], f["cases"])
         assert np.array_equal(e["cur"], f["cur"])
         assert np.allclose(e["grads"], f["grads"], rtol=5e-5, atol=1e-6 * np.abs(e["grads"]).max()), (e["grads"], f["grads"])
+
+
+@pytest.mark.parametrize("quarantine", [False, True])
+def test_pipelined_kernels_are_bit_identical(quarantine):
+    """The TMA bulk-copy pipelined agent kernels (gj_pipe.cuh) against the register-batched ones (gj_lean.cuh):
+    same arithmetic on the same Philox stream -> bit-identical trajectories and state; gradients to fp32 rounding.
+    An odd agent count makes tiles start at unaligned agents (the copies start at the preceding 16-byte granule)."""
+    from grad_june import GradJune, Timer, _lib, ops
+    from grad_june.default_config import default_parameters
+    from grad_june.runner import Runner
+    from grad_june.world import make_synthetic_world
+    n_agents = 333_337
+    params = default_parameters()
+    params["system"]["device"] = DEV
+    params["timer"]["total_days"] = 4
+    params["infection_seed"]["log_fraction_initial_cases"] = -1.5
+    params["policies"] = {}
+    if quarantine:
+        params["policies"] = {"quarantine": {"quarantine": {1: {"start_date": "2022-01-01", "end_date": "2023-01-01",
+                                                                 "stage_threshold": 4}}}}
+    torch.manual_seed(5)
+    data = Runner.get_data(params, data=make_synthetic_world(n_agents, seed=6, device=DEV, agents_per_super_area=5000))
+    model = GradJune.from_parameters(params)
+    keys = list(model.infection_networks.networks.keys())
+    runner = Runner(model=model, data=data, timer=Timer.from_parameters(params), log_fraction_initial_cases=-1.5,
+                    save_path="/tmp/gj_test", parameters=params)
+    outs = {}
+    prev = _lib.pipeline_enable(None)
+    try:
+        for mode in (False, True):
+            _lib.pipeline_enable(mode)
+            leaves = []
+            for k in keys:
+                leaf = torch.tensor(float(params["networks"][k]["log_beta"]) + 0.4, device=DEV, requires_grad=True)
+                model.infection_networks.networks[k].log_beta = leaf
+                leaves.append(leaf)
+            with ops.philox_seed(31):
+                results, is_inf = runner()
+            loss = results["cases_per_timestep"].sum() + results["deaths_per_timestep"].sum() \
+                + 0.5 * results["cases_by_age_65"].sum() + 0.01 * data["agent"].infection_time.sum()
+            loss.backward()
+            agent = data["agent"]
+            outs[mode] = [results["cases_per_timestep"].detach(), results["deaths_per_timestep"].detach(), is_inf.detach(),
+                          agent.susceptibility.detach(), agent.infection_time.detach(), agent.transmission.detach(),
+                          agent.symptoms["current_stage"].detach(), agent.symptoms["next_stage"].detach(),
+                          agent.symptoms["time_to_next_stage"].detach(), torch.stack([l.grad for l in leaves])]
+    finally:
+        _lib.pipeline_enable(prev)
+    assert outs[False][0][-1] > outs[False][0][0] > 0
+    for a, b in zip(outs[False][:-1], outs[True][:-1]):
+        assert torch.equal(a, b)
+    # gradients: per-CTA partial sums are combined in grid order and the two families use different grids
+    ga, gb = outs[False][-1], outs[True][-1]
+    assert torch.allclose(ga, gb, rtol=2e-6, atol=1e-7 * float(ga.abs().max())), (ga, gb)

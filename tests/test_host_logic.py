@@ -155,6 +155,8 @@ def test_world_tiers_reproduce_group_sums():
     u32 = lambda t: t.long() & 0xFFFFFFFF
     tile_begin = u32(dw.tile_begin)
     assert tile_begin[0] == 0 and tile_begin[-1] == n and int((tile_begin[1:] - tile_begin[:-1]).max()) <= W.TILE_AGENTS
+    from grad_june import _lib
+    assert W.TILE_AGENTS == _lib.config()["tile_agents"]      # the pipelined kernels stage one tile per thread block
     for ti, t in enumerate(types):
         ei = data["attends_" + t].edge_index
         G = len(data[t]["id"])
