@@ -396,6 +396,11 @@ __device__ __forceinline__ void lean_forward_agent(const gj_step_params& p, cons
                                                    float s, float inf, float tinf, float cur, float nxt, float ttn,
                                                    int cls, float inv_tau, float dead, uint32_t key0, uint32_t key1,
                                                    float* __restrict__ hist, float* __restrict__ deaths) {
+    // the noise first: it depends on nothing that is loaded, so it covers the latency of the group-sum gather (gv)
+    uint32_t r[4];
+    const uint64_t ga = p.agent_offset + a;  // global agent id = Philox counter
+    philox4x32_10((uint32_t)ga, (uint32_t)(ga >> 32), p.call_index, 0u, key0, key1, r);
+    const float dE = lg2_fast(-lg2_fast(u01_open(r[0]))) - lg2_fast(-lg2_fast(u01_open(r[1])));
     const float rv = (beta_r * rpc) * hs;
     const float house = lp.r_house ? rv : 0.0f;
     const float plain = (gv + Lc) + (lp.r_house ? 0.0f : rv);
@@ -406,11 +411,7 @@ __device__ __forceinline__ void lean_forward_agent(const gj_step_params& p, cons
     io.tape_v[a] = (s == 0.0f) ? X : lam;
     // Gumbel-softmax hard draw from Philox bits (same stream as draw_step_noise):
     // x0 - x1 = (ln2 / tau) * d,  d = lg2 q - lg2(1-q) - lg2 E0 + lg2 E1, E = -ln u (the ln2 factors cancel)
-    uint32_t r[4];
-    const uint64_t ga = p.agent_offset + a;  // global agent id = Philox counter
-    philox4x32_10((uint32_t)ga, (uint32_t)(ga >> 32), p.call_index, 0u, key0, key1, r);
-    const float d = (lg2_fast(q) - lg2_fast(1.0f - q)) -
-                    (lg2_fast(-lg2_fast(u01_open(r[0]))) - lg2_fast(-lg2_fast(u01_open(r[1]))));
+    const float d = (lg2_fast(q) - lg2_fast(1.0f - q)) - dE;
     const float e = ex2_fast(-fabsf(d) * inv_tau);  // exp(x_small - x_big) <= 1
     const float ys = e * rcp_fast(1.0f + e);        // the smaller soft probability
     const bool hit = (d < 0.0f) && (e < 1.0f);      // argmax of the softmax; ties -> not infected

@@ -103,6 +103,22 @@ __device__ __forceinline__ float pipe_range_sum(const float* __restrict__ Ts, ui
   return S;
 }
 
+// tile bounds and cell flags of the tile a CTA is about to compute (CTA-uniform loads)
+#define PIPE_TILE_FACTS                                                                                    \
+  const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];                                      \
+  const bool new_cell = lp.n_cell > 0 && (tile == run.t0 || lean_new_cell(lp, tile - 1, tile));             \
+  const bool flush = lp.n_cell > 0 && (tile + 1 == run.t1 || lean_new_cell(lp, tile, tile + 1));            \
+  (void)new_cell;                                                                                          \
+  (void)flush
+
+// end of a tile: every warp is done with the stage, one thread refills it with the tile kPipeStages ahead.
+// (Letting the last warp to finish do the refill instead of a CTA barrier, and shipping the tile facts with the
+// stage, were both measured: no gain / a loss — see DESIGN.md.)
+__device__ __forceinline__ bool pipe_release() {
+  __syncthreads();
+  return threadIdx.x == 0;
+}
+
 constexpr int kPipeF = kPipeTile + 8;                     // floats of a staged 4-byte array
 constexpr int kPipeH = kPipeTile + 2 * kPipeHalo + 8;     // ... with the halo
 
@@ -187,15 +203,15 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
   const float* L = sh.L[0];
   for (int64_t tile = run.t0; tile < run.t1; ++tile) {
     PipeFwdStage& sg = sh.st[stg];
-    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];
-    if (lp.n_cell > 0 && (tile == run.t0 || lean_new_cell(lp, tile - 1, tile))) {
+    mbar_wait(&sh.full[stg], parity);
+    PIPE_TILE_FACTS;
+    if (new_cell) {
       // rebuilt in the other buffer: a buffer is rewritten two rebuilds later, after the barriers in between
       lean_class_table(sh.L[nbuild & 1], sh.prob, lp, cell_buf, tile);
       L = sh.L[nbuild & 1];
       ++nbuild;
       __syncthreads();
     }
-    mbar_wait(&sh.full[stg], parity);
     const uint32_t sk = a0 & 3u, sk16 = a0 & 15u, tlo = halo_lo(a0);
     uint32_t ent[kPipePer];
     float gen[kPipePer];
@@ -218,8 +234,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
                                        sg.tinf[i], sg.cur[i], sg.nxt[i], sg.ttn[i], cls, inv_tau, dead, key0, key1,
                                        sh.hist, &sh.deaths);
     }
-    __syncthreads();  // every warp is done with this stage: refill it with the tile kPipeStages ahead
-    if (threadIdx.x == 0 && tile + kPipeStages < run.t1)
+    if (pipe_release() && tile + kPipeStages < run.t1)
       pipe_fwd_issue(sg, &sh.full[stg], w, lp, io, Tr, tile + kPipeStages, has_gen, has_range);
     if (++stg == kPipeStages) {
       stg = 0;
@@ -312,8 +327,9 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward(gj_world_desc
   uint32_t parity = 0;
   for (int64_t tile = run.t0; tile < run.t1; ++tile) {
     PipeBwdStage& sg = sh.st[stg];
-    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];
-    // the cotangents of the state outputs stream through registers (issued before the wait on the staged tile)
+    mbar_wait(&sh.full[stg], parity);
+    PIPE_TILE_FACTS;
+    // the cotangents of the state outputs stream through registers
     float c[kPipePer][6];
 #pragma unroll
     for (int h = 0; h < kPipePer; ++h) {
@@ -322,7 +338,6 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward(gj_world_desc
 #pragma unroll
       for (int k = 0; k < 6; ++k) c[h][k] = cot.p[k] ? cot.p[k][al] : 0.0f;
     }
-    mbar_wait(&sh.full[stg], parity);
     const uint32_t sk = a0 & 3u, sk16 = a0 & 15u;
 #pragma unroll
     for (int h = 0; h < kPipePer; ++h) {
@@ -333,15 +348,13 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward(gj_world_desc
                                  sg.cls[j + sk16], c[h][0], c[h][1], c[h][2], c[h][3], c[h][4], c[h][5], inv_tau, dead,
                                  g_deaths, sh.gred_age, sh.prob, acc);
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && tile + kPipeStages < run.t1)
+    if (pipe_release() && tile + kPipeStages < run.t1)
       pipe_bwd_issue(sg, &sh.full[stg], w, io, tile + kPipeStages);
     if (++stg == kPipeStages) {
       stg = 0;
       parity ^= 1u;
     }
     if (lp.n_cell > 0) {   // partial sums of the cell channels: written at the last tile of a cell run (see K1)
-      const bool flush = (tile + 1 == run.t1) || lean_new_cell(lp, tile, tile + 1);
       if (flush) {
         block_sums<float, GJ_MAX_CHANNELS, kPipeWarps>(acc, lp.n_cell, tile_part + tile * GJ_MAX_CHANNELS);
 #pragma unroll
@@ -357,7 +370,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward(gj_world_desc
 // B3p  backward gather
 // =====================================================================================================
 struct alignas(16) PipeGatStage {
-  float rpc[kPipeF], Tm[kPipeF], cur[kPipeF], inf[kPipeF], tinf[kPipeF];
+  float rpc[kPipeF], Tm[kPipeF], cur[kPipeF], inf[kPipeF], tinf[kPipeF], gi[kPipeF], gt[kPipeF];
   uint32_t ent[kPipeF], slot[kPipeF];
   float wr[kPipeH];
   uint8_t cls[kPipeTile + 32];
@@ -375,7 +388,7 @@ __device__ __forceinline__ void pipe_gat_issue(PipeGatStage& sg, uint64_t* bar, 
                                                const LeanPlan& lp, const gj_bwd_io& io, const float* wr, int64_t tile,
                                                bool has_gen, bool has_range) {
   const TileSpan t = tile_span(w, tile);
-  uint32_t total = 2u * t.n4 + (t.hi16 - t.lo16);
+  uint32_t total = 4u * t.n4 + (t.hi16 - t.lo16);
   if (kQuar) total += t.n4;
   if (has_gen) total += t.n4;
   if (has_range) total += 3u * t.n4 + (t.thi - t.tlo) * 4u;
@@ -383,6 +396,8 @@ __device__ __forceinline__ void pipe_gat_issue(PipeGatStage& sg, uint64_t* bar, 
   const Copier c{bar};
   c.f4(sg.inf, io.inf, t);
   c.f4(sg.tinf, io.tinf, t);
+  c.f4(sg.gi, io.g_inf, t);
+  c.f4(sg.gt, io.g_tinf, t);
   if (kQuar) c.f4(sg.cur, io.cur, t);
   if (has_gen) c.f4(sg.ent, w.ent1, t);
   if (has_range) {
@@ -421,25 +436,20 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward_gather(gj_wor
   const float* L = sh.L[0];
   for (int64_t tile = run.t0; tile < run.t1; ++tile) {
     PipeGatStage& sg = sh.st[stg];
-    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tile + 1];
-    if (lp.n_cell > 0 && (tile == run.t0 || lean_new_cell(lp, tile - 1, tile))) {
+    mbar_wait(&sh.full[stg], parity);
+    PIPE_TILE_FACTS;
+    if (new_cell) {
       lean_class_table(sh.L[nbuild & 1], sh.prob, lp, cell_buf, tile);
       L = sh.L[nbuild & 1];
       ++nbuild;
       __syncthreads();
     }
-    // the packed profile and the two read-modify-write cotangents stream through registers
-    float4 pf[kPipePer];
-    float gi[kPipePer], gt[kPipePer];
+    float4 pf[kPipePer];   // the packed profile streams through registers
 #pragma unroll
     for (int h = 0; h < kPipePer; ++h) {
       const uint32_t a = a0 + threadIdx.x + h * kPipeThreads;
-      const uint32_t al = a < a1 ? a : a0;
-      pf[h] = prof[al];
-      gi[h] = io.g_inf[al];
-      gt[h] = io.g_tinf[al];
+      pf[h] = prof[a < a1 ? a : a0];
     }
-    mbar_wait(&sh.full[stg], parity);
     const uint32_t sk = a0 & 3u, sk16 = a0 & 15u, tlo = halo_lo(a0);
     uint32_t ent[kPipePer];
     float gen[kPipePer];
@@ -460,10 +470,9 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward_gather(gj_wor
       const float gv = lean_generic_finish(w, cRP, ent[h], a, gen[h]);
       lean_gather_agent<kQuar>(p, lp, io, a, R, gv, Lc, beta_r, has_range ? sg.rpc[i] : 0.0f,
                                has_range ? sg.Tm[i] : 0.0f, kQuar ? sg.cur[i] : 0.0f, sg.inf[i], sg.tinf[i], pf[h],
-                               gi[h], gt[h], db[0]);
+                               sg.gi[i], sg.gt[i], db[0]);
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && tile + kPipeStages < run.t1)
+    if (pipe_release() && tile + kPipeStages < run.t1)
       pipe_gat_issue<kQuar>(sg, &sh.full[stg], w, lp, io, wr, tile + kPipeStages, has_gen, has_range);
     if (++stg == kPipeStages) {
       stg = 0;

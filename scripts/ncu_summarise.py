@@ -58,7 +58,8 @@ with open(dst + "_kernels.csv", "w") as f:
         f.write(short(r[hdr["Kernel Name"]]) + "," + ",".join(vals) + f",{gb * scale / (us * 1e-6):.0f}\n")
 
 # ---- stall samples by source line for the agent kernels ---------------------------------------------
-for k in ("k_lean_forward", "k_lean_backward", "k_lean_backward_gather", "k_lean_transmission", "k_lean_group_chunk"):
+for k in ("k_pipe_forward", "k_pipe_backward", "k_pipe_backward_gather", "k_lean_forward", "k_lean_backward",
+          "k_lean_backward_gather", "k_lean_transmission", "k_lean_group_chunk", "k_lean_group_small"):
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass",
                           "--kernel-name-base", "function", "--kernel-name", "regex:^" + k + "$", "--launch-count", "1"],
                          capture_output=True, text=True).stdout
