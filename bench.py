@@ -325,13 +325,14 @@ def main():
 
     # warm-up: W >= 3 timesteps
     wsteps = 0
-    while wsteps < max(args.warmup, 3):
+    while wsteps < max(args.warmup, 3) or (world_size > 1 and wsteps < 2 * window):   # N > 1: NCCL channels settle
         one_window(False)
         wsteps += window
     barrier()
 
     # ---- timed region 1: device-resident inputs --------------------------------------------------
-    with ClockSampler(local_rank, period=0.02) as clocks:
+    # (NVML is polled by rank 0 only: eight processes polling it were measured to disturb the step)
+    with ClockSampler(local_rank, period=0.02 if rank == 0 else 1e9) as clocks:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.nvtx.range_push("timed")
@@ -366,8 +367,12 @@ def main():
     h2d = host_log_beta.numel() * 4 / window
     d2h = host_out.numel() * 4 / window
 
+    rank_ms = [ms]
     if world_size > 1:
         t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        every = [torch.zeros_like(t) for _ in range(world_size)]
+        dist.all_gather(every, t)
+        rank_ms = [round(float(x[0]), 3) for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
         if not geo:
@@ -423,7 +428,7 @@ def main():
                        "layout_tiers": dict(zip(world.types, world.type_tier)),
                        "parallelism": parallelism,
                        "l2": "inputs (>= 2 GB per pass) far larger than the 126 MB L2; no flush needed"},
-            "clocks": clk,
+            "clocks": clk, "rank_ms": rank_ms,
             "e2e": {"value": total_units / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "roofline": roof,

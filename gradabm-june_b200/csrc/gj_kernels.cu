@@ -820,6 +820,32 @@ static int lean_backward(const gj_world_desc* w, const gj_step_params* p, const 
   return 0;
 }
 
+// ---- boundary exchange of a partitioned world: pack / unpack of the straddling groups' sums -------------------
+// pack position q holds the sum of boundary group q (all edge types of the step concatenated); inv[q] = index of
+// that group's entry in this rank's group-sum buffers, or -1 if the rank does not attend the group (contributes 0)
+__global__ void __launch_bounds__(kBlock) k_boundary_pack(int64_t n, const int32_t* __restrict__ inv,
+                                                          const float* __restrict__ a, const float* __restrict__ b,
+                                                          float* __restrict__ pack) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
+    const int32_t j = inv[q];
+    pack[q] = j >= 0 ? a[j] : 0.0f;
+    pack[n + q] = j >= 0 ? b[j] : 0.0f;
+  }
+}
+__global__ void __launch_bounds__(kBlock) k_boundary_unpack(int64_t n, const int32_t* __restrict__ inv,
+                                                            const float* __restrict__ pack, float* __restrict__ a,
+                                                            float* __restrict__ b) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
+    const int32_t j = inv[q];
+    if (j >= 0) {
+      a[j] = pack[q];
+      b[j] = pack[n + q];
+    }
+  }
+}
+
 }  // namespace gj
 
 using namespace gj;
@@ -837,6 +863,22 @@ int gj_config(int64_t* out, int n) {
 }
 
 int64_t gj_scratch_bytes(const gj_world_desc* w) { return w ? scratch_bytes(w) : -1; }
+
+int gj_boundary_pack(int64_t n_pack, const int32_t* inv, const float* a, const float* b, float* pack, void* stream) {
+  if (n_pack <= 0) return 0;
+  if (!inv || !a || !b || !pack) return bad("NULL array");
+  k_boundary_pack<<<agent_grid(n_pack), kBlock, 0, (cudaStream_t)stream>>>(n_pack, inv, a, b, pack);
+  GJ_CHECK_LAUNCH("k_boundary_pack");
+  return 0;
+}
+
+int gj_boundary_unpack(int64_t n_pack, const int32_t* inv, const float* pack, float* a, float* b, void* stream) {
+  if (n_pack <= 0) return 0;
+  if (!inv || !a || !b || !pack) return bad("NULL array");
+  k_boundary_unpack<<<agent_grid(n_pack), kBlock, 0, (cudaStream_t)stream>>>(n_pack, inv, pack, a, b);
+  GJ_CHECK_LAUNCH("k_boundary_unpack");
+  return 0;
+}
 
 int gj_pipeline_enable(int on) {
   const int prev = pipe_enabled() ? 1 : 0;

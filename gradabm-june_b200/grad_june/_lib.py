@@ -161,6 +161,8 @@ def lib():
     L.gj_philox4x32_10.restype = None
     L.gj_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
     L.gj_profile_kernel_name.restype = C.c_char_p
+    L.gj_boundary_pack.argtypes = [C.c_int64] + [C.c_void_p] * 5
+    L.gj_boundary_unpack.argtypes = [C.c_int64] + [C.c_void_p] * 5
     cfg = (C.c_int64 * 8)()
     L.gj_config(cfg, 8)
     _config = {
@@ -189,7 +191,7 @@ EXPORTED_SYMBOLS = [
     "gj_abi_version", "gj_last_error", "gj_config", "gj_scratch_bytes", "gj_profile_prepare", "gj_profile_pack",
     "gj_transmission_forward", "gj_transmission_backward", "gj_step_forward", "gj_step_backward",
     "gj_philox_fill", "gj_philox_fill_at", "gj_step_plan", "gj_philox4x32_10", "gj_profile_enable", "gj_profile_read",
-    "gj_profile_kernel_name", "gj_pipeline_enable",
+    "gj_profile_kernel_name", "gj_pipeline_enable", "gj_boundary_pack", "gj_boundary_unpack",
 ]
 
 

@@ -289,6 +289,14 @@ int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fw
 /* reverse-mode derivative of gj_step_forward (replaces autograd's replay of the op tape) */
 int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_bwd_io* io, void* stream);
 
+/* ---- geographic partition: boundary groups (no counterpart in the reference, which is single-device)
+ * Between GJ_STAGE_SUMS and GJ_STAGE_REST the caller all-reduces (NCCL, owned by the caller) the sums of the groups
+ * that straddle partitions.  pack[2][n_pack]: position q = boundary group q of the step's edge types; inv[q] = index
+ * of that group in this rank's two group-sum buffers a / b (S_scaled / S_unscaled forward, cR / R backward), or -1
+ * when this rank does not attend it (packs 0, unpacks nothing). */
+int gj_boundary_pack(int64_t n_pack, const int32_t* inv, const float* a, const float* b, float* pack, void* stream);
+int gj_boundary_unpack(int64_t n_pack, const int32_t* inv, const float* pack, float* a, float* b, void* stream);
+
 /* ---- kernel family of the throughput mode -------------------------------------------------------
  * 1 (default; GJ_PIPE=0 in the environment turns it off): the agent kernels stage every per-agent array of a tile
  * in shared memory with TMA bulk copies (two-stage mbarrier pipeline) — needs every per-agent array 16-byte aligned
