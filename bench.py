@@ -212,6 +212,12 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="geo: every GPU owns --agents agents of a world of N x --agents (weak), or the --agents world "
                          "is cut into N parts (strong)")
+    ap.add_argument("--samples", type=int, default=0,
+                    help="ensemble: beta samples evaluated per window over all GPUs (BASELINE config 5: 1024 on a 9M "
+                         "world, --agents 9000000 --window 30); default one per GPU")
+    ap.add_argument("--graph", action="store_true",
+                    help="capture the window (Runner() + backward) once as a CUDA graph and replay it "
+                         "(grad_june.graphed.GraphedRunner): removes the per-step Python cost that bounds small worlds")
     ap.add_argument("--policies", action="store_true",
                     help="BASELINE config 4: social distancing, school/leisure closures and quarantine from day 15")
     ap.add_argument("--window", type=int, default=0,
@@ -275,14 +281,20 @@ def main():
     gen = torch.Generator().manual_seed(99)
     offsets = 0.05 * torch.randn(max(world_size, 1), len(keys), generator=gen)
     # geo: one parameter vector for the one world; ensemble: every rank evaluates its own beta sample (config 5)
-    host_log_beta = torch.tensor([float(model.infection_networks.networks[k].log_beta) for k in keys]) \
-        + offsets[0 if geo else rank]
+    base_log_beta = torch.tensor([float(model.infection_networks.networks[k].log_beta) for k in keys])
+    n_samples = 1          # parameter samples this rank evaluates per window
+    if not geo and args.samples > max(world_size, 1):
+        n_samples = args.samples // max(world_size, 1)
+        draws = 0.25 * torch.randn(args.samples, len(keys), generator=torch.Generator().manual_seed(1))
+        host_log_beta = (base_log_beta + draws[rank * n_samples:(rank + 1) * n_samples]).contiguous()   # [B/N, K]
+    else:
+        host_log_beta = (base_log_beta + offsets[0 if geo else rank]).reshape(1, -1)
     host_log_beta = host_log_beta.pin_memory()
-    n_total = N
+    n_total = N * n_samples      # agent-trajectories advanced per timestep over all GPUs
     if geo:
         n_total = part.n_global_agents
     elif world_size > 1:
-        n_total = N * world_size
+        n_total = N * n_samples * world_size
 
     def fresh_runner():
         r = Runner(model=model, data=data, timer=Timer.from_parameters(params), log_fraction_initial_cases=-2.0,
@@ -292,11 +304,13 @@ def main():
     runner = fresh_runner()
 
     def one_window(e2e):
-        """forward `window` timesteps + backward; returns device-side loss and grads"""
-        if e2e:
-            lb_dev = host_log_beta.to(dev, non_blocking=True)          # H2D of this window's inputs
-        else:
-            lb_dev = resident_log_beta
+        """every sample of this rank: forward `window` timesteps + backward; device-side results and grads"""
+        lb_all = host_log_beta.to(dev, non_blocking=True) if e2e else resident_log_beta   # H2D of the inputs
+        outs = [one_sample(lb_all[i]) for i in range(n_samples)]
+        out = outs[0] if n_samples == 1 else torch.stack(outs)
+        return out.to("cpu") if e2e else out                                             # D2H of the results
+
+    def one_sample(lb_dev):
         leaves = []
         for i, k in enumerate(keys):
             leaf = lb_dev[i].detach().clone().requires_grad_(True)
@@ -309,19 +323,39 @@ def main():
         grads = torch.stack([l.grad for l in leaves])
         if geo:      # every rank holds the terms of the groups it owns: the world's gradient is their sum
             dist.all_reduce(grads)
-        out = torch.cat([results["cases_per_timestep"], results["deaths_per_timestep"], grads])
-        if e2e:
-            return out.to("cpu")                                     # D2H of the window's results
-        return out
+        return torch.cat([results["cases_per_timestep"], results["deaths_per_timestep"], grads])
 
     resident_log_beta = host_log_beta.to(dev)
     n_windows = max(1, -(-args.steps // window))
     steps_done = n_windows * window
+    eager_window = one_window
 
     def barrier():
         if world_size > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    prof = None
+    if args.graph:
+        from grad_june.graphed import GraphedRunner
+        # per-kernel pass first, eagerly (a replayed graph carries no events), then capture
+        eager_window(False)
+        _lib.profile_enable(True)
+        barrier()
+        eager_window(False)
+        barrier()
+        prof = {k: (v[0] * n_windows, v[1] * n_windows, v[2] * n_windows) for k, v in _lib.profile_read().items()}
+        _lib.profile_enable(False)
+        for k in keys:
+            model.infection_networks.networks[k].log_beta = torch.tensor(0.0)
+        graphed = GraphedRunner(
+            runner, loss_fn=lambda r: r["cases_per_timestep"].sum() + r["deaths_per_timestep"].sum(), seed=7)
+
+        def one_sample(lb_dev):  # noqa: F811
+            _, grads, results = graphed(lb_dev)
+            if geo:
+                dist.all_reduce(grads)
+            return torch.cat([results["cases_per_timestep"], results["deaths_per_timestep"], grads])
 
     # warm-up: W >= 3 timesteps
     wsteps = 0
@@ -347,13 +381,14 @@ def main():
 
     # ---- per-kernel pass: the same K steps again with the library's CUDA events around every kernel (kept out
     #      of the timed region above: two event records per launch cost a few per cent on small worlds) ----------
-    _lib.profile_enable(True)
-    barrier()
-    for _ in range(n_windows):
-        one_window(False)
-    barrier()
-    prof = _lib.profile_read()
-    _lib.profile_enable(False)
+    if prof is None:
+        _lib.profile_enable(True)
+        barrier()
+        for _ in range(n_windows):
+            one_window(False)
+        barrier()
+        prof = _lib.profile_read()
+        _lib.profile_enable(False)
 
     # ---- timed region 2: end to end through Runner with host buffers -------------------------------
     barrier()
@@ -385,8 +420,9 @@ def main():
         parallelism = (f"geographic partition over {world_size} GPUs ({args.scaling} scaling), NCCL all-reduce of the "
                        f"boundary-group sums once per step forward and once backward; boundary groups {nb} "
                        f"of {world.n_groups} local groups")
-    elif world_size > 1:
-        parallelism = "ensemble shard (one beta sample per GPU on replicas of the world, no data-path collective)"
+    elif world_size > 1 or n_samples > 1:
+        parallelism = (f"ensemble shard: {n_samples * world_size} beta samples per window, {n_samples} per GPU evaluated one "
+                       "after the other on a replica of the world, no data-path collective")
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
         total_units = n_total * steps_done
@@ -425,6 +461,7 @@ def main():
             "config": {"workload": workload_name(n_total if geo else N, args.policies), "agents_per_gpu": N,
                        "agents_total": n_total, "edges_per_agent": round(e_bar, 3),
                        "groups_per_agent": round(g_bar, 3), "bptt_window": window, "networks": 11,
+                       "driver": "CUDA graph replay (GraphedRunner)" if args.graph else "Python loop (Runner)",
                        "layout_tiers": dict(zip(world.types, world.type_tier)),
                        "parallelism": parallelism,
                        "l2": "inputs (>= 2 GB per pass) far larger than the 126 MB L2; no flush needed"},
@@ -440,6 +477,15 @@ def main():
                                               f"timesteps fwd+bwd ({secs:.1f} s)"}
         print(json.dumps(line), flush=True)
     if world_size > 1:
+        if args.graph:
+            # a captured graph that contains NCCL kernels must be gone before its communicator is torn down
+            # (destroy_process_group was seen to hang otherwise)
+            graphed.graph.reset()
+            del graphed
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 

@@ -1,0 +1,84 @@
+"""A whole calibration iteration — ``Runner()`` (seeding + T fused timesteps) and ``loss.backward()`` — captured
+once as a CUDA graph and replayed per parameter sample (the caller of the hot path).
+
+The reference drives the path from Python: per timestep ~430 torch ops; here it is ~12 kernels per step whose launch
+cost (≈ 0.55 ms of Python per step fwd+bwd) dominates worlds below ≈ 10 M agents and strongly-scaled partitions.  The
+library's entry points are stream-ordered, never allocate and never synchronise, so the whole window — including
+the NCCL all-reduces of a partitioned world — is capturable with ``torch.cuda.graph``.
+
+    graphed = GraphedRunner(runner, loss_fn=lambda r: r["cases_per_timestep"].sum())
+    loss, grads, results = graphed(log_beta_vector)       # replay: one graph launch
+
+Noise: the Philox key and call indices are kernel arguments, so every replay draws the SAME noise (common random
+numbers across parameter samples — the usual variance reduction for calibration gradients); ``recapture(seed)``
+re-records the graph with another key.
+"""
+import warnings
+from typing import Callable, Optional, Sequence
+
+import torch
+
+from . import ops
+
+
+class GraphedRunner:
+    def __init__(self, runner, loss_fn: Callable[[dict], torch.Tensor], networks: Optional[Sequence[str]] = None,
+                 seed: int = 0, warmup: int = 1):
+        self.runner = runner
+        self.loss_fn = loss_fn
+        nets = runner.model.infection_networks.networks
+        self.names = list(networks) if networks is not None else list(nets.keys())
+        agent = runner.data["agent"]
+        ops.require_cuda(agent.susceptibility, "data['agent'].susceptibility")
+        self.device = agent.susceptibility.device
+        init = [float(torch.as_tensor(nets[k].log_beta).detach().reshape(-1)[0]) for k in self.names]
+        self.log_beta = torch.tensor(init, dtype=torch.float32).to(self.device).requires_grad_(True)
+        self.warmup = warmup
+        self.graph = None
+        self.recapture(seed)
+
+    def _iteration(self):
+        nets = self.runner.model.infection_networks.networks
+        for i, k in enumerate(self.names):
+            nets[k].log_beta = self.log_beta[i]
+        with ops.philox_seed(self.seed):
+            results, is_infected = self.runner()
+        loss = self.loss_fn(results)
+        loss.backward()
+        return loss.detach(), results, is_infected
+
+    def recapture(self, seed: int):
+        """(Re)record the graph with Philox key ``seed``."""
+        self.seed = int(seed)
+        self.graph = None
+        dev = self.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), warnings.catch_warnings():
+            # lazy initialisation (occupancy queries, workspaces, NCCL) happens here; the leaf was created on another
+            # stream than this warm-up's, which autograd remarks on
+            warnings.simplefilter("ignore", UserWarning)
+            for _ in range(max(self.warmup, 1)):
+                self.log_beta.grad = None
+                self._iteration()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.log_beta.grad = None
+        torch.cuda.empty_cache()               # the eager window's tape must not stay cached next to the graph's pool
+        graph = torch.cuda.CUDAGraph()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)
+            with torch.cuda.graph(graph):
+                self.loss, self.results, self.is_infected = self._iteration()
+        self.grads = self.log_beta.grad        # allocated in the graph's pool: refilled by every replay
+        self.graph = graph
+        return self
+
+    @torch.no_grad()
+    def __call__(self, log_beta: Optional[torch.Tensor] = None):
+        """Replay with ``log_beta`` ([K], any device; None = keep).  Returns (loss, d loss / d log_beta, results):
+        static device tensors that the next replay overwrites."""
+        if log_beta is not None:
+            self.log_beta.copy_(log_beta.to(dtype=torch.float32), non_blocking=True)
+        self.graph.replay()
+        return self.loss, self.grads, self.results

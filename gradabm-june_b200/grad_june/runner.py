@@ -100,9 +100,14 @@ class Runner(torch.nn.Module):
 
     def _fraction_tensor(self):
         fraction = 10.0 ** self.log_fraction_initial_cases
+        dev = self.data["agent"].susceptibility.device
         if not torch.is_tensor(fraction):
-            fraction = torch.tensor(float(fraction))
-        return fraction.reshape(1).to(device=self.data["agent"].susceptibility.device, dtype=torch.float32)
+            # a plain number: keep its device copy (no host-to-device copy per run; CUDA-graph capturable)
+            key = (float(fraction), str(dev))
+            if getattr(self, "_fraction_cache", (None, None))[0] != key:
+                self._fraction_cache = (key, torch.tensor([float(fraction)], dtype=torch.float32).to(dev))
+            return self._fraction_cache[1]
+        return fraction.reshape(1).to(device=dev, dtype=torch.float32)
 
     def set_initial_cases(self):
         """infect_fraction_of_people + first symptoms update (runner.py:138-149) as one fused call."""
@@ -129,7 +134,7 @@ class Runner(torch.nn.Module):
             "dates": dates,
             "cases_per_timestep": cases_per_timestep,
             "daily_cases_per_timestep": torch.diff(
-                cases_per_timestep, prepend=torch.tensor([0.0], device=cases_per_timestep.device)),
+                cases_per_timestep, prepend=torch.zeros(1, device=cases_per_timestep.device)),
             "deaths_per_timestep": data["results"]["deaths_per_timestep"],
         }
         for i, key in enumerate(self._age_bins_host[1:]):

@@ -363,3 +363,53 @@ def test_pipelined_kernels_are_bit_identical(quarantine):
     # gradients: per-CTA partial sums are combined in grid order and the two families use different grids
     ga, gb = outs[False][-1], outs[True][-1]
     assert torch.allclose(ga, gb, rtol=2e-6, atol=1e-7 * float(ga.abs().max())), (ga, gb)
+
+
+def test_graphed_runner_replays_the_eager_window():
+    """GraphedRunner (Runner() + backward captured as one CUDA graph) against the eager Python loop on the same
+    Philox key: identical results and gradients; a replay with other log-betas matches an eager run with them."""
+    from grad_june import GradJune, Timer, ops
+    from grad_june.default_config import default_parameters
+    from grad_june.graphed import GraphedRunner
+    from grad_june.runner import Runner
+    from grad_june.world import make_synthetic_world
+    n_agents = 150_000
+    params = default_parameters()
+    params["system"]["device"] = DEV
+    params["timer"]["total_days"] = 5
+    params["infection_seed"]["log_fraction_initial_cases"] = -1.5
+    params["policies"] = {"quarantine": {"quarantine": {1: {"start_date": "2022-02-03", "end_date": "2023-01-01",
+                                                             "stage_threshold": 4}}}}
+    torch.manual_seed(5)
+    data = Runner.get_data(params, data=make_synthetic_world(n_agents, seed=8, device=DEV, agents_per_super_area=5000))
+    model = GradJune.from_parameters(params)
+    keys = list(model.infection_networks.networks.keys())
+    runner = Runner(model=model, data=data, timer=Timer.from_parameters(params), log_fraction_initial_cases=-1.5,
+                    save_path="/tmp/gj_test", parameters=params)
+    loss_fn = lambda r: r["cases_per_timestep"].sum() + r["deaths_per_timestep"].sum() + 0.5 * r["cases_by_age_65"].sum()  # noqa: E731
+
+    def eager(lb):
+        leaves = []
+        for i, k in enumerate(keys):
+            leaf = lb[i].detach().clone().requires_grad_(True)
+            model.infection_networks.networks[k].log_beta = leaf
+            leaves.append(leaf)
+        with ops.philox_seed(123):
+            results, is_inf = runner()
+        loss = loss_fn(results)
+        loss.backward()
+        return (loss.detach().clone(), torch.stack([l.grad for l in leaves]), results["cases_per_timestep"].detach().clone(),
+                is_inf.detach().clone())
+
+    base = torch.tensor([float(params["networks"][k]["log_beta"]) + 0.4 for k in keys], device=DEV)
+    other = base + torch.linspace(-0.2, 0.2, len(keys), device=DEV)
+    e1, e2 = eager(base), eager(other)
+    graphed = GraphedRunner(runner, loss_fn, seed=123)
+    for lb, ref in ((base, e1), (other, e2), (base, e1)):
+        loss, grads, results = graphed(lb)
+        torch.cuda.synchronize()
+        assert torch.equal(results["cases_per_timestep"], ref[2])
+        assert torch.equal(graphed.is_infected, ref[3])
+        assert torch.equal(loss, ref[0])
+        assert torch.equal(grads, ref[1])
+    assert e1[2][-1] > e1[2][0] > 0 and not torch.equal(e1[1], e2[1])
