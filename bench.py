@@ -443,7 +443,7 @@ def main():
             avg_ms = timed[dom][0] / timed[dom][1]
             achieved = alg.get(dom, 0.0) * N / (avg_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                    "frac": achieved / peak, "traffic": ncu_traffic(dom, N), "peak_kind": peak_kind,
                     "alg_bytes_per_agent": alg.get(dom), "avg_launch_ms": avg_ms,
                     "step_alg_bytes_per_agent_timestep": B_ALG_STEP,
                     "step_achieved": B_ALG_STEP * value / world_size / 1e9,
@@ -487,6 +487,23 @@ def main():
             sys.stdout.flush()
             os._exit(0)
         dist.destroy_process_group()
+
+
+def ncu_traffic(kernel, n_agents):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/r1_pipe_v2_56M_kernels.csv, 56 M agents); None for
+    other sizes or kernels (traffic cannot be measured inside an un-profiled run)."""
+    name = {"agent_forward": "k_pipe_forward", "agent_backward": "k_pipe_backward<", "backward_gather": "k_pipe_backward_gather"}.get(kernel)
+    f = ROOT / "profiles" / "r1_pipe_v2_56M_kernels.csv"
+    if name is None or n_agents != 56_000_000 or not f.exists():
+        return None
+    vals = []
+    for line in f.read_text().splitlines()[1:]:
+        cols = line.split(",")
+        if cols[0].startswith(name):
+            k = 1 if "<" in cols[0] and "," in line[:line.index(">")] else 0   # "k_pipe_forward<0, 0>" has a comma
+            vals.append((float(cols[2 + k]) + float(cols[3 + k])) * 1e9)
+    return sum(vals) / len(vals) if vals else None
 
 
 def kernel_alg_bytes(e_gen, g_gen, e_small, g_small):

@@ -546,14 +546,16 @@ static int lean_grid(const gj_world_desc* w, K kernel, int* cache) {
 }
 
 // bulk-copy pipelined kernels (gj_pipe.cuh): on unless GJ_PIPE=0; they need 16-byte aligned per-agent arrays
-static int g_pipe_on = -1;
-static bool pipe_enabled() {
+static int g_pipe_on = -1;   // bit 0: pipelined agent kernels, bit 1: look-ahead transmission pass
+static int pipe_flags() {
   if (g_pipe_on < 0) {
     const char* e = getenv("GJ_PIPE");
-    g_pipe_on = (e && e[0] == '0') ? 0 : 1;
+    g_pipe_on = (e && e[0] >= '0' && e[0] <= '3') ? (e[0] - '0') : 1;   // look-ahead off: measured neutral
   }
-  return g_pipe_on == 1;
+  return g_pipe_on;
 }
+static bool pipe_enabled() { return (pipe_flags() & 1) != 0; }
+static bool lookahead_enabled() { return (pipe_flags() & 3) == 3; }
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 static bool pipe_aligned_fwd(const gj_world_desc* w, const LeanPlan& lp, const gj_fwd_io* io) {
   return aligned16(io->s) && aligned16(io->inf) && aligned16(io->tinf) && aligned16(io->cur) && aligned16(io->nxt) &&
@@ -714,11 +716,13 @@ static int launch_lean_group_pass(const gj_world_desc* w, const gj_step_params* 
   return 0;
 }
 
+// `next` != NULL: also run the transmission pass of the following step inside the agent kernel (pipelined family
+// only); returns 1 when it did
 static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const LeanPlan& lp,
-                        const gj_fwd_io* io, const Scratch& sc, cudaStream_t st) {
+                        const gj_fwd_io* io, const Scratch& sc, cudaStream_t st, const NextStep* next) {
   const bool quar = p->n_quar > 0;
   if (p->stage != GJ_STAGE_REST) {
-    {
+    if (!p->t_ready) {
       ProfScope ps(K_TRANSMISSION, st);
       static int occ[2] = {0, 0};
       if (quar) k_lean_transmission<true><<<lean_grid(w, k_lean_transmission<true>, &occ[1]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
@@ -735,19 +739,32 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
   if (int e = launch_cell_gather(w, p, pl, io->S_scaled, sc, st)) return e;
   if (pipe_enabled() && pipe_aligned_fwd(w, lp, io)) {
     ProfScope ps(K_AGENT_FWD, st);
-    static int occ[4] = {0, 0, 0, 0};
+    static int occ[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const bool diag = io->q || io->n;
     const size_t smem = sizeof(PipeFwdShared);
-#define GJ_PIPE_FWD(Q, D, I)                                                                                         \
-  k_pipe_forward<Q, D><<<pipe_grid(w, k_pipe_forward<Q, D>, kPipeThreads, smem, &occ[I]), kPipeThreads, smem, st>>>(  \
-      *w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets)
-    if (quar && diag) GJ_PIPE_FWD(true, true, 3);
-    else if (quar) GJ_PIPE_FWD(true, false, 2);
-    else if (diag) GJ_PIPE_FWD(false, true, 1);
-    else GJ_PIPE_FWD(false, false, 0);
+    NextStep nx;
+    memset(&nx, 0, sizeof(nx));
+    if (next) {
+      nx = *next;
+      nx.tile_part = sc.tile_part;   // consumed by this step's k_cell_groups before the agent kernel runs
+    }
+#define GJ_PIPE_FWD(Q, D, X, I)                                                                                      \
+  k_pipe_forward<Q, D, X><<<pipe_grid(w, k_pipe_forward<Q, D, X>, kPipeThreads, smem, &occ[I]), kPipeThreads, smem,  \
+                            st>>>(*w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets, nx)
+    if (next) {
+      if (quar && diag) GJ_PIPE_FWD(true, true, true, 7);
+      else if (quar) GJ_PIPE_FWD(true, false, true, 6);
+      else if (diag) GJ_PIPE_FWD(false, true, true, 5);
+      else GJ_PIPE_FWD(false, false, true, 4);
+    } else {
+      if (quar && diag) GJ_PIPE_FWD(true, true, false, 3);
+      else if (quar) GJ_PIPE_FWD(true, false, false, 2);
+      else if (diag) GJ_PIPE_FWD(false, true, false, 1);
+      else GJ_PIPE_FWD(false, false, false, 0);
+    }
 #undef GJ_PIPE_FWD
     GJ_CHECK_LAUNCH("k_pipe_forward");
-    return 0;
+    return next ? 1 : 0;
   }
   {
     ProfScope ps(K_AGENT_FWD, st);
@@ -773,8 +790,8 @@ static int lean_backward(const gj_world_desc* w, const gj_step_params* p, const 
       ProfScope ps(K_AGENT_BWD, st);
       static int occ[2] = {0, 0};
       const size_t smem = sizeof(PipeBwdShared);
-      if (quar) k_pipe_backward<true><<<pipe_grid(w, k_pipe_backward<true>, kPipeThreads, smem, &occ[1]), kPipeThreads, smem, st>>>(*w, *p, lp, *io, sc.tile_part);
-      else k_pipe_backward<false><<<pipe_grid(w, k_pipe_backward<false>, kPipeThreads, smem, &occ[0]), kPipeThreads, smem, st>>>(*w, *p, lp, *io, sc.tile_part);
+      if (quar) k_pipe_backward<true><<<pipe_grid(w, k_pipe_backward<true>, kBwdThreads, smem, &occ[1]), kBwdThreads, smem, st>>>(*w, *p, lp, *io, sc.tile_part);
+      else k_pipe_backward<false><<<pipe_grid(w, k_pipe_backward<false>, kBwdThreads, smem, &occ[0]), kBwdThreads, smem, st>>>(*w, *p, lp, *io, sc.tile_part);
       GJ_CHECK_LAUNCH("k_pipe_backward");
     } else {
       ProfScope ps(K_AGENT_BWD, st);
@@ -881,8 +898,8 @@ int gj_boundary_unpack(int64_t n_pack, const int32_t* inv, const float* pack, fl
 }
 
 int gj_pipeline_enable(int on) {
-  const int prev = pipe_enabled() ? 1 : 0;
-  if (on >= 0) g_pipe_on = on ? 1 : 0;
+  const int prev = pipe_flags();
+  if (on >= 0) g_pipe_on = on & 3;
   return prev;
 }
 
@@ -961,7 +978,8 @@ int gj_transmission_backward(int64_t n, float now, const float* tinf, const floa
   return 0;
 }
 
-int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fwd_io* io, void* stream) {
+static int step_forward_impl(const gj_world_desc* w, const gj_step_params* p, const gj_step_params* next,
+                             const gj_fwd_io* io, void* stream) {
   if (int e = check_world(w)) return e;
   if (!p || !io) return bad("params/io is NULL");
   if (p->n_stages > GJ_MAX_STAGES || p->n_age_bins > GJ_MAX_AGE_BINS || p->n_quar > GJ_MAX_QUAR) return bad("params sizes");
@@ -1000,7 +1018,31 @@ int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fw
       if (!io->inf || !io->tinf || !io->cur || !io->nxt || !io->ttn || !io->T || !io->tape_y0 || !io->stage_prob ||
           !io->s_o || !io->inf_o || !io->tinf_o || !io->cur_o || !io->nxt_o || !io->ttn_o)
         return bad("fused step: state / tape arrays are NULL");
-      return lean_forward(w, &pp, pl, lp, io, sc, st);
+      // look-ahead: the following step must itself run on the throughput-mode kernels (it then honours t_ready)
+      NextStep nx;
+      bool have_next = false;
+      if (next && lookahead_enabled() && io->T_next && next->mode == GJ_MODE_STEP && next->phases == GJ_PHASE_ALL &&
+          (next->n_quar <= 0 || io->Tq_next)) {
+        Channels chn;
+        Plan pln;
+        LeanPlan lpn;
+        if (build_channels(w, next, &chn, &pln) == 0 && lean_plan(w, next, pln, &lpn)) {
+          memset(&nx, 0, sizeof(nx));
+          nx.on = 1;
+          nx.now = next->now;
+          nx.day_type = next->day_type;
+          nx.n_quar = next->n_quar > 0 ? next->n_quar : 0;
+          for (int i = 0; i < GJ_MAX_QUAR; ++i) nx.quar_thr[i] = next->quar_thr[i];
+          nx.n_cell = lpn.n_cell;
+          for (int j = 0; j < GJ_MAX_CHANNELS; ++j) nx.c_row[j] = lpn.c_row[j];
+          nx.n_tc = lpn.n_tc;
+          for (int j = 0; j < GJ_MAX_CHANNELS; ++j) nx.tc[j] = lpn.tc[j];
+          nx.T = io->T_next;
+          nx.Tq = nx.n_quar > 0 ? io->Tq_next : io->T_next;
+          have_next = aligned16(io->T_next) && aligned16(io->Tq_next);
+        }
+      }
+      return lean_forward(w, &pp, pl, lp, io, sc, st, have_next ? &nx : nullptr);
     }
   }
   const int grid = (int)w->n_tiles;
@@ -1026,6 +1068,17 @@ int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fw
     GJ_CHECK_LAUNCH("k_tile_forward");
   }
   return 0;
+}
+
+int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fwd_io* io, void* stream) {
+  const int rc = step_forward_impl(w, p, nullptr, io, stream);
+  return rc > 0 ? 0 : rc;
+}
+
+int gj_step_forward_next(const gj_world_desc* w, const gj_step_params* p, const gj_step_params* next,
+                         const gj_fwd_io* io, void* stream) {
+  if (!next) return bad("next params is NULL");
+  return step_forward_impl(w, p, next, io, stream);
 }
 
 int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_bwd_io* io, void* stream) {

@@ -288,8 +288,12 @@ __global__ void __launch_bounds__(kLeanThreads, 6) k_lean_transmission(gj_world_
 // K2  generic-tier group sums, one value per global group: plain = sum of member values,
 //     scaled = (sum of the betas of the type's networks) * pc_g * plain.  Forward: in = Tq; backward: in = wq.
 // =====================================================================================================
-__device__ __forceinline__ void lean_beta_sums(float* bsum, const gj_step_params& p, const Plan& pl,
-                                               const float* __restrict__ beta) {
+struct LeanGroupShared {
+  float bsum[GJ_MAX_TYPES];     // sum of the betas of the type's generic networks; NaN = no active network
+  uint32_t toff[GJ_MAX_TYPES];  // first global group id of each type (32-bit: n_groups < 2^32 is checked on entry)
+};
+__device__ __forceinline__ void lean_beta_sums(LeanGroupShared& sh, const gj_world_desc& w, const gj_step_params& p,
+                                               const Plan& pl, const float* __restrict__ beta) {
   if (threadIdx.x < GJ_MAX_TYPES) {
     float b = 0.0f;
     bool any = false;
@@ -298,9 +302,17 @@ __device__ __forceinline__ void lean_beta_sums(float* bsum, const gj_step_params
         b += beta[k];
         any = true;
       }
-    bsum[threadIdx.x] = any ? b : nanf("");  // NaN marks "no active network on this type"
+    sh.bsum[threadIdx.x] = any ? b : nanf("");
+    sh.toff[threadIdx.x] = (int)threadIdx.x < w.n_types ? (uint32_t)w.type_group_off[threadIdx.x] : 0xFFFFFFFFu;
   }
   __syncthreads();
+}
+// beta sum of group g's type (type_of_group() with 32-bit compares against shared memory)
+__device__ __forceinline__ float lean_group_beta(const LeanGroupShared& sh, uint32_t g) {
+  int t = 0;
+#pragma unroll
+  for (int i = 1; i < GJ_MAX_TYPES; ++i) t += (g >= sh.toff[i]) ? 1 : 0;
+  return sh.bsum[t];
 }
 
 __global__ void __launch_bounds__(kBlock) k_lean_group_small(gj_world_desc w, gj_step_params p, Plan pl,
@@ -308,12 +320,12 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_small(gj_world_desc w, gj
                                                              const float* __restrict__ in,
                                                              float* __restrict__ out_scaled,
                                                              float* __restrict__ out_plain) {
-  __shared__ float bsum[GJ_MAX_TYPES];
-  lean_beta_sums(bsum, p, pl, beta);
+  __shared__ LeanGroupShared gs;
+  lean_beta_sums(gs, w, p, pl, beta);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= w.n_small) return;
   const uint32_t g = w.small_groups[i];
-  const float b = bsum[type_of_group(w, g)];
+  const float b = lean_group_beta(gs, g);
   float S = 0.0f;
   if (b == b) {
     const uint32_t j0 = w.gm_ptr[g], j1 = w.gm_ptr[g + 1];
@@ -337,25 +349,27 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_chunk(gj_world_desc w, gj
                                                              const float* __restrict__ in,
                                                              float* __restrict__ out_scaled,
                                                              float* __restrict__ out_plain, float* __restrict__ part) {
-  __shared__ float bsum[GJ_MAX_TYPES];
-  lean_beta_sums(bsum, p, pl, beta);
+  __shared__ LeanGroupShared gs;
+  lean_beta_sums(gs, w, p, pl, beta);
   const int lane = threadIdx.x & 31;
   const int64_t ci = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (ci >= w.n_chunks) return;
   const uint32_t g = w.chunk_group[ci];
-  const float b = bsum[type_of_group(w, g)];
+  const float b = lean_group_beta(gs, g);
   float S = 0.0f;
   if (b == b) {
     const uint32_t j0 = w.chunk_begin[ci], j1 = w.chunk_end[ci];
-    for (uint32_t j = j0 + lane; j < j1; j += 128) {  // four member gathers per lane in flight
-      uint32_t m[4];
-      float x[4];
+    constexpr int kDeep = 4;  // member gathers per lane in flight (16 was measured slower); the summation order is
+                              // that of a sequential walk of the lane's members
+    for (uint32_t j = j0 + lane; j < j1; j += 32 * kDeep) {
+      uint32_t m[kDeep];
+      float x[kDeep];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) m[k] = (j + 32 * k < j1) ? w.gm_agent[j + 32 * k] : 0u;
+      for (int k = 0; k < kDeep; ++k) m[k] = (j + 32 * k < j1) ? w.gm_agent[j + 32 * k] : 0u;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) x[k] = (j + 32 * k < j1) ? in[m[k]] : 0.0f;
+      for (int k = 0; k < kDeep; ++k) x[k] = (j + 32 * k < j1) ? in[m[k]] : 0.0f;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) S += x[k];
+      for (int k = 0; k < kDeep; ++k) S += x[k];
     }
     S = warp_sum(S);
   }
@@ -374,12 +388,12 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_fix(gj_world_desc w, gj_s
                                                            const float* __restrict__ part,
                                                            float* __restrict__ out_scaled,
                                                            float* __restrict__ out_plain) {
-  __shared__ float bsum[GJ_MAX_TYPES];
-  lean_beta_sums(bsum, p, pl, beta);
+  __shared__ LeanGroupShared gs;
+  lean_beta_sums(gs, w, p, pl, beta);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= w.n_big) return;
   const uint32_t g = w.big_groups[i];
-  const float b = bsum[type_of_group(w, g)];
+  const float b = lean_group_beta(gs, g);
   float S = 0.0f;
   for (uint32_t j = w.big_part_ptr[i]; j < w.big_part_ptr[i + 1]; ++j) S += part[j];
   out_plain[g] = S;
@@ -390,8 +404,11 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_fix(gj_world_desc w, gj_s
 // kernel of gj_pipe.cuh (identical results): pressure -> q -> Gumbel-softmax draw -> infect -> symptoms -> reductions.
 // hs = sum of the member values of the agent's range-tier group, gv = combined value of its generic groups,
 // Lc = class-table value of the cell channels
+struct FwdOut {
+  float inf, tinf, cur;   // post-step is_infected, infection_time, current_stage
+};
 template <bool kQuar, bool kDiag>
-__device__ __forceinline__ void lean_forward_agent(const gj_step_params& p, const LeanPlan& lp, const gj_fwd_io& io,
+__device__ __forceinline__ FwdOut lean_forward_agent(const gj_step_params& p, const LeanPlan& lp, const gj_fwd_io& io,
                                                    uint32_t a, float hs, float gv, float Lc, float beta_r, float rpc,
                                                    float s, float inf, float tinf, float cur, float nxt, float ttn,
                                                    int cls, float inv_tau, float dead, uint32_t key0, uint32_t key1,
@@ -426,7 +443,8 @@ __device__ __forceinline__ void lean_forward_agent(const gj_step_params& p, cons
     const float inf_o = inf + n;
     io.s_o[a] = fmaxf(0.0f, s - n);
     io.inf_o[a] = inf_o;
-    io.tinf_o[a] = tinf + n * (p.now - tinf);
+    const float tinf_o = tinf + n * (p.now - tinf);
+    io.tinf_o[a] = tinf_o;
     // symptoms (symptoms.py:204-247)
     const uint64_t seed = p.seed;
     const uint32_t call = p.call_index;
@@ -440,6 +458,11 @@ __device__ __forceinline__ void lean_forward_agent(const gj_step_params& p, cons
     // reductions (runner.py:167-171,198-224): small integers, exact in any order
     if (inf_o != 0.0f) atomicAdd(&hist[age], inf_o);
     if (so.cur == dead) atomicAdd(deaths, so.cur / dead);
+    FwdOut out;
+    out.inf = inf_o;
+    out.tinf = tinf_o;
+    out.cur = so.cur;
+    return out;
 }
 
 // =====================================================================================================

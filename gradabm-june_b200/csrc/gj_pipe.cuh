@@ -130,8 +130,35 @@ __device__ __forceinline__ void pipe_init_barriers(uint64_t* full) {
 }
 
 // =====================================================================================================
-// K3p  forward
+// K3p  forward (+ optionally the transmission pass of the FOLLOWING step, from the state just written)
 // =====================================================================================================
+// what the forward has to know about the step after this one to run its transmission pass (K1 of gj_lean.cuh)
+struct NextStep {
+  int on;
+  float now;
+  int day_type;
+  int n_quar;
+  float quar_thr[GJ_MAX_QUAR];
+  int n_cell;                       // cell channels of the next step and their attendance tables
+  int c_row[GJ_MAX_CHANNELS];
+  int n_tc;                         // its distinct tile -> cell maps
+  const uint32_t* tc[GJ_MAX_CHANNELS];
+  float* T;
+  float* Tq;                        // may alias T when n_quar <= 0
+  float* tile_part;
+};
+__device__ __forceinline__ float quar_mask_next(const NextStep& nx, float cur) {
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < GJ_MAX_QUAR; ++i)
+    if (i < nx.n_quar) ok = ok && (cur < nx.quar_thr[i]);
+  return ok ? 1.0f : 0.0f;
+}
+__device__ __forceinline__ bool next_new_cell(const NextStep& nx, int64_t a, int64_t b) {
+  bool changed = false;
+  for (int i = 0; i < nx.n_tc; ++i) changed = changed || (nx.tc[i][a] != nx.tc[i][b]);
+  return changed;
+}
 struct alignas(16) PipeFwdStage {
   float s[kPipeF], inf[kPipeF], tinf[kPipeF], cur[kPipeF], nxt[kPipeF], ttn[kPipeF], rpc[kPipeF];
   uint32_t ent[kPipeF], slot[kPipeF];
@@ -141,6 +168,7 @@ struct alignas(16) PipeFwdStage {
 struct PipeFwdShared {
   PipeFwdStage st[kPipeStages];
   ProbRow prob[200];
+  ProbRow prob_next[200];   // transmission-side tables of the next step (look-ahead only)
   float L[2][200];
   float beta[GJ_MAX_NETS];
   float hist[100];
@@ -172,11 +200,11 @@ __device__ __forceinline__ void pipe_fwd_issue(PipeFwdStage& sg, uint64_t* bar, 
   bulk_g2s(sg.cls, w.cls + t.lo16, t.hi16 - t.lo16, bar);
 }
 
-template <bool kQuar, bool kDiag>
+template <bool kQuar, bool kDiag, bool kNext>
 __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc w, gj_step_params p, LeanPlan lp,
                                                                  gj_fwd_io io, const float* __restrict__ cell_buf,
                                                                  double* __restrict__ red_part,
-                                                                 unsigned int* __restrict__ ticket) {
+                                                                 unsigned int* __restrict__ ticket, NextStep nx) {
   extern __shared__ __align__(128) unsigned char pipe_smem[];
   PipeFwdShared& sh = *reinterpret_cast<PipeFwdShared*>(pipe_smem);
   const TileRun run = lean_tiles(w);
@@ -184,6 +212,12 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
   const bool has_gen = lp.has_generic != 0, has_range = lp.n_range > 0;
   pipe_init_barriers(sh.full);
   lean_load_prob<true>(sh.prob, p, lp, io.leisure_prob);
+  if (kNext) {
+    for (int i = threadIdx.x; i < GJ_MAX_CHANNELS * 200; i += blockDim.x) {
+      const int j = i / 200, c = i - j * 200;
+      sh.prob_next[c].v[j] = j < nx.n_cell ? io.leisure_prob[(size_t)(nx.c_row[j] * 2 + nx.day_type) * 200 + c] : 0.0f;
+    }
+  }
   if (threadIdx.x < p.n_nets) sh.beta[threadIdx.x] = io.beta[threadIdx.x];
   if (threadIdx.x < 100) sh.hist[threadIdx.x] = 0.0f;
   if (threadIdx.x == 0) sh.deaths = 0.0f;
@@ -198,6 +232,10 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
   const uint32_t key0 = (uint32_t)p.seed, key1 = (uint32_t)(p.seed >> 32);
   const float beta_r = lp.n_range > 0 ? sh.beta[lp.r_net] : 0.0f;
 
+  const float4* __restrict__ prof = reinterpret_cast<const float4*>(io.prof4);
+  float acc[GJ_MAX_CHANNELS];   // look-ahead: partial sums of the next step's cell channels
+#pragma unroll
+  for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
   int nbuild = 0, stg = 0;
   uint32_t parity = 0;
   const float* L = sh.L[0];
@@ -215,11 +253,16 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
     const uint32_t sk = a0 & 3u, sk16 = a0 & 15u, tlo = halo_lo(a0);
     uint32_t ent[kPipePer];
     float gen[kPipePer];
+    float4 pfe[kPipePer];   // look-ahead: packed profile of the agents that are already infected (issued early)
 #pragma unroll
     for (int h = 0; h < kPipePer; ++h) {   // the L2 gathers first, for all of this thread's agents
       const uint32_t j = threadIdx.x + h * kPipeThreads;
       ent[h] = (has_gen && a0 + j < a1) ? sg.ent[j + sk] : kEntNone;
       gen[h] = lean_generic_issue(SP, ent[h]);
+      if (kNext) {
+        pfe[h] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (a0 + j < a1 && sg.inf[j + sk] != 0.0f) pfe[h] = prof[a0 + j];
+      }
     }
 #pragma unroll
     for (int h = 0; h < kPipePer; ++h) {
@@ -230,15 +273,38 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
       const int cls = sg.cls[j + sk16];
       const float Lc = lp.n_cell > 0 ? L[cls] : 0.0f;
       const float gv = lean_generic_finish(w, SP, ent[h], a, gen[h]);
-      lean_forward_agent<kQuar, kDiag>(p, lp, io, a, hs, gv, Lc, beta_r, has_range ? sg.rpc[i] : 0.0f, sg.s[i], sg.inf[i],
-                                       sg.tinf[i], sg.cur[i], sg.nxt[i], sg.ttn[i], cls, inv_tau, dead, key0, key1,
-                                       sh.hist, &sh.deaths);
+      const FwdOut o = lean_forward_agent<kQuar, kDiag>(p, lp, io, a, hs, gv, Lc, beta_r, has_range ? sg.rpc[i] : 0.0f,
+                                                        sg.s[i], sg.inf[i], sg.tinf[i], sg.cur[i], sg.nxt[i], sg.ttn[i], cls,
+                                                        inv_tau, dead, key0, key1, sh.hist, &sh.deaths);
+      if (kNext) {   // TransmissionUpdater of the next step (same arithmetic as k_lean_transmission)
+        float T = 0.0f;
+        if (o.inf != 0.0f) {
+          const float4 pf = (sg.inf[i] != 0.0f) ? pfe[h] : prof[a];   // newly infected: fetched now (rare)
+          T = lean_transmission<false>(nx.now, o.tinf, pf).coef * o.inf;
+        }
+        nx.T[a] = T;
+        float Tq = T;
+        if (nx.n_quar > 0) {
+          Tq = quar_mask_next(nx, o.cur) * T;
+          nx.Tq[a] = Tq;
+        }
+        if (Tq != 0.0f && nx.n_cell > 0) lean_channel_fma(acc, sh.prob_next, cls, Tq, nx.n_cell);
+      }
     }
     if (pipe_release() && tile + kPipeStages < run.t1)
       pipe_fwd_issue(sg, &sh.full[stg], w, lp, io, Tr, tile + kPipeStages, has_gen, has_range);
     if (++stg == kPipeStages) {
       stg = 0;
       parity ^= 1u;
+    }
+    if (kNext && nx.n_cell > 0) {   // as in B1p: a cell run's sums go to its last tile, zeros to the others
+      if (tile + 1 == run.t1 || next_new_cell(nx, tile, tile + 1)) {
+        block_sums<float, GJ_MAX_CHANNELS, kPipeWarps>(acc, nx.n_cell, nx.tile_part + tile * GJ_MAX_CHANNELS);
+#pragma unroll
+        for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
+      } else if ((int)threadIdx.x < nx.n_cell) {
+        nx.tile_part[tile * GJ_MAX_CHANNELS + threadIdx.x] = 0.0f;
+      }
     }
   }
   if (io.red) {
@@ -293,8 +359,14 @@ __device__ __forceinline__ void pipe_bwd_issue(PipeBwdStage& sg, uint64_t* bar, 
   bulk_g2s(sg.cls, w.cls + t.lo16, t.hi16 - t.lo16, bar);
 }
 
+#ifndef GJ_PIPE_BWD_THREADS
+#define GJ_PIPE_BWD_THREADS 512
+#endif
+constexpr int kBwdThreads = GJ_PIPE_BWD_THREADS;
+constexpr int kBwdPer = kPipeTile / kBwdThreads;
+constexpr int kBwdCtas = kBwdThreads == 256 ? 3 : 2;
 template <bool kQuar>
-__global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward(gj_world_desc w, gj_step_params p, LeanPlan lp,
+__global__ void __launch_bounds__(kBwdThreads, kBwdCtas) k_pipe_backward(gj_world_desc w, gj_step_params p, LeanPlan lp,
                                                                   gj_bwd_io io, float* __restrict__ tile_part) {
   extern __shared__ __align__(128) unsigned char pipe_smem[];
   PipeBwdShared& sh = *reinterpret_cast<PipeBwdShared*>(pipe_smem);
@@ -330,18 +402,18 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward(gj_world_desc
     mbar_wait(&sh.full[stg], parity);
     PIPE_TILE_FACTS;
     // the cotangents of the state outputs stream through registers
-    float c[kPipePer][6];
+    float c[kBwdPer][6];
 #pragma unroll
-    for (int h = 0; h < kPipePer; ++h) {
-      const uint32_t a = a0 + threadIdx.x + h * kPipeThreads;
+    for (int h = 0; h < kBwdPer; ++h) {
+      const uint32_t a = a0 + threadIdx.x + h * kBwdThreads;
       const uint32_t al = a < a1 ? a : a0;
 #pragma unroll
       for (int k = 0; k < 6; ++k) c[h][k] = cot.p[k] ? cot.p[k][al] : 0.0f;
     }
     const uint32_t sk = a0 & 3u, sk16 = a0 & 15u;
 #pragma unroll
-    for (int h = 0; h < kPipePer; ++h) {
-      const uint32_t j = threadIdx.x + h * kPipeThreads;
+    for (int h = 0; h < kBwdPer; ++h) {
+      const uint32_t j = threadIdx.x + h * kBwdThreads;
       const uint32_t a = a0 + j, i = j + sk;
       if (a >= a1) break;
       lean_backward_agent<kQuar>(p, lp, io, a, sg.s[i], sg.tinf[i], sg.cur[i], sg.nxt[i], sg.ttn[i], sg.ty[i], sg.v[i],
@@ -356,7 +428,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward(gj_world_desc
     }
     if (lp.n_cell > 0) {   // partial sums of the cell channels: written at the last tile of a cell run (see K1)
       if (flush) {
-        block_sums<float, GJ_MAX_CHANNELS, kPipeWarps>(acc, lp.n_cell, tile_part + tile * GJ_MAX_CHANNELS);
+        block_sums<float, GJ_MAX_CHANNELS, (kBwdThreads / 32)>(acc, lp.n_cell, tile_part + tile * GJ_MAX_CHANNELS);
 #pragma unroll
         for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
       } else if ((int)threadIdx.x < lp.n_cell) {

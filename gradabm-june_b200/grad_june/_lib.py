@@ -18,7 +18,7 @@ GJ_MAX_STAGES = 16
 GJ_MAX_QUAR = 4
 GJ_MAX_AGE_BINS = 8
 GJ_MAX_CHANNELS = 8
-GJ_ABI_VERSION = 3
+GJ_ABI_VERSION = 4
 
 KIND_PLAIN, KIND_HOUSEHOLD, KIND_LEISURE, KIND_CARE_VISIT = 0, 1, 2, 3
 PHASE_NETWORKS, PHASE_SAMPLE, PHASE_INFECT, PHASE_SYMPTOMS, PHASE_ALL = 1, 2, 4, 8, 15
@@ -67,7 +67,7 @@ class StepParams(C.Structure):
         ("n_stages", C.c_int32), ("trans_time", Dist * GJ_MAX_STAGES), ("rec_time", Dist * GJ_MAX_STAGES),
         ("n_age_bins", C.c_int32), ("age_bins", C.c_int32 * (GJ_MAX_AGE_BINS + 1)),
         ("tau", C.c_float), ("seed", C.c_uint64), ("call_index", C.c_uint32), ("exact_order", C.c_uint32),
-        ("stage", C.c_uint32), ("_pad1", C.c_uint32), ("agent_offset", C.c_uint64),
+        ("stage", C.c_uint32), ("t_ready", C.c_uint32), ("agent_offset", C.c_uint64),
     ]
 
 
@@ -76,7 +76,7 @@ _FWD_FIELDS = [
     "s", "inf", "tinf", "cur", "nxt", "ttn", "maxinf", "shape", "rate", "shift", "k0", "prof4",
     "T_in", "q_in", "n_in",
     "s_o", "inf_o", "tinf_o", "cur_o", "nxt_o", "ttn_o", "T", "Tq", "q", "lam", "n",
-    "tape_v", "tape_y0", "S_scaled", "S_unscaled", "red", "scratch",
+    "tape_v", "tape_y0", "S_scaled", "S_unscaled", "red", "scratch", "T_next", "Tq_next",
 ]
 _BWD_FIELDS = [
     "beta", "leisure_prob", "stage_prob", "seed_fraction", "inj_E", "inj_u", "inj_z",
@@ -152,6 +152,8 @@ def lib():
     L.gj_transmission_forward.argtypes = [C.c_int64, C.c_float] + [C.c_void_p] * 9
     L.gj_transmission_backward.argtypes = [C.c_int64, C.c_float] + [C.c_void_p] * 11
     L.gj_step_forward.argtypes = [C.POINTER(WorldDesc), C.POINTER(StepParams), C.POINTER(FwdIO), C.c_void_p]
+    L.gj_step_forward_next.argtypes = [C.POINTER(WorldDesc), C.POINTER(StepParams), C.POINTER(StepParams),
+                                       C.POINTER(FwdIO), C.c_void_p]
     L.gj_step_backward.argtypes = [C.POINTER(WorldDesc), C.POINTER(StepParams), C.POINTER(BwdIO), C.c_void_p]
     L.gj_philox_fill_at.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]
@@ -189,15 +191,17 @@ def check(rc, what):
 
 EXPORTED_SYMBOLS = [
     "gj_abi_version", "gj_last_error", "gj_config", "gj_scratch_bytes", "gj_profile_prepare", "gj_profile_pack",
-    "gj_transmission_forward", "gj_transmission_backward", "gj_step_forward", "gj_step_backward",
+    "gj_transmission_forward", "gj_transmission_backward", "gj_step_forward", "gj_step_forward_next", "gj_step_backward",
     "gj_philox_fill", "gj_philox_fill_at", "gj_step_plan", "gj_philox4x32_10", "gj_profile_enable", "gj_profile_read",
     "gj_profile_kernel_name", "gj_pipeline_enable", "gj_boundary_pack", "gj_boundary_unpack",
 ]
 
 
-def pipeline_enable(on=True):
-    """Bulk-copy pipelined agent kernels on/off (bit-identical results); returns the previous setting."""
-    return bool(lib().gj_pipeline_enable(-1 if on is None else (1 if on else 0)))
+def pipeline_enable(on=True, lookahead=False):
+    """Bulk-copy pipelined agent kernels on/off (bit-identical results) and, with them, the fused transmission pass
+    of the following step (``lookahead``); returns the previous setting as (on, lookahead).  ``on=None`` queries."""
+    prev = lib().gj_pipeline_enable(-1 if on is None else ((1 if on else 0) | (2 if (on and lookahead) else 0)))
+    return bool(prev & 1), bool(prev & 2)
 
 
 def profile_enable(on=True):

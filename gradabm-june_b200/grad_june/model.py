@@ -76,14 +76,7 @@ class GradJune(torch.nn.Module):
             cache["static"] = hit = (key, static, rows)
         return hit[1], hit[2]
 
-    def step(self, data, timer, age_bins=None, mode=ops.MODE_STEP, seed_fraction=None, noise=None, want_probs=True):
-        """Fused step; returns (data, reductions) where reductions = [cases, deaths, cases by age bin...]
-        (None unless ``age_bins`` is given).  ``want_probs=False`` skips the two diagnostic per-agent outputs
-        (``not_infected_probs``, ``new_infected``) that the reference keeps only as locals of its forward."""
-        agent = data["agent"]
-        ops.require_cuda(agent.susceptibility, "data['agent'].susceptibility")
-        dev = agent.susceptibility.device
-        static, rows = self._static(data, dev)
+    def _spec(self, timer, rows, age_bins, mode, want_probs):
         policies = self.policies
         if mode == ops.MODE_SEED:
             nets, phases = [], ops.PHASE_SAMPLE | ops.PHASE_INFECT | ops.PHASE_SYMPTOMS
@@ -95,11 +88,30 @@ class GradJune(torch.nn.Module):
             quarantine=_quarantine_thresholds(policies, timer), phases=phases, mode=mode,
             age_bins=tuple(int(b) for b in age_bins) if age_bins is not None else (),
             want_reductions=age_bins is not None, want_probs=want_probs)
+        return spec, nets
+
+    def step(self, data, timer, age_bins=None, mode=ops.MODE_STEP, seed_fraction=None, noise=None, want_probs=True,
+             next_timer=None):
+        """Fused step; returns (data, reductions) where reductions = [cases, deaths, cases by age bin...]
+        (None unless ``age_bins`` is given).  ``want_probs=False`` skips the two diagnostic per-agent outputs
+        (``not_infected_probs``, ``new_infected``) that the reference keeps only as locals of its forward.
+        ``next_timer``: the timer as it will be at the FOLLOWING call (the driver knows the schedule): the
+        kernels then run that step's transmission pass inside this one (used only if the next call matches)."""
+        agent = data["agent"]
+        ops.require_cuda(agent.susceptibility, "data['agent'].susceptibility")
+        dev = agent.susceptibility.device
+        static, rows = self._static(data, dev)
+        policies = self.policies
+        spec, nets = self._spec(timer, rows, age_bins, mode, want_probs)
+        next_spec = None
+        if next_timer is not None and mode == ops.MODE_STEP:
+            next_spec, _ = self._spec(next_timer, rows, age_bins, ops.MODE_STEP, want_probs)
         sym = agent["symptoms"]
         state = {"s": agent.susceptibility, "inf": agent.is_infected, "tinf": agent.infection_time,
                  "cur": sym["current_stage"], "nxt": sym["next_stage"], "ttn": sym["time_to_next_stage"]}
         beta = beta_vector(nets, policies, timer, dev) if nets else None
-        out = ops.infection_step(static, spec, beta, state, seed_fraction=seed_fraction, noise=noise)
+        out = ops.infection_step(static, spec, beta, state, seed_fraction=seed_fraction, noise=noise,
+                                 next_spec=next_spec)
         if out["T"] is not None:
             agent.transmission = out["T"]
         agent.susceptibility = out["s"]

@@ -313,13 +313,25 @@ def transmission(now, tinf, inf, maxinf, shape, rate, shift, k0=None):
 _STATE = ("s", "inf", "tinf", "cur", "nxt", "ttn")
 
 
-def _staged_call(fn, what, static: "StepStatic", desc, p, io, stream, sum_buffers, lean_inputs: bool):
+def _staged_call(fn, what, static: "StepStatic", desc, p, io, stream, sum_buffers, lean_inputs: bool, p_next=None):
     """One library call, or — for a partitioned world — the two stages of it with the all-reduce of the boundary
-    groups' sums (``sum_buffers``: the two group-sum tensors of this call) in between."""
+    groups' sums (``sum_buffers``: the two group-sum tensors of this call) in between.  ``p_next``: parameters of
+    the following step for gj_step_forward_next.  Returns the library's (non-negative) return code."""
+    world = static.world
+    world.__dict__["_calls"] = world.__dict__.get("_calls", 0) + 1   # the per-world scratch changes hands
+
+    def call():
+        if p_next is not None:
+            rc = _lib.lib().gj_step_forward_next(C.byref(desc), C.byref(p), C.byref(p_next), C.byref(io), stream)
+        else:
+            rc = fn(C.byref(desc), C.byref(p), C.byref(io), stream)
+        if rc < 0:
+            _lib.check(rc, what)
+        return rc
+
     ex = static.exchange
     if ex is None or sum_buffers is None:
-        _lib.check(fn(C.byref(desc), C.byref(p), C.byref(io), stream), what)
-        return
+        return call()
     out = (C.c_int64 * 1)()
     lean = _lib.lib().gj_step_plan(C.byref(desc), C.byref(p), out, 1)
     if lean < 0:
@@ -327,11 +339,24 @@ def _staged_call(fn, what, static: "StepStatic", desc, p, io, stream, sum_buffer
     lean = bool(lean) and lean_inputs
     region = ex.regions(lean, int(out[0]), [(p.nets[k].type, p.nets[k].s_off) for k in range(p.n_nets)])
     p.stage = _lib.STAGE_SUMS
-    _lib.check(fn(C.byref(desc), C.byref(p), C.byref(io), stream), what)
+    call()
     ex.exchange(sum_buffers, region)
     p.stage = _lib.STAGE_REST
-    _lib.check(fn(C.byref(desc), C.byref(p), C.byref(io), stream), what)
+    rc = call()
     p.stage = _lib.STAGE_ALL
+    return rc
+
+
+def _spec_key(spec: "StepSpec"):
+    """What the transmission pass of a step depends on besides the state (look-ahead bookkeeping)."""
+    return (float(spec.now), int(spec.day_type), tuple((n.edge_type, n.kind, n.prob_row) for n in spec.nets),
+            None if spec.quarantine is None else tuple(float(t) for t in spec.quarantine), spec.mode, spec.phases,
+            bool(spec.exact_order))
+
+
+def _same(t, ref):
+    return t is not None and ref is not None and t.data_ptr() == ref.data_ptr() and t._version == ref._version \
+        and t.shape == ref.shape
 
 
 class _Step(torch.autograd.Function):
@@ -343,7 +368,7 @@ class _Step(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, static: StepStatic, spec: StepSpec, noise, beta, s, inf, tinf, cur, nxt, ttn, T_in, q_in, n_in,
-                seed_fraction):
+                seed_fraction, next_spec=None):
         world = static.world
         dev = world.device
         N = world.n_agents
@@ -392,12 +417,24 @@ class _Step(torch.autograd.Function):
             for name in ("cur_o", "nxt_o", "ttn_o"):
                 out[name] = new(name)
         T = None
-        if fused_T:
-            T = new("T")
-            io.Tq = _buffer(world, "Tq", N).data_ptr() if p.n_quar > 0 else T.data_ptr()
-        elif nets_on and p.n_quar > 0:
-            io.Tq = _buffer(world, "Tq", N).data_ptr()
         fused_all = fused_T and phases == PHASE_ALL
+        # look-ahead: the previous step's forward may already have run this step's transmission pass
+        pf = world.__dict__.pop("_prefetch", None)
+        tq_name = "Tq0"
+        if (pf is not None and fused_all and E is None and u is None and z is None and pf["key"] == _spec_key(spec)
+                and pf["calls"] == world.__dict__.get("_calls", 0) and _same(st["inf"], pf["inf"])
+                and _same(st["tinf"], pf["tinf"]) and _same(st["cur"], pf["cur"])):
+            T = pf["T"]
+            io.T = T.data_ptr()
+            io.Tq = pf["Tq"].data_ptr() if p.n_quar > 0 else T.data_ptr()
+            tq_name = pf["tq_name"]
+            p.t_ready = 1
+            keep.append(pf)
+        elif fused_T:
+            T = new("T")
+            io.Tq = _buffer(world, tq_name, N).data_ptr() if p.n_quar > 0 else T.data_ptr()
+        elif nets_on and p.n_quar > 0:
+            io.Tq = _buffer(world, tq_name, N).data_ptr()
         probs = spec.want_probs or not fused_all   # the fused step needs neither q nor n for its own backward
         q = new("q") if (nets_on and probs) else None
         lam = new("lam") if (nets_on and spec.want_lam) else None
@@ -420,8 +457,23 @@ class _Step(torch.autograd.Function):
         if static.exchange is not None:
             p.agent_offset = static.exchange.part.agent_lo
         lean_inputs = E is None and u is None and z is None and T_in is None and lam is None and static.prof4 is not None
-        _staged_call(L.gj_step_forward, "gj_step_forward", static, desc, p, io, _stream(dev),
-                     (S_sc, S_un) if nets_on else None, lean_inputs)
+        p_next = T_next = Tq_next = None
+        if next_spec is not None and fused_all and lean_inputs and not seed_mode:
+            # also run the NEXT step's transmission pass inside this step's agent kernel (gj_step_forward_next)
+            p_next, _ = _fill_params(world, next_spec, static.symptoms, 0, 0)
+            T_next = torch.empty(N, dtype=torch.float32, device=dev)
+            io.T_next = T_next.data_ptr()
+            if p_next.n_quar > 0:
+                next_tq_name = "Tq1" if tq_name == "Tq0" else "Tq0"   # this step's kernels still read the other one
+                Tq_next = _buffer(world, next_tq_name, N)
+                io.Tq_next = Tq_next.data_ptr()
+        rc = _staged_call(L.gj_step_forward, "gj_step_forward", static, desc, p, io, _stream(dev),
+                          (S_sc, S_un) if nets_on else None, lean_inputs, p_next=p_next)
+        if p_next is not None and rc == 1:
+            world.__dict__["_prefetch"] = dict(
+                key=_spec_key(next_spec), calls=world.__dict__.get("_calls", 0), T=T_next, Tq=Tq_next,
+                tq_name=next_tq_name if Tq_next is not None else "Tq0", inf=out.get("inf_o"), tinf=out.get("tinf_o"),
+                cur=out.get("cur_o"))
 
         ctx.static, ctx.spec, ctx.noise_key = static, spec, (seed, call_index)
         ctx.set_materialize_grads(False)
@@ -529,11 +581,11 @@ class _Step(torch.autograd.Function):
                 grads.get("s") if need[4] else None, grads.get("inf") if need[5] else None,
                 grads.get("tinf") if need[6] else None, grads.get("cur") if need[7] else None,
                 grads.get("nxt") if need[8] else None, grads.get("ttn") if need[9] else None,
-                g_T_in if need[10] else None, g_q_in, g_n_in, g_frac if need[13] else None)
+                g_T_in if need[10] else None, g_q_in, g_n_in, g_frac if need[13] else None, None)
 
 
 def infection_step(static: StepStatic, spec: StepSpec, beta, state: dict, T_in=None, q_in=None, n_in=None,
-                   seed_fraction=None, noise=None):
+                   seed_fraction=None, noise=None, next_spec=None):
     """Run one (fused or partial) step.  ``state``: s, inf, tinf, cur, nxt, ttn (any may be None when
     the phases do not need it).  Returns a dict with s, inf, tinf, cur, nxt, ttn, T, q, n, red."""
     world = static.world
@@ -547,6 +599,6 @@ def infection_step(static: StepStatic, spec: StepSpec, beta, state: dict, T_in=N
         else:
             noise = (0, 0, None, None, None)
     outs = _Step.apply(static, spec, noise, beta, state.get("s"), state.get("inf"), state.get("tinf"),
-                       state.get("cur"), state.get("nxt"), state.get("ttn"), T_in, q_in, n_in, seed_fraction)
+                       state.get("cur"), state.get("nxt"), state.get("ttn"), T_in, q_in, n_in, seed_fraction, next_spec)
     names = ("s", "inf", "tinf", "cur", "nxt", "ttn", "T", "q", "n", "red", "lam")
     return dict(zip(names, outs))

@@ -6,6 +6,7 @@ fused step.  The per-step result reductions (cases, differentiable deaths, cases
 runner.py:167-171,198-224) are produced inside the step kernel, so the loop issues no extra passes
 over the agents.
 """
+import copy
 from pathlib import Path
 
 import numpy as np
@@ -123,7 +124,11 @@ class Runner(torch.nn.Module):
         dates = [timer.date]
         while timer.date < timer.final_date:
             next(timer)
-            data, red = model.step(data, timer, age_bins=self._age_bins_host, want_probs=False)
+            ahead = None
+            if timer.date < timer.final_date:      # the schedule is known: tell the step what the next one will be
+                ahead = copy.copy(timer)
+                next(ahead)
+            data, red = model.step(data, timer, age_bins=self._age_bins_host, want_probs=False, next_timer=ahead)
             reds.append(red)
             dates.append(timer.date)
         table = torch.stack(reds)                      # [T+1, 2 + n_bins]

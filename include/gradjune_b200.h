@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GJ_ABI_VERSION 3
+#define GJ_ABI_VERSION 4
 
 #define GJ_MAX_TYPES 8      /* edge types (household, company, school, university, care_home, leisure, ...) */
 #define GJ_MAX_NETS 16      /* infection networks active in one step */
@@ -173,7 +173,9 @@ typedef struct gj_step_params {
    * per-group sums (forward: S_scaled / S_unscaled, backward: cR / R) are written, so that the caller can
    * all-reduce the sums of groups that straddle partitions; GJ_STAGE_REST continues from the (summed) buffers */
   uint32_t stage;
-  uint32_t _pad1;
+  /* 1: io->T (and io->Tq) and the scratch tile sums of the cell channels were already produced for this step by the
+   * previous step's gj_step_forward_next (same state tensors, same schedule): skip the transmission pass */
+  uint32_t t_ready;
   /* global id of this rank's first agent: the Philox counter is (agent_offset + local agent index), so a
    * partitioned world draws exactly the noise of the unpartitioned one */
   uint64_t agent_offset;
@@ -216,6 +218,10 @@ typedef struct gj_fwd_io {
   float* S_unscaled; /* plain group sums (saved: d/dbeta) */
   float* red;        /* [2 + n_age_bins] cases, deaths, cases by age bin */
   void* scratch;     /* gj_scratch_bytes() bytes, zero-initialised once by the caller */
+  /* gj_step_forward_next: transmissions of the NEXT step (from this step's output state), [N] each; Tq_next only
+   * when the next step has an active quarantine */
+  float* T_next;
+  float* Tq_next;
 } gj_fwd_io;
 
 typedef struct gj_bwd_io {
@@ -286,6 +292,13 @@ int gj_transmission_backward(int64_t n, float now, const float* tinf, const floa
  *      infection.py:21-28), SymptomsUpdater.forward (symptoms.py:204-247), plus the per-step result
  *      reductions of Runner.forward (runner.py:167-171,198-224) ------------------------------- */
 int gj_step_forward(const gj_world_desc* w, const gj_step_params* p, const gj_fwd_io* io, void* stream);
+/* gj_step_forward that ALSO runs the transmission pass of the following step (params `next`) inside its agent kernel,
+ * from the state it has just written: the next call then sets next->t_ready = 1, passes T_next / Tq_next as its T / Tq,
+ * and skips a whole pass over the agents (TransmissionUpdater.forward of step t+1 fused into GradJune.forward of step
+ * t).  Returns 1 when the look-ahead was produced, 0 when this (world, params, next) combination cannot (then it
+ * behaved exactly like gj_step_forward), < 0 on error. */
+int gj_step_forward_next(const gj_world_desc* w, const gj_step_params* p, const gj_step_params* next,
+                         const gj_fwd_io* io, void* stream);
 /* reverse-mode derivative of gj_step_forward (replaces autograd's replay of the op tape) */
 int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_bwd_io* io, void* stream);
 
@@ -301,7 +314,9 @@ int gj_boundary_unpack(int64_t n_pack, const int32_t* inv, const float* pack, fl
  * 1 (default; GJ_PIPE=0 in the environment turns it off): the agent kernels stage every per-agent array of a tile
  * in shared memory with TMA bulk copies (two-stage mbarrier pipeline) — needs every per-agent array 16-byte aligned
  * and readable up to the next multiple of 16 bytes past its end (true of any allocator with >= 16-byte granules);
- * 0: register-batched loads.  Results are bit-identical.  on < 0 only queries.  Returns the previous setting. */
+ * 0: register-batched loads.  Results are bit-identical.  on < 0 only queries.  Returns the previous setting.
+ * Bit 1 of `on` (value 2, default clear: measured neutral on B200) allows gj_step_forward_next to
+ * produce the look-ahead. */
 int gj_pipeline_enable(int on);
 
 /* ---- measurement (bench.py): CUDA events recorded on the launching stream around every kernel ---- */

@@ -339,7 +339,7 @@ def test_pipelined_kernels_are_bit_identical(quarantine):
     prev = _lib.pipeline_enable(None)
     try:
         for mode in (False, True):
-            _lib.pipeline_enable(mode)
+            _lib.pipeline_enable(mode, lookahead=False)
             leaves = []
             for k in keys:
                 leaf = torch.tensor(float(params["networks"][k]["log_beta"]) + 0.4, device=DEV, requires_grad=True)
@@ -356,7 +356,7 @@ def test_pipelined_kernels_are_bit_identical(quarantine):
                           agent.symptoms["current_stage"].detach(), agent.symptoms["next_stage"].detach(),
                           agent.symptoms["time_to_next_stage"].detach(), torch.stack([l.grad for l in leaves])]
     finally:
-        _lib.pipeline_enable(prev)
+        _lib.pipeline_enable(*prev)
     assert outs[False][0][-1] > outs[False][0][0] > 0
     for a, b in zip(outs[False][:-1], outs[True][:-1]):
         assert torch.equal(a, b)
@@ -413,3 +413,66 @@ def test_graphed_runner_replays_the_eager_window():
         assert torch.equal(loss, ref[0])
         assert torch.equal(grads, ref[1])
     assert e1[2][-1] > e1[2][0] > 0 and not torch.equal(e1[1], e2[1])
+
+
+@pytest.mark.parametrize("policies", [False, True])
+def test_lookahead_transmission_pass(policies):
+    """gj_step_forward_next: step t's agent kernel also runs step t+1's transmission pass (one pass over the agents
+    less per step).  Same arithmetic per agent; only the tile sums of the leisure channels are associated
+    differently, so trajectories agree up to near-tie flips and gradients to fp32 rounding.  With policies the
+    look-ahead has to follow the schedule (quarantine mask, closed venues, weekday/weekend tables of the NEXT step)."""
+    from grad_june import GradJune, Timer, _lib, ops
+    from grad_june.default_config import default_parameters
+    from grad_june.runner import Runner
+    from grad_june.world import make_synthetic_world
+    n_agents = 250_003
+    params = default_parameters()
+    params["system"]["device"] = DEV
+    params["timer"]["total_days"] = 8          # crosses a weekend (2022-02-05/06)
+    params["infection_seed"]["log_fraction_initial_cases"] = -1.5
+    params["policies"] = {}
+    if policies:
+        params["policies"] = {
+            "quarantine": {"quarantine": {1: {"start_date": "2022-02-03", "end_date": "2022-02-07", "stage_threshold": 4}}},
+            "close_venue": {"close_venue": {1: {"start_date": "2022-02-04", "end_date": "2022-02-08",
+                                                "names": ["school", "pub", "gym"]}}},
+            "interaction": {"social_distancing": {1: {"start_date": "2022-02-02", "end_date": "2022-02-06",
+                                                      "beta_factors": {"company": 0.5, "visit": 0.5}}}}}
+    torch.manual_seed(5)
+    data = Runner.get_data(params, data=make_synthetic_world(n_agents, seed=7, device=DEV, agents_per_super_area=5000))
+    model = GradJune.from_parameters(params)
+    keys = list(model.infection_networks.networks.keys())
+    runner = Runner(model=model, data=data, timer=Timer.from_parameters(params), log_fraction_initial_cases=-1.5,
+                    save_path="/tmp/gj_test", parameters=params)
+    outs = {}
+    prev = _lib.pipeline_enable(None)
+    try:
+        for look in (False, True):
+            _lib.pipeline_enable(True, lookahead=look)
+            leaves = []
+            for k in keys:
+                leaf = torch.tensor(float(params["networks"][k]["log_beta"]) + 0.4, device=DEV, requires_grad=True)
+                model.infection_networks.networks[k].log_beta = leaf
+                leaves.append(leaf)
+            _lib.profile_enable(True)
+            with ops.philox_seed(32):
+                results, is_inf = runner()
+            loss = results["cases_per_timestep"].sum() + results["deaths_per_timestep"].sum() \
+                + 0.5 * results["cases_by_age_65"].sum()
+            loss.backward()
+            launches = _lib.profile_read()["transmission"][2]
+            _lib.profile_enable(False)
+            outs[look] = dict(cases=results["cases_per_timestep"].detach().cpu().numpy(), inf=is_inf.detach().cpu().numpy(),
+                              T=data["agent"].transmission.detach().cpu().numpy(),
+                              grads=torch.stack([l.grad for l in leaves]).cpu().numpy(), launches=launches)
+    finally:
+        _lib.pipeline_enable(*prev)
+    a, b = outs[False], outs[True]
+    assert a["launches"] == 8 and b["launches"] == 1          # only the first step still runs the stand-alone pass
+    assert a["cases"][-1] > a["cases"][0] > 0
+    flips = int((a["inf"] != b["inf"]).sum())
+    assert flips <= 20, flips
+    if flips == 0:
+        assert np.array_equal(a["cases"], b["cases"])
+        assert np.array_equal(a["T"], b["T"])
+        assert np.allclose(a["grads"], b["grads"], rtol=5e-5, atol=1e-6 * np.abs(a["grads"]).max()), (a["grads"], b["grads"])
