@@ -696,16 +696,13 @@ static bool lean_plan(const gj_world_desc* w, const gj_step_params* p, const Pla
 static int launch_lean_group_pass(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const float* beta,
                                   const float* in, float* out_scaled, float* out_plain, const Scratch& sc, bool bwd,
                                   cudaStream_t st) {
-  if (w->n_small > 0) {
-    ProfScope ps(bwd ? K_GROUP_SMALL_B : K_GROUP_SMALL_F, st);
-    k_lean_group_small<<<blocks_for(w->n_small, kBlock), kBlock, 0, st>>>(*w, *p, pl, beta, in, out_scaled, out_plain);
-    GJ_CHECK_LAUNCH("k_lean_group_small");
-  }
-  if (w->n_chunks > 0) {
+  if (w->n_small > 0 || w->n_chunks > 0) {
     ProfScope ps(bwd ? K_GROUP_CHUNK_B : K_GROUP_CHUNK_F, st);
-    k_lean_group_chunk<<<blocks_for(w->n_chunks * 32, kBlock), kBlock, 0, st>>>(*w, *p, pl, beta, in, out_scaled,
-                                                                              out_plain, sc.part_a);
-    GJ_CHECK_LAUNCH("k_lean_group_chunk");
+    const int chunk_blocks = w->n_chunks > 0 ? blocks_for(w->n_chunks * 32, kBlock) : 0;
+    const int small_blocks = w->n_small > 0 ? blocks_for(w->n_small, kBlock) : 0;
+    k_lean_group_sums<<<chunk_blocks + small_blocks, kBlock, 0, st>>>(*w, *p, pl, beta, in, out_scaled, out_plain,
+                                                                     sc.part_a, chunk_blocks);
+    GJ_CHECK_LAUNCH("k_lean_group_sums");
   }
   if (w->n_big > 0) {
     ProfScope ps(bwd ? K_GROUP_FIX_B : K_GROUP_FIX_F, st);

@@ -315,14 +315,10 @@ __device__ __forceinline__ float lean_group_beta(const LeanGroupShared& sh, uint
   return sh.bsum[t];
 }
 
-__global__ void __launch_bounds__(kBlock) k_lean_group_small(gj_world_desc w, gj_step_params p, Plan pl,
-                                                             const float* __restrict__ beta,
-                                                             const float* __restrict__ in,
-                                                             float* __restrict__ out_scaled,
-                                                             float* __restrict__ out_plain) {
-  __shared__ LeanGroupShared gs;
-  lean_beta_sums(gs, w, p, pl, beta);
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// one group of <= GJ_SMALL_GROUP members per thread
+__device__ __forceinline__ void lean_group_small_body(const gj_world_desc& w, const LeanGroupShared& gs, int64_t i,
+                                                      const float* __restrict__ in, float* __restrict__ out_scaled,
+                                                      float* __restrict__ out_plain) {
   if (i >= w.n_small) return;
   const uint32_t g = w.small_groups[i];
   const float b = lean_group_beta(gs, g);
@@ -344,15 +340,11 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_small(gj_world_desc w, gj
   out_scaled[g] = (b == b) ? (b * w.pc[g]) * S : 0.0f;
 }
 
-__global__ void __launch_bounds__(kBlock) k_lean_group_chunk(gj_world_desc w, gj_step_params p, Plan pl,
-                                                             const float* __restrict__ beta,
-                                                             const float* __restrict__ in,
-                                                             float* __restrict__ out_scaled,
-                                                             float* __restrict__ out_plain, float* __restrict__ part) {
-  __shared__ LeanGroupShared gs;
-  lean_beta_sums(gs, w, p, pl, beta);
+// one chunk of <= GJ_CHUNK members per warp
+__device__ __forceinline__ void lean_group_chunk_body(const gj_world_desc& w, const LeanGroupShared& gs, int64_t ci,
+                                                      const float* __restrict__ in, float* __restrict__ out_scaled,
+                                                      float* __restrict__ out_plain, float* __restrict__ part) {
   const int lane = threadIdx.x & 31;
-  const int64_t ci = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (ci >= w.n_chunks) return;
   const uint32_t g = w.chunk_group[ci];
   const float b = lean_group_beta(gs, g);
@@ -381,6 +373,23 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_chunk(gj_world_desc w, gj
   } else {
     part[pi] = S;
   }
+}
+
+// ONE launch for both group-size classes: blocks [0, chunk_blocks) take the chunks (the longer work first), the rest
+// the small groups.  Both are latency-bound gathers, so they overlap almost perfectly (measured: 0.058 + 0.166 ms as
+// two launches at 56 M agents).
+__global__ void __launch_bounds__(kBlock) k_lean_group_sums(gj_world_desc w, gj_step_params p, Plan pl,
+                                                            const float* __restrict__ beta,
+                                                            const float* __restrict__ in, float* __restrict__ out_scaled,
+                                                            float* __restrict__ out_plain, float* __restrict__ part,
+                                                            int chunk_blocks) {
+  __shared__ LeanGroupShared gs;
+  lean_beta_sums(gs, w, p, pl, beta);
+  if ((int)blockIdx.x < chunk_blocks)
+    lean_group_chunk_body(w, gs, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, in, out_scaled, out_plain, part);
+  else
+    lean_group_small_body(w, gs, (int64_t)(blockIdx.x - chunk_blocks) * blockDim.x + threadIdx.x, in, out_scaled,
+                          out_plain);
 }
 
 __global__ void __launch_bounds__(kBlock) k_lean_group_fix(gj_world_desc w, gj_step_params p, Plan pl,
