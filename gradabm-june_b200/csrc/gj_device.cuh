@@ -41,20 +41,36 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// 24-bit uniforms: (0,1) for logs, [0,1) for the Bernoulli comparison
-__device__ __forceinline__ float u01_open(uint32_t r) { return ((float)(r >> 8) + 0.5f) * 5.9604644775390625e-08f; }
+// uniforms: (0,1) for logs, [0,1) for the Bernoulli comparison
+// (23 bits + 1/2) * 2^-23: exactly representable, so 0 < u < 1 strictly.  (24 bits + 1/2 rounds its largest value to
+// 1.0f: then E = -ln u = 0, its Gumbel is +inf and the reference-order softmax returns NaN — once per 2^24 draws.)
+__device__ __forceinline__ float u01_open(uint32_t r) { return ((float)(r >> 9) + 0.5f) * 1.1920928955078125e-07f; }
 __device__ __forceinline__ float u01_half(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }
 
 struct StepNoise {
   float E0, E1, u;
 };
 
+// The noise of one (agent, call) — THE definition of the stream; forward, backward and gj_philox_fill all come through
+// these functions.  Stream 0, counter = agent: words 0,1 -> the two exponentials of the Gumbel draw (by inversion with
+// the hardware log2), word 2 -> the uniform of the symptomatic / recovery branch (needed only by the few agents whose
+// stage changes in the step).  Stream 1: the standard normal of the dwell time.
+// (One block per PAIR of neighbouring agents, with a thread of the pipelined forward taking both, was built and
+// measured: fewer instructions but slower — the pair's 32-bit stores touch every sector twice, and 64-bit stores of
+// both agents' results spill at the 64-register budget.)
+__device__ __forceinline__ void philox_step_block(uint64_t seed, uint32_t call, uint64_t agent, uint32_t r[4]) {
+  philox4x32_10((uint32_t)agent, (uint32_t)(agent >> 32), call, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+}
+__device__ __forceinline__ float draw_step_uniform(uint64_t seed, uint32_t call, int64_t agent) {
+  uint32_t r[4];
+  philox_step_block(seed, call, (uint64_t)agent, r);
+  return u01_half(r[2]);
+}
 __device__ __forceinline__ StepNoise draw_step_noise(uint64_t seed, uint32_t call, int64_t agent) {
   uint32_t r[4];
-  philox4x32_10((uint32_t)agent, (uint32_t)((uint64_t)agent >> 32), call, 0u, (uint32_t)seed,
-                (uint32_t)(seed >> 32), r);
-  StepNoise n;  // Exp(1) by inversion with the hardware log2 (this IS the definition of the stream: the
-  n.E0 = -__logf(u01_open(r[0]));  // forward, the backward and gj_philox_fill all come through here)
+  philox_step_block(seed, call, (uint64_t)agent, r);
+  StepNoise n;
+  n.E0 = -__logf(u01_open(r[0]));
   n.E1 = -__logf(u01_open(r[1]));
   n.u = u01_half(r[2]);
   return n;

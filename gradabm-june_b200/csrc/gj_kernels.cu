@@ -738,7 +738,7 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
     ProfScope ps(K_AGENT_FWD, st);
     static int occ[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const bool diag = io->q || io->n;
-    const size_t smem = sizeof(PipeFwdShared);
+    const size_t smem = next ? sizeof(PipeFwdSharedT<true>) : sizeof(PipeFwdSharedT<false>);
     NextStep nx;
     memset(&nx, 0, sizeof(nx));
     if (next) {

@@ -416,62 +416,89 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_fix(gj_world_desc w, gj_s
 struct FwdOut {
   float inf, tinf, cur;   // post-step is_infected, infection_time, current_stage
 };
+struct FwdRes {   // everything one agent's forward produces
+  float tape_v, tape_y0, q, lam, n;
+  float s_o, inf_o, tinf_o, cur_o, nxt_o, ttn_o;
+};
+// r0, r1: words 0, 1 of the agent's Philox block (philox_step_block); ga = global agent id
+template <bool kQuar>
+__device__ __forceinline__ FwdRes lean_forward_core(const gj_step_params& p, const LeanPlan& lp,
+                                                    const float* __restrict__ stage_prob, uint64_t ga, uint32_t r0,
+                                                    uint32_t r1, float hs, float gv, float Lc, float beta_r, float rpc,
+                                                    float s, float inf, float tinf, float cur, float nxt, float ttn,
+                                                    int cls, float inv_tau, float dead, float* __restrict__ hist,
+                                                    float* __restrict__ deaths) {
+  FwdRes o;
+  const float dE = lg2_fast(-lg2_fast(u01_open(r0))) - lg2_fast(-lg2_fast(u01_open(r1)));
+  const float rv = (beta_r * rpc) * hs;
+  const float house = lp.r_house ? rv : 0.0f;
+  const float plain = (gv + Lc) + (lp.r_house ? 0.0f : rv);
+  const float mq = kQuar ? quar_mask(p, cur) : 1.0f;
+  const float X = fmaf(mq, plain, house);  // pressure per unit susceptibility
+  const float lam = X * s;
+  const float q = not_infected_prob(lam, p.dt);
+  o.tape_v = (s == 0.0f) ? X : lam;
+  // Gumbel-softmax hard draw from Philox bits (same stream as draw_step_noise):
+  // x0 - x1 = (ln2 / tau) * d,  d = lg2 q - lg2(1-q) - lg2 E0 + lg2 E1, E = -ln u (the ln2 factors cancel)
+  const float d = (lg2_fast(q) - lg2_fast(1.0f - q)) - dE;
+  const float e = ex2_fast(-fabsf(d) * inv_tau);  // exp(x_small - x_big) <= 1
+  const float ys = e * rcp_fast(1.0f + e);        // the smaller soft probability
+  const bool hit = (d < 0.0f) && (e < 1.0f);      // argmax of the softmax; ties -> not infected
+  const float n = hit ? 1.0f : 0.0f;
+  o.tape_y0 = hit ? -ys : ys;
+  o.q = q;
+  o.lam = lam;
+  o.n = n;
+  // infect (model.py:103-110)
+  o.inf_o = inf + n;
+  o.s_o = fmaxf(0.0f, s - n);
+  o.tinf_o = tinf + n * (p.now - tinf);
+  // symptoms (symptoms.py:204-247); its draws are needed by the few agents whose stage changes
+  const uint64_t seed = p.seed;
+  const uint32_t call = p.call_index;
+  const int age = age_of(cls);
+  const SympOut so = symptoms_forward(p, stage_prob, cur, nxt, ttn, n, age,
+                                      [&]() { return draw_step_uniform(seed, call, (int64_t)ga); },
+                                      [&](int) { return draw_step_normal(seed, call, (int64_t)ga); });
+  o.cur_o = so.cur;
+  o.nxt_o = so.nxt;
+  o.ttn_o = so.ttn;
+  // reductions (runner.py:167-171,198-224): small integers, exact in any order
+  if (o.inf_o != 0.0f) atomicAdd(&hist[age], o.inf_o);
+  if (so.cur == dead) atomicAdd(deaths, so.cur / dead);
+  return o;
+}
+
+// one agent: noise, core, stores
 template <bool kQuar, bool kDiag>
 __device__ __forceinline__ FwdOut lean_forward_agent(const gj_step_params& p, const LeanPlan& lp, const gj_fwd_io& io,
                                                    uint32_t a, float hs, float gv, float Lc, float beta_r, float rpc,
                                                    float s, float inf, float tinf, float cur, float nxt, float ttn,
-                                                   int cls, float inv_tau, float dead, uint32_t key0, uint32_t key1,
-                                                   float* __restrict__ hist, float* __restrict__ deaths) {
-    // the noise first: it depends on nothing that is loaded, so it covers the latency of the group-sum gather (gv)
-    uint32_t r[4];
-    const uint64_t ga = p.agent_offset + a;  // global agent id = Philox counter
-    philox4x32_10((uint32_t)ga, (uint32_t)(ga >> 32), p.call_index, 0u, key0, key1, r);
-    const float dE = lg2_fast(-lg2_fast(u01_open(r[0]))) - lg2_fast(-lg2_fast(u01_open(r[1])));
-    const float rv = (beta_r * rpc) * hs;
-    const float house = lp.r_house ? rv : 0.0f;
-    const float plain = (gv + Lc) + (lp.r_house ? 0.0f : rv);
-    const float mq = kQuar ? quar_mask(p, cur) : 1.0f;
-    const float X = fmaf(mq, plain, house);  // pressure per unit susceptibility
-    const float lam = X * s;
-    const float q = not_infected_prob(lam, p.dt);
-    io.tape_v[a] = (s == 0.0f) ? X : lam;
-    // Gumbel-softmax hard draw from Philox bits (same stream as draw_step_noise):
-    // x0 - x1 = (ln2 / tau) * d,  d = lg2 q - lg2(1-q) - lg2 E0 + lg2 E1, E = -ln u (the ln2 factors cancel)
-    const float d = (lg2_fast(q) - lg2_fast(1.0f - q)) - dE;
-    const float e = ex2_fast(-fabsf(d) * inv_tau);  // exp(x_small - x_big) <= 1
-    const float ys = e * rcp_fast(1.0f + e);        // the smaller soft probability
-    const bool hit = (d < 0.0f) && (e < 1.0f);      // argmax of the softmax; ties -> not infected
-    const float n = hit ? 1.0f : 0.0f;
-    io.tape_y0[a] = hit ? -ys : ys;
-    if (kDiag) {
-      if (io.q) io.q[a] = q;
-      if (io.lam) io.lam[a] = lam;
-      if (io.n) io.n[a] = n;
-    }
-    // infect (model.py:103-110)
-    const float inf_o = inf + n;
-    io.s_o[a] = fmaxf(0.0f, s - n);
-    io.inf_o[a] = inf_o;
-    const float tinf_o = tinf + n * (p.now - tinf);
-    io.tinf_o[a] = tinf_o;
-    // symptoms (symptoms.py:204-247)
-    const uint64_t seed = p.seed;
-    const uint32_t call = p.call_index;
-    const float uu = u01_half(r[2]);
-    const int age = age_of(cls);
-    const SympOut so = symptoms_forward(p, io.stage_prob, cur, nxt, ttn, n, age, [&]() { return uu; },
-                                        [&](int) { return draw_step_normal(seed, call, (int64_t)ga); });
-    io.cur_o[a] = so.cur;
-    io.nxt_o[a] = so.nxt;
-    io.ttn_o[a] = so.ttn;
-    // reductions (runner.py:167-171,198-224): small integers, exact in any order
-    if (inf_o != 0.0f) atomicAdd(&hist[age], inf_o);
-    if (so.cur == dead) atomicAdd(deaths, so.cur / dead);
-    FwdOut out;
-    out.inf = inf_o;
-    out.tinf = tinf_o;
-    out.cur = so.cur;
-    return out;
+                                                   int cls, float inv_tau, float dead, float* __restrict__ hist,
+                                                   float* __restrict__ deaths) {
+  uint32_t r[4];
+  const uint64_t ga = p.agent_offset + a;  // global agent id
+  philox_step_block(p.seed, p.call_index, ga, r);
+  const FwdRes o = lean_forward_core<kQuar>(p, lp, io.stage_prob, ga, r[0], r[1], hs, gv, Lc, beta_r, rpc, s, inf, tinf,
+                                            cur, nxt, ttn, cls, inv_tau, dead, hist, deaths);
+  io.tape_v[a] = o.tape_v;
+  io.tape_y0[a] = o.tape_y0;
+  if (kDiag) {
+    if (io.q) io.q[a] = o.q;
+    if (io.lam) io.lam[a] = o.lam;
+    if (io.n) io.n[a] = o.n;
+  }
+  io.s_o[a] = o.s_o;
+  io.inf_o[a] = o.inf_o;
+  io.tinf_o[a] = o.tinf_o;
+  io.cur_o[a] = o.cur_o;
+  io.nxt_o[a] = o.nxt_o;
+  io.ttn_o[a] = o.ttn_o;
+  FwdOut out;
+  out.inf = o.inf_o;
+  out.tinf = o.tinf_o;
+  out.cur = o.cur_o;
+  return out;
 }
 
 // =====================================================================================================
@@ -510,7 +537,6 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_FWD) k_lean_forward
   const uint32_t* __restrict__ i_slot = lp.r_slot;
   const float dead = (float)(p.n_stages - 1);
   const float inv_tau = 1.0f / p.tau;
-  const uint32_t key0 = (uint32_t)p.seed, key1 = (uint32_t)(p.seed >> 32);
   const float beta_r = lp.n_range > 0 ? sh.beta[lp.r_net] : 0.0f;
   const bool has_gen = lp.has_generic != 0, has_range = lp.n_range > 0;
 
@@ -576,7 +602,7 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_FWD) k_lean_forward
         const float gv = lean_generic_finish(w, SP, ent[h], a, gen[h]);
         const float Lc = lp.n_cell > 0 ? L[cls[h]] : 0.0f;
         lean_forward_agent<kQuar, kDiag>(p, lp, io, a, hs, gv, Lc, beta_r, rpc[h], s[h], inf[h], tinf[h], cur[h], nxt[h],
-                                         ttn[h], cls[h], inv_tau, dead, key0, key1, sh.hist, &sh.deaths);
+                                         ttn[h], cls[h], inv_tau, dead, sh.hist, &sh.deaths);
       }
     }
     tile = tend;
@@ -616,7 +642,7 @@ __device__ __forceinline__ void lean_backward_agent(const gj_step_params& p, con
     const uint32_t call = p.call_index;
     const int64_t ga = (int64_t)p.agent_offset + a;
     const SympOut so = symptoms_forward(p, io.stage_prob, cur, nxt, ttn, n, age,
-                                        [&]() { return draw_step_noise(seed, call, ga).u; },
+                                        [&]() { return draw_step_uniform(seed, call, ga); },
                                         [&](int) { return draw_step_normal(seed, call, ga); });
     float gc = gcur_o;
     if (so.cur == dead) gc += g_deaths;

@@ -165,10 +165,11 @@ struct alignas(16) PipeFwdStage {
   float T[kPipeH];
   uint8_t cls[kPipeTile + 32];
 };
-struct PipeFwdShared {
+template <bool kNext>
+struct PipeFwdSharedT {
   PipeFwdStage st[kPipeStages];
   ProbRow prob[200];
-  ProbRow prob_next[200];   // transmission-side tables of the next step (look-ahead only)
+  ProbRow prob_next[kNext ? 200 : 1];   // transmission-side tables of the next step (look-ahead only)
   float L[2][200];
   float beta[GJ_MAX_NETS];
   float hist[100];
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
                                                                  double* __restrict__ red_part,
                                                                  unsigned int* __restrict__ ticket, NextStep nx) {
   extern __shared__ __align__(128) unsigned char pipe_smem[];
-  PipeFwdShared& sh = *reinterpret_cast<PipeFwdShared*>(pipe_smem);
+  PipeFwdSharedT<kNext>& sh = *reinterpret_cast<PipeFwdSharedT<kNext>*>(pipe_smem);
   const TileRun run = lean_tiles(w);
   const float* __restrict__ Tr = (kQuar && !lp.r_house) ? io.Tq : io.T;
   const bool has_gen = lp.has_generic != 0, has_range = lp.n_range > 0;
@@ -229,7 +230,6 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
   const float* __restrict__ SP = io.S_scaled + lp.gen_base;
   const float dead = (float)(p.n_stages - 1);
   const float inv_tau = 1.0f / p.tau;
-  const uint32_t key0 = (uint32_t)p.seed, key1 = (uint32_t)(p.seed >> 32);
   const float beta_r = lp.n_range > 0 ? sh.beta[lp.r_net] : 0.0f;
 
   const float4* __restrict__ prof = reinterpret_cast<const float4*>(io.prof4);
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
       const float gv = lean_generic_finish(w, SP, ent[h], a, gen[h]);
       const FwdOut o = lean_forward_agent<kQuar, kDiag>(p, lp, io, a, hs, gv, Lc, beta_r, has_range ? sg.rpc[i] : 0.0f,
                                                         sg.s[i], sg.inf[i], sg.tinf[i], sg.cur[i], sg.nxt[i], sg.ttn[i], cls,
-                                                        inv_tau, dead, key0, key1, sh.hist, &sh.deaths);
+                                                        inv_tau, dead, sh.hist, &sh.deaths);
       if (kNext) {   // TransmissionUpdater of the next step (same arithmetic as k_lean_transmission)
         float T = 0.0f;
         if (o.inf != 0.0f) {

@@ -446,7 +446,7 @@ __device__ __forceinline__ BackAgent backward_agent(const gj_step_params& p, con
     const int64_t ga = (int64_t)p.agent_offset + a;
     // the uniform / normal draws are regenerated only for the few agents whose stage actually updates
     const SympOut so = symptoms_forward(p, io.stage_prob, st.cur, st.nxt, st.ttn, n, age,
-                                        [&]() { return inj_u ? inj_u[a] : draw_step_noise(seed, call, ga).u; },
+                                        [&]() { return inj_u ? inj_u[a] : draw_step_uniform(seed, call, ga); },
                                         [&](int row) {
       return inj_z ? inj_z[(int64_t)row * N + a] : draw_step_normal(seed, call, ga);
     });
