@@ -491,18 +491,19 @@ def main():
 
 def ncu_traffic(kernel, n_agents):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this workload (profiles/r1_pipe_v2_56M_kernels.csv, 56 M agents); None for
+    `ncu --set full` capture of this workload (profiles/r1_final_56M_kernels.csv, 56 M agents); None for
     other sizes or kernels (traffic cannot be measured inside an un-profiled run)."""
     name = {"agent_forward": "k_pipe_forward", "agent_backward": "k_pipe_backward<", "backward_gather": "k_pipe_backward_gather"}.get(kernel)
-    f = ROOT / "profiles" / "r1_pipe_v2_56M_kernels.csv"
+    f = ROOT / "profiles" / "r1_final_56M_kernels.csv"
     if name is None or n_agents != 56_000_000 or not f.exists():
         return None
+    lines = f.read_text().splitlines()
+    n_num = len(lines[0].split(",")) - 1            # numeric columns; the kernel name itself may contain commas
     vals = []
-    for line in f.read_text().splitlines()[1:]:
-        cols = line.split(",")
+    for line in lines[1:]:
+        cols = line.rsplit(",", n_num)
         if cols[0].startswith(name):
-            k = 1 if "<" in cols[0] and "," in line[:line.index(">")] else 0   # "k_pipe_forward<0, 0>" has a comma
-            vals.append((float(cols[2 + k]) + float(cols[3 + k])) * 1e9)
+            vals.append((float(cols[2]) + float(cols[3])) * 1e9)   # dram__bytes_read.sum + dram__bytes_write.sum [Gbyte]
     return sum(vals) / len(vals) if vals else None
 
 

@@ -59,7 +59,7 @@ with open(dst + "_kernels.csv", "w") as f:
 
 # ---- stall samples by source line for the agent kernels ---------------------------------------------
 for k in ("k_pipe_forward", "k_pipe_backward", "k_pipe_backward_gather", "k_lean_forward", "k_lean_backward",
-          "k_lean_backward_gather", "k_lean_transmission", "k_lean_group_chunk", "k_lean_group_small"):
+          "k_lean_backward_gather", "k_lean_transmission", "k_lean_group_sums"):
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass",
                           "--kernel-name-base", "function", "--kernel-name", "regex:^" + k + "$", "--launch-count", "1"],
                          capture_output=True, text=True).stdout
