@@ -476,3 +476,44 @@ def test_lookahead_transmission_pass(policies):
         assert np.array_equal(a["cases"], b["cases"])
         assert np.array_equal(a["T"], b["T"])
         assert np.allclose(a["grads"], b["grads"], rtol=5e-5, atol=1e-6 * np.abs(a["grads"]).max()), (a["grads"], b["grads"])
+
+
+def test_ensemble_evaluator_matches_single_runs():
+    """EnsembleEvaluator (calibration ensemble, one graph replay per sample) against eager runs of the same samples."""
+    from grad_june import GradJune, Timer, ops
+    from grad_june.calibration import EnsembleEvaluator
+    from grad_june.default_config import default_parameters
+    from grad_june.runner import Runner
+    from grad_june.world import make_synthetic_world
+    n_agents = 60_000
+    params = default_parameters()
+    params["system"]["device"] = DEV
+    params["timer"]["total_days"] = 3
+    params["infection_seed"]["log_fraction_initial_cases"] = -1.5
+    params["policies"] = {}
+    torch.manual_seed(5)
+    data = Runner.get_data(params, data=make_synthetic_world(n_agents, seed=9, device=DEV, agents_per_super_area=5000))
+    model = GradJune.from_parameters(params)
+    keys = list(model.infection_networks.networks.keys())
+    runner = Runner(model=model, data=data, timer=Timer.from_parameters(params), log_fraction_initial_cases=-1.5,
+                    save_path="/tmp/gj_test", parameters=params)
+    loss_fn = lambda r: r["cases_per_timestep"].sum() + r["deaths_per_timestep"].sum()  # noqa: E731
+    base = torch.tensor([float(params["networks"][k]["log_beta"]) + 0.4 for k in keys], device=DEV)
+    samples = base + 0.25 * torch.randn(3, len(keys), generator=torch.Generator().manual_seed(1)).to(DEV)
+    ref_loss, ref_grads = [], []
+    for lb in samples:
+        leaves = []
+        for i, k in enumerate(keys):
+            leaf = lb[i].detach().clone().requires_grad_(True)
+            model.infection_networks.networks[k].log_beta = leaf
+            leaves.append(leaf)
+        with ops.philox_seed(11):
+            results, _ = runner()
+        loss = loss_fn(results)
+        loss.backward()
+        ref_loss.append(loss.detach())
+        ref_grads.append(torch.stack([l.grad for l in leaves]))
+    losses, grads = EnsembleEvaluator(runner, loss_fn, seed=11)(samples)
+    assert torch.equal(losses, torch.stack(ref_loss))
+    assert torch.equal(grads, torch.stack(ref_grads))
+    assert not torch.equal(grads[0], grads[1])
