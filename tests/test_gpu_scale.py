@@ -48,13 +48,41 @@ def _mid_epidemic_state(n, now, seed, device):
     return {k: v.to(device) for k, v in st.items()}
 
 
-def _setup(n_agents, seed=1):
+def _irregular(data):
+    """Make the synthetic world exercise the rare layout paths: households of up to 20 members (the range tier's
+    loop beyond its eight unrolled neighbours) and agents with two or three generic-tier edges (the agent-major
+    CSR walk behind the one-entry-per-agent word)."""
+    n = len(data["agent"].id)
+    dev = data["agent"].age.device
+    g = torch.Generator(device="cpu").manual_seed(123)
+    sizes = torch.randint(1, 21, (n // 2 + 8,), generator=g).to(dev)
+    ends = torch.cumsum(sizes, 0)
+    n_hh = int(torch.searchsorted(ends, torch.tensor([n], device=dev))[0]) + 1
+    ids = torch.arange(n, device=dev)
+    hh = torch.searchsorted(ends[:n_hh].contiguous(), ids, right=True)
+    data["household"].id = torch.arange(n_hh, device=dev)
+    data["household"].people = torch.bincount(hh, minlength=n_hh)
+    data["attends_household"].edge_index = torch.stack((ids, hh))
+    for src_t, dst_t, frac in (("company", "university", 0.10), ("school", "care_home", 0.05), ("company", "care_home", 0.03)):
+        members = data["attends_" + src_t].edge_index[0]
+        pick = members[torch.rand(members.numel(), generator=g).to(dev) < frac]
+        G = len(data[dst_t].id)
+        grp = torch.randint(0, G, (pick.numel(),), generator=g).to(dev)
+        ei = torch.cat((data["attends_" + dst_t].edge_index, torch.stack((pick, grp))), dim=1)
+        data["attends_" + dst_t].edge_index = ei
+        data[dst_t].people = torch.bincount(ei[1], minlength=G)
+    return data
+
+
+def _setup(n_agents, seed=1, mutate=None):
     from grad_june import GradJune, Timer
     from grad_june.runner import Runner
     from grad_june.world import make_synthetic_world
     params = _params()
     torch.manual_seed(seed)
     data = make_synthetic_world(n_agents, seed=seed, device=DEV)
+    if mutate is not None:
+        data = mutate(data)
     data = Runner.get_data(params, data=data)
     model = GradJune.from_parameters(params)
     for net in model.infection_networks.networks.values():
@@ -221,12 +249,30 @@ def test_properties_at_scale():
     assert torch.allclose(q2[mid], q[mid] ** 2, rtol=2e-5)
 
 
-def test_throughput_mode_matches_reference_order():
+@pytest.mark.parametrize("irregular,pipelined", [(False, True), (True, True), (True, False)])
+def test_throughput_mode_matches_reference_order(irregular, pipelined):
     """The throughput-mode kernels (re-associated sums, hardware log2/exp2 draw; used with in-kernel Philox
-    noise) against the reference-order kernels on the same state and the same Philox stream."""
-    from grad_june import ops
+    noise), pipelined and register-batched, against the reference-order kernels on the same state and the same
+    Philox stream — on the regular synthetic world and on one with 20-member households and multi-edge agents."""
+    from grad_june import _lib, ops
+    from grad_june.world import TIER_RANGE, get_device_world
     n_agents = 300_000
-    params, data, model, timer, state = _setup(n_agents, seed=11)
+    params, data, model, timer, state = _setup(n_agents, seed=11, mutate=_irregular if irregular else None)
+    if irregular:
+        world = get_device_world(data, DEV)
+        assert world.type_tier[world.types.index("household")] == TIER_RANGE
+        assert int((world.ent1.long() & 0xFFFFFFFF == 0xFFFFFFFE).sum()) > 1000      # agents with several generic edges
+        assert int(data["household"].people.max()) > 8
+    prev = _lib.pipeline_enable(None)
+    _lib.pipeline_enable(pipelined, lookahead=False)
+    try:
+        _compare_throughput_with_reference_order(n_agents, data, model, timer, state)
+    finally:
+        _lib.pipeline_enable(*prev)
+
+
+def _compare_throughput_with_reference_order(n_agents, data, model, timer, state):
+    from grad_june import ops
     outs = {}
     for mode in ("exact", "fast"):
         for k in ("susceptibility", "is_infected", "infection_time"):
