@@ -5,13 +5,14 @@
 // samples are long-scoreboard waits at the first use of a loaded value, 35-47 % occupancy).  Here a persistent
 // CTA of 512 threads walks its run of agent tiles (<= 1024 agents each) with a two-stage shared-memory pipeline:
 // one elected thread issues, per tile, one `cp.async.bulk` (TMA 1-D bulk copy, completion counted in bytes on an
-// mbarrier) for each per-agent array of the tile — state, tapes, cotangents, index words, class bytes, packed
-// profile, and the member values of the range-tier (household) network with a halo for the neighbours — while all
-// warps compute the previous tile out of shared memory, two agents per thread.  Memory-level parallelism is then set
-// by the bytes in flight per SM (2 CTAs x 2-3 tiles x 21-30 KB), not by registers x occupancy, and the only global
-// loads left in the agent loop are the L2-resident gathers of the generic groups' sums.  The arithmetic is
-// lean_forward_agent() / lean_backward_agent() / lean_gather_agent() of gj_lean.cuh: results are bit-identical to
-// the register-batched kernels (tests/test_gpu_scale.py::test_pipelined_kernels_are_bit_identical).
+// mbarrier) for each per-agent array of the tile — state, tapes, index words, class bytes, and the member values
+// of the range-tier (household) network with a halo for the neighbours — while all warps compute the previous tile
+// out of shared memory, two agents per thread.  Memory-level parallelism is then set by the bytes in flight per SM
+// (2 CTAs x 1-2 tiles x 30-43 KB), not by registers x occupancy; the global loads left in the agent loops are the
+// L2-resident gathers of the generic groups' sums and a few arrays that stream through registers because staging
+// them would cost the second CTA per SM (the backward's six cotangents, the gather's packed profile).  The
+// arithmetic is lean_forward_core() / lean_backward_agent() / lean_gather_agent() of gj_lean.cuh: trajectories are
+// bit-identical to the register-batched kernels (tests/test_gpu_scale.py::test_pipelined_kernels_are_bit_identical).
 //
 // Requirements checked by the launcher (else the gj_lean.cuh kernels run): every per-agent array 16-byte aligned.
 // Bulk copies move 16-byte granules, so a tile's copy starts at the preceding and ends at the following multiple of
