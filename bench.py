@@ -215,6 +215,10 @@ def main():
     ap.add_argument("--samples", type=int, default=0,
                     help="ensemble: beta samples evaluated per window over all GPUs (BASELINE config 5: 1024 on a 9M "
                          "world, --agents 9000000 --window 30); default one per GPU")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="ensemble + --graph: evaluate this many samples concurrently, each lane with its own replica of "
+                         "the world, captured window and CUDA stream (bandwidth-bound and issue-bound kernels of "
+                         "different samples overlap)")
     ap.add_argument("--graph", action="store_true",
                     help="capture the window (Runner() + backward) once as a CUDA graph and replay it "
                          "(grad_june.graphed.GraphedRunner): removes the per-step Python cost that bounds small worlds")
@@ -348,14 +352,43 @@ def main():
         _lib.profile_enable(False)
         for k in keys:
             model.infection_networks.networks[k].log_beta = torch.tensor(0.0)
-        graphed = GraphedRunner(
-            runner, loss_fn=lambda r: r["cases_per_timestep"].sum() + r["deaths_per_timestep"].sum(), seed=7)
+        loss_fn = lambda r: r["cases_per_timestep"].sum() + r["deaths_per_timestep"].sum()   # noqa: E731
+        graphed = GraphedRunner(runner, loss_fn=loss_fn, seed=7)
 
-        def one_sample(lb_dev):  # noqa: F811
-            _, grads, results = graphed(lb_dev)
+        def one_sample(lb_dev, g=None):  # noqa: F811
+            _, grads, results = (g or graphed)(lb_dev)
             if geo:
                 dist.all_reduce(grads)
             return torch.cat([results["cases_per_timestep"], results["deaths_per_timestep"], grads])
+
+        if args.streams > 1 and not geo and n_samples > 1:
+            # more lanes: each needs its own world object (per-world scratch = one step in flight per world), runner
+            # and captured window; the world arrays are rebuilt from the same seed
+            lanes = [graphed]
+            for _ in range(args.streams - 1):
+                torch.manual_seed(1234 + rank)
+                d2 = Runner.get_data(params, data=make_synthetic_world(N, seed=0, device=dev))
+                freeze_device_world(d2, dev)
+                m2 = GradJune.from_parameters(params)
+                r2 = Runner(model=m2, data=d2, timer=Timer.from_parameters(params), log_fraction_initial_cases=-2.0,
+                            save_path=params["save_path"], parameters=params)
+                lanes.append(GraphedRunner(r2, loss_fn=loss_fn, seed=7))
+            lane_streams = [torch.cuda.Stream(device=dev) for _ in lanes]
+
+            def one_window(e2e):  # noqa: F811
+                lb_all = host_log_beta.to(dev, non_blocking=True) if e2e else resident_log_beta
+                main = torch.cuda.current_stream(dev)
+                for st in lane_streams:
+                    st.wait_stream(main)
+                outs = [None] * n_samples
+                for i in range(n_samples):
+                    k = i % len(lanes)
+                    with torch.cuda.stream(lane_streams[k]):
+                        outs[i] = one_sample(lb_all[i], lanes[k])
+                for st in lane_streams:
+                    main.wait_stream(st)
+                out = torch.stack(outs)
+                return out.to("cpu") if e2e else out
 
     # warm-up: W >= 3 timesteps
     wsteps = 0
@@ -461,7 +494,8 @@ def main():
             "config": {"workload": workload_name(n_total if geo else N, args.policies), "agents_per_gpu": N,
                        "agents_total": n_total, "edges_per_agent": round(e_bar, 3),
                        "groups_per_agent": round(g_bar, 3), "bptt_window": window, "networks": 11,
-                       "driver": "CUDA graph replay (GraphedRunner)" if args.graph else "Python loop (Runner)",
+                       "driver": (f"CUDA graph replay (GraphedRunner), {args.streams} concurrent lane(s)" if args.graph
+                                  else "Python loop (Runner)"),
                        "layout_tiers": dict(zip(world.types, world.type_tier)),
                        "parallelism": parallelism,
                        "l2": "inputs (>= 2 GB per pass) far larger than the 126 MB L2; no flush needed"},
