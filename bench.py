@@ -226,6 +226,10 @@ def main():
                     help="BASELINE config 4: social distancing, school/leisure closures and quarantine from day 15")
     ap.add_argument("--window", type=int, default=0,
                     help="BPTT window (0 = 60 timesteps as in BASELINE.json, fewer if memory does not allow)")
+    ap.add_argument("--shuffle-agents", action="store_true",
+                    help="load the synthetic world with its agents in a RANDOM order (as a world that was not numbered "
+                         "for this layout): Runner.get_data then renumbers it (world.layout_order) and the kernels key "
+                         "their noise by the loaded ids")
     ap.add_argument("--cpu-agents", type=int, default=1_000_000, help="agents of the CPU-baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -278,7 +282,14 @@ def main():
         torch.cuda.empty_cache()
     else:
         data = make_synthetic_world(N, seed=0, device=dev)
+    if args.shuffle_agents:
+        assert not geo, "--shuffle-agents: single-GPU / ensemble runs"
+        from grad_june.world import renumber_world
+        data = renumber_world(data, torch.randperm(N, device=dev))
+        del data["agent"]["original_index"]        # a world that simply arrived in this order
+        torch.cuda.empty_cache()
     data = Runner.get_data(params, data=data)
+    torch.cuda.empty_cache()
     world = freeze_device_world(data, dev)   # the int64 edge lists are not needed once the CSR exists
     model = GradJune.from_parameters(params)
     keys = list(model.infection_networks.networks.keys())
@@ -497,6 +508,8 @@ def main():
                        "driver": (f"CUDA graph replay (GraphedRunner), {args.streams} concurrent lane(s)" if args.graph
                                   else "Python loop (Runner)"),
                        "layout_tiers": dict(zip(world.types, world.type_tier)),
+                       "agents_shuffled_then_renumbered": bool(args.shuffle_agents),
+                       "noise_keyed_by_loaded_id": world.__dict__.get("orig_id") is not None,
                        "parallelism": parallelism,
                        "l2": "inputs (>= 2 GB per pass) far larger than the 126 MB L2; no flush needed"},
             "clocks": clk, "rank_ms": rank_ms,

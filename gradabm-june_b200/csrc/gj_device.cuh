@@ -66,14 +66,24 @@ __device__ __forceinline__ float draw_step_uniform(uint64_t seed, uint32_t call,
   philox_step_block(seed, call, (uint64_t)agent, r);
   return u01_half(r[2]);
 }
+// E = -ln u by inversion.  The largest u is 1 - 2^-24, whose E = 5.96e-8 is below the absolute error of the
+// hardware log2 near 1: without the floor the approximation may return E = 0, a Gumbel value of +inf and a forced
+// draw.  The floor is the exact E of that largest u.
+constexpr float kMinE = 5.9604645e-08f;         // -ln(1 - 2^-24)
+constexpr float kMinE2 = 8.5991327e-08f;        // -log2(1 - 2^-24)
 __device__ __forceinline__ StepNoise draw_step_noise(uint64_t seed, uint32_t call, int64_t agent) {
   uint32_t r[4];
   philox_step_block(seed, call, (uint64_t)agent, r);
   StepNoise n;
-  n.E0 = -__logf(u01_open(r[0]));
-  n.E1 = -__logf(u01_open(r[1]));
+  n.E0 = fmaxf(-__logf(u01_open(r[0])), kMinE);
+  n.E1 = fmaxf(-__logf(u01_open(r[1])), kMinE);
   n.u = u01_half(r[2]);
   return n;
+}
+// counter of agent a's noise: its id in the numbering the world was loaded in (renumbered worlds), else its global
+// index (agent_offset = first agent of this rank's partition)
+__device__ __forceinline__ int64_t noise_agent(const gj_world_desc& w, const gj_step_params& p, int64_t a) {
+  return w.orig_id ? (int64_t)w.orig_id[a] : (int64_t)p.agent_offset + a;
 }
 
 // one standard normal per (agent, call): Box-Muller on stream 1

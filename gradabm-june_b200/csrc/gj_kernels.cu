@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(kBlock) k_agent_forward(gj_world_desc w, gj_st
     float one[kMaxRed];
 #pragma unroll
     for (int r = 0; r < kMaxRed; ++r) one[r] = 0.0f;
-    forward_tail(p, io, N, a, cls % 100, q, st, one);
+    forward_tail(p, io, N, a, noise_agent(w, p, a), cls % 100, q, st, one);
 #pragma unroll
     for (int r = 0; r < kMaxRed; ++r) red[r] += (double)one[r];
   }
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kBlock) k_agent_backward(gj_world_desc w, gj_s
     st.cur = io.cur ? io.cur[a] : 1.0f;
     st.nxt = io.nxt ? io.nxt[a] : 1.0f;
     st.ttn = io.ttn ? io.ttn[a] : 0.0f;
-    const BackAgent r = backward_agent(p, io, N, a, cls % 100, st, false);
+    const BackAgent r = backward_agent(p, io, N, a, noise_agent(w, p, a), cls % 100, st, false);
     if (io.g_q_out) io.g_q_out[a] = r.gq;
     if (io.g_n_out) io.g_n_out[a] = r.gn;
     if (seed_mode) gfrac[0] += (double)(-r.gq);  // q = 1 - fraction
@@ -522,26 +522,40 @@ static int build_channels(const gj_world_desc* w, const gj_step_params* p, Chann
   return 0;
 }
 
-// persistent grids of the throughput-mode kernels
+// persistent grids of the throughput-mode kernels.  Occupancy, the SM count and the opt-in to large dynamic
+// shared memory are properties of (kernel, device): the caches are per device (a process may drive several GPUs,
+// `system.device: cuda:1` — ADVICE r1), indexed by the CURRENT device, which the caller has made the one that owns
+// the stream and the pointers (grad_june.ops wraps every call in torch.cuda.device).
+constexpr int kMaxDevices = 32;
+struct OccCache {
+  int v[kMaxDevices];
+};
+static int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
 static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    n = sms;
+  static int n[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = sms;
   }
-  return n;
+  return n[dev];
 }
 // one resident wave: SMs x (CTAs of this kernel that fit on an SM), at most one CTA per tile
 template <typename K>
-static int lean_grid(const gj_world_desc* w, K kernel, int* cache) {
-  if (*cache == 0) {
+static int lean_grid(const gj_world_desc* w, K kernel, OccCache* cache) {
+  int& c = cache->v[current_device()];
+  if (c == 0) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kLeanThreads, 0) != cudaSuccess || per_sm < 1)
       per_sm = 1;
-    *cache = per_sm;
+    c = per_sm;
   }
-  const int64_t g = (int64_t)sm_count() * *cache;
+  const int64_t g = (int64_t)sm_count() * c;
   return (int)(w->n_tiles < g ? w->n_tiles : g);
 }
 
@@ -560,6 +574,7 @@ static bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 static bool pipe_aligned_fwd(const gj_world_desc* w, const LeanPlan& lp, const gj_fwd_io* io) {
   return aligned16(io->s) && aligned16(io->inf) && aligned16(io->tinf) && aligned16(io->cur) && aligned16(io->nxt) &&
          aligned16(io->ttn) && aligned16(io->T) && aligned16(io->Tq) && aligned16(w->ent1) && aligned16(w->cls) &&
+         aligned16(w->orig_id) &&
          aligned16(lp.r_slot) && aligned16(lp.r_pc);
 }
 static bool pipe_aligned_bwd(const gj_world_desc* w, const LeanPlan& lp, const gj_bwd_io* io) {
@@ -572,15 +587,16 @@ static bool pipe_aligned_bwd(const gj_world_desc* w, const LeanPlan& lp, const g
 }
 // one resident wave of a kernel with dynamic shared memory
 template <typename K>
-static int pipe_grid(const gj_world_desc* w, K kernel, int threads, size_t smem, int* cache) {
-  if (*cache == 0) {
+static int pipe_grid(const gj_world_desc* w, K kernel, int threads, size_t smem, OccCache* cache) {
+  int& c = cache->v[current_device()];
+  if (c == 0) {
     int per_sm = 0;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
       per_sm = 1;
-    *cache = per_sm;
+    c = per_sm;
   }
-  const int64_t g = (int64_t)sm_count() * *cache;
+  const int64_t g = (int64_t)sm_count() * c;
   return (int)(w->n_tiles < g ? w->n_tiles : g);
 }
 
@@ -683,6 +699,10 @@ static bool lean_plan(const gj_world_desc* w, const gj_step_params* p, const Pla
         lp->ctp[lp->n_tc] = w->cell_tile_ptr[t];
         lp->tc[lp->n_tc++] = w->tile_cell[t];
       }
+    } else if (kind == GJ_KIND_HOUSEHOLD) {
+      // generic-tier household (giant or non-contiguous groups, e.g. the two-group world of utils.py:97-133): its
+      // members are summed unmasked, which is the PLAIN sum exactly when no quarantine mask is active
+      if (p->n_quar > 0) return false;
     } else if (kind != GJ_KIND_PLAIN) {
       return false;
     }
@@ -721,7 +741,7 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
   if (p->stage != GJ_STAGE_REST) {
     if (!p->t_ready) {
       ProfScope ps(K_TRANSMISSION, st);
-      static int occ[2] = {0, 0};
+      static OccCache occ[2];
       if (quar) k_lean_transmission<true><<<lean_grid(w, k_lean_transmission<true>, &occ[1]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
       else k_lean_transmission<false><<<lean_grid(w, k_lean_transmission<false>, &occ[0]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
       GJ_CHECK_LAUNCH("k_lean_transmission");
@@ -736,7 +756,7 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
   if (int e = launch_cell_gather(w, p, pl, io->S_scaled, sc, st)) return e;
   if (pipe_enabled() && pipe_aligned_fwd(w, lp, io)) {
     ProfScope ps(K_AGENT_FWD, st);
-    static int occ[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    static OccCache occ[8];
     const bool diag = io->q || io->n;
     const size_t smem = next ? sizeof(PipeFwdSharedT<true>) : sizeof(PipeFwdSharedT<false>);
     NextStep nx;
@@ -765,7 +785,7 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
   }
   {
     ProfScope ps(K_AGENT_FWD, st);
-    static int occ[4] = {0, 0, 0, 0};
+    static OccCache occ[4];
     const bool diag = io->q || io->n;
     if (quar && diag) k_lean_forward<true, true><<<lean_grid(w, k_lean_forward<true, true>, &occ[3]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets);
     else if (quar) k_lean_forward<true, false><<<lean_grid(w, k_lean_forward<true, false>, &occ[2]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.red_part, sc.tickets);
@@ -779,13 +799,13 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
 static int lean_backward(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, LeanPlan lp,
                          const gj_bwd_io* io, const Scratch& sc, cudaStream_t st) {
   const bool quar = p->n_quar > 0;
-  static int occ_b[2] = {0, 0}, occ_g[2] = {0, 0};
+  static OccCache occ_b[2], occ_g[2];
   int gather_grid = 1;
   const bool pipe = pipe_enabled() && pipe_aligned_bwd(w, lp, io);
   if (p->stage != GJ_STAGE_REST) {
     if (pipe) {
       ProfScope ps(K_AGENT_BWD, st);
-      static int occ[2] = {0, 0};
+      static OccCache occ[2];
       const size_t smem = sizeof(PipeBwdShared);
       if (quar) k_pipe_backward<true><<<pipe_grid(w, k_pipe_backward<true>, kBwdThreads, smem, &occ[1]), kBwdThreads, smem, st>>>(*w, *p, lp, *io, sc.tile_part);
       else k_pipe_backward<false><<<pipe_grid(w, k_pipe_backward<false>, kBwdThreads, smem, &occ[0]), kBwdThreads, smem, st>>>(*w, *p, lp, *io, sc.tile_part);
@@ -806,7 +826,7 @@ static int lean_backward(const gj_world_desc* w, const gj_step_params* p, const 
   if (int e = launch_cell_gather(w, p, pl, io->cR, sc, st)) return e;
   if (pipe) {
     ProfScope ps(K_AGENT_BWD_GATHER, st);
-    static int occ[2] = {0, 0};
+    static OccCache occ[2];
     const size_t smem = sizeof(PipeGatShared);
     if (quar) k_pipe_backward_gather<true><<<(gather_grid = pipe_grid(w, k_pipe_backward_gather<true>, kPipeThreads, smem, &occ[1])), kPipeThreads, smem, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.dbeta_tile);
     else k_pipe_backward_gather<false><<<(gather_grid = pipe_grid(w, k_pipe_backward_gather<false>, kPipeThreads, smem, &occ[0])), kPipeThreads, smem, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.dbeta_tile);

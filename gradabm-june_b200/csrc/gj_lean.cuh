@@ -429,7 +429,7 @@ __device__ __forceinline__ FwdRes lean_forward_core(const gj_step_params& p, con
                                                     int cls, float inv_tau, float dead, float* __restrict__ hist,
                                                     float* __restrict__ deaths) {
   FwdRes o;
-  const float dE = lg2_fast(-lg2_fast(u01_open(r0))) - lg2_fast(-lg2_fast(u01_open(r1)));
+  const float dE = lg2_fast(fmaxf(-lg2_fast(u01_open(r0)), kMinE2)) - lg2_fast(fmaxf(-lg2_fast(u01_open(r1)), kMinE2));
   const float rv = (beta_r * rpc) * hs;
   const float house = lp.r_house ? rv : 0.0f;
   const float plain = (gv + Lc) + (lp.r_house ? 0.0f : rv);
@@ -472,13 +472,12 @@ __device__ __forceinline__ FwdRes lean_forward_core(const gj_step_params& p, con
 // one agent: noise, core, stores
 template <bool kQuar, bool kDiag>
 __device__ __forceinline__ FwdOut lean_forward_agent(const gj_step_params& p, const LeanPlan& lp, const gj_fwd_io& io,
-                                                   uint32_t a, float hs, float gv, float Lc, float beta_r, float rpc,
+                                                   uint32_t a, uint64_t ga, float hs, float gv, float Lc, float beta_r, float rpc,
                                                    float s, float inf, float tinf, float cur, float nxt, float ttn,
                                                    int cls, float inv_tau, float dead, float* __restrict__ hist,
                                                    float* __restrict__ deaths) {
   uint32_t r[4];
-  const uint64_t ga = p.agent_offset + a;  // global agent id
-  philox_step_block(p.seed, p.call_index, ga, r);
+  philox_step_block(p.seed, p.call_index, ga, r);   // ga: the agent's id in the noise stream (noise_agent())
   const FwdRes o = lean_forward_core<kQuar>(p, lp, io.stage_prob, ga, r[0], r[1], hs, gv, Lc, beta_r, rpc, s, inf, tinf,
                                             cur, nxt, ttn, cls, inv_tau, dead, hist, deaths);
   io.tape_v[a] = o.tape_v;
@@ -568,7 +567,7 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_FWD) k_lean_forward
       float s[kLeanBatch], inf[kLeanBatch], tinf[kLeanBatch], cur[kLeanBatch], nxt[kLeanBatch], ttn[kLeanBatch];
       float rpc[kLeanBatch], gen[kLeanBatch];
       RangeLoads rl[kLeanBatch];
-      uint32_t ent[kLeanBatch], slot[kLeanBatch];
+      uint32_t ent[kLeanBatch], slot[kLeanBatch], oid[kLeanBatch];
       int cls[kLeanBatch];
       // ---- issue every load of the batch: gathers (addresses known from the previous iteration), streaming
       //      loads, and the next batch's index words --------------------------------------------------------
@@ -588,6 +587,7 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_FWD) k_lean_forward
         ttn[h] = i_ttn[al];
         cls[h] = w.cls[al];
         rpc[h] = has_range ? lp.r_pc[al] : 0.0f;
+        oid[h] = w.orig_id ? w.orig_id[al] : 0u;
         const uint32_t an = a + kLeanBatch * kLeanThreads;
         const uint32_t anl = (an < a1) ? an : a0;
         ent_n[h] = has_gen ? i_ent[anl] : kEntNone;
@@ -601,8 +601,9 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_FWD) k_lean_forward
         const float hs = lean_range_finish(rl[h], Tr, a, slot[h]);
         const float gv = lean_generic_finish(w, SP, ent[h], a, gen[h]);
         const float Lc = lp.n_cell > 0 ? L[cls[h]] : 0.0f;
-        lean_forward_agent<kQuar, kDiag>(p, lp, io, a, hs, gv, Lc, beta_r, rpc[h], s[h], inf[h], tinf[h], cur[h], nxt[h],
-                                         ttn[h], cls[h], inv_tau, dead, sh.hist, &sh.deaths);
+        const uint64_t ga = w.orig_id ? (uint64_t)oid[h] : p.agent_offset + a;
+        lean_forward_agent<kQuar, kDiag>(p, lp, io, a, ga, hs, gv, Lc, beta_r, rpc[h], s[h], inf[h], tinf[h], cur[h],
+                                         nxt[h], ttn[h], cls[h], inv_tau, dead, sh.hist, &sh.deaths);
       }
     }
     tile = tend;
@@ -634,16 +635,18 @@ __device__ __forceinline__ void lean_backward_agent(const gj_step_params& p, con
                                                     float ty, float v, int cls, float gs_o, float ginf_o, float gtinf_o,
                                                     float gcur_o, float gnxt_o, float gttn_o, float inv_tau, float dead,
                                                     float g_deaths, const float* __restrict__ gred_age,
-                                                    const ProbRow* __restrict__ prob, float (&acc)[GJ_MAX_CHANNELS]) {
+                                                    const ProbRow* __restrict__ prob, float (&acc)[GJ_MAX_CHANNELS],
+                                                    const uint32_t* __restrict__ orig_id) {
     const int age = age_of(cls);
     const float n = signbit(ty) ? 1.0f : 0.0f;  // the tape's sign bit is the draw
-    // symptoms^T: the draws are regenerated only for the few agents whose stage actually updates
+    // symptoms^T: the draws (and the agent's id in the noise stream) are fetched only by the few agents whose
+    // stage actually updates
     const uint64_t seed = p.seed;
     const uint32_t call = p.call_index;
-    const int64_t ga = (int64_t)p.agent_offset + a;
+    auto ga = [&]() { return orig_id ? (int64_t)orig_id[a] : (int64_t)p.agent_offset + a; };
     const SympOut so = symptoms_forward(p, io.stage_prob, cur, nxt, ttn, n, age,
-                                        [&]() { return draw_step_uniform(seed, call, ga); },
-                                        [&](int) { return draw_step_normal(seed, call, ga); });
+                                        [&]() { return draw_step_uniform(seed, call, ga()); },
+                                        [&](int) { return draw_step_normal(seed, call, ga()); });
     float gc = gcur_o;
     if (so.cur == dead) gc += g_deaths;
     float gcur1 = gc, gnxt1 = gnxt_o;
@@ -772,7 +775,7 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_BWD) k_lean_backwar
         if (a >= a1) break;
         lean_backward_agent<kQuar>(p, lp, io, a, s[h], tinf[h], cur[h], nxt[h], ttn[h], ty[h], v[h], cls[h], gs_o[h],
                                    ginf_o[h], gtinf_o[h], gcur_o[h], gnxt_o[h], gttn_o[h], inv_tau, dead, g_deaths,
-                                   gred_age, prob, acc);
+                                   gred_age, prob, acc, w.orig_id);
       }
     }
     if (lp.n_cell > 0) {

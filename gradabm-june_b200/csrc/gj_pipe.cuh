@@ -193,7 +193,7 @@ __device__ __forceinline__ bool next_new_cell(const NextStep& nx, int64_t a, int
 }
 struct alignas(16) PipeFwdStage {
   float s[kPipeF], inf[kPipeF], tinf[kPipeF], cur[kPipeF], nxt[kPipeF], ttn[kPipeF], rpc[kPipeF];
-  uint32_t ent[kPipeF], slot[kPipeF];
+  uint32_t ent[kPipeF], slot[kPipeF], oid[kPipeF];
   float T[kPipeH];
   uint8_t cls[kPipeTile + 32];
 };
@@ -215,9 +215,11 @@ __device__ __forceinline__ void pipe_fwd_issue(PipeFwdStage& sg, uint64_t* bar, 
   const TileSpan t = tile_span(w, tile);
   uint32_t total = 6u * t.n4 + (t.hi16 - t.lo16);
   if (has_gen) total += t.n4;
+  if (w.orig_id) total += t.n4;
   if (has_range) total += 2u * t.n4 + (t.thi - t.tlo) * 4u;
   mbar_expect_tx(bar, total);
   const Copier c{bar};
+  if (w.orig_id) c.f4(sg.oid, w.orig_id, t);
   c.f4(sg.s, io.s, t);
   c.f4(sg.inf, io.inf, t);
   c.f4(sg.tinf, io.tinf, t);
@@ -306,7 +308,8 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
       const int cls = sg.cls[j + sk16];
       const float Lc = lp.n_cell > 0 ? L[cls] : 0.0f;
       const float gv = lean_generic_finish(w, SP, ent[h], a, gen[h]);
-      const FwdOut o = lean_forward_agent<kQuar, kDiag>(p, lp, io, a, hs, gv, Lc, beta_r, has_range ? sg.rpc[i] : 0.0f,
+      const uint64_t ga = w.orig_id ? (uint64_t)sg.oid[i] : p.agent_offset + a;
+      const FwdOut o = lean_forward_agent<kQuar, kDiag>(p, lp, io, a, ga, hs, gv, Lc, beta_r, has_range ? sg.rpc[i] : 0.0f,
                                                         sg.s[i], sg.inf[i], sg.tinf[i], sg.cur[i], sg.nxt[i], sg.ttn[i], cls,
                                                         inv_tau, dead, sh.hist, &sh.deaths);
       if (kNext) {   // TransmissionUpdater of the next step (same arithmetic as k_lean_transmission)
@@ -452,7 +455,7 @@ __global__ void __launch_bounds__(kBwdThreads, kBwdCtas) k_pipe_backward(gj_worl
       if (a >= a1) break;
       lean_backward_agent<kQuar>(p, lp, io, a, sg.s[i], sg.tinf[i], sg.cur[i], sg.nxt[i], sg.ttn[i], sg.ty[i], sg.v[i],
                                  sg.cls[j + sk16], c[h][0], c[h][1], c[h][2], c[h][3], c[h][4], c[h][5], inv_tau, dead,
-                                 g_deaths, sh.gred_age, sh.prob, acc);
+                                 g_deaths, sh.gred_age, sh.prob, acc, w.orig_id);
     }
     if (pipe_release() && tile + kPipeStages < run.t1)
       pipe_bwd_issue(sg, &sh.full[stg], w, io, tile + kPipeStages);

@@ -205,8 +205,8 @@ struct AgentState {
   float s, inf, tinf, cur, nxt, ttn;
 };
 
-__device__ __forceinline__ void forward_tail(const gj_step_params& p, const gj_fwd_io& io, int64_t N, int64_t a, int age,
-                                             float q, AgentState st, float* red) {
+__device__ __forceinline__ void forward_tail(const gj_step_params& p, const gj_fwd_io& io, int64_t N, int64_t a,
+                                             int64_t ga, int age, float q, AgentState st, float* red) {
   const int dead = p.n_stages - 1;
   if (p.mode == GJ_MODE_SEED) q = 1.0f - io.seed_fraction[0] * 1.0f;  // infection.py:36-40
   float n = 0.0f;
@@ -214,7 +214,7 @@ __device__ __forceinline__ void forward_tail(const gj_step_params& p, const gj_f
   nz.E0 = nz.E1 = 1.0f;
   nz.u = 0.0f;
   if (p.phases & (GJ_PHASE_SAMPLE | GJ_PHASE_SYMPTOMS)) {
-    if (io.inj_E == nullptr || io.inj_u == nullptr) nz = draw_step_noise(p.seed, p.call_index, (int64_t)p.agent_offset + a);
+    if (io.inj_E == nullptr || io.inj_u == nullptr) nz = draw_step_noise(p.seed, p.call_index, ga);
     if (io.inj_E) {
       nz.E0 = io.inj_E[a];
       nz.E1 = io.inj_E[N + a];
@@ -241,7 +241,6 @@ __device__ __forceinline__ void forward_tail(const gj_step_params& p, const gj_f
     const float* inj_z = io.inj_z;
     const uint64_t seed = p.seed;
     const uint32_t call = p.call_index;
-    const int64_t ga = (int64_t)p.agent_offset + a;
     const float uu = nz.u;
     const SympOut so = symptoms_forward(p, io.stage_prob, st.cur, st.nxt, st.ttn, n, age, [&]() { return uu; },
                                         [&](int row) {
@@ -399,7 +398,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_tile_forward(gj_world_desc w, gj_
     io.tape_v[a] = (st.s == 0.0f) ? pr.X : pr.lam;
     if (io.q) io.q[a] = q;
     if (io.lam) io.lam[a] = pr.lam;
-    forward_tail(p, io, N, a, cls % 100, q, st, red);
+    forward_tail(p, io, N, a, noise_agent(w, p, a), cls % 100, q, st, red);
   }
   if (io.red) {
     double redd[kMaxRed];
@@ -421,7 +420,7 @@ struct BackAgent {
 
 // symptoms^T, infect^T, sampler^T and the clamp/exp chain: shared by the generic and the tiled kernels
 __device__ __forceinline__ BackAgent backward_agent(const gj_step_params& p, const gj_bwd_io& io, int64_t N, int64_t a,
-                                                    int age, const AgentState& st, bool with_networks) {
+                                                    int64_t ga, int age, const AgentState& st, bool with_networks) {
   const int dead = p.n_stages - 1;
   const bool seed_mode = p.mode == GJ_MODE_SEED;
   float n = 0.0f;
@@ -443,7 +442,6 @@ __device__ __forceinline__ BackAgent backward_agent(const gj_step_params& p, con
     const float* inj_z = io.inj_z;
     const uint64_t seed = p.seed;
     const uint32_t call = p.call_index;
-    const int64_t ga = (int64_t)p.agent_offset + a;
     // the uniform / normal draws are regenerated only for the few agents whose stage actually updates
     const SympOut so = symptoms_forward(p, io.stage_prob, st.cur, st.nxt, st.ttn, n, age,
                                         [&]() { return inj_u ? inj_u[a] : draw_step_uniform(seed, call, ga); },
@@ -542,7 +540,7 @@ __global__ void __launch_bounds__(kBlock, 3) k_tile_backward(gj_world_desc w, gj
     st.cur = io.cur ? io.cur[a] : 1.0f;
     st.nxt = io.nxt ? io.nxt[a] : 1.0f;
     st.ttn = io.ttn ? io.ttn[a] : 0.0f;
-    const BackAgent r = backward_agent(p, io, N, a, cls % 100, st, true);
+    const BackAgent r = backward_agent(p, io, N, a, noise_agent(w, p, a), cls % 100, st, true);
     const float mq = (p.n_quar > 0) ? quarantine_mask(p, st.cur) : 1.0f;
     const float wv = r.glam * st.s;
     const float wqv = r.glam * (mq * st.s);

@@ -11,6 +11,7 @@ from .model import GradJune
 from .timer import Timer
 from .policies import Policies
 from .runner import Runner
-from .world import HeteroData, ToUndirected, load_world, make_synthetic_world, create_simple_connected_graph
+from .world import (HeteroData, ToUndirected, create_simple_connected_graph, layout_order_of, load_world,
+                    make_synthetic_world, original_order, renumber_world)
 
 __version__ = "0.1.0"

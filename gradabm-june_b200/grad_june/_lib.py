@@ -18,7 +18,7 @@ GJ_MAX_STAGES = 16
 GJ_MAX_QUAR = 4
 GJ_MAX_AGE_BINS = 8
 GJ_MAX_CHANNELS = 8
-GJ_ABI_VERSION = 4
+GJ_ABI_VERSION = 5
 
 KIND_PLAIN, KIND_HOUSEHOLD, KIND_LEISURE, KIND_CARE_VISIT = 0, 1, 2, 3
 PHASE_NETWORKS, PHASE_SAMPLE, PHASE_INFECT, PHASE_SYMPTOMS, PHASE_ALL = 1, 2, 4, 8, 15
@@ -47,7 +47,7 @@ class WorldDesc(C.Structure):
         ("tile_cell", C.c_void_p * GJ_MAX_TYPES), ("cell_tile_ptr", C.c_void_p * GJ_MAX_TYPES),
         ("cell_grp_ptr", C.c_void_p * GJ_MAX_TYPES), ("cell_grp", C.c_void_p * GJ_MAX_TYPES),
         ("grp_cell_ptr", C.c_void_p * GJ_MAX_TYPES), ("grp_cell", C.c_void_p * GJ_MAX_TYPES),
-        ("ent1", _u32p), ("dbeta_w", _f32p),
+        ("ent1", _u32p), ("dbeta_w", _f32p), ("orig_id", _u32p),
     ]
 
 

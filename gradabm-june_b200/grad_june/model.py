@@ -126,5 +126,14 @@ class GradJune(torch.nn.Module):
             data["agent"]["not_infected_probs"] = out["q"]
         return data, out["red"]
 
+    def kernel_family(self, data, timer) -> str:
+        """"throughput" or "reference-order": the kernel family the fused step at ``timer`` runs on with in-kernel
+        noise (the throughput kernels need the household edge type on the RANGE tier or unquarantined, the leisure
+        type on the CELL tier and plain kinds elsewhere — what :func:`grad_june.world.renumber_world` arranges)."""
+        dev = data["agent"].susceptibility.device
+        static, rows = self._static(data, dev)
+        spec, _ = self._spec(timer, rows, None, ops.MODE_STEP, False)
+        return ops.step_plan(static, spec)
+
     def forward(self, data, timer):
         return self.step(data, timer)[0]

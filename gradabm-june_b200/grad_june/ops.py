@@ -43,6 +43,24 @@ def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _on(device):
+    """Context that makes ``device`` the current CUDA device for a library call: kernels are launched on the
+    current device, so a world on cuda:1 in a process whose current device is cuda:0 would otherwise launch with a
+    foreign stream and foreign pointers."""
+    return torch.cuda.device(device)
+
+
+def _noise_order(world: DeviceWorld, t: Optional[torch.Tensor]):
+    """Injected noise arrives indexed by the agents' ORIGINAL ids (the order the world was loaded in, which is the
+    order the reference / the oracle draws it in); a renumbered world reads it through its permutation."""
+    if t is None or world.__dict__.get("orig_id") is None:
+        return t
+    oi = world.__dict__.get("_orig_index")
+    if oi is None:
+        oi = world.__dict__["_orig_index"] = world.orig_id.long() & 0xFFFFFFFF
+    return t.index_select(-1, oi).contiguous()
+
+
 # --------------------------------------------------------------------------------------
 # noise control
 # --------------------------------------------------------------------------------------
@@ -112,8 +130,9 @@ def philox_fill(seed: int, call_index: int, n: int, device, first_agent: int = 0
     E = torch.empty(2, n, device=device)
     u = torch.empty(n, device=device)
     z = torch.empty(n, device=device)
-    _lib.check(_lib.lib().gj_philox_fill_at(seed, call_index, first_agent, n, E.data_ptr(), u.data_ptr(), z.data_ptr(),
-                                            _stream(E.device)), "gj_philox_fill_at")
+    with _on(E.device):
+        _lib.check(_lib.lib().gj_philox_fill_at(seed, call_index, first_agent, n, E.data_ptr(), u.data_ptr(),
+                                                z.data_ptr(), _stream(E.device)), "gj_philox_fill_at")
     return E, u, z
 
 
@@ -259,17 +278,19 @@ def profile_k0(shape: torch.Tensor) -> torch.Tensor:
     require_cuda(shape, "infection_parameters['shape']")
     shape = _f32(shape)
     k0 = torch.empty_like(shape)
-    _lib.check(_lib.lib().gj_profile_prepare(shape.numel(), shape.data_ptr(), k0.data_ptr(), _stream(shape.device)),
-               "gj_profile_prepare")
+    with _on(shape.device):
+        _lib.check(_lib.lib().gj_profile_prepare(shape.numel(), shape.data_ptr(), k0.data_ptr(), _stream(shape.device)),
+                   "gj_profile_prepare")
     return k0
 
 
 def profile_pack(maxinf, shape, rate, shift, k0) -> torch.Tensor:
     """[N, 4] = {maxinf*k0*rate, rate, shape-1, shift}: the profile as one 16-byte word per agent."""
     out = torch.empty(shape.numel(), 4, dtype=torch.float32, device=shape.device)
-    _lib.check(_lib.lib().gj_profile_pack(shape.numel(), maxinf.data_ptr(), shape.data_ptr(), rate.data_ptr(),
-                                          shift.data_ptr(), k0.data_ptr(), out.data_ptr(), _stream(shape.device)),
-               "gj_profile_pack")
+    with _on(shape.device):
+        _lib.check(_lib.lib().gj_profile_pack(shape.numel(), maxinf.data_ptr(), shape.data_ptr(), rate.data_ptr(),
+                                              shift.data_ptr(), k0.data_ptr(), out.data_ptr(), _stream(shape.device)),
+                   "gj_profile_pack")
     return out
 
 
@@ -281,9 +302,10 @@ class _Transmission(torch.autograd.Function):
         dev = tinf.device
         tinf, inf = _f32(tinf), _f32(inf)
         T = torch.empty_like(tinf)
-        _lib.check(_lib.lib().gj_transmission_forward(
-            tinf.numel(), float(now), tinf.data_ptr(), inf.data_ptr(), maxinf.data_ptr(), shape.data_ptr(),
-            rate.data_ptr(), shift.data_ptr(), k0.data_ptr(), T.data_ptr(), _stream(dev)), "gj_transmission_forward")
+        with _on(dev):
+            _lib.check(_lib.lib().gj_transmission_forward(
+                tinf.numel(), float(now), tinf.data_ptr(), inf.data_ptr(), maxinf.data_ptr(), shape.data_ptr(),
+                rate.data_ptr(), shift.data_ptr(), k0.data_ptr(), T.data_ptr(), _stream(dev)), "gj_transmission_forward")
         ctx.save_for_backward(tinf, inf, maxinf, shape, rate, shift, k0)
         ctx.now = float(now)
         return T
@@ -294,10 +316,11 @@ class _Transmission(torch.autograd.Function):
         gT = _f32(gT)
         g_tinf = torch.empty_like(tinf)
         g_inf = torch.empty_like(tinf)
-        _lib.check(_lib.lib().gj_transmission_backward(
-            tinf.numel(), ctx.now, tinf.data_ptr(), inf.data_ptr(), maxinf.data_ptr(), shape.data_ptr(),
-            rate.data_ptr(), shift.data_ptr(), k0.data_ptr(), gT.data_ptr(), g_tinf.data_ptr(), g_inf.data_ptr(),
-            _stream(tinf.device)), "gj_transmission_backward")
+        with _on(tinf.device):
+            _lib.check(_lib.lib().gj_transmission_backward(
+                tinf.numel(), ctx.now, tinf.data_ptr(), inf.data_ptr(), maxinf.data_ptr(), shape.data_ptr(),
+                rate.data_ptr(), shift.data_ptr(), k0.data_ptr(), gT.data_ptr(), g_tinf.data_ptr(), g_inf.data_ptr(),
+                _stream(tinf.device)), "gj_transmission_backward")
         return None, g_tinf, g_inf, None, None, None, None, None
 
 
@@ -313,6 +336,19 @@ def transmission(now, tinf, inf, maxinf, shape, rate, shift, k0=None):
 _STATE = ("s", "inf", "tinf", "cur", "nxt", "ttn")
 
 
+def step_plan(static: "StepStatic", spec: "StepSpec") -> str:
+    """Which kernel family ``gj_step_forward`` runs for this step when the noise is the in-kernel Philox stream:
+    "throughput" (gj_lean.cuh / gj_pipe.cuh) or "reference-order" (gj_tiled.cuh) — ``gj_step_plan``."""
+    if EXACT_ORDER and not spec.exact_order:
+        spec = replace(spec, exact_order=True)
+    p, _ = _fill_params(static.world, spec, static.symptoms, 0, 0)
+    out = (C.c_int64 * 1)()
+    rc = _lib.lib().gj_step_plan(C.byref(static.world.desc()), C.byref(p), out, 1)
+    if rc < 0:
+        _lib.check(rc, "gj_step_plan")
+    return "throughput" if (rc == 1 and static.prof4 is not None) else "reference-order"
+
+
 def _staged_call(fn, what, static: "StepStatic", desc, p, io, stream, sum_buffers, lean_inputs: bool, p_next=None):
     """One library call, or — for a partitioned world — the two stages of it with the all-reduce of the boundary
     groups' sums (``sum_buffers``: the two group-sum tensors of this call) in between.  ``p_next``: parameters of
@@ -321,10 +357,11 @@ def _staged_call(fn, what, static: "StepStatic", desc, p, io, stream, sum_buffer
     world.__dict__["_calls"] = world.__dict__.get("_calls", 0) + 1   # the per-world scratch changes hands
 
     def call():
-        if p_next is not None:
-            rc = _lib.lib().gj_step_forward_next(C.byref(desc), C.byref(p), C.byref(p_next), C.byref(io), stream)
-        else:
-            rc = fn(C.byref(desc), C.byref(p), C.byref(io), stream)
+        with _on(world.device):
+            if p_next is not None:
+                rc = _lib.lib().gj_step_forward_next(C.byref(desc), C.byref(p), C.byref(p_next), C.byref(io), stream)
+            else:
+                rc = fn(C.byref(desc), C.byref(p), C.byref(io), stream)
         if rc < 0:
             _lib.check(rc, what)
         return rc
@@ -374,6 +411,7 @@ class _Step(torch.autograd.Function):
         N = world.n_agents
         L = _lib.lib()
         seed, call_index, E, u, z = noise
+        E, u, z = _noise_order(world, E), _noise_order(world, u), _noise_order(world, z)
         if EXACT_ORDER and not spec.exact_order:   # pin the choice: the backward must run the same kernel family
             spec = replace(spec, exact_order=True)
         p, s_total = _fill_params(world, spec, static.symptoms, seed, call_index)

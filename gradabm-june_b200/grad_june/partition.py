@@ -260,11 +260,12 @@ class BoundaryExchange:
             if pack is None:
                 pack = self._packs[n] = torch.empty(2, n, dtype=torch.float32, device=a.device)
             st = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
-            _lib.check(L.gj_boundary_pack(n, inv.data_ptr(), a.data_ptr(), b.data_ptr(), pack.data_ptr(), st),
-                       "gj_boundary_pack")
-            dist.all_reduce(pack, group=self.part.process_group)
-            _lib.check(L.gj_boundary_unpack(n, inv.data_ptr(), pack.data_ptr(), a.data_ptr(), b.data_ptr(), st),
-                       "gj_boundary_unpack")
+            with torch.cuda.device(a.device):
+                _lib.check(L.gj_boundary_pack(n, inv.data_ptr(), a.data_ptr(), b.data_ptr(), pack.data_ptr(), st),
+                           "gj_boundary_pack")
+                dist.all_reduce(pack, group=self.part.process_group)
+                _lib.check(L.gj_boundary_unpack(n, inv.data_ptr(), pack.data_ptr(), a.data_ptr(), b.data_ptr(), st),
+                           "gj_boundary_unpack")
             return
         pack = torch.zeros(len(buffers), n, dtype=torch.float32, device=a.device)   # host-logic tests (gloo)
         for i, buf in enumerate(buffers):

@@ -21,7 +21,7 @@ from .paths import ensure_default_config
 from .timer import Timer
 from .transmission import PROFILE_KEYS, TransmissionSampler
 from .utils import read_path
-from .world import load_world
+from .world import load_world, original_order, renumber_world
 
 _STATE_KEYS = ("susceptibility", "is_infected", "infection_time", "transmission")
 _SYMPTOM_KEYS = ("current_stage", "next_stage", "time_to_next_stage")
@@ -71,9 +71,19 @@ class Runner(torch.nn.Module):
         if data is None:
             data = load_world(read_path(params["data_path"]))
         data = data.to(device)
+        # Worlds arrive numbered as the reference's loaders number them (by area and age): renumber the agents
+        # household-contiguous inside their leisure cell so that the streaming layout tiers apply
+        # (world.layout_order).  ``data["agent"].original_index`` keeps the loaded numbering; the noise stream is
+        # keyed by it and ``Runner.forward`` returns ``is_infected`` in it.  ``system: {renumber_agents: false}``
+        # keeps the loaded numbering (one part of a partitioned world is never renumbered on its own).
+        if params["system"].get("renumber_agents", True) and "_gj_partition" not in data.__dict__ \
+                and "_gj_block" not in data.__dict__:
+            data = renumber_world(data)
         n_agents = len(data["agent"]["id"])
         values = TransmissionSampler.from_parameters(params)(n_agents)
-        data["agent"].infection_parameters = {key: values[i, :] for i, key in enumerate(PROFILE_KEYS)}
+        if "original_index" in data["agent"] and "_gj_partition" not in data.__dict__:
+            values = values[:, data["agent"]["original_index"]]     # drawn per ORIGINAL agent: independent of the layout
+        data["agent"].infection_parameters = {key: values[i, :].contiguous() for i, key in enumerate(PROFILE_KEYS)}
         data["agent"].transmission = torch.zeros(n_agents, device=device)
         data["agent"].susceptibility = torch.ones(n_agents, device=device)
         data["agent"].is_infected = torch.zeros(n_agents, device=device)
@@ -144,7 +154,7 @@ class Runner(torch.nn.Module):
         }
         for i, key in enumerate(self._age_bins_host[1:]):
             results[f"cases_by_age_{key:02d}"] = table[:, 2 + i]
-        return results, data["agent"].is_infected
+        return results, original_order(data, data["agent"].is_infected)
 
     def save_results(self, results, is_infected):
         self.save_path.mkdir(exist_ok=True, parents=True)

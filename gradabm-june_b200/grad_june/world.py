@@ -227,7 +227,7 @@ def world_from_arrays(arrays: Dict[str, np.ndarray], types: List[str], device="c
 TIER_GENERIC, TIER_RANGE, TIER_CELL = 0, 1, 2
 TILE_AGENTS = 1024          # agents per CTA tile of the agent-major kernels (== GJ_TILE_AGENTS)
 RANGE_MAX_GROUP = 64        # range tier: every agent re-sums its (small) group from its neighbours
-CELL_MIN_MEAN_AGENTS = 256  # cell tier only pays when cells are much larger than a tile row
+CELL_MIN_MEAN_AGENTS = 64   # cell tier only pays when cells are much larger than a warp
 CELL_MAX_GROUPS = 16
 
 
@@ -280,6 +280,8 @@ class DeviceWorld:
         d.n_cells_total = cell_off
         if self.__dict__.get("dbeta_w") is not None:
             d.dbeta_w = self.dbeta_w.data_ptr()
+        if self.__dict__.get("orig_id") is not None:
+            d.orig_id = self.orig_id.data_ptr()
         self.__dict__["_desc"] = d
         return d
 
@@ -376,12 +378,181 @@ def _try_cell_tier(n_agents, src, dst, n_groups):
             "grp_cell": _u32(grp_cell)}
 
 
+def _degree_and_size(n_agents, ei, n_groups):
+    E = ei.shape[1]
+    if E == 0:
+        return 0, 0
+    return int(torch.bincount(ei[0], minlength=n_agents).max()), int(torch.bincount(ei[1], minlength=n_groups).max())
+
+
+def tier_candidates(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], n_groups: Dict[str, int]):
+    """Which edge type may use the RANGE tier and which the CELL tier (-> (range_type, cell_type), either may be None).
+
+    The throughput-mode kernels take at most one range-tier network (the household re-sum over neighbouring agents)
+    and run the cell tier for the leisure kinds only, and the reference itself addresses these two edge sets by
+    name (``HouseholdNetwork`` -> "attends_household", every ``LeisureNetwork`` -> "attends_leisure",
+    leisure_network.py:44-48,58-59).  So: RANGE = "household" if every agent has at most one such edge and no group
+    exceeds ``RANGE_MAX_GROUP`` members, else the largest other type of that shape; CELL = "leisure" if no agent
+    has more than ``CELL_MAX_GROUPS`` such edges.  Whether the tier is actually used is decided from the agent
+    numbering by :func:`build_csr`; :func:`layout_order` computes the numbering that makes it so."""
+    shape = {t: _degree_and_size(n_agents, edges[t], int(n_groups[t])) for t in types}
+    cell_type = "leisure" if ("leisure" in types and 0 < shape["leisure"][0] <= CELL_MAX_GROUPS) else None
+    ok = [t for t in types if t != cell_type and shape[t][0] == 1 and shape[t][1] <= RANGE_MAX_GROUP]
+    range_type = None
+    if "household" in ok:
+        range_type = "household"
+    elif ok:
+        range_type = max(ok, key=lambda t: edges[t].shape[1])
+    return range_type, cell_type
+
+
+def _list_rank(n_agents, ei, n_groups):
+    """Dense lexicographic rank of every agent's ORDERED group list (edge order; agents without an edge rank 0) and
+    the number of distinct lists."""
+    dev = ei.device
+    src, dst = ei[0], ei[1]
+    deg = torch.bincount(src, minlength=n_agents)
+    _, perm = torch.sort(src, stable=True)
+    s_sorted, d_sorted = src[perm], dst[perm]
+    pos = torch.arange(src.numel(), device=dev) - _ptr_from_counts(deg)[s_sorted]
+    rank = torch.zeros(n_agents, dtype=torch.long, device=dev)
+    n_lists = 1
+    for j in range(int(deg.max()) if src.numel() else 0):
+        gj = torch.zeros(n_agents, dtype=torch.long, device=dev)
+        sel = pos == j
+        gj[s_sorted[sel]] = d_sorted[sel] + 1
+        uniq, rank = torch.unique(rank * (int(n_groups) + 1) + gj, return_inverse=True)
+        n_lists = int(uniq.numel())
+    return rank, n_lists
+
+
+def layout_order(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], n_groups: Dict[str, int]):
+    """Agent renumbering that lets the world use the streaming layout tiers whatever order it was loaded in
+    (SURVEY.md 7 "Random 4-byte gathers"; the reference's loaders number agents by area and age,
+    june_world_loader/network_loader.py:30-44, so the members of a household are scattered over their area).
+
+    Returns ``perm`` with ``perm[new] = old`` or None when the given numbering already has the layout.  Order:
+    (1) the leisure cell — agents with the same ordered list of leisure groups, i.e. the same super-area — in
+    lexicographic order of the lists, so that geography stays contiguous; (2) the household, placed in the cell of
+    its first member; (3) the position of the agent's household edge in the edge list (members keep the reference's
+    edge order, which the reference-order kernels sum in).  Agents without a household are singletons."""
+    range_type, cell_type = tier_candidates(n_agents, types, edges, n_groups)
+    if n_agents == 0 or (range_type is None and cell_type is None):
+        return None
+    dev = edges[types[0]].device
+    ids = torch.arange(n_agents, device=dev)
+    cell = torch.zeros(n_agents, dtype=torch.long, device=dev)
+    n_cells = 1
+    if cell_type is not None:
+        cell, n_cells = _list_rank(n_agents, edges[cell_type], n_groups[cell_type])
+    if range_type is not None:
+        ei = edges[range_type]
+        Gh = int(n_groups[range_type])
+        hkey = Gh + ids                                     # singletons: one pseudo-household per agent
+        hkey[ei[0]] = ei[1]
+        epos = ei.shape[1] + ids
+        epos[ei[0]] = torch.arange(ei.shape[1], device=dev)
+    else:
+        Gh, hkey, epos = 0, ids.clone(), ids
+    n_keys = Gh + n_agents
+    first = torch.full((n_keys,), n_agents, dtype=torch.long, device=dev).scatter_reduce(0, hkey, epos, reduce="amin")
+    hcell = torch.full((n_keys,), n_cells, dtype=torch.long, device=dev)
+    is_first = epos == first[hkey]
+    hcell[hkey[is_first]] = cell[is_first]                 # the cell of the household's first member
+    base = torch.argsort(epos)                             # (3): members in edge order
+    _, order = torch.sort((hcell[hkey] * n_keys + hkey)[base], stable=True)
+    perm = base[order]
+    if bool((perm == ids).all()):
+        return None
+    return perm
+
+
+def _permute_agents(v, perm, n):
+    if torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == n:
+        return v[perm.to(v.device)]
+    if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == n:
+        return v[perm.cpu().numpy()]
+    if isinstance(v, dict):
+        return {k: _permute_agents(x, perm, n) for k, x in v.items()}
+    return v
+
+
+def renumber_world(data: "HeteroData", perm: Optional[torch.Tensor] = None) -> "HeteroData":
+    """The same world with its agents renumbered by :func:`layout_order` (or the given ``perm[new] = old``): every
+    per-agent attribute is permuted, agent indices in the edge lists are rewritten (edge order unchanged), groups
+    keep their ids.  ``data["agent"].original_index[new] = old`` records where each agent came from — the noise
+    stream is keyed by it, so trajectories do not depend on the numbering — and :func:`original_order` maps
+    per-agent results back.  Returns ``data`` itself when the numbering already has the layout."""
+    n = len(data["agent"].id)
+    types = data.venue_types()
+    if perm is None:
+        perm = layout_order(n, types, {t: data["attends_" + t].edge_index for t in types},
+                            {t: len(data[t]["id"]) for t in types})
+        if perm is None:
+            return data
+    perm = perm.long()
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(n, device=perm.device)
+    prev = data["agent"]["original_index"] if "original_index" in data["agent"] else None
+    for key, v in list(data["agent"].items()):
+        data["agent"][key] = _permute_agents(v, perm, n)
+    if prev is None:
+        data["agent"].original_index = perm.clone()
+    for (src, rel, dst), store in data._edge_store_dict.items():
+        ei = store.edge_index
+        row = 0 if src == "agent" else (1 if dst == "agent" else None)
+        if row is None or ei.numel() == 0:
+            continue
+        ei = ei.clone()
+        ei[row] = inv.to(ei.device)[ei[row]]
+        store.edge_index = ei
+    data._gj_cache.clear()
+    return data
+
+
+def layout_order_of(data: "HeteroData", values):
+    """Per-agent ``values`` given in the order the world was loaded in -> the (renumbered) order of ``data``."""
+    agent = data["agent"]
+    if "original_index" not in agent:
+        return values
+    return _permute_agents(values, agent["original_index"], agent["original_index"].numel())
+
+
+def original_order(data: "HeteroData", values: torch.Tensor) -> torch.Tensor:
+    """Per-agent ``values`` of a renumbered world in the order the world was loaded in (differentiable)."""
+    agent = data["agent"]
+    if "original_index" not in agent:
+        return values
+    cache = data.__dict__.setdefault("_gj_cache", {})
+    oi = agent["original_index"]
+    hit = cache.get("inverse_index")
+    if hit is None or hit[0] is not oi:
+        inv = torch.empty_like(oi)
+        inv[oi] = torch.arange(oi.numel(), device=oi.device)
+        cache["inverse_index"] = hit = (oi, inv)
+    return values[hit[1].to(values.device)]
+
+
 def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], people: Dict[str, torch.Tensor],
               n_groups: Dict[str, int], age: torch.Tensor, sex: torch.Tensor, small_group: int, chunk: int,
-              device, tiers: bool = True) -> DeviceWorld:
+              device, tiers: bool = True, orig_id: Optional[torch.Tensor] = None,
+              want_tiers: Optional[Dict[str, int]] = None) -> DeviceWorld:
+    """``orig_id``: [n_agents] id of every agent in the numbering the world was loaded in (None = this one): the
+    counter of the kernels' Philox stream.  ``want_tiers``: the tier to try per type (default: the policy of
+    :func:`tier_candidates`; a partitioned world passes the tiers its ranks agreed on); a type whose structure
+    does not fit the wanted tier is stored GENERIC."""
     if len(types) > MAX_TYPES:
         raise ValueError(f"at most {MAX_TYPES} edge types are supported")
     dev = torch.device(device)
+    edges = {t: edges[t].to(dev) for t in types}
+    if want_tiers is None:
+        want_tiers = {}
+        if tiers and n_agents > 0:
+            range_type, cell_type = tier_candidates(n_agents, types, edges, n_groups)
+            if range_type is not None:
+                want_tiers[range_type] = TIER_RANGE
+            if cell_type is not None:
+                want_tiers[cell_type] = TIER_CELL
     offs = [0]
     for t in types:
         offs.append(offs[-1] + int(n_groups[t]))
@@ -403,14 +574,15 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
             raise ValueError(f"edge type {t}: too many groups")
         n_edges_total += ei.shape[1]
         tier = TIER_GENERIC
-        if tiers and n_agents > 0:
+        want = want_tiers.get(t, TIER_GENERIC) if (tiers and n_agents > 0) else TIER_GENERIC
+        if want == TIER_RANGE:
             r = _try_range_tier(n_agents, ei[0], ei[1], int(n_groups[t]), pc[offs[ti]:offs[ti + 1]])
             if r is not None:
                 tier, range_slot[ti], range_pc[ti] = TIER_RANGE, r["range_slot"], r["range_pc"]
-            else:
-                c = _try_cell_tier(n_agents, ei[0], ei[1], int(n_groups[t]))
-                if c is not None:
-                    tier, cells[ti] = TIER_CELL, c
+        elif want == TIER_CELL:
+            c = _try_cell_tier(n_agents, ei[0], ei[1], int(n_groups[t]))
+            if c is not None:
+                tier, cells[ti] = TIER_CELL, c
         type_tier.append(tier)
         if tier == TIER_GENERIC:
             srcs.append(ei[0])
@@ -493,6 +665,7 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
         chunk_group=_u32(chunk_group), chunk_begin=_u32(chunk_begin), chunk_end=_u32(chunk_end),
         chunk_part=chunk_part.to(torch.int32), big_groups=_u32(big_groups), big_part_ptr=_u32(big_part_ptr),
         n_parts=n_parts, tile_begin=_u32(tile_begin), ent1=_padded(_u32(ent1)), device=dev,
+        orig_id=None if orig_id is None else _padded(_u32(orig_id.to(dev))),
     )
 
 
@@ -508,7 +681,8 @@ def get_device_world(data: HeteroData, device, small_group: Optional[int] = None
         ei = data["attends_" + t].edge_index
         pp = data[t]["people"]
         sig.append((t, id(ei), ei._version, tuple(ei.shape), id(pp), getattr(pp, "_version", 0), len(data[t]["id"])))
-    sig.append((id(data["agent"].age), id(data["agent"].sex)))
+    oi = data["agent"]["original_index"] if "original_index" in data["agent"] else None
+    sig.append((id(data["agent"].age), id(data["agent"].sex), id(oi)))
     sig = tuple(sig)
     if cache.get("sig") == sig:
         return cache["world"]
@@ -524,11 +698,46 @@ def get_device_world(data: HeteroData, device, small_group: Optional[int] = None
         {t: torch.as_tensor(data[t]["people"]) for t in types},
         {t: len(data[t]["id"]) for t in types},
         torch.as_tensor(data["agent"].age), torch.as_tensor(data["agent"].sex), small_group, chunk, device,
+        orig_id=None if oi is None else torch.as_tensor(oi), want_tiers=agreed_tiers(data, device),
     )
     cache["sig"] = sig
     cache["world"] = world
     cache.pop("scratch", None)
     return world
+
+
+def agreed_tiers(data: HeteroData, device):
+    """None for an ordinary world.  For one part of a geographically partitioned world: the layout tier every
+    rank will use per edge type (tiers chosen from the local slice alone can differ between ranks, and
+    then the packed boundary buffers they all-reduce have different layouts).  Each rank tries its tiers locally;
+    a type keeps a streaming tier only if EVERY rank achieved it and — for the RANGE tier, which has no per-group
+    buffer to exchange — no group of the type straddles partitions.  Collective: every rank calls it at its first
+    step."""
+    part = data.__dict__.get("_gj_partition")
+    if part is None or part.world_size == 1:
+        return None
+    import torch.distributed as dist
+
+    types = data.venue_types()
+    n = len(data["agent"].id)
+    edges = {t: data["attends_" + t].edge_index.to(device) for t in types}
+    n_groups = {t: len(data[t]["id"]) for t in types}
+    range_type, cell_type = tier_candidates(n, types, edges, n_groups)
+    mine = torch.zeros(len(types), dtype=torch.long)
+    for ti, t in enumerate(types):
+        ei = edges[t]
+        if t == range_type and part.n_boundary.get(t, 0) == 0:
+            pc = p_contact(torch.as_tensor(data[t]["people"]).to(device))
+            if _try_range_tier(n, ei[0], ei[1], n_groups[t], pc) is not None:
+                mine[ti] = TIER_RANGE
+        elif t == cell_type and _try_cell_tier(n, ei[0], ei[1], n_groups[t]) is not None:
+            mine[ti] = TIER_CELL
+    backend = dist.get_backend(part.process_group)
+    buf = mine.to(device) if backend == "nccl" else mine
+    both = torch.stack((buf, -buf))
+    dist.all_reduce(both, op=dist.ReduceOp.MIN, group=part.process_group)
+    lo, hi = both[0].cpu(), (-both[1]).cpu()
+    return {t: (int(lo[ti]) if int(lo[ti]) == int(hi[ti]) else TIER_GENERIC) for ti, t in enumerate(types)}
 
 
 def freeze_device_world(data: HeteroData, device, drop_edge_lists: bool = True):

@@ -11,8 +11,12 @@
  *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*), performs no
  *     allocation and no host synchronisation;
  *   - return value 0 = ok, negative = error (text via gj_last_error());
- *   - floating point is fp32, compiled without FMA contraction and without fast-math so that the
- *     elementwise arithmetic rounds like the reference's op-by-op torch graph.
+ *   - floating point is fp32, compiled without FMA contraction (--fmad=false) and without --use_fast_math.
+ *     The reference-order kernels (injected noise, exact_order) use the IEEE libdevice expf/logf/powf and true
+ *     divisions, so their elementwise arithmetic rounds like the reference's op-by-op torch graph.  The
+ *     throughput-mode kernels (in-kernel Philox noise) keep q = expf(-lam*dt) IEEE but evaluate the Gumbel draw
+ *     and the infectiousness profile with the hardware lg2.approx / ex2.approx / rcp.approx (explicit fmaf where
+ *     written): masks then differ from the reference only at certified near-ties.
  */
 #ifndef GRADJUNE_B200_H
 #define GRADJUNE_B200_H
@@ -24,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GJ_ABI_VERSION 4
+#define GJ_ABI_VERSION 5
 
 #define GJ_MAX_TYPES 8      /* edge types (household, company, school, university, care_home, leisure, ...) */
 #define GJ_MAX_NETS 16      /* infection networks active in one step */
@@ -130,6 +134,10 @@ typedef struct gj_world_desc {
    * [n_groups] weight of each group in d/dbeta, 1 for groups this rank owns and 0 for groups owned by another
    * rank (their sums are exchanged between the two stages of a step); NULL = all ones */
   const float* dbeta_w;
+  /* agent renumbering (grad_june.world.renumber_world / gj_world_build): [n_agents] id of every agent in the
+   * numbering the world was LOADED in.  The Philox counter of agent a is orig_id[a] (then agent_offset is not
+   * added), so a renumbered world draws exactly the noise of the world as loaded; NULL = the identity */
+  const uint32_t* orig_id;
 } gj_world_desc;
 
 typedef struct gj_net {

@@ -7,13 +7,20 @@ from grad_june import GradJune, Runner, Timer
 from grad_june.world import world_from_arrays
 
 
-def make_runner(tag, device="cuda:0"):
+def make_runner(tag, device="cuda:0", renumber=False):
+    """Runner on the reference's 769-agent sample world with the golden run's profile parameters.  ``renumber``:
+    let Runner.get_data renumber the agents (household-contiguous inside their leisure cell); everything given or
+    returned per agent in the LOADED numbering goes through layout_order_of / original_order."""
+    from grad_june.world import layout_order_of
     g = np.load(H.GOLDEN / f"run_{tag}.npz")
     params, _ = H.load_params(tag)
     params["system"]["device"] = device
+    params["system"]["renumber_agents"] = bool(renumber)
     arrays = np.load(H.GOLDEN / "sample_world.npz")
     data = Runner.get_data(params, data=world_from_arrays(arrays, H.SAMPLE_TYPES))
-    data["agent"].infection_parameters = {k: v.to(device) for k, v in H.profile_params(g).items()}
+    assert ("original_index" in data["agent"]) == bool(renumber)
+    data["agent"].infection_parameters = {k: layout_order_of(data, v.to(device)).contiguous()
+                                          for k, v in H.profile_params(g).items()}
     model = GradJune.from_parameters(params)
     nets = model.infection_networks.networks
     for key in nets.keys():

@@ -141,15 +141,11 @@ def test_teacher_forced_step_vs_oracle(n_agents, oracle_device):
     assert np.max(np.abs(q - qo) / qo) <= 1e-5, np.max(np.abs(q - qo) / qo)
     n, no = cpu(agent["new_infected"]), cpu(aux["new_infected"])
     mism = np.nonzero(n != no)[0]
-    # every mask mismatch must be a certified near-tie of the two perturbed logits
-    if len(mism):
-        qm = torch.from_numpy(qo[mism].astype(np.float64))
-        Em = E[:, torch.from_numpy(mism).to(DEV)].double().cpu()
-        x0 = (qm.log() - Em[0].log()) / 0.1
-        x1 = ((1 - torch.from_numpy(qo[mism]).float()).double().log() - Em[1].log()) / 0.1
-        gap = (x0 - x1).abs() / torch.maximum(x0.abs(), x1.abs())
-        assert float(gap.max()) < 2e-5, f"mask mismatch that is not a near-tie: gap {gap}"
-    assert len(mism) <= max(2, int(2e-5 * n_agents)), len(mism)
+    # every mask mismatch must be a certified near-tie of the two perturbed logits (helpers.certify_near_ties)
+    worst = H.certify_near_ties(qo, E.cpu().numpy(), mism, what=f"teacher-forced step, {n_agents} agents")
+    assert len(mism) <= max(2, int(1e-6 * n_agents)), len(mism)
+    H.report(f"teacher-forced step {n_agents} agents: mask mismatches / worst gap (units of the certificate)",
+             {"mismatches": int(len(mism)), "worst": worst, "q_max_rel": float(np.max(np.abs(q - qo) / qo))})
     ok = np.ones(n_agents, dtype=bool)
     ok[mism] = False
     assert n.sum() > 0.001 * n_agents
@@ -167,45 +163,46 @@ def test_teacher_forced_step_vs_oracle(n_agents, oracle_device):
     # stages really moved (the symptoms machine was exercised)
     assert (cpu(agent.symptoms["current_stage"]) != cpu(state["current_stage"])).sum() > 0.01 * n_agents
 
-    if len(mism) == 0:
-        gw = torch.Generator(device="cpu").manual_seed(5)
-        wts = [torch.rand(n_agents, generator=gw) for _ in range(4)]
-        keys = list(model.infection_networks.networks.keys())
+    # ---- gradients, unconditionally: an agent whose draw differs (certified near-tie above) is left out of the loss
+    #      on both sides, so the comparison never depends on whether a flip happened -------------------------------
+    gw = torch.Generator(device="cpu").manual_seed(5)
+    keep = torch.from_numpy(ok.astype(np.float32))
+    wts = [torch.rand(n_agents, generator=gw) * keep for _ in range(4)]
+    keys = list(model.infection_networks.networks.keys())
 
-        def loss_of(inf, cur, s, tinf, dev, dtype=torch.float32):
-            w0, w1, w2, w3 = (t.to(device=dev, dtype=dtype) for t in wts)
-            return (inf * w0).sum() + (cur * w1).sum() + 0.5 * (s * w2).sum() + 0.05 * (tinf * w3).sum()
+    def loss_of(inf, cur, s, tinf, dev, dtype=torch.float32):
+        w0, w1, w2, w3 = (t.to(device=dev, dtype=dtype) for t in wts)
+        return (inf * w0).sum() + (cur * w1).sum() + 0.5 * (s * w2).sum() + 0.05 * (tinf * w3).sum()
 
-        def oracle_grads(dtype, perturb=None):
-            wo, netso, speco, symo, profo, sto = _oracle_inputs(params, data, model, timer, state, oracle_device)
-            for sp in speco.nets:
-                sp.beta = sp.beta.to(dtype)
-            sto = {k: v.to(dtype) for k, v in sto.items()}
-            profo = {k: v.to(dtype) for k, v in profo.items()}
-            nz = O.StepNoise(E=noise.E.to(dtype), u=noise.u.to(dtype), z=noise.z.to(dtype))
-            if perturb is None:
-                O.step(wo, sto, profo, speco, symo, nz)
-            else:
-                with H.perturb_q(perturb):
-                    O.step(wo, sto, profo, speco, symo, nz)
-            loss_of(sto["is_infected"], sto["current_stage"], sto["susceptibility"], sto["infection_time"],
-                    oracle_device, dtype).backward()
-            gr = np.array([netso.networks[k].log_beta.grad.item() if netso.networks[k].log_beta.grad is not None
-                           else 0.0 for k in keys])
-            return gr, torch.equal(sto["is_infected"].float(), st["is_infected"])
-
-        loss_of(agent.is_infected, agent.symptoms["current_stage"], agent.susceptibility, agent.infection_time, DEV).backward()
-        mine = np.array([model.infection_networks.networks[k].log_beta.grad.item() for k in keys])
-        ref, _ = oracle_grads(torch.float32)
-        g64, same = oracle_grads(torch.float64)
-        sens = np.zeros_like(ref)
-        for sd in (1, 2, 3):
-            gp, _ = oracle_grads(torch.float32, perturb=sd)
-            sens = np.maximum(sens, np.abs(gp - ref))
-        if same:
-            H.assert_grad_parity(mine, ref, g64, sens, rtol=1e-5, what="d/dlog_beta")
+    def oracle_grads(dtype, perturb=None):
+        wo, netso, speco, symo, profo, sto = _oracle_inputs(params, data, model, timer, state, oracle_device)
+        for sp in speco.nets:
+            sp.beta = sp.beta.to(dtype)
+        sto = {k: v.to(dtype) for k, v in sto.items()}
+        profo = {k: v.to(dtype) for k, v in profo.items()}
+        nz = O.StepNoise(E=noise.E.to(dtype), u=noise.u.to(dtype), z=noise.z.to(dtype))
+        if perturb is None:
+            O.step(wo, sto, profo, speco, symo, nz)
         else:
-            assert np.allclose(mine, ref, rtol=1e-3)
+            with H.perturb_q(perturb):
+                O.step(wo, sto, profo, speco, symo, nz)
+        loss_of(sto["is_infected"], sto["current_stage"], sto["susceptibility"], sto["infection_time"],
+                oracle_device, dtype).backward()
+        gr = np.array([netso.networks[k].log_beta.grad.item() if netso.networks[k].log_beta.grad is not None
+                       else 0.0 for k in keys])
+        return gr, torch.equal((sto["is_infected"].float() * keep.to(oracle_device)),
+                               (st["is_infected"] * keep.to(oracle_device)))
+
+    loss_of(agent.is_infected, agent.symptoms["current_stage"], agent.susceptibility, agent.infection_time, DEV).backward()
+    mine = np.array([model.infection_networks.networks[k].log_beta.grad.item() for k in keys])
+    ref, _ = oracle_grads(torch.float32)
+    g64, same = oracle_grads(torch.float64)
+    assert same, "fp64 witness drew different masks"
+    sens = np.zeros_like(ref)
+    for sd in (1, 2, 3):
+        gp, _ = oracle_grads(torch.float32, perturb=sd)
+        sens = np.maximum(sens, np.abs(gp - ref))
+    H.assert_grad_parity(mine, ref, g64, sens, rtol=1e-5, what=f"teacher-forced step {n_agents} agents: d/dlog_beta")
 
 
 def test_properties_at_scale():
@@ -273,13 +270,11 @@ def test_throughput_mode_matches_reference_order(irregular, pipelined):
 
 def _compare_throughput_with_reference_order(n_agents, data, model, timer, state):
     from grad_june import ops
-    outs = {}
+    outs, graphs = {}, {}
     for mode in ("exact", "fast"):
         for k in ("susceptibility", "is_infected", "infection_time"):
             data["agent"][k] = state[k]
         data["agent"].symptoms = {k: state[k] for k in ("current_stage", "next_stage", "time_to_next_stage")}
-        for net in model.infection_networks.networks.values():
-            net.log_beta.grad = None
         ops.EXACT_ORDER = mode == "exact"
         try:
             with ops.philox_seed(77):
@@ -287,14 +282,10 @@ def _compare_throughput_with_reference_order(n_agents, data, model, timer, state
         finally:
             ops.EXACT_ORDER = False
         agent = data["agent"]
-        loss = red[0] + red[1] + 0.3 * red[2] + (agent.susceptibility * torch.linspace(0, 1, n_agents, device=DEV)).sum() \
-            + 0.01 * agent.infection_time.sum() + agent.symptoms["current_stage"].sum()
-        loss.backward()
-        grads = torch.stack([net.log_beta.grad for net in model.infection_networks.networks.values()]).cpu().numpy()
+        graphs[mode] = (agent.is_infected, agent.susceptibility, agent.infection_time, agent.symptoms["current_stage"])
         outs[mode] = dict(q=agent["not_infected_probs"].cpu().numpy(), n=agent["new_infected"].cpu().numpy(),
                           cur=agent.symptoms["current_stage"].detach().cpu().numpy(),
-                          ttn=agent.symptoms["time_to_next_stage"].detach().cpu().numpy(), red=red.detach().cpu().numpy(),
-                          grads=grads)
+                          ttn=agent.symptoms["time_to_next_stage"].detach().cpu().numpy(), red=red.detach().cpu().numpy())
     e, f = outs["exact"], outs["fast"]
     assert np.max(np.abs(e["q"] - f["q"]) / e["q"]) < 2e-6
     mism = np.nonzero(e["n"] != f["n"])[0]
@@ -304,8 +295,21 @@ def _compare_throughput_with_reference_order(n_agents, data, model, timer, state
     assert np.array_equal(e["cur"][ok], f["cur"][ok])
     assert np.allclose(e["ttn"][ok], f["ttn"][ok], rtol=1e-6, atol=1e-6)
     assert np.allclose(e["red"], f["red"], atol=len(mism) + 0.5)
-    if len(mism) == 0:
-        assert np.allclose(e["grads"], f["grads"], rtol=2e-4, atol=1e-7 * np.abs(e["grads"]).max())
+    # gradients, unconditionally: per-agent losses with the flipped agents (if any) left out on both sides
+    keep = torch.from_numpy(ok.astype(np.float32)).to(DEV)
+    ramp = torch.linspace(0, 1, n_agents, device=DEV) * keep
+    grads = {}
+    for mode in ("exact", "fast"):
+        for net in model.infection_networks.networks.values():
+            net.log_beta.grad = None
+        inf, s, tinf, cur = graphs[mode]
+        loss = (inf * keep).sum() + (s * ramp).sum() + 0.01 * (tinf * keep).sum() + (cur * keep).sum() \
+            + 0.3 * (inf * keep * (data["agent"].age < 18)).sum()
+        loss.backward()
+        grads[mode] = torch.stack([net.log_beta.grad for net in model.infection_networks.networks.values()]).cpu().numpy()
+    assert np.abs(grads["exact"]).max() > 0
+    assert np.allclose(grads["exact"], grads["fast"], rtol=2e-4, atol=1e-7 * np.abs(grads["exact"]).max())
+    H.report("throughput vs reference-order kernels, one step: mask mismatches", int(len(mism)))
 
 
 def test_throughput_mode_bptt_window():
@@ -349,12 +353,12 @@ def test_throughput_mode_bptt_window():
                           grads=torch.stack([l.grad for l in leaves]).cpu().numpy())
     e, f = outs["exact"], outs["fast"]
     assert e["cases"][-1] > e["cases"][0] > 0
-    flips = int((e["inf"] != f["inf"]).sum())
-    assert flips <= 20, flips
-    if flips == 0:
-        assert np.array_equal(e["cases"], f["cases"])
-        assert np.array_equal(e["cur"], f["cur"])
-        assert np.allclose(e["grads"], f["grads"], rtol=5e-5, atol=1e-6 * np.abs(e["grads"]).max()), (e["grads"], f["grads"])
+    # unconditional: for this (world, seed) no draw of the window is a near-tie, so the two families must agree
+    # exactly on the trajectory; if a kernel change makes this fail, teacher-forced tests tell a near-tie from a bug
+    assert np.array_equal(e["inf"], f["inf"]), int((e["inf"] != f["inf"]).sum())
+    assert np.array_equal(e["cases"], f["cases"])
+    assert np.array_equal(e["cur"], f["cur"])
+    assert np.allclose(e["grads"], f["grads"], rtol=5e-5, atol=1e-6 * np.abs(e["grads"]).max()), (e["grads"], f["grads"])
 
 
 @pytest.mark.parametrize("quarantine", [False, True])
@@ -516,12 +520,10 @@ def test_lookahead_transmission_pass(policies):
     a, b = outs[False], outs[True]
     assert a["launches"] == 8 and b["launches"] == 1          # only the first step still runs the stand-alone pass
     assert a["cases"][-1] > a["cases"][0] > 0
-    flips = int((a["inf"] != b["inf"]).sum())
-    assert flips <= 20, flips
-    if flips == 0:
-        assert np.array_equal(a["cases"], b["cases"])
-        assert np.array_equal(a["T"], b["T"])
-        assert np.allclose(a["grads"], b["grads"], rtol=5e-5, atol=1e-6 * np.abs(a["grads"]).max()), (a["grads"], b["grads"])
+    assert np.array_equal(a["inf"], b["inf"]), int((a["inf"] != b["inf"]).sum())     # unconditional (see above)
+    assert np.array_equal(a["cases"], b["cases"])
+    assert np.array_equal(a["T"], b["T"])
+    assert np.allclose(a["grads"], b["grads"], rtol=5e-5, atol=1e-6 * np.abs(a["grads"]).max()), (a["grads"], b["grads"])
 
 
 def test_ensemble_evaluator_matches_single_runs():

@@ -218,3 +218,92 @@ def test_cpu_tensors_fail_loudly():
     from grad_june import IsInfectedSampler, _lib
     with pytest.raises(_lib.GradJuneLibraryError):
         IsInfectedSampler()(torch.full((8,), 0.5))
+
+
+def _build(data, orig=None):
+    from grad_june import world as W
+    types = data.venue_types()
+    n = len(data["agent"].id)
+    return W.build_csr(n, types, {t: data["attends_" + t].edge_index for t in types},
+                       {t: torch.as_tensor(data[t]["people"]) for t in types}, {t: len(data[t]["id"]) for t in types},
+                       data["agent"].age, data["agent"].sex, 16, 1024, "cpu",
+                       orig_id=data["agent"]["original_index"] if "original_index" in data["agent"] else None)
+
+
+def test_renumbering_makes_the_reference_sample_world_streamable(golden_dir):
+    """The reference's sample world as loaded (agents by area and age: households scattered) has its household on
+    the GENERIC tier; world.renumber_world puts it on the RANGE tier and leisure on the CELL tier without changing
+    the agent<->group incidence, and original_order / layout_order_of map per-agent values between numberings."""
+    from grad_june import world as W
+    arrays = np.load(golden_dir / "sample_world.npz")
+    data = W.world_from_arrays(arrays, H.SAMPLE_TYPES)
+    before = dict(zip(data.venue_types(), _build(data).type_tier))
+    assert before["household"] == W.TIER_GENERIC and before["leisure"] == W.TIER_CELL
+    n = len(data["agent"].id)
+    age0 = data["agent"].age.clone()
+    edges0 = {t: data["attends_" + t].edge_index.clone() for t in data.venue_types()}
+    data = W.renumber_world(data)
+    oi = data["agent"].original_index
+    assert torch.equal(torch.sort(oi)[0], torch.arange(n))
+    assert torch.equal(data["agent"].age, age0[oi])
+    assert torch.equal(W.original_order(data, data["agent"].age), age0)
+    assert torch.equal(W.layout_order_of(data, age0), data["agent"].age)
+    dw = _build(data)
+    after = dict(zip(data.venue_types(), dw.type_tier))
+    assert after["household"] == W.TIER_RANGE and after["leisure"] == W.TIER_CELL
+    assert all(after[t] == W.TIER_GENERIC for t in ("company", "school", "university", "care_home"))
+    assert torch.equal(dw.orig_id.long() & 0xFFFFFFFF, oi)
+    for t, e0 in edges0.items():          # same edges, same order, agents renamed
+        e1 = data["attends_" + t].edge_index
+        assert torch.equal(oi[e1[0]], e0[0]) and torch.equal(e1[1], e0[1])
+        assert torch.equal(data["rev_attends_" + t].edge_index, e1.flip(0))
+    # household members: consecutive ids, in the reference's edge order
+    hh = data["attends_household"].edge_index
+    _, order = torch.sort(hh[1], stable=True)
+    m, gidx = hh[0][order], hh[1][order]
+    same = gidx[1:] == gidx[:-1]
+    assert bool((m[1:][same] == m[:-1][same] + 1).all())
+    # a second renumbering finds nothing to do
+    assert W.layout_order(n, data.venue_types(), {t: data["attends_" + t].edge_index for t in data.venue_types()},
+                          {t: len(data[t]["id"]) for t in data.venue_types()}) is None
+
+
+def test_renumbering_recovers_a_shuffled_synthetic_world():
+    from grad_june import world as W
+    n = 30_000
+    data = W.make_synthetic_world(n, seed=3, agents_per_super_area=2500)
+    assert W.renumber_world(data) is data and "original_index" not in data["agent"]     # already laid out
+    ref = _build(data)
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(1))
+    data = W.renumber_world(data, perm)
+    assert torch.equal(data["agent"].original_index, perm)
+    shuffled = dict(zip(data.venue_types(), _build(data).type_tier))
+    assert shuffled["household"] == W.TIER_GENERIC and shuffled["leisure"] == W.TIER_GENERIC
+    data = W.renumber_world(data)
+    # original_index composes: it still refers to the first numbering, and the layout is the first one again
+    assert torch.equal(data["agent"].original_index, torch.arange(n))
+    dw = _build(data)
+    assert dw.type_tier == ref.type_tier
+    for name in ("tile_begin", "ent1", "gm_agent", "gm_ptr", "am_ent", "cls"):
+        assert torch.equal(getattr(dw, name), getattr(ref, name)), name
+    ti = data.venue_types().index("household")
+    assert torch.equal(dw.range_slot[ti], ref.range_slot[ti])
+
+
+def test_tier_policy_one_range_type_and_leisure_cells_only():
+    """At most one RANGE-tier type (the throughput kernels re-sum one household-like network per agent) and the
+    CELL tier for "leisure" only, whatever other types happen to look like (university members of the sample
+    world are contiguous runs: they stay GENERIC)."""
+    from grad_june import world as W
+    n = 4000
+    data = W.make_synthetic_world(n, seed=5, agents_per_super_area=1000)
+    ids = torch.arange(n)
+    data["pair"].id = torch.arange(n // 2)
+    data["pair"].people = torch.full((n // 2,), 2)
+    data["agent", "attends_pair", "pair"].edge_index = torch.stack((ids, ids // 2))      # also household-like
+    data["block"].id = torch.arange(4)
+    data["block"].people = torch.full((4,), n // 4)
+    data["agent", "attends_block", "block"].edge_index = torch.stack((ids, ids // (n // 4)))   # also cell-like
+    tiers = dict(zip(data.venue_types(), _build(data).type_tier))
+    assert tiers["household"] == W.TIER_RANGE and tiers["pair"] == W.TIER_GENERIC
+    assert tiers["leisure"] == W.TIER_CELL and tiers["block"] == W.TIER_GENERIC
