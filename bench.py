@@ -198,70 +198,91 @@ def workload_name(n_agents, policies=False):
 
 
 # ------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=120)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--agents", type=int, default=56_000_000,
-                    help="agents per GPU (weak scaling) / of the whole world (strong scaling)")
-    ap.add_argument("--parallelism", default="geo", choices=["geo", "ensemble"],
-                    help="N > 1: geographic partition of ONE world with the boundary-group all-reduce (default), or one "
-                         "beta sample per GPU on replicas of the world (no data-path collective)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="geo: every GPU owns --agents agents of a world of N x --agents (weak), or the --agents world "
-                         "is cut into N parts (strong)")
-    ap.add_argument("--samples", type=int, default=0,
-                    help="ensemble: beta samples evaluated per window over all GPUs (BASELINE config 5: 1024 on a 9M "
-                         "world, --agents 9000000 --window 30); default one per GPU")
-    ap.add_argument("--streams", type=int, default=1,
-                    help="ensemble + --graph: evaluate this many samples concurrently, each lane with its own replica of "
-                         "the world, captured window and CUDA stream (bandwidth-bound and issue-bound kernels of "
-                         "different samples overlap)")
-    ap.add_argument("--graph", action="store_true",
-                    help="capture the window (Runner() + backward) once as a CUDA graph and replay it "
-                         "(grad_june.graphed.GraphedRunner): removes the per-step Python cost that bounds small worlds")
-    ap.add_argument("--policies", action="store_true",
-                    help="BASELINE config 4: social distancing, school/leisure closures and quarantine from day 15")
-    ap.add_argument("--window", type=int, default=0,
-                    help="BPTT window (0 = 60 timesteps as in BASELINE.json, fewer if memory does not allow)")
-    ap.add_argument("--shuffle-agents", action="store_true",
-                    help="load the synthetic world with its agents in a RANDOM order (as a world that was not numbered "
-                         "for this layout): Runner.get_data then renumbers it (world.layout_order) and the kernels key "
-                         "their noise by the loaded ids")
-    ap.add_argument("--cpu-agents", type=int, default=1_000_000, help="agents of the CPU-baseline sample")
-    ap.add_argument("--cpu-steps", type=int, default=3)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
+# parity inside the benchmark: one teacher-forced step at the benchmark's size against the oracle on the same GPU
+# ------------------------------------------------------------------------------------------
+def verify_step(model, data, params, dev, policies, seed=2024):
+    """One fused step of the throughput-mode kernels from a mid-epidemic state against oracle/gj_oracle.py run on
+    the SAME GPU (same CUDA libm) with the kernels' own Philox draws (gj_philox_fill): per-agent q, masks, stages.
+    The oracle is the checker here, nothing of it is timed."""
+    import helpers as H
+    from grad_june import Timer, ops
+    from oracle import gj_oracle as O
 
-    rank = int(os.environ.get("RANK", 0))
-    world_size = int(os.environ.get("WORLD_SIZE", 1))
-    local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    if args.impl == "reference":
-        run_reference_arm(args, rank, world_size)
-        return
+    n = len(data["agent"].id)
+    timer = Timer.from_parameters(params)
+    for _ in range(min(16 if policies else 8, int(params["timer"]["total_days"]) - 1)):
+        next(timer)
+    keep = {k: data["agent"][k] for k in ("susceptibility", "is_infected", "infection_time", "transmission")}
+    keep_sym = dict(data["agent"].symptoms)
+    state = H.mid_epidemic_state(n, timer.now, 11, dev)
+    for k in ("susceptibility", "is_infected", "infection_time"):
+        data["agent"][k] = state[k]
+    data["agent"].symptoms = {k: state[k] for k in ("current_stage", "next_stage", "time_to_next_stage")}
+    out = {"agents": n, "step": f"day {timer.now:.0f}, dt {timer.duration:.2f}", "oracle_device": str(dev)}
+    try:
+        family = model.kernel_family(data, timer)
+        with torch.no_grad(), ops.philox_seed(seed):
+            model.step(data, timer, want_probs=True)
+        agent = data["agent"]
+        E, u, z = ops.philox_fill(seed, 0, n, dev)
+        w, nets, spec, sym, prof, st = H.oracle_step_inputs(params, data, model, timer, state, dev)
+        aux = {}
+        with torch.no_grad():
+            O.step(w, st, prof, spec, sym, H.layout_noise(data, E, u, z, dev), aux)
+        q, qo = agent["not_infected_probs"], aux["q"]
+        T, To = agent.transmission, aux["transmission"]
+        nz = To != 0
+        mism = torch.nonzero(agent["new_infected"] != aux["new_infected"]).flatten()
+        Eo = E if "original_index" not in agent else E[:, agent["original_index"]]
+        worst = H.certify_near_ties(qo[mism].cpu().numpy(), Eo[:, mism].cpu().numpy(), np.arange(mism.numel()),
+                                    what=f"bench --verify, {n} agents")
+        ok = torch.ones(n, dtype=torch.bool, device=dev)
+        ok[mism] = False
+        sym_out = agent.symptoms
+        stage_bad = int(((sym_out["current_stage"] != st["current_stage"]) & ok).sum()) \
+            + int(((sym_out["next_stage"] != st["next_stage"]) & ok).sum()) \
+            + int(((agent.is_infected != st["is_infected"]) & ok).sum())
+        out.update(kernel_family=family,
+                   q_max_rel=float(((q - qo).abs() / qo).max()),
+                   T_max_rel=float(((T[nz] - To[nz]).abs() / To[nz].abs()).max()) if bool(nz.any()) else 0.0,
+                   mask_mismatch=int(mism.numel()), max_gap=worst, near_ties_certified=True,
+                   state_mismatch_outside_near_ties=stage_bad,
+                   new_infections=int(aux["new_infected"].sum()),
+                   stages_moved=int((st["current_stage"] != state["current_stage"]).sum()),
+                   passed=bool(stage_bad == 0 and float(((q - qo).abs() / qo).max()) <= 1e-5))
+    except Exception as e:  # noqa: BLE001 -- the bench line must still be printed
+        out.update(passed=False, error=repr(e)[:300])
+    finally:
+        for k, v in keep.items():
+            data["agent"][k] = v
+        data["agent"].symptoms = keep_sym
+        data["agent"]._mapping.pop("new_infected", None)
+        data["agent"]._mapping.pop("not_infected_probs", None)
+        torch.cuda.empty_cache()
+    return out
 
+
+# ------------------------------------------------------------------------------------------
+# one measured configuration
+# ------------------------------------------------------------------------------------------
+def measure(args, ctx, scaling, graph, full=True):
+    """Build the world of this configuration, warm up, time exactly K steps (device events, max over ranks), and —
+    ``full`` — the per-kernel pass, the end-to-end pass, the repeats and the verification step.  Returns the dict
+    rank 0 turns into the JSON line (None on other ranks)."""
     import torch.distributed as dist
     from grad_june import GradJune, Runner, Timer, _lib, ops
-    from grad_june.world import freeze_device_world, make_synthetic_world
+    from grad_june.world import freeze_device_world, make_synthetic_world, renumber_world
 
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    dev = f"cuda:{local_rank}"
-    if world_size > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
-
+    rank, world_size, dev = ctx["rank"], ctx["world_size"], ctx["dev"]
     geo = world_size > 1 and args.parallelism == "geo"
-    strong = geo and args.scaling == "strong"
+    strong = geo and scaling == "strong"
     N = args.agents // world_size if strong else args.agents      # agents this rank owns (about, for strong)
     free, total = torch.cuda.mem_get_info()
-    # bytes retained per agent per step until backward (pre-state 24 + tape 8 + group sums ~3) + margin
-    per_step = 40.0 * N
+    per_step = 40.0 * N            # bytes retained per agent per step until backward (pre-state 24 + tape 8 + sums ~3)
     resident = 120.0 * N           # world CSR + static arrays + transient workspaces + initial state backup
     max_window = int(max(1, (free * 0.85 - resident) // per_step))
     window = min(args.steps, args.window or min(max_window, 60), max_window)
-    if world_size > 1:     # the ranks of a partitioned world step together
+    if world_size > 1:             # the ranks of a partitioned world step together
         wt = torch.tensor([window], device=dev)
         dist.all_reduce(wt, op=dist.ReduceOp.MIN)
         window = int(wt.item())
@@ -284,14 +305,17 @@ def main():
         data = make_synthetic_world(N, seed=0, device=dev)
     if args.shuffle_agents:
         assert not geo, "--shuffle-agents: single-GPU / ensemble runs"
-        from grad_june.world import renumber_world
         data = renumber_world(data, torch.randperm(N, device=dev))
         del data["agent"]["original_index"]        # a world that simply arrived in this order
         torch.cuda.empty_cache()
     data = Runner.get_data(params, data=data)
     torch.cuda.empty_cache()
-    world = freeze_device_world(data, dev)   # the int64 edge lists are not needed once the CSR exists
     model = GradJune.from_parameters(params)
+    parity = None
+    if full and args.verify and world_size == 1:
+        parity = verify_step(model, data, params, dev, args.policies)
+    world = freeze_device_world(data, dev)   # the int64 edge lists are not needed once the CSR exists
+    torch.cuda.empty_cache()
     keys = list(model.infection_networks.networks.keys())
     gen = torch.Generator().manual_seed(99)
     offsets = 0.05 * torch.randn(max(world_size, 1), len(keys), generator=gen)
@@ -311,12 +335,8 @@ def main():
     elif world_size > 1:
         n_total = N * n_samples * world_size
 
-    def fresh_runner():
-        r = Runner(model=model, data=data, timer=Timer.from_parameters(params), log_fraction_initial_cases=-2.0,
-                   save_path=params["save_path"], parameters=params)
-        return r
-
-    runner = fresh_runner()
+    runner = Runner(model=model, data=data, timer=Timer.from_parameters(params), log_fraction_initial_cases=-2.0,
+                    save_path=params["save_path"], parameters=params)
 
     def one_window(e2e):
         """every sample of this rank: forward `window` timesteps + backward; device-side results and grads"""
@@ -351,25 +371,25 @@ def main():
         torch.cuda.synchronize()
 
     prof = None
-    if args.graph:
+    graphed = None
+    if graph:
         from grad_june.graphed import GraphedRunner
         # per-kernel pass first, eagerly (a replayed graph carries no events), then capture
         eager_window(False)
-        _lib.profile_enable(True)
-        barrier()
-        eager_window(False)
-        barrier()
-        prof = {k: (v[0] * n_windows, v[1] * n_windows, v[2] * n_windows) for k, v in _lib.profile_read().items()}
-        _lib.profile_enable(False)
+        if full:
+            _lib.profile_enable(True)
+            barrier()
+            eager_window(False)
+            barrier()
+            prof = {k: (v[0] * n_windows, v[1] * n_windows, v[2] * n_windows) for k, v in _lib.profile_read().items()}
+            _lib.profile_enable(False)
         for k in keys:
             model.infection_networks.networks[k].log_beta = torch.tensor(0.0)
         loss_fn = lambda r: r["cases_per_timestep"].sum() + r["deaths_per_timestep"].sum()   # noqa: E731
-        graphed = GraphedRunner(runner, loss_fn=loss_fn, seed=7)
+        graphed = GraphedRunner(runner, loss_fn=loss_fn, seed=7)     # partitioned: the gradient all-reduce is captured too
 
         def one_sample(lb_dev, g=None):  # noqa: F811
             _, grads, results = (g or graphed)(lb_dev)
-            if geo:
-                dist.all_reduce(grads)
             return torch.cat([results["cases_per_timestep"], results["deaths_per_timestep"], grads])
 
         if args.streams > 1 and not geo and n_samples > 1:
@@ -408,9 +428,9 @@ def main():
         wsteps += window
     barrier()
 
-    # ---- timed region 1: device-resident inputs --------------------------------------------------
+    # ---- timed region 1: EXACTLY K steps, device-resident inputs ------------------------------------------
     # (NVML is polled by rank 0 only: eight processes polling it were measured to disturb the step)
-    with ClockSampler(local_rank, period=0.02 if rank == 0 else 1e9) as clocks:
+    with ClockSampler(ctx["local_rank"], period=0.02 if rank == 0 else 1e9) as clocks:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.nvtx.range_push("timed")
@@ -421,11 +441,21 @@ def main():
         torch.cuda.nvtx.range_pop()
         barrier()
         ms = e0.elapsed_time(e1)
+        # ---- repeats: the same window R more times, each timed on its own (spread of the measurement) --------
+        rep_ms = []
+        for _ in range(args.repeats if full else 0):
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            one_window(False)
+            r1.record()
+            barrier()
+            rep_ms.append(r0.elapsed_time(r1) / window)
     clk = clocks.summary()
 
     # ---- per-kernel pass: the same K steps again with the library's CUDA events around every kernel (kept out
     #      of the timed region above: two event records per launch cost a few per cent on small worlds) ----------
-    if prof is None:
+    if prof is None and full:
         _lib.profile_enable(True)
         barrier()
         for _ in range(n_windows):
@@ -435,25 +465,27 @@ def main():
         _lib.profile_enable(False)
 
     # ---- timed region 2: end to end through Runner with host buffers -------------------------------
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(n_windows):
-        host_out = one_window(True)
-    torch.cuda.synchronize()
-    if world_size > 1:
-        dist.barrier()
-    e2e_s = time.perf_counter() - t0
-    h2d = host_log_beta.numel() * 4 / window
-    d2h = host_out.numel() * 4 / window
+    e2e_s, h2d, d2h = None, 0.0, 0.0
+    if full:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_windows):
+            host_out = one_window(True)
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+        e2e_s = time.perf_counter() - t0
+        h2d = host_log_beta.numel() * 4 / window
+        d2h = host_out.numel() * 4 / window
 
     rank_ms = [ms]
     if world_size > 1:
-        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s or 0.0] + rep_ms, device=dev, dtype=torch.float64)
         every = [torch.zeros_like(t) for _ in range(world_size)]
         dist.all_gather(every, t)
         rank_ms = [round(float(x[0]), 3) for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
+        ms, e2e_s, rep_ms = float(t[0]), (float(t[1]) if full else None), [float(x) for x in t[2:]]
         if not geo:
             gathered = [torch.zeros_like(out) for _ in range(world_size)]
             dist.all_gather(gathered, out)      # the ensemble's only exchange: losses + gradients
@@ -461,16 +493,102 @@ def main():
     parallelism = "single GPU"
     if geo:
         nb = {t: part.n_boundary[t] for t in part.types if part.n_boundary[t]}
-        parallelism = (f"geographic partition over {world_size} GPUs ({args.scaling} scaling), NCCL all-reduce of the "
-                       f"boundary-group sums once per step forward and once backward; boundary groups {nb} "
-                       f"of {world.n_groups} local groups")
+        parallelism = (f"geographic partition over {world_size} GPUs ({scaling} scaling), boundary-group sums exchanged "
+                       f"once per step forward and once backward ({ctx.get('exchange', 'NCCL all-reduce')}); boundary "
+                       f"groups {nb} of {world.n_groups} local groups")
     elif world_size > 1 or n_samples > 1:
         parallelism = (f"ensemble shard: {n_samples * world_size} beta samples per window, {n_samples} per GPU evaluated one "
                        "after the other on a replica of the world, no data-path collective")
+    res = None
+    if rank == 0:
+        total_units = n_total * steps_done
+        res = dict(value=total_units / (ms * 1e-3), ms=ms, steps_done=steps_done, window=window, N=N, n_total=n_total,
+                   world=world, prof=prof, clk=clk, rank_ms=rank_ms, e2e_s=e2e_s, h2d=h2d, d2h=d2h, rep_ms=rep_ms,
+                   parallelism=parallelism, parity=parity, graph=graph, scaling=scaling, total_units=total_units)
+    if graphed is not None:
+        ctx["captured_nccl"] = ctx.get("captured_nccl", False) or geo
+        graphed.graph.reset()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=120)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--agents", type=int, default=56_000_000,
+                    help="agents of the whole world (strong scaling, the default for N > 1: BASELINE config 3 is THE 56M "
+                         "world on 1/2/4/8 GPUs) / per GPU (weak scaling)")
+    ap.add_argument("--parallelism", default="geo", choices=["geo", "ensemble"],
+                    help="N > 1: geographic partition of ONE world with the boundary-group exchange (default), or one "
+                         "beta sample per GPU on replicas of the world (no data-path collective)")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="geo: the --agents world is cut into N parts (strong, default), or every GPU owns --agents agents "
+                         "of a world of N x --agents (weak; also measured and reported as `weak_scaling` by default)")
+    ap.add_argument("--no-weak-companion", action="store_true",
+                    help="N > 1, strong scaling: skip the additional weak-scaling measurement")
+    ap.add_argument("--samples", type=int, default=0,
+                    help="ensemble: beta samples evaluated per window over all GPUs (BASELINE config 5: 1024 on a 9M "
+                         "world, --agents 9000000 --window 30); default one per GPU")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="ensemble + graph: evaluate this many samples concurrently, each lane with its own replica of "
+                         "the world, captured window and CUDA stream (bandwidth-bound and issue-bound kernels of "
+                         "different samples overlap)")
+    ap.add_argument("--graph", action="store_true",
+                    help="capture the window (Runner() + backward) once as a CUDA graph and replay it "
+                         "(grad_june.graphed.GraphedRunner): removes the per-step Python cost that bounds small worlds. "
+                         "Default for worlds of <= 10M agents per GPU and for strong-scaling partitions")
+    ap.add_argument("--no-graph", action="store_true", help="always drive the window from the Python loop (Runner)")
+    ap.add_argument("--policies", action="store_true",
+                    help="BASELINE config 4: social distancing, school/leisure closures and quarantine from day 15")
+    ap.add_argument("--window", type=int, default=0,
+                    help="BPTT window (0 = 60 timesteps as in BASELINE.json, fewer if memory does not allow)")
+    ap.add_argument("--repeats", type=int, default=5, help="further windows timed one by one (median / spread)")
+    ap.add_argument("--no-verify", dest="verify", action="store_false",
+                    help="skip the teacher-forced parity step against the oracle (N = 1)")
+    ap.add_argument("--shuffle-agents", action="store_true",
+                    help="load the synthetic world with its agents in a RANDOM order (as a world that was not numbered "
+                         "for this layout): Runner.get_data then renumbers it (world.layout_order) and the kernels key "
+                         "their noise by the loaded ids")
+    ap.add_argument("--cpu-agents", type=int, default=1_000_000, help="agents of the CPU-baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    world_size = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world_size)
+        return
+
+    import torch.distributed as dist
+    from grad_june import _lib
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    ctx = {"rank": rank, "world_size": world_size, "local_rank": local_rank, "dev": dev}
+
+    geo = world_size > 1 and args.parallelism == "geo"
+    scaling = args.scaling or ("strong" if geo else "weak")
+    per_gpu = args.agents // world_size if (geo and scaling == "strong") else args.agents
+    graph = (not args.no_graph) and (args.graph or per_gpu <= 10_000_000 or (geo and scaling == "strong"))
+    m = measure(args, ctx, scaling, graph, full=True)
+    weak = None
+    if geo and scaling == "strong" and not args.no_weak_companion:
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        weak = measure(args, ctx, "weak", False, full=False)
+
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
-        total_units = n_total * steps_done
-        value = total_units / (ms * 1e-3)
+        world, prof, N, value = m["world"], m["prof"], m["N"], m["value"]
+        steps_done = m["steps_done"]
         # dominant kernel + its algorithmic bytes per launch (DESIGN.md "Roofline")
         e_bar = world.n_edges / N
         g_bar = world.n_groups / N
@@ -486,37 +604,60 @@ def main():
         if dom is not None:
             avg_ms = timed[dom][0] / timed[dom][1]
             achieved = alg.get(dom, 0.0) * N / (avg_ms * 1e-3) / 1e9
+            traffic = ncu_traffic(N)
+            step_frac = B_ALG_STEP * value / world_size / 1e9 / peak
             roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": ncu_traffic(dom, N), "peak_kind": peak_kind,
+                    "frac": achieved / peak, "traffic": traffic["kernels"].get(dom) if traffic else None,
+                    "traffic_source": traffic["source"] if traffic else None, "peak_kind": peak_kind,
                     "alg_bytes_per_agent": alg.get(dom), "avg_launch_ms": avg_ms,
                     "step_alg_bytes_per_agent_timestep": B_ALG_STEP,
                     "step_achieved": B_ALG_STEP * value / world_size / 1e9,
-                    "step_frac": B_ALG_STEP * value / world_size / 1e9 / peak,
+                    "step_frac": step_frac, "step_frac_contract_279B": step_frac,
+                    "kernel_frac": {k: round(alg[k] * N / (v[0] / v[1] * 1e-3) / 1e9 / peak, 4)
+                                    for k, v in timed.items() if alg.get(k)},
                     "kernel_ms_share": {k: round(v[0] / sum(x[0] for x in timed.values()), 4) for k, v in timed.items()},
                     "kernel_avg_ms": {k: round(v[0] / v[1], 4) for k, v in timed.items()},
                     "kernel_ms_per_step": round(sum(x[0] for x in timed.values()) / steps_done, 4),
                     "note": "per-kernel CUDA events from a second, identical pass over the K steps"}
+            if traffic and traffic.get("step_bytes_per_agent"):
+                # the same throughput against the bytes ncu counted for one whole step (every kernel, fwd + bwd)
+                roof["step_ncu_bytes_per_agent_timestep"] = traffic["step_bytes_per_agent"]
+                roof["step_frac_ncu_bytes"] = traffic["step_bytes_per_agent"] * value / world_size / 1e9 / peak
         launches = int(sum(v[2] for v in prof.values()))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": steps_done,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / steps_done, "higher_is_better": True,
-            "scaling": "strong" if strong else "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": m["ms"] / steps_done, "higher_is_better": True,
+            "scaling": m["scaling"] if geo else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(n_total if geo else N, args.policies), "agents_per_gpu": N,
-                       "agents_total": n_total, "edges_per_agent": round(e_bar, 3),
-                       "groups_per_agent": round(g_bar, 3), "bptt_window": window, "networks": 11,
-                       "driver": (f"CUDA graph replay (GraphedRunner), {args.streams} concurrent lane(s)" if args.graph
+            "config": {"workload": workload_name(m["n_total"] if geo else N, args.policies), "agents_per_gpu": N,
+                       "agents_total": m["n_total"], "edges_per_agent": round(e_bar, 3),
+                       "groups_per_agent": round(g_bar, 3), "bptt_window": m["window"], "networks": 11,
+                       "driver": (f"CUDA graph replay (GraphedRunner), {args.streams} concurrent lane(s)" if m["graph"]
                                   else "Python loop (Runner)"),
                        "layout_tiers": dict(zip(world.types, world.type_tier)),
                        "agents_shuffled_then_renumbered": bool(args.shuffle_agents),
                        "noise_keyed_by_loaded_id": world.__dict__.get("orig_id") is not None,
-                       "parallelism": parallelism,
+                       "parallelism": m["parallelism"],
                        "l2": "inputs (>= 2 GB per pass) far larger than the 126 MB L2; no flush needed"},
-            "clocks": clk, "rank_ms": rank_ms,
-            "e2e": {"value": total_units / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "clocks": m["clk"], "rank_ms": m["rank_ms"],
+            "e2e": {"value": m["total_units"] / m["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": m["h2d"],
+                    "d2h_bytes_per_step": m["d2h"]},
             "gpu_launches": launches,
             "roofline": roof,
         }
+        if m["rep_ms"]:
+            r = sorted(m["rep_ms"])
+            line["repeats"] = {"n": len(r), "ms_per_step_median": r[len(r) // 2], "ms_per_step_min": r[0],
+                               "ms_per_step_max": r[-1], "spread_pct": round(100 * (r[-1] - r[0]) / r[len(r) // 2], 2),
+                               "value_median": m["n_total"] / (r[len(r) // 2] * 1e-3),
+                               "note": "further single windows after the timed K steps, each between its own events"}
+        if m["parity"] is not None:
+            line["parity"] = m["parity"]
+        if weak is not None:
+            line["weak_scaling"] = {"value": weak["value"], "unit": UNIT, "ms_per_step": weak["ms"] / weak["steps_done"],
+                                    "agents_per_gpu": weak["N"], "agents_total": weak["n_total"],
+                                    "driver": "Python loop (Runner)", "parallelism": weak["parallelism"],
+                                    "rank_ms": weak["rank_ms"]}
         if not args.no_cpu_baseline and world_size == 1:
             thr, secs, cores = cpu_reference_run(args.cpu_agents, args.cpu_steps, policies=args.policies)
             line["cpu_baseline"] = {"value": thr, "unit": UNIT, "cores": cores, "kind": "port",
@@ -524,11 +665,8 @@ def main():
                                               f"timesteps fwd+bwd ({secs:.1f} s)"}
         print(json.dumps(line), flush=True)
     if world_size > 1:
-        if args.graph:
-            # a captured graph that contains NCCL kernels must be gone before its communicator is torn down
-            # (destroy_process_group was seen to hang otherwise)
-            graphed.graph.reset()
-            del graphed
+        if ctx.get("captured_nccl"):
+            # a captured graph that contained NCCL kernels: destroy_process_group was seen to hang after it
             torch.cuda.synchronize()
             dist.barrier()
             sys.stdout.flush()
@@ -536,22 +674,24 @@ def main():
         dist.destroy_process_group()
 
 
-def ncu_traffic(kernel, n_agents):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this workload (profiles/r1_final_56M_kernels.csv, 56 M agents); None for
-    other sizes or kernels (traffic cannot be measured inside an un-profiled run)."""
-    name = {"agent_forward": "k_pipe_forward", "agent_backward": "k_pipe_backward<", "backward_gather": "k_pipe_backward_gather"}.get(kernel)
-    f = ROOT / "profiles" / "r1_final_56M_kernels.csv"
-    if name is None or n_agents != 56_000_000 or not f.exists():
+def ncu_traffic(n_agents):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum, per launch) of the throughput-mode kernels from the
+    NEWEST committed `ncu --set full` capture of this workload size: profiles/r*_traffic.json, written by
+    scripts/ncu_summarise.py together with the git revision it was taken at.  None when no capture matches the
+    size (traffic cannot be measured inside an un-profiled run)."""
+    best = None
+    for f in sorted((ROOT / "profiles").glob("r*_traffic.json")):
+        try:
+            t = json.load(open(f))
+        except Exception:  # noqa: BLE001
+            continue
+        if int(t.get("agents", -1)) == int(n_agents):
+            best = (f, t)            # sorted by name: the round tag orders them
+    if best is None:
         return None
-    lines = f.read_text().splitlines()
-    n_num = len(lines[0].split(",")) - 1            # numeric columns; the kernel name itself may contain commas
-    vals = []
-    for line in lines[1:]:
-        cols = line.rsplit(",", n_num)
-        if cols[0].startswith(name):
-            vals.append((float(cols[2]) + float(cols[3])) * 1e9)   # dram__bytes_read.sum + dram__bytes_write.sum [Gbyte]
-    return sum(vals) / len(vals) if vals else None
+    f, t = best
+    return {"kernels": t["kernels"], "step_bytes_per_agent": t.get("step_bytes_per_agent"),
+            "source": {"file": f"profiles/{f.name}", "git": t.get("git"), "captured": t.get("when")}}
 
 
 def kernel_alg_bytes(e_gen, g_gen, e_small, g_small):

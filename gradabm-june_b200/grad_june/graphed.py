@@ -40,11 +40,20 @@ class GraphedRunner:
     def _iteration(self):
         nets = self.runner.model.infection_networks.networks
         for i, k in enumerate(self.names):
+            # a network built with log_beta=nn.Parameter(...) holds it as a registered parameter, and nn.Module
+            # refuses to assign a plain tensor over one: unregister it first
+            nets[k]._parameters.pop("log_beta", None)
             nets[k].log_beta = self.log_beta[i]
         with ops.philox_seed(self.seed):
             results, is_infected = self.runner()
         loss = self.loss_fn(results)
         loss.backward()
+        part = self.runner.data.__dict__.get("_gj_partition")
+        if part is not None and part.world_size > 1:
+            # geographic partition: every rank holds the d/dbeta terms of the groups it owns; the sum over ranks
+            # is part of the captured iteration (one more NCCL kernel in the graph, no eager collective per replay)
+            import torch.distributed as dist
+            dist.all_reduce(self.log_beta.grad, group=part.process_group)
         return loss.detach(), results, is_infected
 
     def recapture(self, seed: int):

@@ -63,7 +63,7 @@ class GradJune(torch.nn.Module):
         tables = tuple((id(t), t._version) for t in (getattr(net, "leisure_probabilities", None) for net in nets)
                        if t is not None)
         key = (id(world), id(prof[4]), tables, tuple(id(net) for net in nets),
-               id(self.symptoms_updater.symptoms_sampler.stage_transition_probabilities))
+               self.symptoms_updater.symptoms_sampler.tables_key())
         cache = data.__dict__.setdefault("_gj_cache", {})
         hit = cache.get("static")
         if hit is None or hit[0] != key:

@@ -59,10 +59,39 @@ class SymptomsSampler:
             out[i] = (_DIST_KINDS[spec["dist"]], float(spec["loc"]), float(spec["scale"]))
         return out
 
+    @staticmethod
+    def _dist_entry(dist):
+        """(kind, loc, scale) of a dwell-time distribution OBJECT (utils.parse_distribution: LogNormal / Normal).
+        Read from the object, not from the YAML it was built from, so that replacing or retuning
+        ``stage_transition_times[i]`` / ``recovery_times[i]`` takes effect as it does in the reference."""
+        if dist is None:
+            return None
+        name = type(dist).__name__
+        if name not in _DIST_KINDS:
+            raise NotImplementedError(f"dwell-time distribution {name} (supported: LogNormal, Normal)")
+        return (_DIST_KINDS[name], float(dist.loc), float(dist.scale))
+
+    def tables_key(self):
+        """Changes whenever a distribution object or the probability table is replaced or edited in place."""
+        dists = [d for table in (self.stage_transition_times, self.recovery_times) for d in table.values()]
+        vers = tuple((id(d), getattr(d.loc, "_version", 0), getattr(d.scale, "_version", 0)) for d in dists if d is not None)
+        p = self.stage_transition_probabilities
+        return (id(p), p._version, vers)
+
     def tables(self, device):
-        return ops.SymptomsTables(n_stages=len(self.stages),
-                                  stage_prob=ops._f32(self.stage_transition_probabilities, torch.device(device)),
-                                  trans=self._host_times[0], rec=self._host_times[1])
+        key = (self.tables_key(), str(device))
+        hit = self.__dict__.get("_tables_cache")
+        if hit is None or hit[0] != key:
+            n = len(self.stages)
+            trans = {i: self._dist_entry(self.stage_transition_times.get(i)) for i in range(n)}
+            rec = {i: self._dist_entry(self.recovery_times.get(i)) for i in range(n)}
+            self._host_times = (trans, rec)
+            tabs = ops.SymptomsTables(n_stages=n, stage_prob=ops._f32(self.stage_transition_probabilities,
+                                                                       torch.device(device)), trans=trans, rec=rec)
+            # the cache holds the objects its key was made from (an id() can be reused once they are gone)
+            hit = self.__dict__["_tables_cache"] = (key, tabs, (self.stage_transition_probabilities,
+                                                               dict(self.stage_transition_times), dict(self.recovery_times)))
+        return hit[1]
 
     # reference helpers kept for API parity (symptoms.py:65-80)
     def _get_need_to_transition(self, current_stage, time_to_next_stage, time):

@@ -57,6 +57,35 @@ with open(dst + "_kernels.csv", "w") as f:
         us = float(r[hdr["gpu__time_duration.sum"]]) * {"us": 1.0, "ms": 1e3, "ns": 1e-3}.get(rr[1][hdr["gpu__time_duration.sum"]], 1.0)
         f.write(short(r[hdr["Kernel Name"]]) + "," + ",".join(vals) + f",{gb * scale / (us * 1e-6):.0f}\n")
 
+# ---- DRAM traffic per launch for bench.py's roofline record (roofline.traffic / traffic_source) ----------
+import datetime
+import json
+
+ids = {"k_lean_transmission": "transmission", "k_pipe_forward": "agent_forward", "k_lean_forward": "agent_forward",
+       "k_pipe_backward_gather": "backward_gather", "k_lean_backward_gather": "backward_gather",
+       "k_pipe_backward": "agent_backward", "k_lean_backward": "agent_backward", "k_lean_group_sums": "group_sums",
+       "k_lean_group_fix": "group_fix"}
+per = {}
+for r in rr[2:]:
+    base = re.sub(r"<.*", "", short(r[hdr["Kernel Name"]]))
+    unit = rr[1][hdr["dram__bytes_read.sum"]]
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0)
+    per.setdefault(ids.get(base, base), []).append(
+        (float(r[hdr["dram__bytes_read.sum"]]) + float(r[hdr["dram__bytes_write.sum"]])) * scale)
+# a full MIDDLE step: the backward kernel's largest launches are the middle steps (see scripts/ncu_profile.sh)
+kern = {k: (max(v) if k == "agent_backward" else sum(v) / len(v)) for k, v in per.items()}
+kern["group_chunk<fwd>"] = kern["group_chunk<bwd>"] = kern.get("group_sums", 0.0)
+n_agents = int(sys.argv[3]) if len(sys.argv) > 3 else 56_000_000
+step = sum(kern.get(k, 0.0) for k in ("transmission", "agent_forward", "agent_backward", "backward_gather")) \
+    + 2 * (kern.get("group_sums", 0.0) + kern.get("group_fix", 0.0))
+git = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+json.dump({"agents": n_agents, "git": git, "when": datetime.datetime.utcnow().isoformat(timespec="seconds") + "Z",
+           "source": rep, "kernels": kern, "launches": {k: len(v) for k, v in per.items()},
+           "step_bytes_per_agent": step / n_agents,
+           "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full); agent_backward = its "
+                   "largest launch = a middle step of the window; group kernels run twice per step"},
+          open(dst + "_traffic.json", "w"), indent=1)
+
 # ---- stall samples by source line for the agent kernels ---------------------------------------------
 for k in ("k_pipe_forward", "k_pipe_backward", "k_pipe_backward_gather", "k_lean_forward", "k_lean_backward",
           "k_lean_backward_gather", "k_lean_transmission", "k_lean_group_sums"):

@@ -293,3 +293,64 @@ def certify_near_ties(q, E, mism, what=""):
     ok = (np.abs(d) <= tol) | (np.sign(lo) != np.sign(hi)) | (np.sign(lo) != np.sign(d))
     assert ok.all(), f"{what}: mask mismatch that is not a near-tie: d = {d[~ok]}, tol = {tol[~ok]}, q = {q32[~ok]}"
     return float(np.max(np.abs(d) / tol))
+
+
+def mid_epidemic_state(n, now, seed, device):
+    """A plausible state in the middle of an epidemic (a quarter of the agents infected at various stages, some
+    recovered / dead), generated ON ``device`` so that it also serves the 56 M-agent verification of bench.py."""
+    g = torch.Generator(device=device).manual_seed(seed)
+
+    def rand():
+        return torch.rand(n, generator=g, device=device)
+
+    inf = rand() < 0.25
+    zeros, ones = torch.zeros(n, device=device), torch.ones(n, device=device)
+    stage = torch.randint(2, 7, (n,), generator=g, device=device).float()
+    cur = torch.where(inf, stage, ones)
+    nxt = torch.where(inf, torch.where(rand() < 0.4, zeros, stage + 1), ones)
+    done = inf & (rand() < 0.2)                        # already recovered / dead
+    cur = torch.where(done, torch.where(rand() < 0.9, zeros, torch.full_like(zeros, 7.0)), cur)
+    nxt = torch.where(done, cur, nxt)
+    tinf = torch.where(inf, now - 12.0 * rand(), zeros)
+    ttn = torch.where(inf, now + 4.0 * rand() - 1.5, zeros)
+    s = torch.where(inf, zeros, ones)
+    return {"susceptibility": s, "is_infected": inf.float(), "infection_time": tinf, "current_stage": cur,
+            "next_stage": nxt, "time_to_next_stage": ttn}
+
+
+def oracle_step_inputs(params, data, model, timer, state, device):
+    """Oracle inputs of ONE step of ``model`` on ``data`` (in data's own agent numbering) at ``timer``:
+    (world, leaf networks, StepSpec, SymptomsSpec, profile, state copy)."""
+    w = O.OracleWorld(n_agents=len(data["agent"].id), age=data["agent"].age.to(device), sex=data["agent"].sex.to(device))
+    for t in data.venue_types():
+        ei = data["attends_" + t].edge_index.to(device)
+        w.edges[t] = O.EdgeType(src=ei[0], dst=ei[1], people=torch.as_tensor(data[t]["people"]).to(device),
+                                n_groups=len(data[t]["id"]))
+    nets = make_leaf_networks({**params, "system": {"device": "cpu"}})
+    with torch.no_grad():
+        for k, net in nets.networks.items():
+            net.log_beta.copy_(torch.as_tensor(model.infection_networks.networks[k].log_beta).detach().cpu())
+    policies = model.policies
+    specs = []
+    for net in nets.active_networks(timer, policies):
+        prob = getattr(net, "leisure_probabilities", None)
+        specs.append(O.NetSpec(net.name, net.edge_type(), net.kind, net.beta_eff(policies, timer).to(device),
+                               None if prob is None else prob.to(device)))
+    quar = policies.quarantine_policies.active_thresholds(timer) if policies.quarantine_policies else None
+    spec = O.StepSpec(now=timer.now, dt=timer.duration, day_type=0 if timer.day_type == "weekday" else 1, nets=specs,
+                      quarantine=quar)
+    sym = oracle_symptoms(SymptomsSampler.from_parameters(params), device)
+    prof = {k: v.to(device) for k, v in data["agent"].infection_parameters.items()}
+    st = {k: v.detach().clone().to(device) for k, v in state.items()}
+    return w, nets, spec, sym, prof, st
+
+
+def layout_noise(data, E, u, z, device):
+    """The kernels' Philox draws for LOADED ids 0..n-1 (ops.philox_fill) as the oracle's StepNoise in ``data``'s
+    own numbering (a renumbered world reads agent i's draw at original_index[i])."""
+    agent = data["agent"]
+    if "original_index" in agent:
+        oi = agent["original_index"].to(E.device)
+        E, u, z = E[:, oi], u[oi], z[oi]
+    n = u.numel()
+    return O.StepNoise(E=E.to(device), u=u.to(device), z=z.to(device).expand(10, n))

@@ -28,24 +28,7 @@ def _params(device=DEV):
 
 
 def _mid_epidemic_state(n, now, seed, device):
-    g = torch.Generator(device="cpu").manual_seed(seed)
-    r = torch.rand(n, generator=g)
-    inf = (r < 0.25)
-    cur = torch.ones(n)
-    nxt = torch.ones(n)
-    stage = torch.randint(2, 7, (n,), generator=g).float()
-    cur[inf] = stage[inf]
-    rec_next = torch.rand(n, generator=g) < 0.4
-    nxt[inf] = torch.where(rec_next[inf], torch.zeros(int(inf.sum())), stage[inf] + 1)
-    done = inf & (torch.rand(n, generator=g) < 0.2)      # already recovered / dead
-    cur[done] = torch.where(torch.rand(int(done.sum()), generator=g) < 0.9, 0.0, 7.0)
-    nxt[done] = cur[done]
-    tinf = torch.where(inf, now - 12.0 * torch.rand(n, generator=g), torch.zeros(n))
-    ttn = torch.where(inf, now + 4.0 * torch.rand(n, generator=g) - 1.5, torch.zeros(n))
-    s = torch.where(inf, torch.zeros(n), torch.ones(n))
-    st = {"susceptibility": s, "is_infected": inf.float(), "infection_time": tinf, "current_stage": cur,
-          "next_stage": nxt, "time_to_next_stage": ttn}
-    return {k: v.to(device) for k, v in st.items()}
+    return H.mid_epidemic_state(n, now, seed, device)
 
 
 def _irregular(data):
@@ -98,24 +81,7 @@ def _setup(n_agents, seed=1, mutate=None):
 
 
 def _oracle_inputs(params, data, model, timer, state, device):
-    from grad_june.symptoms import SymptomsSampler
-    w = O.OracleWorld(n_agents=len(data["agent"].id), age=data["agent"].age.to(device), sex=data["agent"].sex.to(device))
-    for t in data.venue_types():
-        ei = data["attends_" + t].edge_index.to(device)
-        w.edges[t] = O.EdgeType(src=ei[0], dst=ei[1], people=data[t]["people"].to(device), n_groups=len(data[t]["id"]))
-    nets = H.make_leaf_networks({**params, "system": {"device": "cpu"}})
-    policies = model.policies
-    specs = []
-    for net in nets.active_networks(timer, policies):
-        prob = getattr(net, "leisure_probabilities", None)
-        specs.append(O.NetSpec(net.name, net.edge_type(), net.kind, net.beta_eff(policies, timer).to(device),
-                               None if prob is None else prob.to(device)))
-    spec = O.StepSpec(now=timer.now, dt=timer.duration, day_type=0 if timer.day_type == "weekday" else 1, nets=specs,
-                      quarantine=policies.quarantine_policies.active_thresholds(timer))
-    sym = H.oracle_symptoms(SymptomsSampler.from_parameters(params), device)
-    prof = {k: v.to(device) for k, v in data["agent"].infection_parameters.items()}
-    st = {k: v.detach().clone().to(device) for k, v in state.items()}
-    return w, nets, spec, sym, prof, st
+    return H.oracle_step_inputs(params, data, model, timer, state, device)
 
 
 @pytest.mark.parametrize("n_agents,oracle_device", [(30_000, "cpu"), (400_000, DEV)])
