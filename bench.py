@@ -703,7 +703,9 @@ def kernel_alg_bytes(e_gen, g_gen, e_small, g_small):
     return {
         # is_infected in, T out; the profile (tinf 4 + packed 16) is read for infected agents only: not counted
         "transmission": 4 + 4,
-        "group_small<fwd>": grp(e_small, g_small), "group_chunk<fwd>": grp(e_gen - e_small, g_gen - g_small),
+        # forward: the scatter tier's finalize pass (accumulator 8 + dirty 1 + row pointers 8 + pc 4 + two outputs 8 per
+        # group; the adds themselves come from the infectious few inside the transmission pass) / giant groups only
+        "group_small<fwd>": 29 * g_gen, "group_chunk<fwd>": 0.0,
         "group_small<bwd>": grp(e_small, g_small), "group_chunk<bwd>": grp(e_gen - e_small, g_gen - g_small),
         # state in 24 + class 1 + generic entry 4 + household slot+pc 8 + T 4 + group value + state out 24 + tape 8
         "agent_forward": 24 + 1 + 4 + 8 + 4 + 4 * e_gen + 24 + 8,

@@ -96,6 +96,8 @@ struct Scratch {
   float* tile_part;    // [n_tiles][GJ_MAX_CHANNELS]
   float* cell_buf;     // [n_cells_total][GJ_MAX_CHANNELS]
   double* dbeta_tile;  // [n_tiles][GJ_MAX_RANGE_NETS]
+  unsigned long long* sct_acc;  // [n_groups] fixed-point accumulators of the scatter tier (zero between steps)
+  uint8_t* sct_dirty;           // [n_groups]
 };
 static inline int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
 static inline Scratch carve(const gj_world_desc* w, void* base, int64_t* total) {
@@ -119,6 +121,9 @@ static inline Scratch carve(const gj_world_desc* w, void* base, int64_t* total) 
   s.tile_part = (float*)take((int64_t)sizeof(float) * GJ_MAX_CHANNELS * n_tiles);
   s.cell_buf = (float*)take((int64_t)sizeof(float) * GJ_MAX_CHANNELS * n_cells);
   s.dbeta_tile = (double*)take((int64_t)sizeof(double) * GJ_MAX_RANGE_NETS * n_tiles);
+  const int64_t n_groups = w->n_groups > 0 ? w->n_groups : 1;
+  s.sct_acc = (unsigned long long*)take((int64_t)sizeof(unsigned long long) * n_groups);
+  s.sct_dirty = (uint8_t*)take(n_groups);
   if (total) *total = off;
   return s;
 }
@@ -385,9 +390,9 @@ __global__ void __launch_bounds__(kBlock) k_agent_forward(gj_world_desc w, gj_st
                                                           unsigned int* __restrict__ ticket) {
   const int64_t N = w.n_agents;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  double red[kMaxRed];
+  float redf[kMaxRed];   // per-thread sums of small integers (<= 2 per agent, < 2^24 agents per thread): exact in fp32
 #pragma unroll
-  for (int r = 0; r < kMaxRed; ++r) red[r] = 0.0;
+  for (int r = 0; r < kMaxRed; ++r) redf[r] = 0.0f;
   for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < N; a += stride) {
     const int cls = w.cls ? w.cls[a] : 0;
     AgentState st;
@@ -398,14 +403,14 @@ __global__ void __launch_bounds__(kBlock) k_agent_forward(gj_world_desc w, gj_st
     st.nxt = io.nxt ? io.nxt[a] : 1.0f;
     st.ttn = io.ttn ? io.ttn[a] : 0.0f;
     const float q = io.q_in ? io.q_in[a] : 1.0f;
-    float one[kMaxRed];
-#pragma unroll
-    for (int r = 0; r < kMaxRed; ++r) one[r] = 0.0f;
-    forward_tail(p, io, N, a, noise_agent(w, p, a), cls % 100, q, st, one);
-#pragma unroll
-    for (int r = 0; r < kMaxRed; ++r) red[r] += (double)one[r];
+    forward_tail(p, io, N, a, noise_agent(w, p, a), cls % 100, q, st, redf);
   }
-  if (io.red) block_reduce_finish<kMaxRed>(red, 2 + p.n_age_bins, red_part, ticket, io.red);
+  if (io.red) {
+    double red[kMaxRed];
+#pragma unroll
+    for (int r = 0; r < kMaxRed; ++r) red[r] = (double)redf[r];
+    block_reduce_finish<kMaxRed>(red, 2 + p.n_age_bins, red_part, ticket, io.red);
+  }
 }
 
 __global__ void __launch_bounds__(kBlock) k_agent_backward(gj_world_desc w, gj_step_params p, gj_bwd_io io,
@@ -713,6 +718,31 @@ static bool lean_plan(const gj_world_desc* w, const gj_step_params* p, const Pla
   return true;
 }
 
+// forward: the scatter tier was accumulated by the transmission pass; giant groups are summed group-major (the first
+// n_giant_chunks chunks / n_giant_big multi-chunk groups of the lists), then the accumulators become fp32 sums
+static int launch_lean_group_pass(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const float* beta,
+                                  const float* in, float* out_scaled, float* out_plain, const Scratch& sc, bool bwd,
+                                  cudaStream_t st);
+static int launch_lean_forward_sums(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const float* beta,
+                                    const float* in, float* out_scaled, float* out_plain, const Scratch& sc,
+                                    cudaStream_t st) {
+  if (w->n_giant_chunks > 0) {
+    gj_world_desc wg = *w;
+    wg.n_small = 0;
+    wg.n_chunks = w->n_giant_chunks;
+    wg.n_big = w->n_giant_big;
+    if (int e = launch_lean_group_pass(&wg, p, pl, beta, in, out_scaled, out_plain, sc, false, st)) return e;
+  }
+  {
+    ProfScope ps(K_GROUP_SMALL_F, st);
+    Scatter sct{sc.sct_acc, sc.sct_dirty};
+    k_lean_scatter_finalize<<<blocks_for(w->n_groups, kBlock), kBlock, 0, st>>>(*w, *p, pl, beta, in, sct, out_scaled,
+                                                                               out_plain);
+    GJ_CHECK_LAUNCH("k_lean_scatter_finalize");
+  }
+  return 0;
+}
+
 static int launch_lean_group_pass(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const float* beta,
                                   const float* in, float* out_scaled, float* out_plain, const Scratch& sc, bool bwd,
                                   cudaStream_t st) {
@@ -742,13 +772,14 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
     if (!p->t_ready) {
       ProfScope ps(K_TRANSMISSION, st);
       static OccCache occ[2];
-      if (quar) k_lean_transmission<true><<<lean_grid(w, k_lean_transmission<true>, &occ[1]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
-      else k_lean_transmission<false><<<lean_grid(w, k_lean_transmission<false>, &occ[0]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part);
+      const Scatter sct{sc.sct_acc, sc.sct_dirty};
+      if (quar) k_lean_transmission<true><<<lean_grid(w, k_lean_transmission<true>, &occ[1]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part, sct);
+      else k_lean_transmission<false><<<lean_grid(w, k_lean_transmission<false>, &occ[0]), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.tile_part, sct);
       GJ_CHECK_LAUNCH("k_lean_transmission");
     }
     if (lp.has_generic)
-      if (int e = launch_lean_group_pass(w, p, pl, io->beta, quar ? io->Tq : io->T, io->S_scaled + lp.gen_base,
-                                         io->S_unscaled + lp.gen_base, sc, false, st))
+      if (int e = launch_lean_forward_sums(w, p, pl, io->beta, quar ? io->Tq : io->T, io->S_scaled + lp.gen_base,
+                                           io->S_unscaled + lp.gen_base, sc, st))
         return e;
     if (int e = launch_cell_groups(w, p, pl, io->beta, io->S_scaled, io->S_unscaled, sc, st)) return e;
   }
@@ -764,6 +795,7 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
     if (next) {
       nx = *next;
       nx.tile_part = sc.tile_part;   // consumed by this step's k_cell_groups before the agent kernel runs
+      nx.sct = Scatter{sc.sct_acc, sc.sct_dirty};   // zeroed by this step's finalize pass, which has already run
     }
 #define GJ_PIPE_FWD(Q, D, X, I)                                                                                      \
   k_pipe_forward<Q, D, X><<<pipe_grid(w, k_pipe_forward<Q, D, X>, kPipeThreads, smem, &occ[I]), kPipeThreads, smem,  \
@@ -890,10 +922,11 @@ int gj_abi_version(void) { return GJ_ABI_VERSION; }
 const char* gj_last_error(void) { return g_err; }
 
 int gj_config(int64_t* out, int n) {
-  const int64_t v[8] = {GJ_SMALL_GROUP,      GJ_CHUNK,          (int64_t)sizeof(gj_world_desc), (int64_t)sizeof(gj_step_params),
-                        (int64_t)sizeof(gj_fwd_io), (int64_t)sizeof(gj_bwd_io), kRedBlocks, GJ_TILE_AGENTS};
-  for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
-  return 8;
+  const int64_t v[9] = {GJ_SMALL_GROUP,      GJ_CHUNK,          (int64_t)sizeof(gj_world_desc), (int64_t)sizeof(gj_step_params),
+                        (int64_t)sizeof(gj_fwd_io), (int64_t)sizeof(gj_bwd_io), kRedBlocks, GJ_TILE_AGENTS,
+                        GJ_SCATTER_MAX_GROUP};
+  for (int i = 0; i < n && i < 9; ++i) out[i] = v[i];
+  return 9;
 }
 
 int64_t gj_scratch_bytes(const gj_world_desc* w) { return w ? scratch_bytes(w) : -1; }
@@ -1005,6 +1038,10 @@ static int step_forward_impl(const gj_world_desc* w, const gj_step_params* p, co
   const int64_t N = w->n_agents;
   if (N == 0) return 0;
   const Scratch sc = carve(w, io->scratch, nullptr);
+  if (p->reset_scatter && w->n_groups > 0) {   // an unused look-ahead left its transmissions in the accumulators
+    cudaMemsetAsync(sc.sct_acc, 0, sizeof(unsigned long long) * (size_t)w->n_groups, st);
+    cudaMemsetAsync(sc.sct_dirty, 0, (size_t)w->n_groups, st);
+  }
   Channels ch;
   Plan pl;
   if (int e = build_channels(w, p, &ch, &pl)) return e;
@@ -1054,6 +1091,7 @@ static int step_forward_impl(const gj_world_desc* w, const gj_step_params* p, co
           for (int j = 0; j < GJ_MAX_CHANNELS; ++j) nx.c_row[j] = lpn.c_row[j];
           nx.n_tc = lpn.n_tc;
           for (int j = 0; j < GJ_MAX_CHANNELS; ++j) nx.tc[j] = lpn.tc[j];
+          nx.has_generic = lpn.has_generic;
           nx.T = io->T_next;
           nx.Tq = nx.n_quar > 0 ? io->Tq_next : io->T_next;
           have_next = aligned16(io->T_next) && aligned16(io->Tq_next);

@@ -38,6 +38,41 @@ constexpr int kLeanThreads = 256;
 #endif
 constexpr uint32_t kEntNone = 0xFFFFFFFFu;   // ent1: no generic edge
 constexpr uint32_t kEntMulti = 0xFFFFFFFEu;  // ent1: several generic edges -> agent-major CSR
+constexpr uint32_t kEntGiant = 0x80000000u;  // ent1 bit 31: the group has more than GJ_SCATTER_MAX_GROUP members
+constexpr uint32_t kEntId = 0x7FFFFFFFu;
+
+// ---- forward sums of the generic tier by scatter -----------------------------------------------------------
+// Only infectious agents transmit (a few per cent of the world): instead of a group-major pass that gathers every
+// member's transmission (a 32-byte DRAM sector per 4-byte member: 2.7x the algorithmic traffic, r1 profile), the
+// transmission pass lets each infectious agent ADD its value to its group's accumulator.  The accumulators are
+// 64-bit FIXED-POINT integers (GJ_SCATTER_FRAC fractional bits): integer addition is exact and order-independent,
+// so the sums are bit-reproducible whatever order the atomics land in — and more accurate than an fp32 sum.  A value
+// outside [0, 2^GJ_SCATTER_CAP_LOG2) (never seen with the reference's profiles; non-finite included) marks its group
+// dirty: the finalize pass re-sums such a group from its member list.  k_lean_scatter_finalize turns accumulators
+// into the fp32 group sums and leaves them zero.
+struct Scatter {
+  unsigned long long* acc;   // [n_groups] zero between steps
+  uint8_t* dirty;            // [n_groups]
+};
+constexpr float kScatterScale = (float)(1ull << GJ_SCATTER_FRAC);
+constexpr float kScatterCap = (float)(1u << GJ_SCATTER_CAP_LOG2);
+__device__ __forceinline__ void scatter_one(const Scatter& sc, uint32_t g, float v) {
+  if (v > 0.0f && v < kScatterCap) atomicAdd(&sc.acc[g], (unsigned long long)__float2ll_rn(v * kScatterScale));
+  else sc.dirty[g] = 1;
+}
+// v != 0: add it to every scatter-tier group of agent a (ent = its ent1 word)
+__device__ __forceinline__ void lean_scatter(const gj_world_desc& w, const Scatter& sc, uint32_t ent, uint32_t a,
+                                             float v) {
+  if (ent < kEntGiant) {
+    scatter_one(sc, ent, v);
+  } else if (ent == kEntMulti) {
+    for (uint32_t j = w.am_ptr[a]; j < w.am_ptr[a + 1]; ++j) {
+      const uint32_t e = w.am_ent[j];
+      const uint32_t g = (uint32_t)w.type_group_off[e >> 28] + (e & 0x0FFFFFFFu);
+      if (w.gm_ptr[g + 1] - w.gm_ptr[g] <= (uint32_t)GJ_SCATTER_MAX_GROUP) scatter_one(sc, g, v);
+    }
+  }
+}
 
 struct LeanPlan {
   int n_range;                              // networks on RANGE-tier types: 0 or 1
@@ -184,7 +219,7 @@ __device__ __forceinline__ void lean_class_table(float* __restrict__ L, const Pr
 // generic tier: combined value of the agent's group(s): the single-entry gather is issued early, the (rare)
 // several-entries case walks the agent-major CSR afterwards
 __device__ __forceinline__ float lean_generic_issue(const float* __restrict__ buf, uint32_t ent) {
-  return (ent < kEntMulti) ? buf[ent] : 0.0f;
+  return (ent < kEntMulti) ? buf[ent & kEntId] : 0.0f;
 }
 __device__ __forceinline__ float lean_generic_finish(const gj_world_desc& w, const float* __restrict__ buf, uint32_t ent,
                                                      uint32_t a, float v) {
@@ -237,8 +272,9 @@ __device__ __forceinline__ float quar_mask(const gj_step_params& p, float cur) {
 constexpr int kK1Batch = 8;
 
 template <bool kQuar>
-__global__ void __launch_bounds__(kLeanThreads, 6) k_lean_transmission(gj_world_desc w, gj_step_params p, LeanPlan lp,
-                                                                    gj_fwd_io io, float* __restrict__ tile_part) {
+__global__ void __launch_bounds__(kLeanThreads, kQuar ? 5 : 6) k_lean_transmission(gj_world_desc w, gj_step_params p, LeanPlan lp,
+                                                                    gj_fwd_io io, float* __restrict__ tile_part,
+                                                                    Scatter sct) {
   __shared__ ProbRow prob[200];
   lean_load_prob<false>(prob, p, lp, io.leisure_prob);
   __syncthreads();
@@ -272,7 +308,10 @@ __global__ void __launch_bounds__(kLeanThreads, 6) k_lean_transmission(gj_world_
           Tq = quar_mask(p, cur[h]) * T;
           io.Tq[a] = Tq;
         }
-        if (Tq != 0.0f && lp.n_cell > 0) lean_channel_fma(acc, prob, w.cls[a], Tq, lp.n_cell);
+        if (Tq != 0.0f) {   // the infectious few: cell-channel partial sums and the generic groups' accumulators
+          if (lp.n_cell > 0) lean_channel_fma(acc, prob, w.cls[a], Tq, lp.n_cell);
+          if (lp.has_generic) lean_scatter(w, sct, w.ent1[a], a, Tq);
+        }
       }
     }
     if (lp.n_cell > 0) {
@@ -405,6 +444,34 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_fix(gj_world_desc w, gj_s
   const float b = lean_group_beta(gs, g);
   float S = 0.0f;
   for (uint32_t j = w.big_part_ptr[i]; j < w.big_part_ptr[i + 1]; ++j) S += part[j];
+  out_plain[g] = S;
+  out_scaled[g] = (b == b) ? (b * w.pc[g]) * S : 0.0f;
+}
+
+// accumulators -> fp32 sums of the scatter-tier groups (every generic group that is not giant); leaves them zero.
+// A dirty group (a member value outside the fixed-point range) is re-summed from its member list in CSR order.
+__global__ void __launch_bounds__(kBlock) k_lean_scatter_finalize(gj_world_desc w, gj_step_params p, Plan pl,
+                                                                  const float* __restrict__ beta,
+                                                                  const float* __restrict__ in, Scatter sct,
+                                                                  float* __restrict__ out_scaled,
+                                                                  float* __restrict__ out_plain) {
+  __shared__ LeanGroupShared gs;
+  lean_beta_sums(gs, w, p, pl, beta);
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= w.n_groups) return;
+  const uint32_t j0 = w.gm_ptr[g], j1 = w.gm_ptr[g + 1];
+  if (j1 - j0 > (uint32_t)GJ_SCATTER_MAX_GROUP) return;                 // giant: the chunk kernels wrote it
+  if (w.type_tier[type_of_group(w, (uint32_t)g)] != GJ_TIER_GENERIC) return;
+  const unsigned long long acc = sct.acc[g];
+  const bool dirty = sct.dirty[g] != 0;
+  if (acc != 0ull) sct.acc[g] = 0ull;
+  const float b = lean_group_beta(gs, (uint32_t)g);
+  float S = (float)((double)(long long)acc * (1.0 / (double)(1ull << GJ_SCATTER_FRAC)));
+  if (dirty) {
+    sct.dirty[g] = 0;
+    S = 0.0f;
+    for (uint32_t j = j0; j < j1; ++j) S += in[w.gm_agent[j]];
+  }
   out_plain[g] = S;
   out_scaled[g] = (b == b) ? (b * w.pc[g]) * S : 0.0f;
 }

@@ -178,6 +178,8 @@ struct NextStep {
   float* T;
   float* Tq;                        // may alias T when n_quar <= 0
   float* tile_part;
+  int has_generic;                  // the next step has generic-tier networks: scatter into their accumulators
+  Scatter sct;
 };
 __device__ __forceinline__ float quar_mask_next(const NextStep& nx, float cur) {
   bool ok = true;
@@ -324,7 +326,10 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
           Tq = quar_mask_next(nx, o.cur) * T;
           nx.Tq[a] = Tq;
         }
-        if (Tq != 0.0f && nx.n_cell > 0) lean_channel_fma(acc, sh.prob_next, cls, Tq, nx.n_cell);
+        if (Tq != 0.0f) {
+          if (nx.n_cell > 0) lean_channel_fma(acc, sh.prob_next, cls, Tq, nx.n_cell);
+          if (nx.has_generic) lean_scatter(w, nx.sct, has_gen ? ent[h] : w.ent1[a], a, Tq);
+        }
       }
     }
     if (pipe_release() && tile + kPipeStages < run.t1)

@@ -18,7 +18,7 @@ GJ_MAX_STAGES = 16
 GJ_MAX_QUAR = 4
 GJ_MAX_AGE_BINS = 8
 GJ_MAX_CHANNELS = 8
-GJ_ABI_VERSION = 5
+GJ_ABI_VERSION = 6
 
 KIND_PLAIN, KIND_HOUSEHOLD, KIND_LEISURE, KIND_CARE_VISIT = 0, 1, 2, 3
 PHASE_NETWORKS, PHASE_SAMPLE, PHASE_INFECT, PHASE_SYMPTOMS, PHASE_ALL = 1, 2, 4, 8, 15
@@ -47,7 +47,7 @@ class WorldDesc(C.Structure):
         ("tile_cell", C.c_void_p * GJ_MAX_TYPES), ("cell_tile_ptr", C.c_void_p * GJ_MAX_TYPES),
         ("cell_grp_ptr", C.c_void_p * GJ_MAX_TYPES), ("cell_grp", C.c_void_p * GJ_MAX_TYPES),
         ("grp_cell_ptr", C.c_void_p * GJ_MAX_TYPES), ("grp_cell", C.c_void_p * GJ_MAX_TYPES),
-        ("ent1", _u32p), ("dbeta_w", _f32p), ("orig_id", _u32p),
+        ("ent1", _u32p), ("n_giant_chunks", C.c_int64), ("n_giant_big", C.c_int64), ("dbeta_w", _f32p), ("orig_id", _u32p),
     ]
 
 
@@ -67,7 +67,8 @@ class StepParams(C.Structure):
         ("n_stages", C.c_int32), ("trans_time", Dist * GJ_MAX_STAGES), ("rec_time", Dist * GJ_MAX_STAGES),
         ("n_age_bins", C.c_int32), ("age_bins", C.c_int32 * (GJ_MAX_AGE_BINS + 1)),
         ("tau", C.c_float), ("seed", C.c_uint64), ("call_index", C.c_uint32), ("exact_order", C.c_uint32),
-        ("stage", C.c_uint32), ("t_ready", C.c_uint32), ("agent_offset", C.c_uint64),
+        ("stage", C.c_uint32), ("t_ready", C.c_uint32), ("reset_scatter", C.c_uint32), ("_pad1", C.c_uint32),
+        ("agent_offset", C.c_uint64),
     ]
 
 
@@ -165,10 +166,10 @@ def lib():
     L.gj_profile_kernel_name.restype = C.c_char_p
     L.gj_boundary_pack.argtypes = [C.c_int64] + [C.c_void_p] * 5
     L.gj_boundary_unpack.argtypes = [C.c_int64] + [C.c_void_p] * 5
-    cfg = (C.c_int64 * 8)()
-    L.gj_config(cfg, 8)
+    cfg = (C.c_int64 * 9)()
+    L.gj_config(cfg, 9)
     _config = {
-        "small_group": cfg[0], "chunk": cfg[1], "red_blocks": cfg[6], "tile_agents": cfg[7],
+        "small_group": cfg[0], "chunk": cfg[1], "red_blocks": cfg[6], "tile_agents": cfg[7], "scatter_max": cfg[8],
     }
     sizes = {"gj_world_desc": (cfg[2], C.sizeof(WorldDesc)), "gj_step_params": (cfg[3], C.sizeof(StepParams)),
              "gj_fwd_io": (cfg[4], C.sizeof(FwdIO)), "gj_bwd_io": (cfg[5], C.sizeof(BwdIO))}

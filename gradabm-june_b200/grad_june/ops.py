@@ -468,6 +468,7 @@ class _Step(torch.autograd.Function):
             tq_name = pf["tq_name"]
             p.t_ready = 1
             keep.append(pf)
+            world.__dict__["_scatter_pending"] = False
         elif fused_T:
             T = new("T")
             io.Tq = _buffer(world, tq_name, N).data_ptr() if p.n_quar > 0 else T.data_ptr()
@@ -492,6 +493,11 @@ class _Step(torch.autograd.Function):
             io.red = red.data_ptr()
         io.scratch = _scratch(world).data_ptr()
         desc = world.desc()
+        if world.__dict__.get("_scatter_pending"):
+            # a look-ahead scattered the next step's transmissions into the group accumulators, but this call is not
+            # that step: have the library clear them first
+            p.reset_scatter = 1
+            world.__dict__["_scatter_pending"] = False
         if static.exchange is not None:
             p.agent_offset = static.exchange.part.agent_lo
         lean_inputs = E is None and u is None and z is None and T_in is None and lam is None and static.prof4 is not None
@@ -508,6 +514,7 @@ class _Step(torch.autograd.Function):
         rc = _staged_call(L.gj_step_forward, "gj_step_forward", static, desc, p, io, _stream(dev),
                           (S_sc, S_un) if nets_on else None, lean_inputs, p_next=p_next)
         if p_next is not None and rc == 1:
+            world.__dict__["_scatter_pending"] = True
             world.__dict__["_prefetch"] = dict(
                 key=_spec_key(next_spec), calls=world.__dict__.get("_calls", 0), T=T_next, Tq=Tq_next,
                 tq_name=next_tq_name if Tq_next is not None else "Tq0", inf=out.get("inf_o"), tinf=out.get("tinf_o"),

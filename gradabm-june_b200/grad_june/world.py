@@ -229,6 +229,7 @@ TILE_AGENTS = 1024          # agents per CTA tile of the agent-major kernels (==
 RANGE_MAX_GROUP = 64        # range tier: every agent re-sums its (small) group from its neighbours
 CELL_MIN_MEAN_AGENTS = 64   # cell tier only pays when cells are much larger than a warp
 CELL_MAX_GROUPS = 16
+SCATTER_MAX_GROUP = 32768   # == GJ_SCATTER_MAX_GROUP: larger generic groups are "giant" (summed group-major in the forward)
 
 
 class DeviceWorld:
@@ -263,6 +264,7 @@ class DeviceWorld:
             setattr(d, name, getattr(self, name).data_ptr())
         d.n_small, d.n_chunks = self.small_groups.numel(), self.chunk_group.numel()
         d.n_big, d.n_parts = self.big_groups.numel(), self.n_parts
+        d.n_giant_chunks, d.n_giant_big = self.__dict__.get("n_giant_chunks", 0), self.__dict__.get("n_giant_big", 0)
         d.n_tiles = self.tile_begin.numel() - 1
         cell_off = 0
         for ti in range(len(self.types)):
@@ -536,7 +538,7 @@ def original_order(data: "HeteroData", values: torch.Tensor) -> torch.Tensor:
 def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], people: Dict[str, torch.Tensor],
               n_groups: Dict[str, int], age: torch.Tensor, sex: torch.Tensor, small_group: int, chunk: int,
               device, tiers: bool = True, orig_id: Optional[torch.Tensor] = None,
-              want_tiers: Optional[Dict[str, int]] = None) -> DeviceWorld:
+              want_tiers: Optional[Dict[str, int]] = None, scatter_max: int = SCATTER_MAX_GROUP) -> DeviceWorld:
     """``orig_id``: [n_agents] id of every agent in the numbering the world was loaded in (None = this one): the
     counter of the kernels' Philox stream.  ``want_tiers``: the tier to try per type (default: the policy of
     :func:`tier_candidates`; a partitioned world passes the tiers its ranks agreed on); a type whose structure
@@ -608,9 +610,13 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
     am_ptr = _ptr_from_counts(deg)
     del perm
     # one-entry-per-agent view for the throughput-mode kernels: global group id | none | "several: use the CSR"
+    if G >= (1 << 31):
+        raise ValueError("too many groups for the one-entry-per-agent view")
+    if scatter_max < chunk:
+        raise ValueError("scatter_max must be at least one chunk")
     ent1 = torch.full((n_agents,), 0xFFFFFFFF, dtype=torch.long, device=dev)
     if E:
-        ent1[src] = gkey
+        ent1[src] = gkey + ((size[gkey] > scatter_max).long() << 31)      # bit 31: a giant group
         ent1[deg > 1] = 0xFFFFFFFE
     age = age.to(dev).long()
     sex = sex.to(dev).long()
@@ -626,8 +632,11 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
     gids = torch.arange(G, device=dev)
     small = gids[(size <= small_group) & generic_group]
     big_mask = (size > small_group) & generic_group
-    bg = gids[big_mask]
-    nchunk = (size[big_mask] + chunk - 1) // chunk
+    giant = size > scatter_max
+    bg = torch.cat((gids[big_mask & giant], gids[big_mask & ~giant]))     # giant groups lead the chunk lists
+    n_giant_big = int((big_mask & giant).sum())
+    nchunk = (size[bg] + chunk - 1) // chunk
+    n_giant_chunks = int(nchunk[:n_giant_big].sum())
     chunk_group = torch.repeat_interleave(bg, nchunk)
     first = _ptr_from_counts(nchunk)
     within = torch.arange(chunk_group.numel(), device=dev) - torch.repeat_interleave(first[:-1], nchunk)
@@ -666,6 +675,7 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
         chunk_part=chunk_part.to(torch.int32), big_groups=_u32(big_groups), big_part_ptr=_u32(big_part_ptr),
         n_parts=n_parts, tile_begin=_u32(tile_begin), ent1=_padded(_u32(ent1)), device=dev,
         orig_id=None if orig_id is None else _padded(_u32(orig_id.to(dev))),
+        n_giant_chunks=n_giant_chunks, n_giant_big=n_giant_big,
     )
 
 

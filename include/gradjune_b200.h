@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GJ_ABI_VERSION 5
+#define GJ_ABI_VERSION 6
 
 #define GJ_MAX_TYPES 8      /* edge types (household, company, school, university, care_home, leisure, ...) */
 #define GJ_MAX_NETS 16      /* infection networks active in one step */
@@ -41,6 +41,15 @@ extern "C" {
  * read them through gj_config) */
 #define GJ_SMALL_GROUP 16   /* <= this many members: one lane sums the group sequentially */
 #define GJ_CHUNK 1024       /* larger groups are cut into chunks of this many members, one warp each */
+
+/* throughput-mode forward: members of a generic-tier group of at most this many agents ADD their transmission into
+ * the group's 64-bit fixed-point accumulator (exact, order-independent: deterministic); larger ("giant") groups are
+ * summed group-major by the chunk kernel.  Fixed point: GJ_SCATTER_FRAC fractional bits, member values below
+ * 2^GJ_SCATTER_CAP_LOG2 (a larger / non-finite value marks its group for an exact re-sum): the sum of
+ * GJ_SCATTER_MAX_GROUP such members stays below 2^62 */
+#define GJ_SCATTER_MAX_GROUP 32768
+#define GJ_SCATTER_CAP_LOG2 10
+#define GJ_SCATTER_FRAC 37
 
 enum { GJ_TIER_GENERIC = 0, GJ_TIER_RANGE = 1, GJ_TIER_CELL = 2 };
 #define GJ_TILE_AGENTS 1024
@@ -128,8 +137,13 @@ typedef struct gj_world_desc {
   const uint32_t* grp_cell_ptr[GJ_MAX_TYPES];  /* [G_type+1] */
   const uint32_t* grp_cell[GJ_MAX_TYPES];      /* cells of each group, ascending */
   /* one-entry-per-agent view of the GENERIC types (throughput-mode kernels): the GLOBAL id of the agent's only
-   * generic group, 0xFFFFFFFF = none, 0xFFFFFFFE = several (walk am_ptr / am_ent); NULL = not built */
+   * generic group (bit 31 set: a giant group, > GJ_SCATTER_MAX_GROUP members), 0xFFFFFFFF = none,
+   * 0xFFFFFFFE = several (walk am_ptr / am_ent); NULL = not built */
   const uint32_t* ent1;
+  /* the chunk list starts with the n_giant_chunks chunks of the giant groups and the list of multi-chunk groups
+   * with the n_giant_big giant ones: the throughput-mode forward sums only those group-major */
+  int64_t n_giant_chunks;
+  int64_t n_giant_big;
   /* geographic partition (one process per GPU, each owning an agent range and the groups its agents attend):
    * [n_groups] weight of each group in d/dbeta, 1 for groups this rank owns and 0 for groups owned by another
    * rank (their sums are exchanged between the two stages of a step); NULL = all ones */
@@ -184,6 +198,10 @@ typedef struct gj_step_params {
   /* 1: io->T (and io->Tq) and the scratch tile sums of the cell channels were already produced for this step by the
    * previous step's gj_step_forward_next (same state tensors, same schedule): skip the transmission pass */
   uint32_t t_ready;
+  /* 1: a look-ahead (gj_step_forward_next) whose result was then NOT used left transmissions in the scratch
+   * accumulators of the generic groups: clear them before this step's transmission pass */
+  uint32_t reset_scatter;
+  uint32_t _pad1;
   /* global id of this rank's first agent: the Philox counter is (agent_offset + local agent index), so a
    * partitioned world draws exactly the noise of the unpartitioned one */
   uint64_t agent_offset;
@@ -276,7 +294,8 @@ typedef struct gj_bwd_io {
 int gj_abi_version(void);
 const char* gj_last_error(void);
 /* out[0]=GJ_SMALL_GROUP, out[1]=GJ_CHUNK, out[2]=sizeof(gj_world_desc), out[3]=sizeof(gj_step_params),
- * out[4]=sizeof(gj_fwd_io), out[5]=sizeof(gj_bwd_io), out[6]=reduction grid size */
+ * out[4]=sizeof(gj_fwd_io), out[5]=sizeof(gj_bwd_io), out[6]=reduction grid size, out[7]=GJ_TILE_AGENTS,
+ * out[8]=GJ_SCATTER_MAX_GROUP */
 int gj_config(int64_t* out, int n);
 /* bytes of the caller-provided scratch buffer (zero it once; the library leaves it zeroed) */
 int64_t gj_scratch_bytes(const gj_world_desc* w);
