@@ -736,8 +736,17 @@ static int launch_lean_forward_sums(const gj_world_desc* w, const gj_step_params
   {
     ProfScope ps(K_GROUP_SMALL_F, st);
     Scatter sct{sc.sct_acc, sc.sct_dirty};
-    k_lean_scatter_finalize<<<blocks_for(w->n_groups, kBlock), kBlock, 0, st>>>(*w, *p, pl, beta, in, sct, out_scaled,
-                                                                               out_plain);
+    GenericRanges gr;
+    memset(&gr, 0, sizeof(gr));
+    for (int t = 0; t < w->n_types; ++t)
+      if (w->type_tier[t] == GJ_TIER_GENERIC && w->type_group_off[t + 1] > w->type_group_off[t]) {
+        gr.first[gr.n] = w->type_group_off[t];
+        gr.start[gr.n + 1] = gr.start[gr.n] + (w->type_group_off[t + 1] - w->type_group_off[t]);
+        ++gr.n;
+      }
+    if (gr.n == 0) return 0;
+    k_lean_scatter_finalize<<<blocks_for(gr.start[gr.n], kBlock), kBlock, 0, st>>>(*w, *p, pl, gr, beta, in, sct,
+                                                                                 out_scaled, out_plain);
     GJ_CHECK_LAUNCH("k_lean_scatter_finalize");
   }
   return 0;

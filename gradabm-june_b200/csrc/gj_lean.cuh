@@ -450,18 +450,27 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_fix(gj_world_desc w, gj_s
 
 // accumulators -> fp32 sums of the scatter-tier groups (every generic group that is not giant); leaves them zero.
 // A dirty group (a member value outside the fixed-point range) is re-summed from its member list in CSR order.
+// the generic-tier types' global group id ranges, concatenated: thread i -> group (host-built, passed by value)
+struct GenericRanges {
+  int n;
+  int64_t first[GJ_MAX_TYPES];   // first global group id of the range
+  int64_t start[GJ_MAX_TYPES + 1];   // first linear index of the range
+};
 __global__ void __launch_bounds__(kBlock) k_lean_scatter_finalize(gj_world_desc w, gj_step_params p, Plan pl,
-                                                                  const float* __restrict__ beta,
+                                                                  GenericRanges gr, const float* __restrict__ beta,
                                                                   const float* __restrict__ in, Scatter sct,
                                                                   float* __restrict__ out_scaled,
                                                                   float* __restrict__ out_plain) {
   __shared__ LeanGroupShared gs;
   lean_beta_sums(gs, w, p, pl, beta);
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= w.n_groups) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= gr.start[gr.n]) return;
+  int r = 0;
+#pragma unroll
+  for (int k = 1; k < GJ_MAX_TYPES; ++k) r += (k < gr.n && i >= gr.start[k]) ? 1 : 0;
+  const int64_t g = gr.first[r] + (i - gr.start[r]);
   const uint32_t j0 = w.gm_ptr[g], j1 = w.gm_ptr[g + 1];
   if (j1 - j0 > (uint32_t)GJ_SCATTER_MAX_GROUP) return;                 // giant: the chunk kernels wrote it
-  if (w.type_tier[type_of_group(w, (uint32_t)g)] != GJ_TIER_GENERIC) return;
   const unsigned long long acc = sct.acc[g];
   const bool dirty = sct.dirty[g] != 0;
   if (acc != 0ull) sct.acc[g] = 0ull;

@@ -116,7 +116,7 @@ class Runner(torch.nn.Module):
         saves ~5 GB of copies and dtype conversions per window.  The backup is re-read (identity check) if the user
         replaced it."""
         key = tuple(id(self.data_backup[k]) for k in _STATE_KEYS) + \
-            tuple(id(self.data_backup["symptoms"][k]) for k in _SYMPTOM_KEYS)
+            tuple((id(self.data_backup["symptoms"][k]), self.data_backup["symptoms"][k]._version) for k in _SYMPTOM_KEYS)
         hit = self.__dict__.get("_window_start")
         if hit is None or hit[0] != key:
             state = {k: self.data_backup[k].detach() for k in _STATE_KEYS}
