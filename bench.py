@@ -492,9 +492,10 @@ def measure(args, ctx, scaling, graph, full=True):
 
     parallelism = "single GPU"
     if geo:
+        from grad_june.partition import exchange_for
         nb = {t: part.n_boundary[t] for t in part.types if part.n_boundary[t]}
         parallelism = (f"geographic partition over {world_size} GPUs ({scaling} scaling), boundary-group sums exchanged "
-                       f"once per step forward and once backward ({ctx.get('exchange', 'NCCL all-reduce')}); boundary "
+                       f"once per step forward and once backward ({exchange_for(data, world).mode}); boundary "
                        f"groups {nb} of {world.n_groups} local groups")
     elif world_size > 1 or n_samples > 1:
         parallelism = (f"ensemble shard: {n_samples * world_size} beta samples per window, {n_samples} per GPU evaluated one "

@@ -921,9 +921,110 @@ __global__ void __launch_bounds__(kBlock) k_boundary_unpack(int64_t n, const int
   }
 }
 
+// ---- peer-memory exchange (see gradjune_b200.h) -----------------------------------------------------------
+// receive buffer of one rank: [2 sets][world_size sources][2 arrays][capacity] floats, then the flags
+// [2 sets][world_size] uint32, then {exchange counter, ticket A, ticket B, error} uint32
+constexpr int kPeerBlocks = 148;     // co-resident by construction: blocks wait on flags other GPUs raise
+constexpr int kPeerThreads = 256;
+struct PeerView {
+  int rank, world;
+  int64_t cap;
+  float* recv[32];       // every rank's receive buffer (own included), mapped into this process
+  uint32_t* flags[32];   // every rank's flag array
+  uint32_t* ctl;         // own {counter, ticket A, ticket B, error}
+};
+__device__ __forceinline__ float* peer_slot(const PeerView& v, int dst, uint32_t set, int src, int arr) {
+  return v.recv[dst] + (((int64_t)set * v.world + src) * 2 + arr) * v.cap;
+}
+__global__ void __launch_bounds__(kPeerThreads) k_peer_exchange(PeerView v, int64_t n, const int32_t* __restrict__ inv,
+                                                                 const uint32_t* __restrict__ attend,
+                                                                 float* __restrict__ a, float* __restrict__ b) {
+  __shared__ uint32_t s_epoch;
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) s_epoch = *(volatile uint32_t*)&v.ctl[0] + 1u;   // bumped by the last block at the very end
+  __syncthreads();
+  const uint32_t e = s_epoch, set = e & 1u;
+  const uint32_t me = 1u << v.rank;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // ---- push: my partial sums into the receive buffers of the other ranks attending each group ---------------
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
+    const int32_t j = inv[q];
+    if (j < 0) continue;
+    const float va = a[j], vb = b[j];
+    uint32_t m = attend[q] & ~me;
+    while (m) {
+      const int dst = __ffs(m) - 1;
+      m &= m - 1;
+      peer_slot(v, dst, set, v.rank, 0)[q] = va;
+      peer_slot(v, dst, set, v.rank, 1)[q] = vb;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&v.ctl[1], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {   // every block of this rank has pushed (and fenced): tell the peers
+    __threadfence_system();
+    if ((int)threadIdx.x < v.world && (int)threadIdx.x != v.rank)
+      *(volatile uint32_t*)&v.flags[threadIdx.x][set * v.world + v.rank] = e;
+    if (threadIdx.x == 0) v.ctl[1] = 0u;
+    __threadfence_system();
+  }
+  // ---- wait for every peer's flag in my own memory ----------------------------------------------------------
+  if ((int)threadIdx.x < v.world && (int)threadIdx.x != v.rank) {
+    volatile uint32_t* f = (volatile uint32_t*)&v.flags[v.rank][set * v.world + threadIdx.x];
+    unsigned long long t0 = 0, t1 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*f != e) {
+      __nanosleep(64);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 10000000000ull) {   // ~10 s: a peer is gone; give up rather than hang the GPU
+        v.ctl[3] = 1u;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  // ---- reduce in ascending rank order (my own term in its place): identical on every rank -------------------
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
+    const int32_t j = inv[q];
+    if (j < 0) continue;
+    uint32_t m = attend[q];
+    float sa = 0.0f, sb = 0.0f;
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      if (src == v.rank) {
+        sa += a[j];
+        sb += b[j];
+      } else {
+        sa += __ldcg(peer_slot(v, v.rank, set, src, 0) + q);
+        sb += __ldcg(peer_slot(v, v.rank, set, src, 1) + q);
+      }
+    }
+    a[j] = sa;
+    b[j] = sb;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(&v.ctl[2], 1u) == gridDim.x - 1) {   // the last block closes the exchange
+    v.ctl[2] = 0u;
+    *(volatile uint32_t*)&v.ctl[0] = e;
+  }
+}
+
 }  // namespace gj
 
 using namespace gj;
+
+struct gj_peer {
+  int rank, world, device;
+  int64_t cap;
+  size_t bytes, flag_off, ctl_off;
+  char* own;           // cudaMalloc'ed
+  char* mapped[32];    // every rank's buffer in this process (own = own)
+  bool connected;
+};
 
 extern "C" {
 
@@ -953,6 +1054,96 @@ int gj_boundary_unpack(int64_t n_pack, const int32_t* inv, const float* pack, fl
   if (!inv || !a || !b || !pack) return bad("NULL array");
   k_boundary_unpack<<<agent_grid(n_pack), kBlock, 0, (cudaStream_t)stream>>>(n_pack, inv, pack, a, b);
   GJ_CHECK_LAUNCH("k_boundary_unpack");
+  return 0;
+}
+
+int gj_peer_create(int rank, int world_size, int64_t capacity, gj_peer** out) {
+  if (!out || rank < 0 || world_size < 1 || world_size > 32 || rank >= world_size || capacity < 0) return bad("gj_peer_create arguments");
+  gj_peer* p = new gj_peer();
+  p->rank = rank;
+  p->world = world_size;
+  p->cap = capacity > 0 ? (capacity + 63) / 64 * 64 : 64;
+  p->connected = false;
+  cudaGetDevice(&p->device);
+  const size_t data = sizeof(float) * 2ull * world_size * 2ull * (size_t)p->cap;
+  p->flag_off = (data + 255) / 256 * 256;
+  p->ctl_off = p->flag_off + 256 * ((sizeof(uint32_t) * 2 * world_size + 255) / 256);
+  p->bytes = p->ctl_off + 256;
+  for (int i = 0; i < 32; ++i) p->mapped[i] = nullptr;
+  cudaError_t e = cudaMalloc((void**)&p->own, p->bytes);
+  if (e != cudaSuccess) {
+    delete p;
+    return fail("cudaMalloc (peer buffer)", e);
+  }
+  e = cudaMemset(p->own, 0, p->bytes);
+  if (e != cudaSuccess) return fail("cudaMemset (peer buffer)", e);
+  p->mapped[rank] = p->own;
+  *out = p;
+  return 0;
+}
+
+int gj_peer_handle(gj_peer* p, void* handle) {
+  if (!p || !handle) return bad("gj_peer_handle arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == GJ_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p->own);
+  if (e != cudaSuccess) return fail("cudaIpcGetMemHandle", e);
+  memcpy(handle, &h, sizeof(h));
+  return 0;
+}
+
+int gj_peer_connect(gj_peer* p, const void* handles) {
+  if (!p || !handles) return bad("gj_peer_connect arguments");
+  for (int r = 0; r < p->world; ++r) {
+    if (r == p->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * GJ_IPC_HANDLE_BYTES, sizeof(h));
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail("cudaIpcOpenMemHandle", e);
+    p->mapped[r] = (char*)ptr;
+  }
+  p->connected = true;
+  return 0;
+}
+
+int gj_peer_exchange(gj_peer* p, int64_t n_pack, const int32_t* inv, const uint32_t* attend, float* a, float* b,
+                     void* stream) {
+  if (!p || !p->connected) return bad("peer context is not connected");
+  if (n_pack > p->cap) return bad("n_pack exceeds the peer buffers' capacity");
+  if (n_pack > 0 && (!inv || !attend || !a || !b)) return bad("NULL array");
+  PeerView v;
+  v.rank = p->rank;
+  v.world = p->world;
+  v.cap = p->cap;
+  for (int r = 0; r < 32; ++r) {
+    v.recv[r] = r < p->world ? (float*)p->mapped[r] : nullptr;
+    v.flags[r] = r < p->world ? (uint32_t*)(p->mapped[r] + p->flag_off) : nullptr;
+  }
+  v.ctl = (uint32_t*)(p->own + p->ctl_off);
+  k_peer_exchange<<<kPeerBlocks, kPeerThreads, 0, (cudaStream_t)stream>>>(v, n_pack, inv, attend, a, b);
+  GJ_CHECK_LAUNCH("k_peer_exchange");
+  return 0;
+}
+
+int gj_peer_status(gj_peer* p) {
+  if (!p) return bad("peer is NULL");
+  uint32_t err = 0;
+  cudaError_t e = cudaMemcpy(&err, p->own + p->ctl_off + 3 * sizeof(uint32_t), sizeof(err), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return fail("cudaMemcpy (peer status)", e);
+  if (err) {
+    cudaMemset(p->own + p->ctl_off + 3 * sizeof(uint32_t), 0, sizeof(uint32_t));
+    snprintf(g_err, sizeof(g_err), "a peer did not arrive at a boundary exchange within 10 s");
+  }
+  return err ? 1 : 0;
+}
+
+int gj_peer_destroy(gj_peer* p) {
+  if (!p) return 0;
+  for (int r = 0; r < p->world; ++r)
+    if (r != p->rank && p->mapped[r]) cudaIpcCloseMemHandle(p->mapped[r]);
+  cudaFree(p->own);
+  delete p;
   return 0;
 }
 

@@ -166,6 +166,12 @@ def lib():
     L.gj_profile_kernel_name.restype = C.c_char_p
     L.gj_boundary_pack.argtypes = [C.c_int64] + [C.c_void_p] * 5
     L.gj_boundary_unpack.argtypes = [C.c_int64] + [C.c_void_p] * 5
+    L.gj_peer_create.argtypes = [C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]
+    L.gj_peer_handle.argtypes = [C.c_void_p, C.c_void_p]
+    L.gj_peer_connect.argtypes = [C.c_void_p, C.c_void_p]
+    L.gj_peer_exchange.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5
+    L.gj_peer_status.argtypes = [C.c_void_p]
+    L.gj_peer_destroy.argtypes = [C.c_void_p]
     cfg = (C.c_int64 * 9)()
     L.gj_config(cfg, 9)
     _config = {
@@ -195,6 +201,7 @@ EXPORTED_SYMBOLS = [
     "gj_transmission_forward", "gj_transmission_backward", "gj_step_forward", "gj_step_forward_next", "gj_step_backward",
     "gj_philox_fill", "gj_philox_fill_at", "gj_step_plan", "gj_philox4x32_10", "gj_profile_enable", "gj_profile_read",
     "gj_profile_kernel_name", "gj_pipeline_enable", "gj_boundary_pack", "gj_boundary_unpack",
+    "gj_peer_create", "gj_peer_handle", "gj_peer_connect", "gj_peer_exchange", "gj_peer_status", "gj_peer_destroy",
 ]
 
 

@@ -34,6 +34,7 @@ class Partition:
     touch_lid: Dict[str, torch.Tensor]     # type -> their local group ids
     owned: Dict[str, torch.Tensor]         # type -> [G_local] bool: this rank is the lowest one attending the group
     process_group: object = None
+    attend: Dict[str, torch.Tensor] = field(default_factory=dict)   # type -> [n_boundary] bit mask of the attending ranks
 
     @property
     def agent_lo(self):
@@ -122,6 +123,8 @@ def partition_world(data: HeteroData, rank: int, world_size: int, bounds: Option
         local["agent", "attends_" + t, t].edge_index = torch.stack((lsrc, ldst))
         is_b = n_ranks[mine] >= 2
         lid = torch.nonzero(is_b).flatten()
+        bits = torch.zeros(G, dtype=torch.long, device=dev).scatter_add_(0, pg, torch.ones_like(pr) << pr)
+        part.attend[t] = bits[boundary_ids]
         part.local_groups[t] = mine
         part.n_boundary[t] = int(boundary_ids.numel())
         part.touch_lid[t] = lid
@@ -170,6 +173,7 @@ def partition_from_blocks(block: HeteroData, process_group=None) -> HeteroData:
             n_ranks_mine = torch.ones(mine.numel(), dtype=torch.long, device=dev)
             owner_mine = torch.full((mine.numel(),), rank, dtype=torch.long, device=dev)
             boundary_ids = torch.zeros(0, dtype=torch.long, device=dev)
+            attend_b = torch.zeros(0, dtype=torch.long, device=dev)
         else:
             mask = (cnt > 0).to(torch.uint8)
             masks = [torch.empty_like(mask) for _ in range(world_size)]
@@ -182,6 +186,8 @@ def partition_from_blocks(block: HeteroData, process_group=None) -> HeteroData:
             people = cnt[mine]
             n_ranks_mine, owner_mine = n_ranks[mine], owner[mine]
             boundary_ids = torch.nonzero(n_ranks >= 2).flatten()
+            shifts = torch.arange(world_size, device=dev).reshape(-1, 1)
+            attend_b = (masks[:, boundary_ids].long() << shifts).sum(0)
             del masks, n_ranks, owner
         local[t].id = torch.arange(mine.numel(), device=dev)
         local[t].people = people
@@ -192,6 +198,7 @@ def partition_from_blocks(block: HeteroData, process_group=None) -> HeteroData:
         part.touch_lid[t] = lid
         part.touch_pos[t] = torch.searchsorted(boundary_ids, mine[lid])
         part.owned[t] = owner_mine == rank
+        part.attend[t] = attend_b
     local.__dict__["_gj_partition"] = part
     return local
 
@@ -204,6 +211,8 @@ class BoundaryExchange:
         self.world = world
         self._regions = {}
         self._packs = {}
+        self._peer = None          # gj_peer* once connected; False = not available (the NCCL path runs)
+        self.mode = "NCCL all-reduce of the packed buffer"
         dev = world.device
         w = torch.zeros(world.n_groups, dtype=torch.float32, device=dev)
         for ti, t in enumerate(world.types):
@@ -238,16 +247,84 @@ class BoundaryExchange:
         src, dst = cat(src), cat(dst)
         inv = torch.full((base,), -1, dtype=torch.int32, device=dev)   # pack position -> entry of the sum buffers
         inv[dst] = src.to(torch.int32)
-        hit = (src, dst, base, inv)
+        # which ranks attend each packed group (peer-memory exchange: where to store, whom to add, in rank order)
+        attend = cat([part.attend[world.types[ti]].to(dev) for ti, _ in offsets]) if part.attend else None
+        if attend is not None:
+            attend = attend.to(torch.int32)
+        self._check_layout(base, [ti for ti, _ in offsets])
+        hit = (src, dst, base, inv, attend)
         self._regions[key] = hit
         return hit
+
+    def _check_layout(self, n_pack, type_order):
+        """Every rank must exchange the same packed layout (tiers chosen per rank once gave packs of
+        different length).  Collective, once per new region: compare (length, type order) across ranks."""
+        import torch.distributed as dist
+
+        if self.part.world_size == 1 or not dist.is_initialized():
+            return
+        sig = torch.tensor([n_pack] + list(type_order) + [-1] * (8 - len(type_order)), dtype=torch.long)
+        if dist.get_backend(self.part.process_group) == "nccl":
+            sig = sig.to(self.world.device)
+        both = torch.stack((sig, -sig))
+        dist.all_reduce(both, op=dist.ReduceOp.MAX, group=self.part.process_group)
+        if not torch.equal(both[0], -both[1]):
+            raise RuntimeError(f"boundary exchange layout differs between ranks: this rank packs {sig.tolist()}")
+
+    def _peer_context(self, device):
+        """Connect the NVLink peer-memory exchange (gj_peer_*) on first use; False if it cannot be had on every rank
+        (then the NCCL path runs).  GJ_PEER=0 in the environment forces NCCL."""
+        import ctypes as C
+        import os
+
+        import torch.distributed as dist
+
+        from . import _lib
+        if self._peer is not None:
+            return self._peer
+        part = self.part
+        ok, peer = 1, C.c_void_p()
+        why = ""
+        L = _lib.lib()
+        capacity = int(sum(part.n_boundary.values()))
+        if os.environ.get("GJ_PEER", "1") == "0" or part.world_size > 32 or not part.attend:
+            ok, why = 0, "disabled"
+        handles = torch.zeros(part.world_size, 64, dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            if ok:
+                if L.gj_peer_create(part.rank, part.world_size, capacity, C.byref(peer)) != 0:
+                    ok, why = 0, L.gj_last_error().decode()
+            if ok:
+                buf = (C.c_uint8 * 64)()
+                if L.gj_peer_handle(peer, buf) != 0:
+                    ok, why = 0, L.gj_last_error().decode()
+                else:
+                    handles[part.rank] = torch.tensor(list(buf), dtype=torch.uint8).to(device)
+            flag = torch.tensor([ok], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=part.process_group)
+            if int(flag) == 1:
+                dist.all_reduce(handles, group=part.process_group)       # every row is zero except its owner's
+                host = handles.cpu().contiguous()
+                if L.gj_peer_connect(peer, C.c_void_p(host.data_ptr())) != 0:
+                    ok, why = 0, L.gj_last_error().decode()
+                flag = torch.tensor([ok], device=device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=part.process_group)
+            torch.cuda.synchronize(device)
+            dist.barrier(group=part.process_group)
+        if int(flag) == 1:
+            self._peer = peer
+            self.mode = "NVLink peer-memory stores + flags, one kernel (gj_peer_exchange)"
+        else:
+            self._peer = False
+            self.mode = "NCCL all-reduce of the packed buffer" + (f" (peer memory unavailable: {why})" if why else "")
+        return self._peer
 
     def exchange(self, buffers, region):
         """In place: every buffer's boundary entries become the sum over ranks.  On a GPU this is one pack
         kernel, one NCCL all-reduce of the packed [2, n_boundary] buffer and one unpack kernel."""
         import torch.distributed as dist
 
-        src, dst, n, inv = region
+        src, dst, n, inv, attend = region
         if n == 0 or self.part.world_size == 1:
             return
         a, b = buffers
@@ -256,6 +333,13 @@ class BoundaryExchange:
 
             from . import _lib
             L = _lib.lib()
+            peer = self._peer_context(a.device) if attend is not None else False
+            if peer:
+                st = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+                with torch.cuda.device(a.device):
+                    _lib.check(L.gj_peer_exchange(peer, n, inv.data_ptr(), attend.data_ptr(), a.data_ptr(), b.data_ptr(),
+                                                  st), "gj_peer_exchange")
+                return
             pack = self._packs.get(n)
             if pack is None:
                 pack = self._packs[n] = torch.empty(2, n, dtype=torch.float32, device=a.device)

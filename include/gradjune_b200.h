@@ -337,6 +337,29 @@ int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_b
 int gj_boundary_pack(int64_t n_pack, const int32_t* inv, const float* a, const float* b, float* pack, void* stream);
 int gj_boundary_unpack(int64_t n_pack, const int32_t* inv, const float* pack, float* a, float* b, void* stream);
 
+/* ---- the same exchange over NVLink peer memory, ONE kernel instead of pack -> ncclAllReduce -> unpack.
+ * Every rank owns a receive buffer (cudaMalloc'ed by the library, exported as a CUDA IPC handle, opened by its
+ * peers).  gj_peer_exchange: each rank STORES the partial sums of the boundary groups it attends straight into the
+ * receive buffers of the other ranks attending them (attend[q] = bit mask of ranks), raises a flag in every peer's
+ * memory, waits for the peers' flags in its own, and adds the contributions in ascending rank order — the same
+ * order on every rank, so the totals are bit-identical everywhere and run to run.  Two buffer sets alternate
+ * (a rank can be at most one exchange ahead of a peer); the exchange counter lives on the device, so the call can
+ * be captured in a CUDA graph and replayed.  A peer that does not arrive within ~10 s sets an error flag (read by
+ * gj_peer_status) instead of hanging the GPU.  One process per GPU; every rank must issue the same sequence of
+ * exchanges. */
+typedef struct gj_peer gj_peer;
+#define GJ_IPC_HANDLE_BYTES 64
+/* capacity: the largest n_pack that will be exchanged; allocates and zeroes this rank's buffers */
+int gj_peer_create(int rank, int world_size, int64_t capacity, gj_peer** out);
+int gj_peer_handle(gj_peer* peer, void* handle /* GJ_IPC_HANDLE_BYTES */);
+/* handles: world_size x GJ_IPC_HANDLE_BYTES, rank-major (an all-gather of gj_peer_handle) */
+int gj_peer_connect(gj_peer* peer, const void* handles);
+int gj_peer_exchange(gj_peer* peer, int64_t n_pack, const int32_t* inv, const uint32_t* attend, float* a, float* b,
+                     void* stream);
+/* 0 = ok, 1 = a wait timed out since the last call (synchronises on nothing: read it after a stream sync) */
+int gj_peer_status(gj_peer* peer);
+int gj_peer_destroy(gj_peer* peer);
+
 /* ---- kernel family of the throughput mode -------------------------------------------------------
  * 1 (default; GJ_PIPE=0 in the environment turns it off): the agent kernels stage every per-agent array of a tile
  * in shared memory with TMA bulk copies (two-stage mbarrier pipeline) — needs every per-agent array 16-byte aligned

@@ -83,6 +83,23 @@ def _worker(rank, world_size, port, out):
             attended = torch.zeros(G)
             attended[data["attends_" + t].edge_index[1]] = 1.0
             assert torch.equal(own, attended), t
+        # attendance masks (peer-memory exchange): bit r of a boundary group's mask <=> rank r has a member
+        for t in world.types:
+            ei = data["attends_" + t].edge_index
+            G = len(data[t]["id"])
+            r_of = torch.bucketize(ei[0], torch.tensor(part.bounds[1:-1]), right=True)
+            truth = torch.zeros(G, dtype=torch.long)
+            for r in range(world_size):
+                has = torch.zeros(G, dtype=torch.bool)
+                has[ei[1][r_of == r]] = True
+                truth += has.long() << r
+            multi = torch.tensor([bin(int(v)).count("1") >= 2 for v in truth])
+            assert torch.equal(part.attend[t], truth[multi]), t
+            assert part.n_boundary[t] == int(multi.sum())
+            mine_bit = (part.attend[t][part.touch_pos[t]] >> rank) & 1
+            assert bool(mine_bit.all())
+        region5 = ex.regions(False, 0, nets)
+        assert region5[4].numel() == region5[2] and int((region5[4] != 0).all()) == 1
         # differentiable sum over ranks of the per-rank result table
         leaf = torch.full((3,), float(rank + 1), requires_grad=True)
         tot = all_reduce_sum(leaf * 2.0, part)
@@ -163,6 +180,7 @@ def _block_worker(rank, world_size, port, out):
             assert part.n_boundary[t] == rp.n_boundary[t], t
             assert torch.equal(part.touch_lid[t], rp.touch_lid[t]) and torch.equal(part.touch_pos[t], rp.touch_pos[t]), t
             assert torch.equal(part.owned[t], rp.owned[t]), t
+            assert torch.equal(part.attend[t], rp.attend[t]), t
         assert part.n_boundary["household"] == 0 and part.n_boundary["company"] > 0 and part.n_boundary["leisure"] > 0
         # commuting stays inside the home region: only companies of the regions cut by a block border are shared
         assert part.n_boundary["company"] < 0.5 * int(mine["company"].n_global)
