@@ -51,6 +51,18 @@ class WorldDesc(C.Structure):
     ]
 
 
+class WorldSrc(C.Structure):
+    """gj_world_src: the reference's own arrays (device pointers for gj_world_build, host for gj_world_build_host)."""
+    _fields_ = [
+        ("n_agents", C.c_int64), ("n_types", C.c_int32), ("renumber", C.c_int32),
+        ("type_name", C.c_char_p * GJ_MAX_TYPES),
+        ("edge_agent", C.c_void_p * GJ_MAX_TYPES), ("edge_group", C.c_void_p * GJ_MAX_TYPES),
+        ("n_edges", C.c_int64 * GJ_MAX_TYPES), ("n_groups", C.c_int64 * GJ_MAX_TYPES),
+        ("people_i64", C.c_void_p * GJ_MAX_TYPES), ("people_f32", C.c_void_p * GJ_MAX_TYPES),
+        ("age", C.c_void_p), ("sex", C.c_void_p), ("original_index", C.c_void_p), ("want_tier", C.c_void_p),
+    ]
+
+
 class Net(C.Structure):
     _fields_ = [("type", C.c_int32), ("kind", C.c_int32), ("prob_row", C.c_int32), ("s_off", C.c_int32)]
 
@@ -106,21 +118,36 @@ _config = None
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
-    "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+    "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "--extended-lambda",
 ]
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/*.cu into libgradjune_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu into libgradjune_b200.so for sm_100a (nvcc cross-compiles without a GPU): one object per
+    source file, compiled in parallel, then linked."""
     srcs = sorted(CSRC_DIR.glob("*.cu"))
     deps = srcs + sorted(CSRC_DIR.glob("*.cuh")) + sorted(INCLUDE_DIR.glob("*.h"))
     if not force and LIB_PATH.exists() and all(LIB_PATH.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", str(INCLUDE_DIR), "-I", str(CSRC_DIR), "-o", str(LIB_PATH)] + [str(s) for s in srcs]
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    objdir = PKG_DIR.parent / "build"
+    objdir.mkdir(exist_ok=True)
+    procs = []
+    for src in srcs:
+        obj = objdir / (src.stem + ".o")
+        cmd = [nvcc] + flags + ["-I", str(INCLUDE_DIR), "-I", str(CSRC_DIR), "-c", "-o", str(obj), str(src)]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((cmd, obj, subprocess.Popen(cmd)))
+    for cmd, obj, proc in procs:
+        if proc.wait() != 0:
+            raise subprocess.CalledProcessError(proc.returncode, cmd)
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", str(LIB_PATH)] \
+        + [str(obj) for _, obj, _ in procs]
     if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True)
+        print(" ".join(link))
+    subprocess.run(link, check=True)
     return LIB_PATH
 
 
@@ -172,6 +199,14 @@ def lib():
     L.gj_peer_exchange.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5
     L.gj_peer_status.argtypes = [C.c_void_p]
     L.gj_peer_destroy.argtypes = [C.c_void_p]
+    L.gj_world_build.argtypes = [C.POINTER(WorldSrc), C.POINTER(C.c_void_p)]
+    L.gj_world_build_host.argtypes = [C.POINTER(WorldSrc), C.POINTER(C.c_void_p)]
+    L.gj_world_descriptor.argtypes = [C.c_void_p]
+    L.gj_world_descriptor.restype = C.POINTER(WorldDesc)
+    L.gj_world_permutation.argtypes = [C.c_void_p]
+    L.gj_world_permutation.restype = C.c_void_p
+    L.gj_world_last_error.restype = C.c_char_p
+    L.gj_world_destroy.argtypes = [C.c_void_p]
     cfg = (C.c_int64 * 9)()
     L.gj_config(cfg, 9)
     _config = {
@@ -202,6 +237,8 @@ EXPORTED_SYMBOLS = [
     "gj_philox_fill", "gj_philox_fill_at", "gj_step_plan", "gj_philox4x32_10", "gj_profile_enable", "gj_profile_read",
     "gj_profile_kernel_name", "gj_pipeline_enable", "gj_boundary_pack", "gj_boundary_unpack",
     "gj_peer_create", "gj_peer_handle", "gj_peer_connect", "gj_peer_exchange", "gj_peer_status", "gj_peer_destroy",
+    "gj_world_build", "gj_world_build_host", "gj_world_descriptor", "gj_world_permutation", "gj_world_last_error",
+    "gj_world_destroy",
 ]
 
 

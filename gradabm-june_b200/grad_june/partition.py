@@ -271,7 +271,7 @@ class BoundaryExchange:
         if not torch.equal(both[0], -both[1]):
             raise RuntimeError(f"boundary exchange layout differs between ranks: this rank packs {sig.tolist()}")
 
-    def _peer_context(self, device):
+    def _peer_context(self, device, n_needed=0):
         """Connect the NVLink peer-memory exchange (gj_peer_*) on first use; False if it cannot be had on every rank
         (then the NCCL path runs).  GJ_PEER=0 in the environment forces NCCL."""
         import ctypes as C
@@ -280,13 +280,21 @@ class BoundaryExchange:
         import torch.distributed as dist
 
         from . import _lib
+        L = _lib.lib()
         if self._peer is not None:
-            return self._peer
+            if self._peer is False or n_needed <= self._peer_capacity:
+                return self._peer
+            # a packed layout larger than the buffers (e.g. one entry per NETWORK of a shared edge type): every rank
+            # sees the same n_needed (regions() checks the layout across ranks), so all of them reconnect together
+            torch.cuda.synchronize(device)
+            dist.barrier(group=self.part.process_group)
+            L.gj_peer_destroy(self._peer)
+            self._peer = None
         part = self.part
         ok, peer = 1, C.c_void_p()
         why = ""
-        L = _lib.lib()
-        capacity = int(sum(part.n_boundary.values()))
+        capacity = max(int(sum(part.n_boundary.values())), int(n_needed))
+        self._peer_capacity = capacity
         if os.environ.get("GJ_PEER", "1") == "0" or part.world_size > 32 or not part.attend:
             ok, why = 0, "disabled"
         handles = torch.zeros(part.world_size, 64, dtype=torch.uint8, device=device)
@@ -333,7 +341,7 @@ class BoundaryExchange:
 
             from . import _lib
             L = _lib.lib()
-            peer = self._peer_context(a.device) if attend is not None else False
+            peer = self._peer_context(a.device, n) if attend is not None else False
             if peer:
                 st = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
                 with torch.cuda.device(a.device):

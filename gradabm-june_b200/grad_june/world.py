@@ -457,7 +457,8 @@ def layout_order(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor]
     else:
         Gh, hkey, epos = 0, ids.clone(), ids
     n_keys = Gh + n_agents
-    first = torch.full((n_keys,), n_agents, dtype=torch.long, device=dev).scatter_reduce(0, hkey, epos, reduce="amin")
+    first = torch.full((n_keys,), int(epos.max()) + 1, dtype=torch.long, device=dev).scatter_reduce(
+        0, hkey, epos, reduce="amin")
     hcell = torch.full((n_keys,), n_cells, dtype=torch.long, device=dev)
     is_first = epos == first[hkey]
     hcell[hkey[is_first]] = cell[is_first]                 # the cell of the household's first member
@@ -677,6 +678,104 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
         orig_id=None if orig_id is None else _padded(_u32(orig_id.to(dev))),
         n_giant_chunks=n_giant_chunks, n_giant_big=n_giant_big,
     )
+
+
+class NativeWorld:
+    """A world built by ``gj_world_build`` (the C-ABI builder, csrc/gj_world.cu) from the reference's arrays of
+    ``data``: the handle owns the device arrays; ``desc()`` is what the step entry points take.  ``host=True`` runs
+    the same build on the CPU (``gj_world_build_host``; its arrays then live in host memory — for comparing with
+    :func:`build_csr` in the CPU tests, never for stepping)."""
+
+    def __init__(self, data: "HeteroData", device="cuda:0", renumber=True, host=False, want_tiers=None):
+        import ctypes as C
+
+        from . import _lib
+        L = _lib.lib()
+        dev = torch.device("cpu" if host else device)
+        types = data.venue_types()
+        src = _lib.WorldSrc()
+        keep = []
+
+        def ptr(t, dtype):
+            t = torch.as_tensor(t).to(device=dev, dtype=dtype).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        n = len(data["agent"].id)
+        src.n_agents, src.n_types, src.renumber = n, len(types), 1 if renumber else 0
+        for i, t in enumerate(types):
+            ei = data["attends_" + t].edge_index
+            src.type_name[i] = t.encode()
+            src.edge_agent[i], src.edge_group[i] = ptr(ei[0], torch.long), ptr(ei[1], torch.long)
+            src.n_edges[i], src.n_groups[i] = ei.shape[1], len(data[t]["id"])
+            people = torch.as_tensor(data[t]["people"])
+            if people.dtype.is_floating_point:
+                src.people_f32[i] = ptr(people, torch.float32)
+            else:
+                src.people_i64[i] = ptr(people, torch.long)
+        src.age, src.sex = ptr(data["agent"].age, torch.long), ptr(data["agent"].sex, torch.long)
+        if "original_index" in data["agent"]:
+            src.original_index = ptr(data["agent"]["original_index"], torch.long)
+        if want_tiers is not None:
+            src.want_tier = ptr(torch.tensor([int(want_tiers.get(t, TIER_GENERIC)) for t in types]), torch.int32)
+        handle = C.c_void_p()
+        ctx = torch.cuda.device(dev) if dev.type == "cuda" else _NullContext()
+        with ctx:
+            rc = (L.gj_world_build_host if host else L.gj_world_build)(C.byref(src), C.byref(handle))
+        if rc != 0:
+            raise _lib.GradJuneLibraryError(f"gj_world_build failed ({rc}): {L.gj_world_last_error().decode()}")
+        self._lib, self.handle, self.device, self.host, self.types, self.n_agents = L, handle, dev, host, types, n
+        self._desc = L.gj_world_descriptor(handle).contents
+
+    def desc(self):
+        return self._desc
+
+    def permutation(self):
+        """perm[new] = old of the renumbering the build applied (int64 tensor on the build's device), None = identity."""
+        p = self._lib.gj_world_permutation(self.handle)
+        if not p:
+            return None
+        return self._view(p, self.n_agents, torch.long)
+
+    def _view(self, address, count, dtype):
+        """Copy of ``count`` elements at ``address`` (host or device memory of the handle) as a tensor."""
+        import ctypes as C
+        out = torch.empty(count, dtype=dtype)
+        nbytes = out.numel() * out.element_size()
+        if self.host:
+            C.memmove(out.data_ptr(), address, nbytes)
+            return out
+        out = out.to(self.device)
+        from cuda import cudart  # cuda-python ships with the image; device-to-device copy of the handle's array
+        cudart.cudaMemcpy(out.data_ptr(), address, nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice)
+        return out
+
+    def array(self, name, count, dtype=torch.int32, index=None):
+        """Copy of one descriptor array (``index``: the edge type of a per-type array)."""
+        field = getattr(self._desc, name)
+        address = field[index] if index is not None else field
+        if not address or count == 0:
+            return torch.zeros(0, dtype=dtype)
+        return self._view(address, count, dtype)
+
+    def close(self):
+        if self.handle:
+            self._lib.gj_world_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 -- interpreter shutdown
+            pass
+
+
+class _NullContext:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 def get_device_world(data: HeteroData, device, small_group: Optional[int] = None, chunk: Optional[int] = None):

@@ -154,6 +154,39 @@ typedef struct gj_world_desc {
   const uint32_t* orig_id;
 } gj_world_desc;
 
+/* ---- building the world behind the C ABI (replaces the repo-side Python builder for callers that bind the .so
+ * directly): the reference's own arrays in, the layout above out.  All pointers are DEVICE memory
+ * (gj_world_build) — the reference keeps its HeteroData on `system.device` (runner.py:65-91) — or HOST memory
+ * (gj_world_build_host, the same code on the CPU: test infrastructure for boxes without a GPU). */
+typedef struct gj_world_src {
+  int64_t n_agents;
+  int32_t n_types;
+  int32_t renumber;                            /* 1: renumber the agents household-contiguous inside their leisure
+                                                  cell (grad_june.world.layout_order) before building */
+  const char* type_name[GJ_MAX_TYPES];         /* "household", "company", ..., "leisure": data["attends_<name>"] */
+  const int64_t* edge_agent[GJ_MAX_TYPES];     /* edge_index[0]  [n_edges[t]]  unsorted */
+  const int64_t* edge_group[GJ_MAX_TYPES];     /* edge_index[1] */
+  int64_t n_edges[GJ_MAX_TYPES];
+  int64_t n_groups[GJ_MAX_TYPES];              /* len(data[name]["id"]) */
+  const int64_t* people_i64[GJ_MAX_TYPES];     /* data[name]["people"] as int64 (pickles) ... */
+  const float* people_f32[GJ_MAX_TYPES];       /* ... or as float32 (test fixtures); exactly one is non-NULL */
+  const int64_t* age;                          /* [n_agents] in [0, 99] */
+  const int64_t* sex;                          /* [n_agents] in {0, 1} */
+  const int64_t* original_index;               /* optional [n_agents]: ids in an earlier numbering (composed) */
+  const int32_t* want_tier;                    /* optional [n_types]: the tier to try per type (partitioned worlds
+                                                  pass the tiers their ranks agreed on); NULL = the default policy */
+} gj_world_src;
+typedef struct gj_world gj_world;
+int gj_world_build(const gj_world_src* src, gj_world** out);
+int gj_world_build_host(const gj_world_src* src, gj_world** out);
+/* the descriptor to pass to gj_step_forward / gj_step_backward (owned by the handle; pointers into its arrays) */
+const struct gj_world_desc* gj_world_descriptor(const gj_world* world);
+/* [n_agents] perm[new] = old of the renumbering (same memory space as the build), NULL = identity: per-agent
+ * inputs (state, profile parameters) are gathered through it, outputs scattered back */
+const int64_t* gj_world_permutation(const gj_world* world);
+const char* gj_world_last_error(void);
+int gj_world_destroy(gj_world* world);
+
 typedef struct gj_net {
   int32_t type;     /* edge type index */
   int32_t kind;     /* GJ_KIND_* */
