@@ -757,6 +757,21 @@ const int64_t* gj_world_permutation(const gj_world* w) {
   return w->host->perm.empty() ? nullptr : thrust::raw_pointer_cast(w->host->perm.data());
 }
 
+// copy out of (or into) a handle's arrays: any direction between host and device memory (unified addressing)
+int gj_memcpy(void* dst, const void* src, int64_t bytes) {
+  if (bytes <= 0) return 0;
+  if (!dst || !src) {
+    snprintf(g_world_err, sizeof(g_world_err), "gj_memcpy: NULL argument");
+    return -1;
+  }
+  const cudaError_t e = cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDefault);
+  if (e != cudaSuccess) {
+    snprintf(g_world_err, sizeof(g_world_err), "gj_memcpy: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  return 0;
+}
+
 int gj_world_destroy(gj_world* w) {
   if (!w) return 0;
   delete w->dev;

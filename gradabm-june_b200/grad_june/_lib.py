@@ -207,6 +207,7 @@ def lib():
     L.gj_world_permutation.restype = C.c_void_p
     L.gj_world_last_error.restype = C.c_char_p
     L.gj_world_destroy.argtypes = [C.c_void_p]
+    L.gj_memcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     cfg = (C.c_int64 * 9)()
     L.gj_config(cfg, 9)
     _config = {
@@ -238,7 +239,7 @@ EXPORTED_SYMBOLS = [
     "gj_profile_kernel_name", "gj_pipeline_enable", "gj_boundary_pack", "gj_boundary_unpack",
     "gj_peer_create", "gj_peer_handle", "gj_peer_connect", "gj_peer_exchange", "gj_peer_status", "gj_peer_destroy",
     "gj_world_build", "gj_world_build_host", "gj_world_descriptor", "gj_world_permutation", "gj_world_last_error",
-    "gj_world_destroy",
+    "gj_world_destroy", "gj_memcpy",
 ]
 
 

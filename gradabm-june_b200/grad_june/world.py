@@ -746,8 +746,9 @@ class NativeWorld:
             C.memmove(out.data_ptr(), address, nbytes)
             return out
         out = out.to(self.device)
-        from cuda import cudart  # cuda-python ships with the image; device-to-device copy of the handle's array
-        cudart.cudaMemcpy(out.data_ptr(), address, nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice)
+        from . import _lib
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gj_memcpy(out.data_ptr(), address, nbytes), "gj_memcpy")
         return out
 
     def array(self, name, count, dtype=torch.int32, index=None):

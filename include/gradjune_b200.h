@@ -184,6 +184,8 @@ const struct gj_world_desc* gj_world_descriptor(const gj_world* world);
 /* [n_agents] perm[new] = old of the renumbering (same memory space as the build), NULL = identity: per-agent
  * inputs (state, profile parameters) are gathered through it, outputs scattered back */
 const int64_t* gj_world_permutation(const gj_world* world);
+/* synchronous copy between any two of host / device memory (cudaMemcpyDefault): reading a handle's arrays */
+int gj_memcpy(void* dst, const void* src, int64_t bytes);
 const char* gj_world_last_error(void);
 int gj_world_destroy(gj_world* world);
 
