@@ -61,7 +61,7 @@ def test_c_abi_only_build_and_step_of_the_sample_world(golden_dir):
     keep = []
 
     def dev(x, dtype):
-        t = torch.as_tensor(np.asarray(x)).to(device=DEV, dtype=dtype).contiguous()
+        t = (x if torch.is_tensor(x) else torch.as_tensor(np.asarray(x))).to(device=DEV, dtype=dtype).contiguous()
         keep.append(t)
         return t
 
