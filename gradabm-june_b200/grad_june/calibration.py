@@ -49,3 +49,65 @@ class EnsembleEvaluator:
         else:
             table = mine[:B]
         return table[:, 0].clone(), table[:, 1:].clone()
+
+
+class Calibrator:
+    """Gradient-based calibration of the networks' log-betas (the consumer of the hot path).
+
+    The reference's workflow (example_scripts/run_model.py:5-11; docs: fit log_beta by back-propagating a loss on the
+    simulated time series) as a loop: every iteration is ONE replay of the captured window (forward T steps +
+    backward, :class:`grad_june.graphed.GraphedRunner`) followed by a torch optimiser step on the log-beta vector.
+    The Philox key is fixed per capture (common random numbers: the loss surface the optimiser walks is deterministic);
+    ``reseed_every`` re-captures with a new key every so many iterations (stochastic optimisation over the noise).
+
+        cal = Calibrator(runner, loss_fn=lambda r: ((r["cases_per_timestep"] - target) ** 2).mean())
+        history = cal.fit(50)              # pandas DataFrame: iteration, loss, log_beta_<network>..., grad_<network>...
+        cal.save(history)                  # <save_path>/calibration.csv + the reference's results.csv of the last run
+    """
+
+    def __init__(self, runner, loss_fn: Callable[[dict], torch.Tensor], networks: Optional[Sequence[str]] = None,
+                 lr: float = 0.05, optimizer: str = "adam", seed: int = 0, reseed_every: int = 0):
+        self.runner = runner
+        self.graphed = GraphedRunner(runner, loss_fn, networks=networks, seed=seed)
+        self.names = self.graphed.names
+        dev = self.graphed.device
+        self.log_beta = self.graphed.log_beta.detach().clone().requires_grad_(True)
+        opt = {"adam": torch.optim.Adam, "sgd": torch.optim.SGD}[optimizer.lower()]
+        self.optimizer = opt([self.log_beta], lr=lr)
+        self.seed, self.reseed_every, self.iteration = int(seed), int(reseed_every), 0
+        self.device = dev
+
+    def step(self):
+        """One iteration: replay at the current log-betas, optimiser step.  Returns (loss, log_beta before the step,
+        gradient) as host floats / lists."""
+        if self.reseed_every and self.iteration and self.iteration % self.reseed_every == 0:
+            self.seed += 1
+            self.graphed.recapture(self.seed)
+        loss, grads, _ = self.graphed(self.log_beta.detach())
+        before = self.log_beta.detach().cpu().tolist()
+        self.log_beta.grad = grads.detach().clone()
+        self.optimizer.step()
+        self.iteration += 1
+        return float(loss), before, grads.detach().cpu().tolist()
+
+    def fit(self, n_iterations: int, callback=None):
+        import pandas as pd
+        rows = []
+        for _ in range(n_iterations):
+            loss, lb, grads = self.step()
+            row = {"iteration": self.iteration, "loss": loss}
+            row.update({f"log_beta_{k}": v for k, v in zip(self.names, lb)})
+            row.update({f"grad_{k}": v for k, v in zip(self.names, grads)})
+            rows.append(row)
+            if callback is not None:
+                callback(row)
+        return pd.DataFrame(rows).set_index("iteration")
+
+    def save(self, history):
+        """calibration.csv next to the reference's results.csv / results_is_infected.csv (runner.py:185-196) of the
+        last evaluated window."""
+        path = self.runner.save_path
+        path.mkdir(exist_ok=True, parents=True)
+        history.to_csv(path / "calibration.csv")
+        self.runner.save_results(self.graphed.results, self.graphed.is_infected)
+        return path

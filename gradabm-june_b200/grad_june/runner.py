@@ -211,8 +211,19 @@ class Runner(torch.nn.Module):
         return {int(self.age_bins[i].item()): self._age_mask(i).sum() for i in range(1, self.age_bins.shape[0])}
 
     def get_cases_by_ethnicity(self, data):
-        ret = torch.zeros(len(self.ethnicities), device=self.device)
-        for i, ethnicity in enumerate(self.ethnicities):
-            mask = torch.tensor(self.data["agent"].ethnicity == ethnicity, device=self.device)
-            ret[i] = (mask * data["agent"].is_infected).sum()
-        return ret
+        """runner.py:226-242, in one pass on the device: the per-agent ethnicity code is built once (the reference
+        rebuilds a boolean mask from the numpy strings per ethnicity and call), the sums are one index_add —
+        differentiable with respect to is_infected like the reference's masked sums."""
+        agent = data["agent"]
+        eth = agent.ethnicity
+        hit = self.__dict__.get("_ethnicity_codes")
+        if hit is None or hit[0] is not eth or hit[2] != agent.is_infected.device:
+            labels = np.asarray(eth)
+            n = agent.is_infected.shape[0]
+            if labels.shape[0] != n:             # synthetic worlds carry one label for everybody
+                labels = np.broadcast_to(labels[:1], (n,))
+            codes = np.searchsorted(self.ethnicities, labels)
+            hit = self.__dict__["_ethnicity_codes"] = (eth, torch.as_tensor(codes, dtype=torch.long).to(
+                agent.is_infected.device), agent.is_infected.device)
+        ret = torch.zeros(len(self.ethnicities), device=agent.is_infected.device, dtype=agent.is_infected.dtype)
+        return ret.index_add(0, hit[1], agent.is_infected)

@@ -531,3 +531,50 @@ def test_ensemble_evaluator_matches_single_runs():
     assert torch.equal(losses, torch.stack(ref_loss))
     assert torch.equal(grads, torch.stack(ref_grads))
     assert not torch.equal(grads[0], grads[1])
+
+
+def test_calibrator_recovers_a_shifted_log_beta(tmp_path):
+    """Calibrator (optimiser loop over the captured window): fit one network's log-beta to the time series
+    the model itself produced at another value; the loss must fall by orders of magnitude and the parameter move
+    towards the truth.  Also the CSV outputs of save_results (runner.py:185-196) and the one-pass ethnicity reduction."""
+    import pandas as pd
+    from grad_june import GradJune, Timer, ops
+    from grad_june.calibration import Calibrator
+    from grad_june.default_config import default_parameters
+    from grad_june.runner import Runner
+    from grad_june.world import make_synthetic_world
+    n_agents = 50_000
+    params = default_parameters()
+    params["system"]["device"] = DEV
+    params["timer"]["total_days"] = 8
+    params["infection_seed"]["log_fraction_initial_cases"] = -2.0
+    params["policies"] = {}
+    params["save_path"] = str(tmp_path / "out")
+    torch.manual_seed(5)
+    data = Runner.get_data(params, data=make_synthetic_world(n_agents, seed=3, device=DEV, agents_per_super_area=5000))
+    data["agent"].ethnicity = np.array(["A", "B", "C"])[np.arange(n_agents) % 3]
+    model = GradJune.from_parameters(params)
+    runner = Runner(model=model, data=data, timer=Timer.from_parameters(params), log_fraction_initial_cases=-2.0,
+                    save_path=params["save_path"], parameters=params)
+    nets = model.infection_networks.networks
+    truth = float(nets["household"].log_beta) + 0.5
+    start = float(nets["household"].log_beta)
+    nets["household"].log_beta = torch.tensor(truth)
+    with torch.no_grad(), ops.philox_seed(3):
+        target = runner()[0]["cases_per_timestep"].detach().clone()
+    by_eth = runner.get_cases_by_ethnicity(runner.data)
+    inf = runner.data["agent"].is_infected
+    codes = torch.arange(n_agents, device=DEV) % 3
+    assert torch.equal(by_eth, torch.stack([(inf * (codes == k)).sum() for k in range(3)]))
+    nets["household"].log_beta = torch.tensor(start)
+    scale = float(target.max())
+    cal = Calibrator(runner, loss_fn=lambda r: (((r["cases_per_timestep"] - target) / scale) ** 2).mean(),
+                     networks=["household"], lr=0.1, seed=3)
+    history = cal.fit(30)
+    assert history["loss"].iloc[-1] < 0.05 * history["loss"].iloc[0]
+    assert abs(history["log_beta_household"].iloc[-1] - truth) < 0.5 * abs(start - truth)
+    path = cal.save(history)
+    res = pd.read_csv(path / "results.csv")
+    assert list(res.columns[:4]) == ["date", "cases_per_timestep", "daily_cases_per_timestep", "deaths_per_timestep"]
+    assert len(res) == 9 and len(pd.read_csv(path / "results_is_infected.csv")) == n_agents
+    assert len(pd.read_csv(path / "calibration.csv")) == 30
