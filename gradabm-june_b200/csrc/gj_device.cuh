@@ -41,6 +41,23 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// Philox2x32-10 (same family, Random123): one 32x32->64 multiply per round instead of two.  The hot draw of a step
+// needs exactly two words per agent (the two exponentials of the Gumbel-softmax), so it comes from this generator:
+// about half the integer work of a 4x32 block per agent in the forward kernel (Philox was ~18 % of its
+// instructions, profiles/r1_final_56M_stalls_k_pipe_forward.txt).  Known answers: tests/test_host_logic.py.
+__host__ __device__ __forceinline__ void philox2x32_10(uint32_t c0, uint32_t c1, uint32_t k, uint32_t out[2]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    if (r > 0) k += 0x9E3779B9u;
+    const uint64_t p = (uint64_t)0xD256D193u * c0;
+    const uint32_t n0 = (uint32_t)(p >> 32) ^ k ^ c1;
+    c1 = (uint32_t)p;
+    c0 = n0;
+  }
+  out[0] = c0;
+  out[1] = c1;
+}
+
 // uniforms: (0,1) for logs, [0,1) for the Bernoulli comparison
 // (23 bits + 1/2) * 2^-23: exactly representable, so 0 < u < 1 strictly.  (24 bits + 1/2 rounds its largest value to
 // 1.0f: then E = -ln u = 0, its Gumbel is +inf and the reference-order softmax returns NaN — once per 2^24 draws.)
@@ -52,14 +69,19 @@ struct StepNoise {
 };
 
 // The noise of one (agent, call) — THE definition of the stream; forward, backward and gj_philox_fill all come through
-// these functions.  Stream 0, counter = agent: words 0,1 -> the two exponentials of the Gumbel draw (by inversion with
-// the hardware log2), word 2 -> the uniform of the symptomatic / recovery branch (needed only by the few agents whose
-// stage changes in the step).  Stream 1: the standard normal of the dwell time.
+// these functions.  The two exponentials of the Gumbel draw (by inversion with the hardware log2): Philox2x32-10,
+// counter = (agent, call + seed_hi), key = seed_lo (philox_step_pair).  The uniform of the symptomatic / recovery
+// branch (needed only by the few agents whose stage changes in the step): word 2 of the Philox4x32-10 block of
+// stream 0, counter = (agent, call).  Stream 1 of Philox4x32-10: the standard normal of the dwell time.
+// Agent ids are < 2^32 (checked where worlds are built).
 // (One block per PAIR of neighbouring agents, with a thread of the pipelined forward taking both, was built and
 // measured: fewer instructions but slower — the pair's 32-bit stores touch every sector twice, and 64-bit stores of
 // both agents' results spill at the 64-register budget.)
 __device__ __forceinline__ void philox_step_block(uint64_t seed, uint32_t call, uint64_t agent, uint32_t r[4]) {
   philox4x32_10((uint32_t)agent, (uint32_t)(agent >> 32), call, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+}
+__device__ __forceinline__ void philox_step_pair(uint64_t seed, uint32_t call, uint64_t agent, uint32_t r[2]) {
+  philox2x32_10((uint32_t)agent, call + (uint32_t)(seed >> 32), (uint32_t)seed, r);
 }
 __device__ __forceinline__ float draw_step_uniform(uint64_t seed, uint32_t call, int64_t agent) {
   uint32_t r[4];
@@ -72,11 +94,12 @@ __device__ __forceinline__ float draw_step_uniform(uint64_t seed, uint32_t call,
 constexpr float kMinE = 5.9604645e-08f;         // -ln(1 - 2^-24)
 constexpr float kMinE2 = 8.5991327e-08f;        // -log2(1 - 2^-24)
 __device__ __forceinline__ StepNoise draw_step_noise(uint64_t seed, uint32_t call, int64_t agent) {
-  uint32_t r[4];
+  uint32_t r[4], e[2];
+  philox_step_pair(seed, call, (uint64_t)agent, e);
   philox_step_block(seed, call, (uint64_t)agent, r);
   StepNoise n;
-  n.E0 = fmaxf(-__logf(u01_open(r[0])), kMinE);
-  n.E1 = fmaxf(-__logf(u01_open(r[1])), kMinE);
+  n.E0 = fmaxf(-__logf(u01_open(e[0])), kMinE);
+  n.E1 = fmaxf(-__logf(u01_open(e[1])), kMinE);
   n.u = u01_half(r[2]);
   return n;
 }

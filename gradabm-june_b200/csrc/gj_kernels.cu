@@ -1432,4 +1432,6 @@ void gj_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out
   philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
 }
 
+void gj_philox2x32_10(const uint32_t ctr[2], uint32_t key, uint32_t out[2]) { philox2x32_10(ctr[0], ctr[1], key, out); }
+
 }  // extern "C"

@@ -496,7 +496,7 @@ struct FwdRes {   // everything one agent's forward produces
   float tape_v, tape_y0, q, lam, n;
   float s_o, inf_o, tinf_o, cur_o, nxt_o, ttn_o;
 };
-// r0, r1: words 0, 1 of the agent's Philox block (philox_step_block); ga = global agent id
+// r0, r1: the agent's Philox2x32 pair (philox_step_pair); ga = its id in the noise stream
 template <bool kQuar>
 __device__ __forceinline__ FwdRes lean_forward_core(const gj_step_params& p, const LeanPlan& lp,
                                                     const float* __restrict__ stage_prob, uint64_t ga, uint32_t r0,
@@ -552,8 +552,8 @@ __device__ __forceinline__ FwdOut lean_forward_agent(const gj_step_params& p, co
                                                    float s, float inf, float tinf, float cur, float nxt, float ttn,
                                                    int cls, float inv_tau, float dead, float* __restrict__ hist,
                                                    float* __restrict__ deaths) {
-  uint32_t r[4];
-  philox_step_block(p.seed, p.call_index, ga, r);   // ga: the agent's id in the noise stream (noise_agent())
+  uint32_t r[2];
+  philox_step_pair(p.seed, p.call_index, ga, r);   // ga: the agent's id in the noise stream (noise_agent())
   const FwdRes o = lean_forward_core<kQuar>(p, lp, io.stage_prob, ga, r[0], r[1], hs, gv, Lc, beta_r, rpc, s, inf, tinf,
                                             cur, nxt, ttn, cls, inv_tau, dead, hist, deaths);
   io.tape_v[a] = o.tape_v;

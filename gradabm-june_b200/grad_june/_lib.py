@@ -189,6 +189,8 @@ def lib():
     L.gj_philox_fill.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gj_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.gj_philox4x32_10.restype = None
+    L.gj_philox2x32_10.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32)]
+    L.gj_philox2x32_10.restype = None
     L.gj_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
     L.gj_profile_kernel_name.restype = C.c_char_p
     L.gj_boundary_pack.argtypes = [C.c_int64] + [C.c_void_p] * 5
@@ -235,7 +237,7 @@ def check(rc, what):
 EXPORTED_SYMBOLS = [
     "gj_abi_version", "gj_last_error", "gj_config", "gj_scratch_bytes", "gj_profile_prepare", "gj_profile_pack",
     "gj_transmission_forward", "gj_transmission_backward", "gj_step_forward", "gj_step_forward_next", "gj_step_backward",
-    "gj_philox_fill", "gj_philox_fill_at", "gj_step_plan", "gj_philox4x32_10", "gj_profile_enable", "gj_profile_read",
+    "gj_philox_fill", "gj_philox_fill_at", "gj_step_plan", "gj_philox4x32_10", "gj_philox2x32_10", "gj_profile_enable", "gj_profile_read",
     "gj_profile_kernel_name", "gj_pipeline_enable", "gj_boundary_pack", "gj_boundary_unpack",
     "gj_peer_create", "gj_peer_handle", "gj_peer_connect", "gj_peer_exchange", "gj_peer_status", "gj_peer_destroy",
     "gj_world_build", "gj_world_build_host", "gj_world_descriptor", "gj_world_permutation", "gj_world_last_error",

@@ -218,8 +218,9 @@ typedef struct gj_step_params {
   int32_t n_age_bins;
   int32_t age_bins[GJ_MAX_AGE_BINS + 1];
   float tau; /* gumbel-softmax temperature (0.1, infection.py:15) */
-  /* noise: Philox4x32-10 keyed by seed, counter (agent, call_index, stream); ignored where an
-   * injected array is given */
+  /* noise: counter-based Philox keyed by seed, counter (agent, call_index[, stream]) — Philox2x32-10 for the two
+   * exponentials of the draw, Philox4x32-10 for the symptoms' uniform and normal; ignored where an injected array
+   * is given */
   uint64_t seed;
   uint32_t call_index;
   /* 0: with in-kernel Philox noise run the throughput-mode kernels where the step allows it (same arithmetic,
@@ -425,6 +426,8 @@ int gj_philox_fill_at(uint64_t seed, uint32_t call_index, uint64_t first_agent, 
                       void* stream);
 /* raw Philox4x32-10 block for known-answer tests: out[4] = philox(ctr[4], key[2]) (host function) */
 void gj_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* raw Philox2x32-10 block (the generator of the step's two exponentials): out[2] = philox(ctr[2], key) */
+void gj_philox2x32_10(const uint32_t ctr[2], uint32_t key, uint32_t out[2]);
 
 #ifdef __cplusplus
 }

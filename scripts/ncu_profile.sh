@@ -12,10 +12,11 @@ KERNELS='regex:k_lean|k_pipe|k_cell|k_dbeta|k_agent|k_tile|k_group'
 python bench.py $args > gpurun_out/${tag}_plain.json 2> gpurun_out/${tag}_plain.err || { echo "plain run failed"; tail -5 gpurun_out/${tag}_plain.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KERNELS" -c 400 --csv \
     --log-file gpurun_out/${tag}_launches.csv python bench.py $args > gpurun_out/${tag}_ncu1.log 2>&1
-# a window of 4 steps launches 32 throughput-mode agent / group kernels (4 x [transmission, group sums, fix, forward] +
-# 4 x [backward, group sums, fix, gather]): the warm-up window is skipped, the timed window is captured.  Its 2nd and
-# 3rd backward launches are TRUE middle steps (all six state cotangents flow in and out); the 1st has no incoming
-# cotangents and the 4th writes none (the seeding step before it needs no gradient).
-ncu --set full --clock-control none --import-source on -k "regex:k_lean|k_pipe" -s 32 -c 32 -f \
+# a window of 4 steps launches 28 throughput-mode agent / group kernels: 4 x [transmission (+ scatter), scatter
+# finalize, forward] + 4 x [backward, group sums, fix, gather].  Skipped: the warm-up window (28) and the first forward
+# step (3).  Captured (17, the report must stay below gpurun's 64 MiB): three forward steps, then the window's last
+# step's backward (no incoming cotangents) and the backward of its third step — a TRUE middle step (all six state
+# cotangents flow in and out).
+ncu --set full --clock-control none --import-source on -k "regex:k_lean|k_pipe" -s 31 -c 17 -f \
     -o gpurun_out/${tag}_lean_full python bench.py $args > gpurun_out/${tag}_ncu2.log 2>&1
 ls -la gpurun_out/${tag}_*

@@ -46,6 +46,16 @@ def test_philox_known_answers():
     assert philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
 
+    # Philox2x32-10 (the step's two exponentials): Random123 kat_vectors
+    def philox2(ctr, key):
+        c = (ctypes.c_uint32 * 2)(*ctr)
+        out = (ctypes.c_uint32 * 2)()
+        L.gj_philox2x32_10(c, key, out)
+        return list(out)
+    assert philox2([0, 0], 0) == [0xff1dae59, 0x6cd10df2]
+    assert philox2([0xffffffff, 0xffffffff], 0xffffffff) == [0x2c3f628b, 0xab4fd7ad]
+    assert philox2([0x243f6a88, 0x85a308d3], 0x13198a2e) == [0xdd7ce038, 0xf62a4c12]
+
 
 def test_default_config_equals_reference(golden_dir):
     from grad_june.default_config import default_parameters
