@@ -43,12 +43,13 @@ static int bad(const char* what) {
 // ---- optional per-kernel timing with CUDA events on the launching stream (gj_profile_*) -------------
 enum KernelId {
   K_TRANSMISSION = 0, K_GROUP_SMALL_F, K_GROUP_CHUNK_F, K_GROUP_FIX_F, K_AGENT_FWD,
-  K_AGENT_BWD, K_GROUP_SMALL_B, K_GROUP_CHUNK_B, K_GROUP_FIX_B, K_DBETA, K_AGENT_BWD_GATHER, K_CELL, K_OTHER, K_COUNT
+  K_AGENT_BWD, K_GROUP_SMALL_B, K_GROUP_CHUNK_B, K_GROUP_FIX_B, K_DBETA, K_AGENT_BWD_GATHER, K_CELL, K_OTHER, K_SEED,
+  K_EXCHANGE, K_COUNT
 };
 static const char* kKernelNames[K_COUNT] = {
   "transmission", "group_small<fwd>", "group_chunk<fwd>", "group_fix<fwd>", "agent_forward",
   "agent_backward", "group_small<bwd>", "group_chunk<bwd>", "group_fix<bwd>", "dbeta",
-  "backward_gather", "cell_groups+gather", "other"};
+  "backward_gather", "cell_groups+gather", "other", "seeding", "boundary_exchange"};
 constexpr int kMaxProfiled = 16384;
 struct Profiler {
   bool on = false;
@@ -1121,6 +1122,7 @@ int gj_peer_exchange(gj_peer* p, int64_t n_pack, const int32_t* inv, const uint3
     v.flags[r] = r < p->world ? (uint32_t*)(p->mapped[r] + p->flag_off) : nullptr;
   }
   v.ctl = (uint32_t*)(p->own + p->ctl_off);
+  ProfScope ps(K_EXCHANGE, (cudaStream_t)stream);
   k_peer_exchange<<<kPeerBlocks, kPeerThreads, 0, (cudaStream_t)stream>>>(v, n_pack, inv, attend, a, b);
   GJ_CHECK_LAUNCH("k_peer_exchange");
   return 0;
@@ -1249,6 +1251,21 @@ static int step_forward_impl(const gj_world_desc* w, const gj_step_params* p, co
   if (p->mode == GJ_MODE_SEED) {
     pp.phases &= ~GJ_PHASE_NETWORKS;
     if (!io->seed_fraction) return bad("seed_fraction is NULL");
+  }
+  if (p->mode == GJ_MODE_SEED && pp.phases == (GJ_PHASE_SAMPLE | GJ_PHASE_INFECT | GJ_PHASE_SYMPTOMS) &&
+      !p->exact_order && !io->inj_E && !io->inj_u && !io->inj_z && io->s && io->inf && io->tinf && io->cur && io->nxt &&
+      io->ttn && io->tape_y0 && io->stage_prob && io->s_o && io->inf_o && io->tinf_o && io->cur_o && io->nxt_o &&
+      io->ttn_o) {   // Runner.set_initial_cases with in-kernel noise: the throughput-mode seeding kernel
+    ProfScope ps(K_SEED, st);
+    static OccCache occ[2];
+    const bool diag = io->n != nullptr;
+    int64_t g = (N + (int64_t)kLeanThreads * kLeanBatch - 1) / ((int64_t)kLeanThreads * kLeanBatch);
+    gj_world_desc wt = *w;
+    wt.n_tiles = g;   // lean_grid clips the persistent grid to the work available
+    if (diag) k_lean_seed<true><<<lean_grid(&wt, k_lean_seed<true>, &occ[1]), kLeanThreads, 0, st>>>(*w, pp, *io, sc.red_part, sc.tickets);
+    else k_lean_seed<false><<<lean_grid(&wt, k_lean_seed<false>, &occ[0]), kLeanThreads, 0, st>>>(*w, pp, *io, sc.red_part, sc.tickets);
+    GJ_CHECK_LAUNCH("k_lean_seed");
+    return 0;
   }
   if (!(pp.phases & GJ_PHASE_NETWORKS)) {  // stand-alone sampler / infect / symptoms, seeding
     ProfScope ps(K_AGENT_FWD, st);

@@ -503,7 +503,7 @@ __device__ __forceinline__ FwdRes lean_forward_core(const gj_step_params& p, con
                                                     uint32_t r1, float hs, float gv, float Lc, float beta_r, float rpc,
                                                     float s, float inf, float tinf, float cur, float nxt, float ttn,
                                                     int cls, float inv_tau, float dead, float* __restrict__ hist,
-                                                    float* __restrict__ deaths) {
+                                                    float* __restrict__ deaths, float q_seed = -1.0f) {
   FwdRes o;
   const float dE = lg2_fast(fmaxf(-lg2_fast(u01_open(r0)), kMinE2)) - lg2_fast(fmaxf(-lg2_fast(u01_open(r1)), kMinE2));
   const float rv = (beta_r * rpc) * hs;
@@ -512,7 +512,8 @@ __device__ __forceinline__ FwdRes lean_forward_core(const gj_step_params& p, con
   const float mq = kQuar ? quar_mask(p, cur) : 1.0f;
   const float X = fmaf(mq, plain, house);  // pressure per unit susceptibility
   const float lam = X * s;
-  const float q = not_infected_prob(lam, p.dt);
+  // q_seed >= 0: the seeding step (infect_fraction_of_people, infection.py:31-42): a uniform q = 1 - fraction
+  const float q = (q_seed >= 0.0f) ? q_seed : not_infected_prob(lam, p.dt);
   o.tape_v = (s == 0.0f) ? X : lam;
   // Gumbel-softmax hard draw from Philox bits (same stream as draw_step_noise):
   // x0 - x1 = (ln2 / tau) * d,  d = lg2 q - lg2(1-q) - lg2 E0 + lg2 E1, E = -ln u (the ln2 factors cancel)
@@ -696,6 +697,83 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_LEAN_MINB_FWD) k_lean_forward
       } else {
         const int b = threadIdx.x - 2;
         for (int c = max(p.age_bins[b] + 1, 0); c < p.age_bins[b + 1] && c < 100; ++c) v += (double)sh.hist[c];
+      }
+      red_part[(int64_t)blockIdx.x * kMaxRed + threadIdx.x] = v;
+    }
+    finish_partials<kMaxRed>(nr, red_part, gridDim.x, ticket, io.red);
+  }
+}
+
+// =====================================================================================================
+// seeding step in throughput mode (GJ_MODE_SEED with in-kernel noise): sample with q = 1 - fraction, infect (clamp
+// variant: same values), first symptoms update, reductions — the arithmetic of lean_forward_core without networks.
+// Replaces the generic k_agent_forward (IEEE libm, 1.45 ms per window at 56 M agents) for Runner.set_initial_cases.
+// =====================================================================================================
+template <bool kDiag>
+__global__ void __launch_bounds__(kLeanThreads, 4) k_lean_seed(gj_world_desc w, gj_step_params p, gj_fwd_io io,
+                                                              double* __restrict__ red_part,
+                                                              unsigned int* __restrict__ ticket) {
+  __shared__ float hist[100];
+  __shared__ float deaths;
+  if (threadIdx.x < 100) hist[threadIdx.x] = 0.0f;
+  if (threadIdx.x == 0) deaths = 0.0f;
+  __syncthreads();
+  LeanPlan lp;
+  lp.r_house = 0;
+  const float q_seed = 1.0f - io.seed_fraction[0] * 1.0f;
+  const float dead = (float)(p.n_stages - 1);
+  const float inv_tau = 1.0f / p.tau;
+  const uint32_t N = (uint32_t)w.n_agents;
+  const uint32_t stride = gridDim.x * kLeanThreads * kLeanBatch;
+  for (uint32_t base = blockIdx.x * kLeanThreads * kLeanBatch + threadIdx.x; base < N; base += stride) {
+    float s[kLeanBatch], inf[kLeanBatch], tinf[kLeanBatch], cur[kLeanBatch], nxt[kLeanBatch], ttn[kLeanBatch];
+    uint32_t oid[kLeanBatch];
+    int cls[kLeanBatch];
+#pragma unroll
+    for (int h = 0; h < kLeanBatch; ++h) {
+      const uint32_t a = base + h * kLeanThreads;
+      const uint32_t al = a < N ? a : 0u;
+      s[h] = io.s[al];
+      inf[h] = io.inf[al];
+      tinf[h] = io.tinf[al];
+      cur[h] = io.cur[al];
+      nxt[h] = io.nxt[al];
+      ttn[h] = io.ttn[al];
+      cls[h] = w.cls ? w.cls[al] : 0;
+      oid[h] = w.orig_id ? w.orig_id[al] : 0u;
+    }
+#pragma unroll
+    for (int h = 0; h < kLeanBatch; ++h) {
+      const uint32_t a = base + h * kLeanThreads;
+      if (a >= N) break;
+      const uint64_t ga = w.orig_id ? (uint64_t)oid[h] : p.agent_offset + a;
+      uint32_t r[2];
+      philox_step_pair(p.seed, p.call_index, ga, r);
+      const FwdRes o = lean_forward_core<false>(p, lp, io.stage_prob, ga, r[0], r[1], 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, s[h],
+                                                inf[h], tinf[h], cur[h], nxt[h], ttn[h], cls[h], inv_tau, dead, hist,
+                                                &deaths, q_seed);
+      io.tape_y0[a] = o.tape_y0;
+      if (kDiag && io.n) io.n[a] = o.n;
+      io.s_o[a] = o.s_o;
+      io.inf_o[a] = o.inf_o;
+      io.tinf_o[a] = o.tinf_o;
+      io.cur_o[a] = o.cur_o;
+      io.nxt_o[a] = o.nxt_o;
+      io.ttn_o[a] = o.ttn_o;
+    }
+  }
+  if (io.red) {
+    __syncthreads();
+    const int nr = 2 + p.n_age_bins;
+    if ((int)threadIdx.x < nr) {
+      double v = 0.0;
+      if (threadIdx.x == 0) {
+        for (int c = 0; c < 100; ++c) v += (double)hist[c];
+      } else if (threadIdx.x == 1) {
+        v = (double)deaths;
+      } else {
+        const int b = threadIdx.x - 2;
+        for (int c = max(p.age_bins[b] + 1, 0); c < p.age_bins[b + 1] && c < 100; ++c) v += (double)hist[c];
       }
       red_part[(int64_t)blockIdx.x * kMaxRed + threadIdx.x] = v;
     }

@@ -258,7 +258,7 @@ def profile_enable(on=True):
 
 def profile_read():
     """{kernel name: (summed ms, timed launches, launches)} since profile_enable()."""
-    n = 16
+    n = 24
     ms, timed, launches = (C.c_double * n)(), (C.c_int64 * n)(), (C.c_int64 * n)()
     k = lib().gj_profile_read(ms, timed, launches, n)
     if k < 0:
