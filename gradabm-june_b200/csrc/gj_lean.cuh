@@ -269,10 +269,10 @@ __device__ __forceinline__ float quar_mask(const gj_step_params& p, float cur) {
 //     is walked cell by cell ("segments"); a segment's partial sums are written to its first tile and zeros to its
 //     other tiles: k_cell_groups adds a cell's tiles, so the per-cell totals are unchanged.
 // =====================================================================================================
-constexpr int kK1Batch = 8;
+constexpr int kK1Batch = 4;
 
 template <bool kQuar>
-__global__ void __launch_bounds__(kLeanThreads, kQuar ? 5 : 6) k_lean_transmission(gj_world_desc w, gj_step_params p, LeanPlan lp,
+__global__ void __launch_bounds__(kLeanThreads, 4) k_lean_transmission(gj_world_desc w, gj_step_params p, LeanPlan lp,
                                                                     gj_fwd_io io, float* __restrict__ tile_part,
                                                                     Scatter sct) {
   __shared__ ProbRow prob[200];
@@ -296,21 +296,36 @@ __global__ void __launch_bounds__(kLeanThreads, kQuar ? 5 : 6) k_lean_transmissi
         inf[h] = (a < a1) ? g_inf[a] : 0.0f;
         cur[h] = (kQuar && a < a1) ? g_cur[a] : 0.0f;
       }
+      // the infectious few: ALL their dependent loads (infection time, packed profile, group word, class) are issued
+      // before the first use — one exposed DRAM latency per batch instead of one per infectious agent
+      float tinf[kK1Batch];
+      float4 pf[kK1Batch];
+      uint32_t ent[kK1Batch];
+      int cls[kK1Batch];
+#pragma unroll
+      for (int h = 0; h < kK1Batch; ++h) {
+        const uint32_t a = base + h * kLeanThreads;
+        const bool on = inf[h] != 0.0f;   // false beyond a1
+        tinf[h] = on ? io.tinf[a] : 0.0f;
+        pf[h] = on ? prof[a] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        ent[h] = (on && lp.has_generic) ? w.ent1[a] : kEntNone;
+        cls[h] = (on && lp.n_cell > 0) ? (int)w.cls[a] : 0;
+      }
 #pragma unroll
       for (int h = 0; h < kK1Batch; ++h) {
         const uint32_t a = base + h * kLeanThreads;
         if (a >= a1) break;
         float T = 0.0f;
-        if (inf[h] != 0.0f) T = lean_transmission<false>(p.now, io.tinf[a], prof[a]).coef * inf[h];
+        if (inf[h] != 0.0f) T = lean_transmission<false>(p.now, tinf[h], pf[h]).coef * inf[h];
         io.T[a] = T;
         float Tq = T;
         if (kQuar) {
           Tq = quar_mask(p, cur[h]) * T;
           io.Tq[a] = Tq;
         }
-        if (Tq != 0.0f) {   // the infectious few: cell-channel partial sums and the generic groups' accumulators
-          if (lp.n_cell > 0) lean_channel_fma(acc, prob, w.cls[a], Tq, lp.n_cell);
-          if (lp.has_generic) lean_scatter(w, sct, w.ent1[a], a, Tq);
+        if (Tq != 0.0f) {   // cell-channel partial sums and the generic groups' accumulators
+          if (lp.n_cell > 0) lean_channel_fma(acc, prob, cls[h], Tq, lp.n_cell);
+          if (lp.has_generic) lean_scatter(w, sct, ent[h], a, Tq);
         }
       }
     }
