@@ -218,7 +218,8 @@ class BoundaryExchange:
         for ti, t in enumerate(world.types):
             w[world.type_group_off[ti]:world.type_group_off[ti + 1]] = part.owned[t].to(dev, torch.float32)
         world.dbeta_w = w
-        world.__dict__.pop("_desc", None)   # the descriptor carries the pointer
+        if not hasattr(world, "handle"):
+            world.__dict__.pop("_desc", None)   # the descriptor carries the pointer (a native world patches its own)
 
     def regions(self, lean: bool, gen_base: int, nets):
         """(index into the group-sum buffers, index into the packed buffer, packed length) for this step:

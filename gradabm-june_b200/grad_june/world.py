@@ -726,9 +726,25 @@ class NativeWorld:
             raise _lib.GradJuneLibraryError(f"gj_world_build failed ({rc}): {L.gj_world_last_error().decode()}")
         self._lib, self.handle, self.device, self.host, self.types, self.n_agents = L, handle, dev, host, types, n
         self._desc = L.gj_world_descriptor(handle).contents
+        # what grad_june.ops / partition read from a world object (so that a native world can be stepped like a
+        # DeviceWorld: get_device_world(..., native=True))
+        d = self._desc
+        self.n_groups, self.n_edges = int(d.n_groups), int(d.n_edges)
+        self.type_group_off = [int(d.type_group_off[i]) for i in range(len(types) + 1)]
+        self.type_tier = [int(d.type_tier[i]) for i in range(len(types))]
+        self.orig_id = self.array("orig_id", n) if d.orig_id else None
 
     def desc(self):
         return self._desc
+
+    @property
+    def dbeta_w(self):
+        return self.__dict__.get("_dbeta_w")
+
+    @dbeta_w.setter
+    def dbeta_w(self, t):       # partitioned worlds: the per-group ownership weights live with the caller
+        self.__dict__["_dbeta_w"] = t
+        self._desc.dbeta_w = t.data_ptr()
 
     def permutation(self):
         """perm[new] = old of the renumbering the build applied (int64 tensor on the build's device), None = identity."""
@@ -779,9 +795,15 @@ class _NullContext:
         return False
 
 
-def get_device_world(data: HeteroData, device, small_group: Optional[int] = None, chunk: Optional[int] = None):
+def get_device_world(data: HeteroData, device, small_group: Optional[int] = None, chunk: Optional[int] = None,
+                     native: Optional[bool] = None):
     """CSR layout of ``data`` on ``device``; cached on the world object and rebuilt when an edge list,
-    ``people`` or the agent attributes are replaced (identity + version check)."""
+    ``people`` or the agent attributes are replaced (identity + version check).  ``native`` (default: the
+    environment variable GJ_NATIVE_BUILD=1): build it with the C-ABI builder ``gj_world_build`` instead of the torch
+    code below (identical arrays, tests/test_world_build.py)."""
+    import os
+    if native is None:
+        native = os.environ.get("GJ_NATIVE_BUILD", "0") == "1"
     cache = data.__dict__.setdefault("_gj_cache", {})
     if cache.get("frozen") == str(device):
         return cache["world"]
@@ -802,6 +824,12 @@ def get_device_world(data: HeteroData, device, small_group: Optional[int] = None
         cfg = _lib.config()
         small_group, chunk = cfg["small_group"], cfg["chunk"]
     n = len(data["agent"].id)
+    if native and torch.device(device).type == "cuda":
+        world = NativeWorld(data, device=device, renumber=False, want_tiers=agreed_tiers(data, device))
+        cache["sig"] = sig
+        cache["world"] = world
+        cache.pop("scratch", None)
+        return world
     world = build_csr(
         n, types,
         {t: data["attends_" + t].edge_index for t in types},

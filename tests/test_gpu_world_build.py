@@ -173,3 +173,25 @@ def test_c_abi_only_build_and_step_of_the_sample_world(golden_dir):
         assert np.array_equal(orig(outs[k]), ost[name].numpy()), name
     assert red[0].item() == ost["is_infected"].sum().item()
     assert L.gj_world_destroy(world) == 0
+
+
+def test_runner_on_the_native_world_is_bit_identical(monkeypatch):
+    """The whole drop-in path (Runner on the renumbered sample world, Philox mode, backward) with the world built by
+    gj_world_build instead of the torch builder: identical arrays, so bit-identical results and gradients."""
+    from grad_june import ops
+    from grad_june.world import NativeWorld, get_device_world
+    from gpu_helpers import make_runner
+    outs = []
+    for native in ("0", "1"):
+        monkeypatch.setenv("GJ_NATIVE_BUILD", native)
+        runner, g, params = make_runner("sample_policies", DEV, renumber=True)
+        assert isinstance(get_device_world(runner.data, DEV), NativeWorld) == (native == "1")
+        with ops.philox_seed(5):
+            results, is_inf = runner()
+        (results["cases_per_timestep"].sum() + results["deaths_per_timestep"].sum()).backward()
+        nets = runner.model.infection_networks.networks
+        outs.append((results["cases_per_timestep"].detach().clone(), is_inf.detach().clone(),
+                     torch.stack([nets[k].log_beta.grad for k in nets.keys()]).clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert outs[0][0][-1] > outs[0][0][0]
