@@ -108,40 +108,34 @@ __device__ __forceinline__ float pipe_range_sum(const float* __restrict__ Ts, ui
 // CTA-uniform dependent global loads that every warp sat out right after the barrier (ncu: 10-14 % of the stall
 // samples of the three kernels); issued a tile early, their latency hides behind the tile's arithmetic.
 struct TileWalk {
-  uint32_t a0, a1;   // the current tile's agents [a0, a1)
-  bool new_cell;     // it starts a new cell (or the CTA's run): rebuild the class table
-  bool flush;        // it ends a cell (or the run): write the partial sums of the cell channels
-  uint32_t nxt_a1;   // prefetched: end of the following tile
-  bool nxt_new;      // prefetched: the following tile starts a new cell
+  uint32_t a1;       // end of the current tile (= start of the following one)
+  // prefetched RAW, consumed one tile later (no compare or select at load time: that would wait for the load right
+  // away, which is what made these CTA-uniform loads 17 % of the forward kernel's stall samples and 11 % of its
+  // instructions in profiles/r2_56M_stalls_k_pipe_forward.txt):
+  uint32_t nxt_a1;   // end of the following tile
+  uint32_t nxt_flag; // gj_world_desc.tile_flags of the following tile (bit 0: it starts a new cell)
 };
 __device__ __forceinline__ TileWalk tile_walk_begin(const gj_world_desc& w, const LeanPlan& lp, const TileRun& run) {
   TileWalk t;
-  t.a0 = t.a1 = t.nxt_a1 = 0;
-  t.new_cell = t.flush = t.nxt_new = false;
+  t.a1 = t.nxt_a1 = 0;
+  t.nxt_flag = 1u;                      // the run's first tile always builds its class table
   if (run.t0 < run.t1) {
-    t.a1 = w.tile_begin[run.t0];        // shifted into a0 by the first tile_walk_next
+    t.a1 = w.tile_begin[run.t0];
     t.nxt_a1 = w.tile_begin[run.t0 + 1];
-    t.nxt_new = lp.n_cell > 0;
   }
   return t;
 }
-// top of tile `tile`: take the prefetched facts, issue the loads of the following tile's
-__device__ __forceinline__ void tile_walk_next(TileWalk& t, const gj_world_desc& w, const LeanPlan& lp,
-                                               const TileRun& run, int64_t tile) {
-  t.a0 = t.a1;
-  t.a1 = t.nxt_a1;
-  t.new_cell = t.nxt_new;
-  const bool last = tile + 1 == run.t1;
-  t.nxt_a1 = last ? t.a1 : w.tile_begin[tile + 2];
-  t.nxt_new = !last && lp.n_cell > 0 && lean_new_cell(lp, tile, tile + 1);
-  t.flush = lp.n_cell > 0 && (last || t.nxt_new);
-}
-#define PIPE_TILE_FACTS                              \
-  tile_walk_next(tw, w, lp, run, tile);              \
-  const uint32_t a0 = tw.a0, a1 = tw.a1;             \
-  const bool new_cell = tw.new_cell, flush = tw.flush; \
-  (void)new_cell;                                    \
-  (void)flush
+// top of tile `tile`: take the facts prefetched a tile ago, issue the loads of the following tile's.  Both arrays carry
+// readable slack behind their last element, so the loads need no bounds branch (past the run's end they are unused).
+#define PIPE_TILE_FACTS                                                   \
+  const uint32_t a0 = tw.a1, a1 = tw.nxt_a1;                              \
+  const bool new_cell = lp.n_cell > 0 && (tw.nxt_flag & 1u);              \
+  (void)new_cell;                                                         \
+  tw.a1 = a1;                                                             \
+  tw.nxt_flag = w.tile_flags[tile + 1];                                   \
+  tw.nxt_a1 = w.tile_begin[tile + 2]
+// does the current tile end a cell (or the run)?  Evaluated at the END of the tile, from the flag loaded at its top.
+#define PIPE_FLUSH(tw, lp) ((lp).n_cell > 0 && (tile + 1 == run.t1 || ((tw).nxt_flag & 1u)))
 
 // end of a tile: every warp is done with the stage, one thread refills it with the tile kPipeStages ahead.
 // (Letting the last warp to finish do the refill instead of a CTA barrier, and shipping the tile facts with the
@@ -469,7 +463,7 @@ __global__ void __launch_bounds__(kBwdThreads, kBwdCtas) k_pipe_backward(gj_worl
       parity ^= 1u;
     }
     if (lp.n_cell > 0) {   // partial sums of the cell channels: written at the last tile of a cell run (see K1)
-      if (flush) {
+      if (PIPE_FLUSH(tw, lp)) {
         block_sums<float, GJ_MAX_CHANNELS, (kBwdThreads / 32)>(acc, lp.n_cell, tile_part + tile * GJ_MAX_CHANNELS);
 #pragma unroll
         for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;

@@ -29,6 +29,8 @@
 #include <thrust/gather.h>
 #include <thrust/host_vector.h>
 #include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/zip_iterator.h>
+#include <thrust/tuple.h>
 #include <thrust/reduce.h>
 #include <thrust/scan.h>
 #include <thrust/scatter.h>
@@ -178,7 +180,7 @@ struct World {
   using vec = typename B::template vec<T>;
   gj_world_desc desc;
   vec<uint32_t> am_ptr, am_ent, gm_ptr, gm_agent, small_groups, chunk_group, chunk_begin, chunk_end, big_groups,
-      big_part_ptr, tile_begin, ent1, orig_id;
+      big_part_ptr, tile_begin, tile_flags, ent1, orig_id;
   vec<int32_t> chunk_part;
   vec<float> pc;
   vec<uint8_t> cls;
@@ -624,6 +626,8 @@ static int build(const gj_world_src* s, World<B>* W) {
     tile_begin = I64(1, 0);
   }
   const int64_t n_tiles = (int64_t)tile_begin.size() - 1;
+  I64 tile_flags(n_tiles, 0);
+  if (n_tiles > 0) tile_flags[0] = 1;
   int64_t cell_off = 0;
   for (int t = 0; t < nt; ++t) {
     d.type_tier[t] = tier[t];
@@ -634,7 +638,14 @@ static int build(const gj_world_src* s, World<B>* W) {
     } else if (tier[t] == GJ_TIER_CELL) {
       auto& c = cells[t];
       I64 tb0(tile_begin.begin(), tile_begin.end() - 1);
-      W->tile_cell[t] = Bd::to_u32(O::gather(c.cell_of_agent, tb0));
+      I64 tc = O::gather(c.cell_of_agent, tb0);
+      if (n_tiles > 1)
+        thrust::transform(thrust::make_zip_iterator(thrust::make_tuple(tc.begin() + 1, tc.begin(), tile_flags.begin() + 1)),
+                          thrust::make_zip_iterator(thrust::make_tuple(tc.end(), tc.end() - 1, tile_flags.end())),
+                          tile_flags.begin() + 1, [] __host__ __device__(thrust::tuple<int64_t, int64_t, int64_t> x) {
+                            return thrust::get<2>(x) | (int64_t)(thrust::get<0>(x) != thrust::get<1>(x));
+                          });
+      W->tile_cell[t] = Bd::to_u32(tc);
       I64 ctp = O::searchsorted_left(tb0, c.cell_start);
       ctp.push_back(n_tiles);
       W->cell_tile_ptr[t] = Bd::to_u32(ctp);
@@ -662,7 +673,8 @@ static int build(const gj_world_src* s, World<B>* W) {
   W->chunk_end = Bd::to_u32(chunk_end);
   W->big_groups = Bd::to_u32(big_groups);
   W->big_part_ptr = Bd::to_u32(big_part_ptr);
-  W->tile_begin = Bd::to_u32(tile_begin);
+  W->tile_begin = Bd::to_u32(tile_begin, 4);
+  W->tile_flags = Bd::to_u32(tile_flags, 4);
   if (!orig.empty()) W->orig_id = Bd::to_u32(orig, 32);
 
   d.n_agents = n;
@@ -689,6 +701,7 @@ static int build(const gj_world_src* s, World<B>* W) {
   d.n_parts = n_parts;
   d.n_tiles = n_tiles;
   d.tile_begin = Bd::raw(W->tile_begin);
+  d.tile_flags = Bd::raw(W->tile_flags);
   d.ent1 = Bd::raw(W->ent1);
   d.n_giant_chunks = n_giant_chunks;
   d.n_giant_big = n_giant_big;

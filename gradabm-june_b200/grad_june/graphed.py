@@ -33,6 +33,13 @@ class GraphedRunner:
         self.device = agent.susceptibility.device
         init = [float(torch.as_tensor(nets[k].log_beta).detach().reshape(-1)[0]) for k in self.names]
         self.log_beta = torch.tensor(init, dtype=torch.float32).to(self.device).requires_grad_(True)
+        # the networks that are NOT calibrated keep their log-betas as constants of the graph: they must already
+        # live on the device (a host-to-device copy cannot be captured)
+        for k, net in nets.items():
+            if k not in self.names:
+                value = torch.as_tensor(net.log_beta).detach().to(device=self.device, dtype=torch.float32)
+                net._parameters.pop("log_beta", None)
+                net.log_beta = value
         self.warmup = warmup
         self.graph = None
         self.recapture(seed)

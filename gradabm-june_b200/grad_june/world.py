@@ -260,7 +260,8 @@ class DeviceWorld:
         for i, off in enumerate(self.type_group_off):
             d.type_group_off[i] = off
         for name in ("am_ptr", "am_ent", "gm_ptr", "gm_agent", "pc", "cls", "small_groups", "chunk_group",
-                     "chunk_begin", "chunk_end", "chunk_part", "big_groups", "big_part_ptr", "tile_begin", "ent1"):
+                     "chunk_begin", "chunk_end", "chunk_part", "big_groups", "big_part_ptr", "tile_begin", "tile_flags",
+                     "ent1"):
             setattr(d, name, getattr(self, name).data_ptr())
         d.n_small, d.n_chunks = self.small_groups.numel(), self.chunk_group.numel()
         d.n_big, d.n_parts = self.big_groups.numel(), self.n_parts
@@ -661,6 +662,12 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
     tw = torch.arange(int(ntile.sum()), device=dev) - torch.repeat_interleave(tfirst[:-1], ntile)
     tile_begin = torch.cat((torch.repeat_interleave(seg_start, ntile) + tw * TILE_AGENTS,
                             torch.tensor([n_agents], device=dev)))
+    tile_flags = torch.zeros(tile_begin.numel() - 1, dtype=torch.long, device=dev)
+    if tile_flags.numel():
+        tile_flags[0] = 1
+    for ti, c in cells.items():
+        tc = c["cell_of_agent"][tile_begin[:-1]]
+        tile_flags[1:] |= (tc[1:] != tc[:-1]).long()
     for ti, c in cells.items():
         c["tile_cell"] = _u32(c["cell_of_agent"][tile_begin[:-1]])
         c["cell_tile_ptr"] = _u32(torch.cat((torch.searchsorted(tile_begin[:-1].contiguous(), c["cell_start"]),
@@ -674,7 +681,8 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
         gm_agent=gm_agent.contiguous(), pc=pc.contiguous(), cls=_padded(cls.contiguous(), 64), small_groups=_u32(small),
         chunk_group=_u32(chunk_group), chunk_begin=_u32(chunk_begin), chunk_end=_u32(chunk_end),
         chunk_part=chunk_part.to(torch.int32), big_groups=_u32(big_groups), big_part_ptr=_u32(big_part_ptr),
-        n_parts=n_parts, tile_begin=_u32(tile_begin), ent1=_padded(_u32(ent1)), device=dev,
+        n_parts=n_parts, tile_begin=_padded(_u32(tile_begin), 4), tile_flags=_padded(_u32(tile_flags), 4),
+        ent1=_padded(_u32(ent1)), device=dev,
         orig_id=None if orig_id is None else _padded(_u32(orig_id.to(dev))),
         n_giant_chunks=n_giant_chunks, n_giant_big=n_giant_big,
     )

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GJ_ABI_VERSION 6
+#define GJ_ABI_VERSION 7
 
 #define GJ_MAX_TYPES 8      /* edge types (household, company, school, university, care_home, leisure, ...) */
 #define GJ_MAX_NETS 16      /* infection networks active in one step */
@@ -126,6 +126,9 @@ typedef struct gj_world_desc {
    * GJ_TILE_AGENTS, never straddling a cell boundary of a CELL-tier type */
   int64_t n_tiles;
   const uint32_t* tile_begin;
+  /* [n_tiles] bit 0: the tile lies in another cell (of any CELL-tier type) than the tile before it; tile 0 has it set.
+   * What the pipelined kernels' tile walk prefetches instead of comparing the tile -> cell maps per tile */
+  const uint32_t* tile_flags;
   /* CELL tier: runs of consecutive agents with the same ordered group list */
   int64_t n_cells[GJ_MAX_TYPES];
   int64_t cell_off[GJ_MAX_TYPES]; /* offset of the type's cells in per-cell buffers */

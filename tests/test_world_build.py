@@ -33,7 +33,7 @@ def _compare(native, ref, types):
     for name, count in (("am_ptr", n + 1), ("am_ent", E), ("gm_ptr", G + 1), ("gm_agent", E), ("small_groups", d.n_small),
                         ("chunk_group", d.n_chunks), ("chunk_begin", d.n_chunks), ("chunk_end", d.n_chunks),
                         ("chunk_part", d.n_chunks), ("big_groups", d.n_big), ("big_part_ptr", d.n_big + 1),
-                        ("tile_begin", d.n_tiles + 1), ("ent1", n)):
+                        ("tile_begin", d.n_tiles + 1), ("tile_flags", d.n_tiles), ("ent1", n)):
         mine = native.array(name, count)
         assert torch.equal(mine, getattr(ref, name)[:count].cpu().to(torch.int32)), name
     assert torch.equal(native.array("pc", G, torch.float32), ref.pc.cpu())
