@@ -372,6 +372,8 @@ struct PipeBwdShared {
   PipeBwdStage st[kPipeStages];
   ProbRow prob[200];
   float gred_age[100];
+  uint32_t next_flag[kPipeStages];   // tile_flags of the tile AFTER the one in the stage (thread 0 fetches it at the
+                                     // tile's top; read after the end-of-tile barrier: no register, no exposed load)
   alignas(8) uint64_t full[kPipeStages];
 };
 struct BwdCot {
@@ -432,10 +434,15 @@ __global__ void __launch_bounds__(kBwdThreads, kBwdCtas) k_pipe_backward(gj_worl
   for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
   int stg = 0;
   uint32_t parity = 0;
-  TileWalk tw = tile_walk_begin(w, lp, run);
+  // this kernel runs at its register cap: the tile bounds are prefetched raw as in the other two kernels, the cell flag
+  // of the following tile goes through shared memory instead of living in a register across the tile
+  uint32_t w_a1 = run.t0 < run.t1 ? w.tile_begin[run.t0] : 0u, w_nxt = run.t0 < run.t1 ? w.tile_begin[run.t0 + 1] : 0u;
   for (int64_t tile = run.t0; tile < run.t1; ++tile) {
     PipeBwdStage& sg = sh.st[stg];
-    PIPE_TILE_FACTS;
+    const uint32_t a0 = w_a1, a1 = w_nxt;
+    w_a1 = a1;
+    w_nxt = w.tile_begin[tile + 2];
+    if (threadIdx.x == 0 && lp.n_cell > 0) sh.next_flag[stg] = w.tile_flags[tile + 1];
     mbar_wait(&sh.full[stg], parity);
     // the cotangents of the state outputs stream through registers
     float c[kBwdPer][6];
@@ -458,12 +465,13 @@ __global__ void __launch_bounds__(kBwdThreads, kBwdCtas) k_pipe_backward(gj_worl
     }
     if (pipe_release() && tile + kPipeStages < run.t1)
       pipe_bwd_issue(sg, &sh.full[stg], w, io, tile + kPipeStages);
+    const bool ends_cell = lp.n_cell > 0 && (tile + 1 == run.t1 || (sh.next_flag[stg] & 1u));   // after the barrier
     if (++stg == kPipeStages) {
       stg = 0;
       parity ^= 1u;
     }
     if (lp.n_cell > 0) {   // partial sums of the cell channels: written at the last tile of a cell run (see K1)
-      if (PIPE_FLUSH(tw, lp)) {
+      if (ends_cell) {
         block_sums<float, GJ_MAX_CHANNELS, (kBwdThreads / 32)>(acc, lp.n_cell, tile_part + tile * GJ_MAX_CHANNELS);
 #pragma unroll
         for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
