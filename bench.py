@@ -171,6 +171,11 @@ def cpu_reference_run(n_agents, steps, repeats=1, policies=False):
 def run_reference_arm(args, rank, world_size):
     if rank != 0:
         return
+    # every host thread this process may use (torchrun pins OMP_NUM_THREADS=1 per rank: the other ranks do no work here)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     n_sample = args.cpu_agents
     # warm-up
     for _ in range(max(args.warmup, 0) and 1):
