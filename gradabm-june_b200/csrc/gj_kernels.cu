@@ -926,7 +926,10 @@ __global__ void __launch_bounds__(kBlock) k_boundary_unpack(int64_t n, const int
 // receive buffer of one rank: [2 sets][world_size sources][2 arrays][capacity] floats, then the flags
 // [2 sets][world_size] uint32, then {exchange counter, ticket A, ticket B, error} uint32
 constexpr int kPeerBlocks = 148;     // co-resident by construction: blocks wait on flags other GPUs raise
-constexpr int kPeerThreads = 256;
+constexpr int kPeerThreads = 1024;   // one CTA per SM: the SMs are idle between the two stages of a step anyway
+constexpr int kPeerBatch = 4;        // packed groups a thread keeps in flight (the loop is a chain of dependent loads:
+                                     // inv -> a[j], b[j] -> remote store; 256 threads x 1 in flight measured 61 us per
+                                     // exchange of 655 k groups at 8 GPUs, profiles/r2_bench_56M_n8_strong_run14.json)
 struct PeerView {
   int rank, world;
   int64_t cap;
@@ -947,17 +950,34 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_exchange(PeerView v, int6
   const uint32_t e = s_epoch, set = e & 1u;
   const uint32_t me = 1u << v.rank;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t q0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   // ---- push: my partial sums into the receive buffers of the other ranks attending each group ---------------
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
-    const int32_t j = inv[q];
-    if (j < 0) continue;
-    const float va = a[j], vb = b[j];
-    uint32_t m = attend[q] & ~me;
-    while (m) {
-      const int dst = __ffs(m) - 1;
-      m &= m - 1;
-      peer_slot(v, dst, set, v.rank, 0)[q] = va;
-      peer_slot(v, dst, set, v.rank, 1)[q] = vb;
+  for (int64_t base = q0; base < n; base += stride * kPeerBatch) {
+    int32_t j[kPeerBatch];
+    uint32_t m[kPeerBatch];
+    float va[kPeerBatch], vb[kPeerBatch];
+#pragma unroll
+    for (int h = 0; h < kPeerBatch; ++h) {
+      const int64_t q = base + h * stride;
+      j[h] = q < n ? inv[q] : -1;
+      m[h] = q < n ? (attend[q] & ~me) : 0u;
+    }
+#pragma unroll
+    for (int h = 0; h < kPeerBatch; ++h) {
+      va[h] = j[h] >= 0 ? a[j[h]] : 0.0f;
+      vb[h] = j[h] >= 0 ? b[j[h]] : 0.0f;
+    }
+#pragma unroll
+    for (int h = 0; h < kPeerBatch; ++h) {
+      if (j[h] < 0) continue;
+      const int64_t q = base + h * stride;
+      uint32_t mm = m[h];
+      while (mm) {
+        const int dst = __ffs(mm) - 1;
+        mm &= mm - 1;
+        peer_slot(v, dst, set, v.rank, 0)[q] = va[h];
+        peer_slot(v, dst, set, v.rank, 1)[q] = vb[h];
+      }
     }
   }
   __threadfence_system();
@@ -977,7 +997,7 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_exchange(PeerView v, int6
     unsigned long long t0 = 0, t1 = 0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (*f != e) {
-      __nanosleep(64);
+      __nanosleep(32);
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       if (t1 - t0 > 10000000000ull) {   // ~10 s: a peer is gone; give up rather than hang the GPU
         v.ctl[3] = 1u;
@@ -988,24 +1008,41 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_exchange(PeerView v, int6
   __threadfence_system();
   __syncthreads();
   // ---- reduce in ascending rank order (my own term in its place): identical on every rank -------------------
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
-    const int32_t j = inv[q];
-    if (j < 0) continue;
-    uint32_t m = attend[q];
-    float sa = 0.0f, sb = 0.0f;
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      if (src == v.rank) {
-        sa += a[j];
-        sb += b[j];
-      } else {
-        sa += __ldcg(peer_slot(v, v.rank, set, src, 0) + q);
-        sb += __ldcg(peer_slot(v, v.rank, set, src, 1) + q);
-      }
+  for (int64_t base = q0; base < n; base += stride * kPeerBatch) {
+    int32_t j[kPeerBatch];
+    uint32_t m[kPeerBatch];
+    float oa[kPeerBatch], ob[kPeerBatch];
+#pragma unroll
+    for (int h = 0; h < kPeerBatch; ++h) {
+      const int64_t q = base + h * stride;
+      j[h] = q < n ? inv[q] : -1;
+      m[h] = q < n ? attend[q] : 0u;
     }
-    a[j] = sa;
-    b[j] = sb;
+#pragma unroll
+    for (int h = 0; h < kPeerBatch; ++h) {
+      oa[h] = j[h] >= 0 ? a[j[h]] : 0.0f;
+      ob[h] = j[h] >= 0 ? b[j[h]] : 0.0f;
+    }
+#pragma unroll
+    for (int h = 0; h < kPeerBatch; ++h) {
+      if (j[h] < 0) continue;
+      const int64_t q = base + h * stride;
+      uint32_t mm = m[h];
+      float sa = 0.0f, sb = 0.0f;
+      while (mm) {
+        const int src = __ffs(mm) - 1;
+        mm &= mm - 1;
+        if (src == v.rank) {
+          sa += oa[h];
+          sb += ob[h];
+        } else {
+          sa += __ldcg(peer_slot(v, v.rank, set, src, 0) + q);
+          sb += __ldcg(peer_slot(v, v.rank, set, src, 1) + q);
+        }
+      }
+      a[j[h]] = sa;
+      b[j[h]] = sb;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0 && atomicAdd(&v.ctl[2], 1u) == gridDim.x - 1) {   // the last block closes the exchange
