@@ -269,10 +269,16 @@ __device__ __forceinline__ float quar_mask(const gj_step_params& p, float cur) {
 //     is walked cell by cell ("segments"); a segment's partial sums are written to its first tile and zeros to its
 //     other tiles: k_cell_groups adds a cell's tiles, so the per-cell totals are unchanged.
 // =====================================================================================================
-constexpr int kK1Batch = 4;
+#ifndef GJ_K1_BATCH
+#define GJ_K1_BATCH 2   // measured on B200 (56 M agents): batch x CTAs/SM = 2x7 0.208 ms, 2x8 0.208, 4x4 0.236, 1x8 0.244, 8x3 0.273
+#endif
+#ifndef GJ_K1_MINB
+#define GJ_K1_MINB 7
+#endif
+constexpr int kK1Batch = GJ_K1_BATCH;
 
 template <bool kQuar>
-__global__ void __launch_bounds__(kLeanThreads, 4) k_lean_transmission(gj_world_desc w, gj_step_params p, LeanPlan lp,
+__global__ void __launch_bounds__(kLeanThreads, GJ_K1_MINB) k_lean_transmission(gj_world_desc w, gj_step_params p, LeanPlan lp,
                                                                     gj_fwd_io io, float* __restrict__ tile_part,
                                                                     Scatter sct) {
   __shared__ ProbRow prob[200];
