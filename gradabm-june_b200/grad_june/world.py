@@ -789,9 +789,12 @@ class NativeWorld:
             self.handle = None
 
     def __del__(self):
+        import sys
+        if sys.is_finalizing():      # the CUDA context may already be gone: leave the arrays to process teardown
+            return
         try:
             self.close()
-        except Exception:  # noqa: BLE001 -- interpreter shutdown
+        except Exception:  # noqa: BLE001
             pass
 
 
