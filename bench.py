@@ -537,7 +537,7 @@ def main():
     ap.add_argument("--samples", type=int, default=0,
                     help="ensemble: beta samples evaluated per window over all GPUs (BASELINE config 5: 1024 on a 9M "
                          "world, --agents 9000000 --window 30); default one per GPU")
-    ap.add_argument("--streams", type=int, default=1,
+    ap.add_argument("--streams", type=int, default=0,
                     help="ensemble + graph: evaluate this many samples concurrently, each lane with its own replica of "
                          "the world, captured window and CUDA stream (bandwidth-bound and issue-bound kernels of "
                          "different samples overlap)")
@@ -580,6 +580,8 @@ def main():
     ctx = {"rank": rank, "world_size": world_size, "local_rank": local_rank, "dev": dev}
 
     geo = world_size > 1 and args.parallelism == "geo"
+    if args.streams <= 0:      # ensembles: three concurrent lanes per GPU by default (+17 % over one, profiles/README.md)
+        args.streams = 3 if (not geo and args.samples > max(world_size, 1)) else 1
     scaling = args.scaling or ("strong" if geo else "weak")
     per_gpu = args.agents // world_size if (geo and scaling == "strong") else args.agents
     # the captured window (GraphedRunner: Runner() + backward() as one CUDA graph) is the default driver: it removes the

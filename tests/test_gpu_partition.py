@@ -153,3 +153,64 @@ def test_blockwise_partition_stepped_matches_single_gpu():
     out = mgr.dict()
     mp.spawn(_worker, args=(world_size, _free_port(), False, True, False, True, out), nprocs=world_size, join=True)
     _compare(out, world_size)
+
+
+def _ensemble_worker(rank, world_size, port, out):
+    import torch.distributed as dist
+    from grad_june import GradJune, Timer, ops
+    from grad_june.calibration import EnsembleEvaluator
+    from grad_june.runner import Runner
+    from grad_june.world import make_synthetic_world
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world_size, device_id=torch.device(dev))
+    try:
+        params = _params(dev)
+        params["policies"] = {}
+        torch.manual_seed(5)
+        data = Runner.get_data(params, data=make_synthetic_world(60_000, seed=9, device=dev, agents_per_super_area=5000))
+        model = GradJune.from_parameters(params)
+        keys = list(model.infection_networks.networks.keys())
+        runner = Runner(model=model, data=data, timer=Timer.from_parameters(params), log_fraction_initial_cases=-1.5,
+                        save_path="/tmp/gj_test", parameters=params)
+        loss_fn = lambda r: r["cases_per_timestep"].sum() + r["deaths_per_timestep"].sum()  # noqa: E731
+        base = torch.tensor([float(params["networks"][k]["log_beta"]) + 0.4 for k in keys], device=dev)
+        samples = base + 0.25 * torch.randn(5, len(keys), generator=torch.Generator().manual_seed(1)).to(dev)
+        losses, grads = EnsembleEvaluator(runner, loss_fn, seed=11)(samples)      # 5 samples dealt out over 2 ranks
+        out[f"ens{rank}"] = (losses.cpu().numpy(), grads.cpu().numpy())
+        if rank == 0:                                                             # the same samples one by one
+            ref_l, ref_g = [], []
+            for lb in samples:
+                leaves = []
+                for i, k in enumerate(keys):
+                    leaf = lb[i].detach().clone().requires_grad_(True)
+                    model.infection_networks.networks[k]._parameters.pop("log_beta", None)
+                    model.infection_networks.networks[k].log_beta = leaf
+                    leaves.append(leaf)
+                with ops.philox_seed(11):
+                    results, _ = runner()
+                loss = loss_fn(results)
+                loss.backward()
+                ref_l.append(loss.item())
+                ref_g.append(torch.stack([l.grad for l in leaves]).cpu().numpy())
+            out["ref"] = (np.array(ref_l, dtype=np.float32), np.stack(ref_g))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ensemble_evaluator_shards_samples_over_two_gpus():
+    """EnsembleEvaluator (BASELINE config 5: a batch of log-beta samples sharded over the GPUs, replicas of the world,
+    no data-path collective) on two ranks against one-by-one evaluation: same losses and gradients on every rank."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_ensemble_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    ref_l, ref_g = out["ref"]
+    for r in range(2):
+        losses, grads = out[f"ens{r}"]
+        assert np.array_equal(losses, ref_l) and np.array_equal(grads, ref_g)
+    assert not np.array_equal(ref_g[0], ref_g[1])
