@@ -594,7 +594,7 @@ def main():
         import gc
         gc.collect()
         torch.cuda.empty_cache()
-        weak = measure(args, ctx, "weak", False, full=False)
+        weak = measure(args, ctx, "weak", graph, full=False)
 
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
@@ -667,7 +667,8 @@ def main():
         if weak is not None:
             line["weak_scaling"] = {"value": weak["value"], "unit": UNIT, "ms_per_step": weak["ms"] / weak["steps_done"],
                                     "agents_per_gpu": weak["N"], "agents_total": weak["n_total"],
-                                    "driver": "Python loop (Runner)", "parallelism": weak["parallelism"],
+                                    "driver": "CUDA graph replay (GraphedRunner)" if weak["graph"] else "Python loop (Runner)",
+                                    "parallelism": weak["parallelism"],
                                     "rank_ms": weak["rank_ms"]}
         if not args.no_cpu_baseline and world_size == 1:
             thr, secs, cores = cpu_reference_run(args.cpu_agents, args.cpu_steps, policies=args.policies)

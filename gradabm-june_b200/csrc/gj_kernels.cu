@@ -766,8 +766,8 @@ static int launch_lean_group_pass(const gj_world_desc* w, const gj_step_params* 
   }
   if (w->n_big > 0) {
     ProfScope ps(bwd ? K_GROUP_FIX_B : K_GROUP_FIX_F, st);
-    k_lean_group_fix<<<blocks_for(w->n_big, kBlock), kBlock, 0, st>>>(*w, *p, pl, beta, sc.part_a, out_scaled,
-                                                                    out_plain);
+    k_lean_group_fix<<<blocks_for(w->n_big * 32, kBlock), kBlock, 0, st>>>(*w, *p, pl, beta, sc.part_a, out_scaled,
+                                                                         out_plain);
     GJ_CHECK_LAUNCH("k_lean_group_fix");
   }
   return 0;
@@ -940,9 +940,12 @@ struct PeerView {
 __device__ __forceinline__ float* peer_slot(const PeerView& v, int dst, uint32_t set, int src, int arr) {
   return v.recv[dst] + (((int64_t)set * v.world + src) * 2 + arr) * v.cap;
 }
-__global__ void __launch_bounds__(kPeerThreads) k_peer_exchange(PeerView v, int64_t n, const int32_t* __restrict__ inv,
+// n_mine / mine: the packed positions this rank attends (inv[q] >= 0), ascending; NULL = walk all n positions
+__global__ void __launch_bounds__(kPeerThreads) k_peer_exchange(PeerView v, int64_t n_all, const int32_t* __restrict__ inv,
                                                                  const uint32_t* __restrict__ attend,
-                                                                 float* __restrict__ a, float* __restrict__ b) {
+                                                                 float* __restrict__ a, float* __restrict__ b,
+                                                                 int64_t n_mine, const int32_t* __restrict__ mine) {
+  const int64_t n = mine ? n_mine : n_all;
   __shared__ uint32_t s_epoch;
   __shared__ bool s_last;
   if (threadIdx.x == 0) s_epoch = *(volatile uint32_t*)&v.ctl[0] + 1u;   // bumped by the last block at the very end
@@ -956,11 +959,16 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_exchange(PeerView v, int6
     int32_t j[kPeerBatch];
     uint32_t m[kPeerBatch];
     float va[kPeerBatch], vb[kPeerBatch];
+    int64_t qq[kPeerBatch];
 #pragma unroll
     for (int h = 0; h < kPeerBatch; ++h) {
-      const int64_t q = base + h * stride;
-      j[h] = q < n ? inv[q] : -1;
-      m[h] = q < n ? (attend[q] & ~me) : 0u;
+      const int64_t i = base + h * stride;
+      qq[h] = i < n ? (mine ? (int64_t)mine[i] : i) : -1;
+    }
+#pragma unroll
+    for (int h = 0; h < kPeerBatch; ++h) {
+      j[h] = qq[h] >= 0 ? inv[qq[h]] : -1;
+      m[h] = qq[h] >= 0 ? (attend[qq[h]] & ~me) : 0u;
     }
 #pragma unroll
     for (int h = 0; h < kPeerBatch; ++h) {
@@ -970,7 +978,7 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_exchange(PeerView v, int6
 #pragma unroll
     for (int h = 0; h < kPeerBatch; ++h) {
       if (j[h] < 0) continue;
-      const int64_t q = base + h * stride;
+      const int64_t q = qq[h];
       uint32_t mm = m[h];
       while (mm) {
         const int dst = __ffs(mm) - 1;
@@ -1012,11 +1020,16 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_exchange(PeerView v, int6
     int32_t j[kPeerBatch];
     uint32_t m[kPeerBatch];
     float oa[kPeerBatch], ob[kPeerBatch];
+    int64_t qq[kPeerBatch];
 #pragma unroll
     for (int h = 0; h < kPeerBatch; ++h) {
-      const int64_t q = base + h * stride;
-      j[h] = q < n ? inv[q] : -1;
-      m[h] = q < n ? attend[q] : 0u;
+      const int64_t i = base + h * stride;
+      qq[h] = i < n ? (mine ? (int64_t)mine[i] : i) : -1;
+    }
+#pragma unroll
+    for (int h = 0; h < kPeerBatch; ++h) {
+      j[h] = qq[h] >= 0 ? inv[qq[h]] : -1;
+      m[h] = qq[h] >= 0 ? attend[qq[h]] : 0u;
     }
 #pragma unroll
     for (int h = 0; h < kPeerBatch; ++h) {
@@ -1026,7 +1039,7 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_exchange(PeerView v, int6
 #pragma unroll
     for (int h = 0; h < kPeerBatch; ++h) {
       if (j[h] < 0) continue;
-      const int64_t q = base + h * stride;
+      const int64_t q = qq[h];
       uint32_t mm = m[h];
       float sa = 0.0f, sb = 0.0f;
       while (mm) {
@@ -1146,7 +1159,7 @@ int gj_peer_connect(gj_peer* p, const void* handles) {
 }
 
 int gj_peer_exchange(gj_peer* p, int64_t n_pack, const int32_t* inv, const uint32_t* attend, float* a, float* b,
-                     void* stream) {
+                     int64_t n_mine, const int32_t* mine, void* stream) {
   if (!p || !p->connected) return bad("peer context is not connected");
   if (n_pack > p->cap) return bad("n_pack exceeds the peer buffers' capacity");
   if (n_pack > 0 && (!inv || !attend || !a || !b)) return bad("NULL array");
@@ -1160,7 +1173,7 @@ int gj_peer_exchange(gj_peer* p, int64_t n_pack, const int32_t* inv, const uint3
   }
   v.ctl = (uint32_t*)(p->own + p->ctl_off);
   ProfScope ps(K_EXCHANGE, (cudaStream_t)stream);
-  k_peer_exchange<<<kPeerBlocks, kPeerThreads, 0, (cudaStream_t)stream>>>(v, n_pack, inv, attend, a, b);
+  k_peer_exchange<<<kPeerBlocks, kPeerThreads, 0, (cudaStream_t)stream>>>(v, n_pack, inv, attend, a, b, n_mine, mine);
   GJ_CHECK_LAUNCH("k_peer_exchange");
   return 0;
 }

@@ -452,6 +452,8 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_sums(gj_world_desc w, gj_
                           out_plain);
 }
 
+// groups spanning several chunks: one WARP per group adds the chunk partials (lanes stride over them, then the fixed
+// shuffle tree): a handful of groups, so the kernel is pure latency — a serial walk per thread measured 8.6 us
 __global__ void __launch_bounds__(kBlock) k_lean_group_fix(gj_world_desc w, gj_step_params p, Plan pl,
                                                            const float* __restrict__ beta,
                                                            const float* __restrict__ part,
@@ -459,18 +461,19 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_fix(gj_world_desc w, gj_s
                                                            float* __restrict__ out_plain) {
   __shared__ LeanGroupShared gs;
   lean_beta_sums(gs, w, p, pl, beta);
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= w.n_big) return;
   const uint32_t g = w.big_groups[i];
   const float b = lean_group_beta(gs, g);
   float S = 0.0f;
-  for (uint32_t j = w.big_part_ptr[i]; j < w.big_part_ptr[i + 1]; ++j) S += part[j];
+  for (uint32_t j = w.big_part_ptr[i] + lane; j < w.big_part_ptr[i + 1]; j += 32) S += part[j];
+  S = warp_sum(S);
+  if (lane != 0) return;
   out_plain[g] = S;
   out_scaled[g] = (b == b) ? (b * w.pc[g]) * S : 0.0f;
 }
 
-// accumulators -> fp32 sums of the scatter-tier groups (every generic group that is not giant); leaves them zero.
-// A dirty group (a member value outside the fixed-point range) is re-summed from its member list in CSR order.
 // the generic-tier types' global group id ranges, concatenated: thread i -> group (host-built, passed by value)
 struct GenericRanges {
   int n;

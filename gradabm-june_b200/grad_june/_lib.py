@@ -18,7 +18,7 @@ GJ_MAX_STAGES = 16
 GJ_MAX_QUAR = 4
 GJ_MAX_AGE_BINS = 8
 GJ_MAX_CHANNELS = 8
-GJ_ABI_VERSION = 7
+GJ_ABI_VERSION = 8
 
 KIND_PLAIN, KIND_HOUSEHOLD, KIND_LEISURE, KIND_CARE_VISIT = 0, 1, 2, 3
 PHASE_NETWORKS, PHASE_SAMPLE, PHASE_INFECT, PHASE_SYMPTOMS, PHASE_ALL = 1, 2, 4, 8, 15
@@ -198,7 +198,7 @@ def lib():
     L.gj_peer_create.argtypes = [C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]
     L.gj_peer_handle.argtypes = [C.c_void_p, C.c_void_p]
     L.gj_peer_connect.argtypes = [C.c_void_p, C.c_void_p]
-    L.gj_peer_exchange.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5
+    L.gj_peer_exchange.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p]
     L.gj_peer_status.argtypes = [C.c_void_p]
     L.gj_peer_destroy.argtypes = [C.c_void_p]
     L.gj_world_build.argtypes = [C.POINTER(WorldSrc), C.POINTER(C.c_void_p)]

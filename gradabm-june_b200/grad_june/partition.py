@@ -253,7 +253,8 @@ class BoundaryExchange:
         if attend is not None:
             attend = attend.to(torch.int32)
         self._check_layout(base, [ti for ti, _ in offsets])
-        hit = (src, dst, base, inv, attend)
+        mine = torch.sort(dst)[0].to(torch.int32)        # the packed positions this rank attends, ascending
+        hit = (src, dst, base, inv, attend, mine)
         self._regions[key] = hit
         return hit
 
@@ -333,7 +334,7 @@ class BoundaryExchange:
         kernel, one NCCL all-reduce of the packed [2, n_boundary] buffer and one unpack kernel."""
         import torch.distributed as dist
 
-        src, dst, n, inv, attend = region
+        src, dst, n, inv, attend, mine = region
         if n == 0 or self.part.world_size == 1:
             return
         a, b = buffers
@@ -347,7 +348,7 @@ class BoundaryExchange:
                 st = C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
                 with torch.cuda.device(a.device):
                     _lib.check(L.gj_peer_exchange(peer, n, inv.data_ptr(), attend.data_ptr(), a.data_ptr(), b.data_ptr(),
-                                                  st), "gj_peer_exchange")
+                                                  mine.numel(), mine.data_ptr(), st), "gj_peer_exchange")
                 return
             pack = self._packs.get(n)
             if pack is None:

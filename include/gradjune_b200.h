@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GJ_ABI_VERSION 7
+#define GJ_ABI_VERSION 8
 
 #define GJ_MAX_TYPES 8      /* edge types (household, company, school, university, care_home, leisure, ...) */
 #define GJ_MAX_NETS 16      /* infection networks active in one step */
@@ -393,8 +393,10 @@ int gj_peer_create(int rank, int world_size, int64_t capacity, gj_peer** out);
 int gj_peer_handle(gj_peer* peer, void* handle /* GJ_IPC_HANDLE_BYTES */);
 /* handles: world_size x GJ_IPC_HANDLE_BYTES, rank-major (an all-gather of gj_peer_handle) */
 int gj_peer_connect(gj_peer* peer, const void* handles);
+/* mine[n_mine]: the packed positions q this rank attends (inv[q] >= 0), ascending — the kernel then walks only
+ * those; NULL walks all n_pack positions */
 int gj_peer_exchange(gj_peer* peer, int64_t n_pack, const int32_t* inv, const uint32_t* attend, float* a, float* b,
-                     void* stream);
+                     int64_t n_mine, const int32_t* mine, void* stream);
 /* 0 = ok, 1 = a wait timed out since the last call (synchronises on nothing: read it after a stream sync) */
 int gj_peer_status(gj_peer* peer);
 int gj_peer_destroy(gj_peer* peer);
