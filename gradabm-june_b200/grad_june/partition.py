@@ -329,6 +329,16 @@ class BoundaryExchange:
             self.mode = "NCCL all-reduce of the packed buffer" + (f" (peer memory unavailable: {why})" if why else "")
         return self._peer
 
+    def check(self):
+        """Raise if a peer did not arrive at an exchange in time (``gj_peer_status``; the kernel then carried on with
+        incomplete sums rather than hang the GPU).  Synchronises the device: call it between windows, not per step."""
+        if self._peer:
+            from . import _lib
+            with torch.cuda.device(self.world.device):
+                torch.cuda.synchronize(self.world.device)
+                if _lib.lib().gj_peer_status(self._peer) != 0:
+                    raise _lib.GradJuneLibraryError("boundary exchange: " + _lib.lib().gj_last_error().decode())
+
     def exchange(self, buffers, region):
         """In place: every buffer's boundary entries become the sum over ranks.  On a GPU this is one pack
         kernel, one NCCL all-reduce of the packed [2, n_boundary] buffer and one unpack kernel."""

@@ -165,6 +165,9 @@ class Runner(torch.nn.Module):
             dates.append(timer.date)
         table = torch.stack(reds)                      # [T+1, 2 + n_bins]
         table = all_reduce_sum(table, data.__dict__.get("_gj_partition"))   # partitioned world: sum over ranks
+        ex = data.__dict__.get("_gj_cache", {}).get("exchange")
+        if ex is not None and not torch.cuda.is_current_stream_capturing():
+            ex.check()      # a peer that never arrived at an exchange must not go unnoticed (once per window)
         cases_per_timestep = table[:, 0]
         data["results"]["deaths_per_timestep"] = table[:, 1]
         results = {

@@ -525,8 +525,8 @@ def layout_order_of(data: "HeteroData", values):
 def original_order(data: "HeteroData", values: torch.Tensor) -> torch.Tensor:
     """Per-agent ``values`` of a renumbered world in the order the world was loaded in (differentiable)."""
     agent = data["agent"]
-    if "original_index" not in agent:
-        return values
+    if "original_index" not in agent or "_gj_partition" in data.__dict__:
+        return values       # one part of a partitioned world keeps its local order: the caller assembles the parts
     cache = data.__dict__.setdefault("_gj_cache", {})
     oi = agent["original_index"]
     hit = cache.get("inverse_index")
