@@ -13,6 +13,7 @@ the GPU for England-scale worlds and on the CPU for tests.
 """
 import io
 import pickle
+import sys
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -789,8 +790,7 @@ class NativeWorld:
             self.handle = None
 
     def __del__(self):
-        import sys
-        if sys.is_finalizing():      # the CUDA context may already be gone: leave the arrays to process teardown
+        if sys is None or sys.is_finalizing():   # the CUDA context may already be gone: leave it to process teardown
             return
         try:
             self.close()
