@@ -11,6 +11,15 @@
 
 namespace gj {
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
+// become resident while its predecessor in the stream is still running its last CTAs; it runs its own prologue
+// (shared-memory tables, barrier init, static index loads) and then waits for the predecessor's completion and memory
+// flush in pdl_wait().  pdl_launch() at a kernel's top lets ITS successor do the same.  Launched without the attribute
+// both are no-ops.  Rule: nothing written by an earlier kernel (state, beta, sums, scratch) is read, and no global
+// memory is written, before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 constexpr int kBlock = 256;
 constexpr int kRedBlocks = 148 * 8;  // persistent grid of the agent passes: 8 CTAs per SM
 constexpr int kMaxRed = 2 + GJ_MAX_AGE_BINS;

@@ -282,7 +282,9 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_K1_MINB) k_lean_transmission(
                                                                     gj_fwd_io io, float* __restrict__ tile_part,
                                                                     Scatter sct) {
   __shared__ ProbRow prob[200];
+  pdl_launch();
   lean_load_prob<false>(prob, p, lp, io.leisure_prob);
+  pdl_wait();
   __syncthreads();
   const float4* __restrict__ prof = reinterpret_cast<const float4*>(io.prof4);
   const float* __restrict__ g_inf = io.inf;
@@ -444,6 +446,8 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_sums(gj_world_desc w, gj_
                                                             float* __restrict__ out_plain, float* __restrict__ part,
                                                             int chunk_blocks) {
   __shared__ LeanGroupShared gs;
+  pdl_launch();
+  pdl_wait();
   lean_beta_sums(gs, w, p, pl, beta);
   if ((int)blockIdx.x < chunk_blocks)
     lean_group_chunk_body(w, gs, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, in, out_scaled, out_plain, part);
@@ -460,6 +464,8 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_fix(gj_world_desc w, gj_s
                                                            float* __restrict__ out_scaled,
                                                            float* __restrict__ out_plain) {
   __shared__ LeanGroupShared gs;
+  pdl_launch();
+  pdl_wait();
   lean_beta_sums(gs, w, p, pl, beta);
   const int lane = threadIdx.x & 31;
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -486,6 +492,8 @@ __global__ void __launch_bounds__(kBlock) k_lean_scatter_finalize(gj_world_desc 
                                                                   float* __restrict__ out_scaled,
                                                                   float* __restrict__ out_plain) {
   __shared__ LeanGroupShared gs;
+  pdl_launch();
+  pdl_wait();
   lean_beta_sums(gs, w, p, pl, beta);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= gr.start[gr.n]) return;
@@ -739,8 +747,10 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_seed(gj_world_desc w, 
                                                               unsigned int* __restrict__ ticket) {
   __shared__ float hist[100];
   __shared__ float deaths;
+  pdl_launch();
   if (threadIdx.x < 100) hist[threadIdx.x] = 0.0f;
   if (threadIdx.x == 0) deaths = 0.0f;
+  pdl_wait();
   __syncthreads();
   LeanPlan lp;
   lp.r_house = 0;

@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
   const TileRun run = lean_tiles(w);
   const float* __restrict__ Tr = (kQuar && !lp.r_house) ? io.Tq : io.T;
   const bool has_gen = lp.has_generic != 0, has_range = lp.n_range > 0;
+  pdl_launch();
   pipe_init_barriers(sh.full);
   lean_load_prob<true>(sh.prob, p, lp, io.leisure_prob);
   if (kNext) {
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
       sh.prob_next[c].v[j] = j < nx.n_cell ? io.leisure_prob[(size_t)(nx.c_row[j] * 2 + nx.day_type) * 200 + c] : 0.0f;
     }
   }
+  pdl_wait();   // everything below reads what earlier kernels of the stream wrote
   if (threadIdx.x < p.n_nets) sh.beta[threadIdx.x] = io.beta[threadIdx.x];
   if (threadIdx.x < 100) sh.hist[threadIdx.x] = 0.0f;
   if (threadIdx.x == 0) sh.deaths = 0.0f;
@@ -409,8 +411,10 @@ __global__ void __launch_bounds__(kBwdThreads, kBwdCtas) k_pipe_backward(gj_worl
   PipeBwdShared& sh = *reinterpret_cast<PipeBwdShared*>(pipe_smem);
   const TileRun run = lean_tiles(w);
   const BwdCot cot{{io.g_s_o, io.g_inf_o, io.g_tinf_o, io.g_cur_o, io.g_nxt_o, io.g_ttn_o}};
+  pdl_launch();
   pipe_init_barriers(sh.full);
   lean_load_prob<true>(sh.prob, p, lp, io.leisure_prob);
+  pdl_wait();   // everything below reads what earlier kernels of the stream wrote
   if (threadIdx.x < 100) {
     float g = 0.0f;
     if (io.g_red) {
@@ -535,8 +539,10 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward_gather(gj_wor
   const TileRun run = lean_tiles(w);
   const float* __restrict__ wr = (kQuar && !lp.r_house) ? io.wq : io.w;  // member values of the range network
   const bool has_gen = lp.has_generic != 0, has_range = lp.n_range > 0;
+  pdl_launch();
   pipe_init_barriers(sh.full);
   lean_load_prob<false>(sh.prob, p, lp, io.leisure_prob);
+  pdl_wait();   // everything below reads what earlier kernels of the stream wrote
   if (threadIdx.x < p.n_nets) sh.beta[threadIdx.x] = io.beta[threadIdx.x];
   __syncthreads();
   if (threadIdx.x == 0) {

@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(kBlock) k_cell_groups(gj_world_desc w, gj_step
                                                         const float* __restrict__ beta,
                                                         const float* __restrict__ tile_part,
                                                         float* __restrict__ out_scaled, float* __restrict__ out_plain) {
+  pdl_launch();
+  pdl_wait();
   const int j = blockIdx.y;
   const int k = pl.t2_net[j];
   const gj_net net = p.nets[k];
@@ -187,6 +189,8 @@ __global__ void __launch_bounds__(kBlock) k_cell_groups(gj_world_desc w, gj_step
 __global__ void __launch_bounds__(kBlock) k_cell_gather(gj_world_desc w, gj_step_params p, Plan pl,
                                                         const float* __restrict__ in_scaled,
                                                         float* __restrict__ cell_buf) {
+  pdl_launch();
+  pdl_wait();
   const int j = blockIdx.y;
   const gj_net net = p.nets[pl.t2_net[j]];
   const int t = net.type;
