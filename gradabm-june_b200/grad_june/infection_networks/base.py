@@ -61,14 +61,61 @@ class InfectionNetwork(torch.nn.Module):
     def net_spec(self, prob_row=-1):
         return ops.NetSpec(name=self.name, edge_type=self.edge_type(), kind=self.kind, prob_row=prob_row)
 
+    # ---- the reference's per-agent masking hooks (base.py:47-59).  The built-in classes' versions are what the
+    # kernels evaluate in registers from `kind`; a USER SUBCLASS that overrides one of them (or `forward`) is detected
+    # (`is_custom`) and its networks then run through the modular path: the hook's tensors are scattered / gathered by
+    # the same CSR kernels without any built-in mask (`_custom_pressure`), and the step is sequenced module by module
+    # like the reference's GradJune.forward instead of as one fused call.
+    def _agent_mask(self, data, policies, timer):
+        qp = None if policies is None else policies.quarantine_policies
+        return qp.quarantine_mask if qp else 1.0
+
+    def _get_transmissions(self, data, policies, timer):
+        return self._agent_mask(data, policies, timer) * data["agent"].transmission
+
+    def _get_susceptibilities(self, data, policies, timer):
+        return self._agent_mask(data, policies, timer) * data["agent"].susceptibility
+
+    def is_custom(self):
+        hooks = ("_get_transmissions", "_get_susceptibilities", "_agent_mask", "forward", "_get_beta")
+        for name in hooks:
+            owner = next(k for k in type(self).__mro__ if name in k.__dict__)
+            if owner.__module__.split(".")[0] != __name__.split(".")[0]:
+                return True
+        return False
+
+    def _custom_pressure(self, data, timer, policies):
+        """base.py:61-84 with the hooks' own tensors: C_g = sum of T'_a * beta_eff * pc_g over the members, P_a = C_g(a)
+        * s'_a, through the stand-alone NETWORKS phase with no built-in mask (differentiable with respect to T', s'
+        and beta_eff)."""
+        agent = data["agent"]
+        dev = agent.susceptibility.device
+        world = get_device_world(data, dev)
+        Tm = self._get_transmissions(data, policies, timer)
+        sm = self._get_susceptibilities(data, policies, timer)
+        spec = ops.StepSpec(now=timer.now, dt=timer.duration, day_type=0 if timer.day_type == "weekday" else 1,
+                            nets=[ops.NetSpec(name=self.name, edge_type=self.edge_type(), kind=ops.KIND_HOUSEHOLD)],
+                            quarantine=None, phases=ops.PHASE_NETWORKS, want_reductions=False, want_lam=True)
+        from ..partition import exchange_for
+
+        static = ops.StepStatic(world=world, exchange=exchange_for(data, world))
+        beta = self.beta_eff(policies, timer).reshape(1).to(device=dev, dtype=torch.float32)
+        out = ops.infection_step(static, spec, beta, {"s": ops._f32(sm, dev)}, T_in=ops._f32(Tm, dev))
+        return out["lam"]
+
     def forward(self, data, timer, policies):
         """Pressure this network alone exerts on every agent (the reference's per-network output)."""
+        if self.is_custom():
+            return self._custom_pressure(data, timer, policies)
         out = _run_networks([self], data, timer, policies, self.device, want_lam=True)
         return out["lam"]
 
 
 class HouseholdNetwork(InfectionNetwork):
     kind = ops.KIND_HOUSEHOLD   # ignores the quarantine mask (base.py:144-149)
+
+    def _agent_mask(self, data, policies, timer):
+        return 1.0
 
 
 class CareHomeNetwork(InfectionNetwork):
@@ -179,7 +226,19 @@ class InfectionNetworks(torch.nn.Module):
             order = policies.close_venue_policies.apply(edge_types=order, timer=timer)
         return [self.networks[name] for name in order]
 
+    def has_custom(self, nets=None):
+        return any(net.is_custom() for net in (self.networks.values() if nets is None else nets))
+
     def forward(self, data, timer, policies):
         policies.apply(timer=timer, data=data)
         nets = self.active_networks(timer, policies)
-        return _run_networks(nets, data, timer, policies, self.device)["q"]
+        if not self.has_custom(nets):
+            return _run_networks(nets, data, timer, policies, self.device)["q"]
+        # a user-defined network among them: network by network in the activity order, then the reference's clamp /
+        # exp chain (base.py:133-140) in torch
+        agent = data["agent"]
+        lam = torch.zeros_like(agent.susceptibility)
+        for net in nets:
+            lam = lam + net(data=data, timer=timer, policies=policies)
+        lam = torch.clamp(lam, min=1e-6, max=100)
+        return torch.clamp(torch.exp(-lam * timer.duration), min=0.0, max=1.0)

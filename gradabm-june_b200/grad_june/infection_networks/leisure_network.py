@@ -44,6 +44,13 @@ class LeisureNetwork(InfectionNetwork):
     def edge_type(self):
         return "leisure"
 
+    def _agent_mask(self, data, policies, timer):
+        """quarantine mask x attendance probability by (day type, sex, age) — leisure_network.py:61-85."""
+        if self.weekday_probabilities is None:
+            self.initialize_leisure_probabilities(data)
+        prob = self.weekday_probabilities if timer.day_type == "weekday" else self.weekend_probabilities
+        return super()._agent_mask(data, policies, timer) * prob
+
 
 class PubNetwork(LeisureNetwork):
     pass
@@ -67,3 +74,6 @@ class VisitNetwork(LeisureNetwork):
 
 class CareVisitNetwork(LeisureNetwork):
     kind = ops.KIND_CARE_VISIT   # susceptibilities additionally masked by age > 75
+
+    def _get_susceptibilities(self, data, policies, timer):
+        return super()._get_susceptibilities(data, policies, timer) * (data["agent"].age > 75)

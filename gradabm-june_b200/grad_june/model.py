@@ -100,6 +100,9 @@ class GradJune(torch.nn.Module):
         agent = data["agent"]
         ops.require_cuda(agent.susceptibility, "data['agent'].susceptibility")
         dev = agent.susceptibility.device
+        if mode == ops.MODE_STEP and self.infection_networks.has_custom(
+                self.infection_networks.active_networks(timer, self.policies)):
+            return self._step_modular(data, timer, age_bins)
         static, rows = self._static(data, dev)
         policies = self.policies
         spec, nets = self._spec(timer, rows, age_bins, mode, want_probs)
@@ -126,11 +129,33 @@ class GradJune(torch.nn.Module):
             data["agent"]["not_infected_probs"] = out["q"]
         return data, out["red"]
 
+    def _step_modular(self, data, timer, age_bins):
+        """The reference's own sequencing (model.py:112-144), module by module, for steps with a user-defined network
+        subclass (its masking hooks return arbitrary tensors, which the fused kernels cannot evaluate in registers):
+        every module is still a CUDA kernel of the library (stand-alone phases), only the fusion is lost."""
+        agent = data["agent"]
+        agent.transmission = self.transmission_updater(data=data, timer=timer)
+        q = self.infection_networks(data=data, timer=timer, policies=self.policies)
+        n = self.is_infected_sampler(q)
+        self.infect_people(data, timer, n)
+        self.symptoms_updater(data=data, timer=timer, new_infected=n)
+        agent["new_infected"], agent["not_infected_probs"] = n, q
+        red = None
+        if age_bins is not None:      # runner.py:167-171,198-224
+            cur, inf, age = agent.symptoms["current_stage"], agent.is_infected, agent.age
+            dead = float(len(self.symptoms_updater.stages_ids) - 1)
+            red = [inf.sum(), ((cur == dead) * cur / dead).sum()]
+            red += [(inf * ((age < hi) * (age > lo))).sum() for lo, hi in zip(age_bins[:-1], age_bins[1:])]
+            red = torch.stack(red)
+        return data, red
+
     def kernel_family(self, data, timer) -> str:
         """"throughput" or "reference-order": the kernel family the fused step at ``timer`` runs on with in-kernel
         noise (the throughput kernels need the household edge type on the RANGE tier or unquarantined, the leisure
         type on the CELL tier and plain kinds elsewhere — what :func:`grad_june.world.renumber_world` arranges)."""
         dev = data["agent"].susceptibility.device
+        if self.infection_networks.has_custom(self.infection_networks.active_networks(timer, self.policies)):
+            return "modular (user-defined network)"
         static, rows = self._static(data, dev)
         spec, _ = self._spec(timer, rows, None, ops.MODE_STEP, False)
         return ops.step_plan(static, spec)

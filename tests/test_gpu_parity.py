@@ -220,3 +220,66 @@ def test_gradient_locality(golden_dir):
     cases[in_school[0]].backward(retain_graph=True)
     assert nets["school"].log_beta.grad.item() != 0.0
     assert nets["company"].log_beta.grad.item() == 0.0
+
+
+def test_user_defined_network_subclass(golden_dir):
+    """A user subclass overriding the reference's masking hooks (base.py:47-59).  (1) One that restates the built-in
+    behaviour must reproduce the fused path's probabilities; (2) a genuinely different mask (school susceptibility
+    halved below age 10) must match a plain torch evaluation of base.py:61-84,118-141 and keep gradients flowing."""
+    from grad_june import infection_networks as IN
+    from grad_june import ops
+    g, data, model, nets, timer = _step100(golden_dir)
+    pre = {k: data["agent"][k].clone() for k in ("susceptibility", "is_infected", "infection_time")}
+    pre_sym = {k: v.clone() for k, v in data["agent"].symptoms.items()}
+
+    def reset():
+        for k, v in pre.items():
+            data["agent"][k] = v.clone()
+        data["agent"].symptoms = {k: v.clone() for k, v in pre_sym.items()}
+
+    with ops.philox_seed(3):
+        model(data=data, timer=timer)
+    q_fused = data["agent"]["not_infected_probs"].clone()
+    assert model.kernel_family(data, timer) in ("throughput", "reference-order")
+
+    class SchoolNetwork(IN.SchoolNetwork):            # (1) same behaviour, spelled out by the user
+        def _get_transmissions(self, data, policies, timer):
+            qp = policies.quarantine_policies
+            return (qp.quarantine_mask if qp else 1.0) * data["agent"].transmission
+
+    reset()
+    nets.networks["school"] = SchoolNetwork(log_beta=torch.nn.Parameter(torch.tensor(0.4)))
+    assert nets.networks["school"].is_custom() and model.kernel_family(data, timer).startswith("modular")
+    with ops.philox_seed(3):
+        model(data=data, timer=timer)
+    q_mod = data["agent"]["not_infected_probs"]
+    assert torch.allclose(q_mod, q_fused, rtol=2e-6, atol=0)
+
+    class SchoolNetwork(IN.SchoolNetwork):            # noqa: F811  (2) a different mask
+        def _get_susceptibilities(self, data, policies, timer):
+            young = (data["agent"].age < 10).float()
+            return (1.0 - 0.5 * young) * data["agent"].susceptibility
+
+    reset()
+    nets.networks["school"] = SchoolNetwork(log_beta=torch.nn.Parameter(torch.tensor(0.4)))
+    with ops.philox_seed(3):
+        res = model(data=data, timer=timer)
+    q_custom = res["agent"]["not_infected_probs"]
+    # plain torch evaluation of the same step's pressure
+    T = res["agent"].transmission.detach()
+    s0, age = pre["susceptibility"], data["agent"].age
+    lam = torch.zeros_like(s0)
+    for name in timer.get_activity_order():
+        ei = data["attends_" + name].edge_index
+        people = data[name]["people"].float()
+        pc = torch.clamp(1.0 / (people - 1), 0.0, 1.0)
+        beta = 10.0 ** float(nets.networks[name].log_beta)
+        sm = s0 * (1.0 - 0.5 * (age < 10).float()) if name == "school" else s0
+        C = torch.zeros(len(people), device=DEV).index_add_(0, ei[1], T[ei[0]] * (beta * pc)[ei[1]])
+        lam = lam + torch.zeros_like(s0).index_add_(0, ei[0], C[ei[1]] * sm[ei[0]])
+    q_ref = torch.exp(-torch.clamp(lam, 1e-6, 100) * timer.duration)
+    assert torch.allclose(q_custom, q_ref, rtol=1e-5, atol=0)
+    assert not torch.allclose(q_custom, q_fused, rtol=1e-4)
+    (res["agent"].is_infected.sum() + res["agent"].symptoms["current_stage"].sum()).backward()
+    assert nets.networks["school"].log_beta.grad is not None and nets.networks["school"].log_beta.grad.item() != 0.0
+    assert nets.networks["household"].log_beta.grad.item() != 0.0
