@@ -722,6 +722,7 @@ static bool lean_plan(const gj_world_desc* w, const gj_step_params* p, const Pla
       lp->n_range = 1;
       lp->r_slot = w->range_slot[t];
       lp->r_pc = w->range_pc[t];
+      lp->r_pc_lut = w->range_pc_from_size[t] != 0;
       lp->r_net = k;
       lp->r_house = kind == GJ_KIND_HOUSEHOLD;
     } else if (pl.tier[k] == GJ_TIER_CELL) {

@@ -78,6 +78,7 @@ struct LeanPlan {
   int n_range;                              // networks on RANGE-tier types: 0 or 1
   const uint32_t* r_slot;                   // per agent (offset << 16) | size, kNoSlot = not a member
   const float* r_pc;                        // per agent contact probability of its group
+  int r_pc_lut;                             // 1: it equals clamp(1/(size-1), 0, 1): the pipelined kernels use a table
   int r_net;                                // index of the network (beta)
   int r_house;                              // 1: HOUSEHOLD kind (ignores quarantine), 0: PLAIN
   int n_cell;                               // networks on CELL-tier types, same order as Plan::t2_net

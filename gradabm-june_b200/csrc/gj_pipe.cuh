@@ -145,6 +145,13 @@ __device__ __forceinline__ bool pipe_release() {
   return threadIdx.x == 0;
 }
 
+// contact probability of a range-tier group from its size (gj_world_desc.range_pc_from_size): the same fp32 formula
+// as the world builders' p_contact, so the table entries are bit-identical to the per-agent array they replace
+constexpr int kPcLut = kPipeHalo + 8;
+__device__ __forceinline__ void pipe_fill_pc_lut(float* lut) {
+  for (int n = threadIdx.x; n < kPcLut; n += blockDim.x) lut[n] = fmaxf(fminf(1.0f / (float)(n - 1), 1.0f), 0.0f);
+}
+
 constexpr int kPipeF = kPipeTile + 8;                     // floats of a staged 4-byte array
 constexpr int kPipeH = kPipeTile + 2 * kPipeHalo + 8;     // ... with the halo
 
@@ -202,6 +209,7 @@ struct PipeFwdSharedT {
   float beta[GJ_MAX_NETS];
   float hist[100];
   float deaths;
+  float pc_lut[kPcLut];
   alignas(8) uint64_t full[kPipeStages];
 };
 
@@ -212,7 +220,7 @@ __device__ __forceinline__ void pipe_fwd_issue(PipeFwdStage& sg, uint64_t* bar, 
   uint32_t total = 6u * t.n4 + (t.hi16 - t.lo16);
   if (has_gen) total += t.n4;
   if (w.orig_id) total += t.n4;
-  if (has_range) total += 2u * t.n4 + (t.thi - t.tlo) * 4u;
+  if (has_range) total += (lp.r_pc_lut ? 1u : 2u) * t.n4 + (t.thi - t.tlo) * 4u;
   mbar_expect_tx(bar, total);
   const Copier c{bar};
   if (w.orig_id) c.f4(sg.oid, w.orig_id, t);
@@ -225,7 +233,7 @@ __device__ __forceinline__ void pipe_fwd_issue(PipeFwdStage& sg, uint64_t* bar, 
   if (has_gen) c.f4(sg.ent, w.ent1, t);
   if (has_range) {
     c.f4(sg.slot, lp.r_slot, t);
-    c.f4(sg.rpc, lp.r_pc, t);
+    if (!lp.r_pc_lut) c.f4(sg.rpc, lp.r_pc, t);
     bulk_g2s(sg.T, Tr + t.tlo, (t.thi - t.tlo) * 4u, bar);
   }
   bulk_g2s(sg.cls, w.cls + t.lo16, t.hi16 - t.lo16, bar);
@@ -244,6 +252,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
   pdl_launch();
   pipe_init_barriers(sh.full);
   lean_load_prob<true>(sh.prob, p, lp, io.leisure_prob);
+  pipe_fill_pc_lut(sh.pc_lut);
   if (kNext) {
     for (int i = threadIdx.x; i < GJ_MAX_CHANNELS * 200; i += blockDim.x) {
       const int j = i / 200, c = i - j * 200;
@@ -307,7 +316,9 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
       const float Lc = lp.n_cell > 0 ? L[cls] : 0.0f;
       const float gv = lean_generic_finish(w, SP, ent[h], a, gen[h]);
       const uint64_t ga = w.orig_id ? (uint64_t)sg.oid[i] : p.agent_offset + a;
-      const FwdOut o = lean_forward_agent<kQuar, kDiag>(p, lp, io, a, ga, hs, gv, Lc, beta_r, has_range ? sg.rpc[i] : 0.0f,
+      const float rpc = !has_range ? 0.0f : (lp.r_pc_lut ? ((sg.slot[i] == kNoSlot) ? 0.0f : sh.pc_lut[sg.slot[i] & 0xFFFFu])
+                                                         : sg.rpc[i]);
+      const FwdOut o = lean_forward_agent<kQuar, kDiag>(p, lp, io, a, ga, hs, gv, Lc, beta_r, rpc,
                                                         sg.s[i], sg.inf[i], sg.tinf[i], sg.cur[i], sg.nxt[i], sg.ttn[i], cls,
                                                         inv_tau, dead, sh.hist, &sh.deaths);
       if (kNext) {   // TransmissionUpdater of the next step (same arithmetic as k_lean_transmission)
@@ -500,6 +511,7 @@ struct PipeGatShared {
   ProbRow prob[200];
   float L[2][200];
   float beta[GJ_MAX_NETS];
+  float pc_lut[kPcLut];
   alignas(8) uint64_t full[kPipeStages];
 };
 
@@ -511,7 +523,7 @@ __device__ __forceinline__ void pipe_gat_issue(PipeGatStage& sg, uint64_t* bar, 
   uint32_t total = 4u * t.n4 + (t.hi16 - t.lo16);
   if (kQuar) total += t.n4;
   if (has_gen) total += t.n4;
-  if (has_range) total += 3u * t.n4 + (t.thi - t.tlo) * 4u;
+  if (has_range) total += (lp.r_pc_lut ? 2u : 3u) * t.n4 + (t.thi - t.tlo) * 4u;
   mbar_expect_tx(bar, total);
   const Copier c{bar};
   c.f4(sg.inf, io.inf, t);
@@ -522,7 +534,7 @@ __device__ __forceinline__ void pipe_gat_issue(PipeGatStage& sg, uint64_t* bar, 
   if (has_gen) c.f4(sg.ent, w.ent1, t);
   if (has_range) {
     c.f4(sg.slot, lp.r_slot, t);
-    c.f4(sg.rpc, lp.r_pc, t);
+    if (!lp.r_pc_lut) c.f4(sg.rpc, lp.r_pc, t);
     c.f4(sg.Tm, io.T_in, t);
     bulk_g2s(sg.wr, wr + t.tlo, (t.thi - t.tlo) * 4u, bar);
   }
@@ -542,6 +554,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward_gather(gj_wor
   pdl_launch();
   pipe_init_barriers(sh.full);
   lean_load_prob<false>(sh.prob, p, lp, io.leisure_prob);
+  pipe_fill_pc_lut(sh.pc_lut);
   pdl_wait();   // everything below reads what earlier kernels of the stream wrote
   if (threadIdx.x < p.n_nets) sh.beta[threadIdx.x] = io.beta[threadIdx.x];
   __syncthreads();
@@ -591,7 +604,9 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward_gather(gj_wor
       const int cls = sg.cls[j + sk16];
       const float Lc = lp.n_cell > 0 ? L[cls] : 0.0f;
       const float gv = lean_generic_finish(w, cRP, ent[h], a, gen[h]);
-      lean_gather_agent<kQuar>(p, lp, io, a, R, gv, Lc, beta_r, has_range ? sg.rpc[i] : 0.0f,
+      const float rpc = !has_range ? 0.0f : (lp.r_pc_lut ? ((sg.slot[i] == kNoSlot) ? 0.0f : sh.pc_lut[sg.slot[i] & 0xFFFFu])
+                                                         : sg.rpc[i]);
+      lean_gather_agent<kQuar>(p, lp, io, a, R, gv, Lc, beta_r, rpc,
                                has_range ? sg.Tm[i] : 0.0f, kQuar ? sg.cur[i] : 0.0f, sg.inf[i], sg.tinf[i], pf[h],
                                sg.gi[i], sg.gt[i], db[0]);
     }

@@ -317,7 +317,7 @@ struct Builder {
 
   // grad_june/world.py::_try_range_tier
   static bool try_range(int64_t n, const I64& src, const I64& dst, int64_t G, const vec<float>& pc, int64_t pc_off,
-                        I64* slot_out, vec<float>* rpc_out) {
+                        I64* slot_out, vec<float>* rpc_out, bool* from_size) {
     const int64_t E = (int64_t)src.size();
     if (E == 0) return false;
     if (O::max_of(O::bincount(src, n)) > 1) return false;
@@ -338,6 +338,17 @@ struct Builder {
     vec<float> rpc(n + 32, 0.0f);
     thrust::scatter(thrust::make_permutation_iterator(pc.begin() + pc_off, gid.begin()),
                     thrust::make_permutation_iterator(pc.begin() + pc_off, gid.end()), members.begin(), rpc.begin());
+    {   // does `people` equal the member count (contact probability derivable from the slot's size)?
+      vec<float> have(E), want(E);
+      thrust::copy(thrust::make_permutation_iterator(pc.begin() + pc_off, gid.begin()),
+                   thrust::make_permutation_iterator(pc.begin() + pc_off, gid.end()), have.begin());
+      I64 sz = O::gather(size, gid);
+      thrust::transform(sz.begin(), sz.end(), want.begin(), [] __host__ __device__(int64_t x) {
+        const float v = 1.0f / (float)(x - 1);
+        return fmaxf(fminf(v, 1.0f), 0.0f);
+      });
+      *from_size = thrust::equal(have.begin(), have.end(), want.begin());
+    }
     *slot_out = slot;
     *rpc_out = rpc;
     return true;
@@ -518,8 +529,10 @@ static int build(const gj_world_src* s, World<B>* W) {
     if (n > 0 && want[t] == GJ_TIER_RANGE) {
       I64 slot;
       typename B::template vec<float> rpc;
-      if (Bd::try_range(n, src[t], dst[t], types[t].G, W->pc, offs[t], &slot, &rpc)) {
+      bool from_size = false;
+      if (Bd::try_range(n, src[t], dst[t], types[t].G, W->pc, offs[t], &slot, &rpc, &from_size)) {
         tier[t] = GJ_TIER_RANGE;
+        d.range_pc_from_size[t] = from_size ? 1 : 0;
         W->range_slot[t] = Bd::to_u32(slot, 32);
         W->range_pc[t] = rpc;
       }

@@ -18,7 +18,7 @@ GJ_MAX_STAGES = 16
 GJ_MAX_QUAR = 4
 GJ_MAX_AGE_BINS = 8
 GJ_MAX_CHANNELS = 8
-GJ_ABI_VERSION = 8
+GJ_ABI_VERSION = 9
 
 KIND_PLAIN, KIND_HOUSEHOLD, KIND_LEISURE, KIND_CARE_VISIT = 0, 1, 2, 3
 PHASE_NETWORKS, PHASE_SAMPLE, PHASE_INFECT, PHASE_SYMPTOMS, PHASE_ALL = 1, 2, 4, 8, 15
@@ -42,6 +42,7 @@ class WorldDesc(C.Structure):
         ("big_groups", _u32p), ("big_part_ptr", _u32p), ("n_big", C.c_int64), ("n_parts", C.c_int64),
         ("type_tier", C.c_int32 * GJ_MAX_TYPES),
         ("range_slot", C.c_void_p * GJ_MAX_TYPES), ("range_pc", C.c_void_p * GJ_MAX_TYPES),
+        ("range_pc_from_size", C.c_int32 * GJ_MAX_TYPES),
         ("n_tiles", C.c_int64), ("tile_begin", _u32p), ("tile_flags", _u32p),
         ("n_cells", C.c_int64 * GJ_MAX_TYPES), ("cell_off", C.c_int64 * GJ_MAX_TYPES), ("n_cells_total", C.c_int64),
         ("tile_cell", C.c_void_p * GJ_MAX_TYPES), ("cell_tile_ptr", C.c_void_p * GJ_MAX_TYPES),

@@ -275,6 +275,7 @@ class DeviceWorld:
             if self.type_tier[ti] == TIER_RANGE:
                 d.range_slot[ti] = self.range_slot[ti].data_ptr()
                 d.range_pc[ti] = self.range_pc[ti].data_ptr()
+                d.range_pc_from_size[ti] = 1 if self.__dict__.get("range_pc_from_size", {}).get(ti) else 0
             elif self.type_tier[ti] == TIER_CELL:
                 c = self.cells[ti]
                 d.n_cells[ti] = c["n_cells"]
@@ -339,7 +340,8 @@ def _try_range_tier(n_agents, src, dst, n_groups, pc_t):
     slot[members] = (offset << 16) | size[gid]
     rpc = torch.zeros(n_agents, dtype=torch.float32, device=dev)
     rpc[members] = pc_t[gid]
-    return {"range_slot": _padded(_u32(slot)), "range_pc": _padded(rpc.contiguous())}
+    from_size = bool(torch.equal(pc_t[gid], p_contact(size[gid])))     # `people` is the member count
+    return {"range_slot": _padded(_u32(slot)), "range_pc": _padded(rpc.contiguous()), "pc_from_size": from_size}
 
 
 def _try_cell_tier(n_agents, src, dst, n_groups):
@@ -565,7 +567,7 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
     pc = torch.cat([p_contact(torch.as_tensor(people[t]).to(dev)) for t in types]) if types else torch.zeros(0, device=dev)
     if pc.numel() != G:
         raise ValueError("people arrays do not match the number of groups")
-    type_tier, range_slot, range_pc, cells = [], {}, {}, {}
+    type_tier, range_slot, range_pc, cells, range_from_size = [], {}, {}, {}, {}
     srcs, gkeys, ents = [], [], []
     n_edges_total = 0
     for ti, t in enumerate(types):
@@ -584,6 +586,7 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
             r = _try_range_tier(n_agents, ei[0], ei[1], int(n_groups[t]), pc[offs[ti]:offs[ti + 1]])
             if r is not None:
                 tier, range_slot[ti], range_pc[ti] = TIER_RANGE, r["range_slot"], r["range_pc"]
+                range_from_size[ti] = r["pc_from_size"]
         elif want == TIER_CELL:
             c = _try_cell_tier(n_agents, ei[0], ei[1], int(n_groups[t]))
             if c is not None:
@@ -678,6 +681,7 @@ def build_csr(n_agents: int, types: List[str], edges: Dict[str, torch.Tensor], p
     return DeviceWorld(
         n_agents=n_agents, n_groups=G, n_edges=n_edges_total, n_generic_edges=E, types=list(types),
         type_group_off=offs, type_tier=type_tier, range_slot=range_slot, range_pc=range_pc, cells=cells,
+        range_pc_from_size=range_from_size,
         group_size=size, am_ptr=_padded(_u32(am_ptr)), am_ent=_padded(_u32(am_ent)), gm_ptr=_u32(gm_ptr),
         gm_agent=gm_agent.contiguous(), pc=pc.contiguous(), cls=_padded(cls.contiguous(), 64), small_groups=_u32(small),
         chunk_group=_u32(chunk_group), chunk_begin=_u32(chunk_begin), chunk_end=_u32(chunk_end),

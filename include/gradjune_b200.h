@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GJ_ABI_VERSION 8
+#define GJ_ABI_VERSION 9
 
 #define GJ_MAX_TYPES 8      /* edge types (household, company, school, university, care_home, leisure, ...) */
 #define GJ_MAX_NETS 16      /* infection networks active in one step */
@@ -122,6 +122,10 @@ typedef struct gj_world_desc {
    * contact probability of the agent's group */
   const uint32_t* range_slot[GJ_MAX_TYPES];
   const float* range_pc[GJ_MAX_TYPES];
+  /* 1: range_pc of this type equals clamp(1 / (group_size - 1), 0, 1) for every member, i.e. `people` is the member
+   * count (true of every JUNE world): the pipelined kernels then take the contact probability from a 65-entry table
+   * indexed by the size in the slot word instead of streaming 4 more bytes per agent and pass */
+  int32_t range_pc_from_size[GJ_MAX_TYPES];
   /* CTA tiles of the agent-major kernels: tile i = agents [tile_begin[i], tile_begin[i+1]), at most
    * GJ_TILE_AGENTS, never straddling a cell boundary of a CELL-tier type */
   int64_t n_tiles;

@@ -45,6 +45,7 @@ def _compare(native, ref, types):
     cells_total = 0
     for ti, t in enumerate(types):
         if ref.type_tier[ti] == W.TIER_RANGE:
+            assert bool(d.range_pc_from_size[ti]) == bool(ref.range_pc_from_size[ti]) == True, t   # noqa: E712
             assert torch.equal(native.array("range_slot", n, index=ti), ref.range_slot[ti][:n].cpu()), t
             assert torch.equal(native.array("range_pc", n, torch.float32, index=ti), ref.range_pc[ti][:n].cpu()), t
         elif ref.type_tier[ti] == W.TIER_CELL:
