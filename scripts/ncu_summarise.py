@@ -64,7 +64,7 @@ import json
 ids = {"k_lean_transmission": "transmission", "k_pipe_forward": "agent_forward", "k_lean_forward": "agent_forward",
        "k_pipe_backward_gather": "backward_gather", "k_lean_backward_gather": "backward_gather",
        "k_pipe_backward": "agent_backward", "k_lean_backward": "agent_backward", "k_lean_group_sums": "group_sums",
-       "k_lean_group_fix": "group_fix"}
+       "k_lean_group_fix": "group_fix", "k_lean_scatter_finalize": "group_small<fwd>", "k_lean_seed": "seeding"}
 per = {}
 for r in rr[2:]:
     base = re.sub(r"<.*", "", short(r[hdr["Kernel Name"]]))
@@ -72,14 +72,17 @@ for r in rr[2:]:
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0)
     per.setdefault(ids.get(base, base), []).append(
         (float(r[hdr["dram__bytes_read.sum"]]) + float(r[hdr["dram__bytes_write.sum"]])) * scale)
-# a full MIDDLE step: the backward kernel's largest launches are the middle steps (see scripts/ncu_profile.sh)
-kern = {k: (max(v) if k == "agent_backward" else sum(v) / len(v)) for k, v in per.items()}
-kern["group_chunk<fwd>"] = kern["group_chunk<bwd>"] = kern.get("group_sums", 0.0)
+# a full MIDDLE step on a WEEKDAY: the backward kernel's largest launches are the middle steps (see
+# scripts/ncu_profile.sh), the group sums' largest launches the weekdays (companies and schools active)
+kern = {k: (max(v) if k in ("agent_backward", "group_sums") else sum(v) / len(v)) for k, v in per.items()}
+kern["group_chunk<bwd>"] = kern.get("group_sums", 0.0)
+kern["group_fix<bwd>"] = kern.get("group_fix", 0.0)
 n_agents = int(sys.argv[3]) if len(sys.argv) > 3 else 56_000_000
-step = sum(kern.get(k, 0.0) for k in ("transmission", "agent_forward", "agent_backward", "backward_gather")) \
-    + 2 * (kern.get("group_sums", 0.0) + kern.get("group_fix", 0.0))
+# forward: transmission (+ scatter), scatter finalize, agent forward; backward: agent backward, group sums + fix, gather
+step = sum(kern.get(k, 0.0) for k in ("transmission", "group_small<fwd>", "agent_forward", "agent_backward", "group_sums",
+                                      "group_fix", "backward_gather"))
 git = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
-json.dump({"agents": n_agents, "git": git, "when": datetime.datetime.utcnow().isoformat(timespec="seconds") + "Z",
+json.dump({"agents": n_agents, "git": git, "when": datetime.datetime.now(datetime.timezone.utc).isoformat(timespec="seconds"),
            "source": rep, "kernels": kern, "launches": {k: len(v) for k, v in per.items()},
            "step_bytes_per_agent": step / n_agents,
            "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full); agent_backward = its "
