@@ -377,7 +377,46 @@ def measure(args, ctx, scaling, graph, full=True):
 
     prof = None
     graphed = None
-    if graph:
+    B = args.batch if (args.batch > 1 and not geo and graph) else 0      # [N, b] batching of the ensemble's samples
+    if B:
+        # batched ensemble: every replay steps B of this rank's samples through gj_step_*_batch
+        from grad_june.graphed import GraphedRunner
+        assert n_samples % B == 0, "--samples per GPU must be a multiple of --batch"
+        loss_fn_b = lambda r: r["cases_per_timestep"].sum(0) + r["deaths_per_timestep"].sum(0)   # noqa: E731
+
+        def eager_batched(lb):          # the same window through the Python loop (per-kernel events need eager launches)
+            runner.batch = B
+            leaves = []
+            for i, k in enumerate(keys):
+                leaf = lb[:, i].detach().clone().requires_grad_(True)
+                model.infection_networks.networks[k].log_beta = leaf
+                leaves.append(leaf)
+            with ops.philox_seed(7):
+                results, _ = runner()
+            loss_fn_b(results).sum().backward()
+
+        eager_batched(resident_log_beta[:B])
+        if full:
+            _lib.profile_enable(True)
+            barrier()
+            eager_batched(resident_log_beta[:B])
+            barrier()
+            scale = n_windows * (n_samples // B)
+            prof = {k: (v[0] * scale, v[1] * scale, v[2] * scale) for k, v in _lib.profile_read().items()}
+            _lib.profile_enable(False)
+        for k in keys:
+            model.infection_networks.networks[k].log_beta = torch.tensor(0.0)
+        graphed = GraphedRunner(runner, loss_fn=loss_fn_b, seed=7, batch=B)
+
+        def one_window(e2e):  # noqa: F811
+            lb_all = host_log_beta.to(dev, non_blocking=True) if e2e else resident_log_beta
+            outs = []
+            for j in range(0, n_samples, B):
+                _, grads, results = graphed(lb_all[j:j + B])
+                outs.append(torch.cat([results["cases_per_timestep"].t(), results["deaths_per_timestep"].t(), grads], dim=1))
+            out = torch.cat(outs)
+            return out.to("cpu") if e2e else out
+    elif graph:
         from grad_june.graphed import GraphedRunner
         # per-kernel pass first, eagerly (a replayed graph carries no events), then capture
         eager_window(False)
@@ -503,14 +542,17 @@ def measure(args, ctx, scaling, graph, full=True):
                        f"once per step forward and once backward ({exchange_for(data, world).mode}); boundary "
                        f"groups {nb} of {world.n_groups} local groups")
     elif world_size > 1 or n_samples > 1:
-        parallelism = (f"ensemble shard: {n_samples * world_size} beta samples per window, {n_samples} per GPU evaluated one "
-                       "after the other on a replica of the world, no data-path collective")
+        how = (f"{B} at a time as one batched [N, b] step (gj_step_forward_batch: one read of the world's index data and "
+               "profile per b samples)") if B else "one after the other"
+        parallelism = (f"ensemble shard: {n_samples * world_size} beta samples per window, {n_samples} per GPU evaluated "
+                       f"{how} on a replica of the world, no data-path collective")
     res = None
     if rank == 0:
         total_units = n_total * steps_done
         res = dict(value=total_units / (ms * 1e-3), ms=ms, steps_done=steps_done, window=window, N=N, n_total=n_total,
                    world=world, prof=prof, clk=clk, rank_ms=rank_ms, e2e_s=e2e_s, h2d=h2d, d2h=d2h, rep_ms=rep_ms,
-                   parallelism=parallelism, parity=parity, graph=graph, scaling=scaling, total_units=total_units)
+                   parallelism=parallelism, parity=parity, graph=graph, scaling=scaling, total_units=total_units,
+                   batch=B)
     if graphed is not None:
         ctx["captured_nccl"] = ctx.get("captured_nccl", False) or geo
         graphed.graph.reset()
@@ -537,6 +579,9 @@ def main():
     ap.add_argument("--samples", type=int, default=0,
                     help="ensemble: beta samples evaluated per window over all GPUs (BASELINE config 5: 1024 on a 9M "
                          "world, --agents 9000000 --window 30); default one per GPU")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="ensemble: step this many samples together as one batched [N, b] call (gj_step_forward_batch / "
+                         "gj_step_backward_batch); 0 = one sample per replay")
     ap.add_argument("--streams", type=int, default=0,
                     help="ensemble + graph: evaluate this many samples concurrently, each lane with its own replica of "
                          "the world, captured window and CUDA stream (bandwidth-bound and issue-bound kernels of "
@@ -580,6 +625,8 @@ def main():
     ctx = {"rank": rank, "world_size": world_size, "local_rank": local_rank, "dev": dev}
 
     geo = world_size > 1 and args.parallelism == "geo"
+    if args.batch > 1:         # a batched replay already fills the GPU: one lane
+        args.streams = 1
     if args.streams <= 0:      # ensembles: three concurrent lanes per GPU by default (+17 % over one, profiles/README.md)
         args.streams = 3 if (not geo and args.samples > max(world_size, 1)) else 1
     scaling = args.scaling or ("strong" if geo else "weak")
@@ -609,12 +656,22 @@ def main():
         e_gen = world.n_generic_edges / N
         g_gen = float((world.group_size > 0).sum()) / N
         alg = kernel_alg_bytes(e_gen, g_gen, e_small, g_small)
+        per_launch = N          # agents (agent-samples) one launch processes
+        if m.get("batch"):
+            # a batched launch steps b samples: the world's index words, class bytes and the packed profile are read
+            # once per b samples, everything else per sample
+            b = m["batch"]
+            shared = {"agent_forward": 1 + 4 + 8, "agent_backward": 1, "backward_gather": 1 + 4 + 8 + 16,
+                      "group_small<bwd>": 4 * e_small + 8 * g_small,
+                      "group_chunk<bwd>": 4 * (e_gen - e_small) + 8 * (g_gen - g_small)}
+            alg = {k: v - shared.get(k, 0.0) * (b - 1) / b for k, v in alg.items()}
+            per_launch = N * b
         timed = {k: v for k, v in prof.items() if v[1] > 0}
         dom = max(timed, key=lambda k: timed[k][0]) if timed else None
         roof = None
         if dom is not None:
             avg_ms = timed[dom][0] / timed[dom][1]
-            achieved = alg.get(dom, 0.0) * N / (avg_ms * 1e-3) / 1e9
+            achieved = alg.get(dom, 0.0) * per_launch / (avg_ms * 1e-3) / 1e9
             traffic = ncu_traffic(N)
             step_frac = B_ALG_STEP * value / world_size / 1e9 / peak
             roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -624,7 +681,7 @@ def main():
                     "step_alg_bytes_per_agent_timestep": B_ALG_STEP,
                     "step_achieved": B_ALG_STEP * value / world_size / 1e9,
                     "step_frac": step_frac, "step_frac_contract_279B": step_frac,
-                    "kernel_frac": {k: round(alg[k] * N / (v[0] / v[1] * 1e-3) / 1e9 / peak, 4)
+                    "kernel_frac": {k: round(alg[k] * per_launch / (v[0] / v[1] * 1e-3) / 1e9 / peak, 4)
                                     for k, v in timed.items() if alg.get(k)},
                     "kernel_ms_share": {k: round(v[0] / sum(x[0] for x in timed.values()), 4) for k, v in timed.items()},
                     "kernel_avg_ms": {k: round(v[0] / v[1], 4) for k, v in timed.items()},
@@ -643,6 +700,7 @@ def main():
             "config": {"workload": workload_name(m["n_total"] if geo else N, args.policies), "agents_per_gpu": N,
                        "agents_total": m["n_total"], "edges_per_agent": round(e_bar, 3),
                        "groups_per_agent": round(g_bar, 3), "bptt_window": m["window"], "networks": 11,
+                       "ensemble_batch": m.get("batch") or None,
                        "driver": (f"CUDA graph replay (GraphedRunner), {args.streams} concurrent lane(s)" if m["graph"]
                                   else "Python loop (Runner)"),
                        "layout_tiers": dict(zip(world.types, world.type_tier)),

@@ -483,9 +483,19 @@ struct DbetaPlan {
 __global__ void __launch_bounds__(kBlock) k_dbeta(gj_world_desc w, gj_step_params p, Plan pl, DbetaPlan dp,
                                                   const float* __restrict__ S_un, const float* __restrict__ R,
                                                   const double* __restrict__ dbeta_tile, double* __restrict__ partials,
-                                                  unsigned int* __restrict__ tickets, float* __restrict__ g_beta) {
+                                                  unsigned int* __restrict__ tickets, float* __restrict__ g_beta,
+                                                  Batch bt) {
   pdl_launch();
   pdl_wait();
+  if (bt.nb > 1) {   // batched ensemble: sample blockIdx.z
+    const int s = blockIdx.z;
+    S_un += (int64_t)s * bt.sG;
+    R += (int64_t)s * bt.sG;
+    dbeta_tile = scr_shift(dbeta_tile, bt, s);
+    partials = scr_shift(partials, bt, s);
+    tickets = scr_shift(tickets, bt, s);
+    g_beta += (int64_t)s * bt.sBeta;
+  }
   const int k = blockIdx.y;
   const gj_net net = p.nets[k];
   double acc[1] = {0.0};
@@ -560,6 +570,16 @@ static int build_channels(const gj_world_desc* w, const gj_step_params* p, Chann
   return 0;
 }
 
+static const Batch kNoBatch = {1, 0u, 0, 0, 0, 0};
+// grid of a persistent kernel in a batched launch: the resident wave is split between the samples (block = run * nb +
+// sample), at least one CTA and at most one per tile for each
+static inline int batch_grid(const gj_world_desc* w, int64_t resident, const Batch& bt) {
+  int64_t per = resident / bt.nb;
+  if (per < 1) per = 1;
+  if (per > w->n_tiles) per = w->n_tiles;
+  return (int)(per * bt.nb);
+}
+
 // persistent grids of the throughput-mode kernels.  Occupancy, the SM count and the opt-in to large dynamic
 // shared memory are properties of (kernel, device): the caches are per device (a process may drive several GPUs,
 // `system.device: cuda:1` — ADVICE r1), indexed by the CURRENT device, which the caller has made the one that owns
@@ -585,7 +605,7 @@ static int sm_count() {
 }
 // one resident wave: SMs x (CTAs of this kernel that fit on an SM), at most one CTA per tile
 template <typename K>
-static int lean_grid(const gj_world_desc* w, K kernel, OccCache* cache) {
+static int lean_grid(const gj_world_desc* w, K kernel, OccCache* cache, const Batch& bt = kNoBatch) {
   int& c = cache->v[current_device()];
   if (c == 0) {
     int per_sm = 0;
@@ -594,6 +614,7 @@ static int lean_grid(const gj_world_desc* w, K kernel, OccCache* cache) {
     c = per_sm;
   }
   const int64_t g = (int64_t)sm_count() * c;
+  if (bt.nb > 1) return batch_grid(w, g, bt);
   return (int)(w->n_tiles < g ? w->n_tiles : g);
 }
 
@@ -625,7 +646,8 @@ static bool pipe_aligned_bwd(const gj_world_desc* w, const LeanPlan& lp, const g
 }
 // one resident wave of a kernel with dynamic shared memory
 template <typename K>
-static int pipe_grid(const gj_world_desc* w, K kernel, int threads, size_t smem, OccCache* cache) {
+static int pipe_grid(const gj_world_desc* w, K kernel, int threads, size_t smem, OccCache* cache,
+                     const Batch& bt = kNoBatch) {
   int& c = cache->v[current_device()];
   if (c == 0) {
     int per_sm = 0;
@@ -635,6 +657,7 @@ static int pipe_grid(const gj_world_desc* w, K kernel, int threads, size_t smem,
     c = per_sm;
   }
   const int64_t g = (int64_t)sm_count() * c;
+  if (bt.nb > 1) return batch_grid(w, g, bt);
   return (int)(w->n_tiles < g ? w->n_tiles : g);
 }
 
@@ -674,7 +697,8 @@ static int launch_group_pass(const gj_world_desc* w, const gj_step_params* p, co
 
 // cell tier, part 1: tile partials -> per-group sums (plain + beta*pc-scaled)
 static int launch_cell_groups(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const float* beta,
-                              float* out_scaled, float* out_plain, const Scratch& sc, cudaStream_t st) {
+                              float* out_scaled, float* out_plain, const Scratch& sc, cudaStream_t st,
+                              const Batch& bt = kNoBatch) {
   if (pl.n_t2 == 0) return 0;
   int64_t maxG = 1;
   for (int j = 0; j < pl.n_t2; ++j) {
@@ -683,15 +707,15 @@ static int launch_cell_groups(const gj_world_desc* w, const gj_step_params* p, c
     if (G > maxG) maxG = G;
   }
   ProfScope ps(K_CELL, st);
-  launch_pdl(k_cell_groups, dim3(blocks_for(maxG, kBlock), pl.n_t2), dim3(kBlock), 0, st, *w, *p, pl, beta, sc.tile_part,
-             out_scaled, out_plain);
+  launch_pdl(k_cell_groups, dim3(blocks_for(maxG, kBlock), pl.n_t2, bt.nb), dim3(kBlock), 0, st, *w, *p, pl, beta,
+             (const float*)sc.tile_part, out_scaled, out_plain, bt);
   GJ_CHECK_LAUNCH("k_cell_groups");
   return 0;
 }
 
 // cell tier, part 2: per-cell sum of the scaled group sums (after the sums of straddling groups were exchanged)
 static int launch_cell_gather(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const float* in_scaled,
-                              const Scratch& sc, cudaStream_t st) {
+                              const Scratch& sc, cudaStream_t st, const Batch& bt = kNoBatch) {
   if (pl.n_t2 == 0) return 0;
   int64_t maxC = 1;
   for (int j = 0; j < pl.n_t2; ++j) {
@@ -699,7 +723,8 @@ static int launch_cell_gather(const gj_world_desc* w, const gj_step_params* p, c
     if (w->n_cells[t] > maxC) maxC = w->n_cells[t];
   }
   ProfScope ps(K_CELL, st);
-  launch_pdl(k_cell_gather, dim3(blocks_for(maxC, kBlock), pl.n_t2), dim3(kBlock), 0, st, *w, *p, pl, in_scaled, sc.cell_buf);
+  launch_pdl(k_cell_gather, dim3(blocks_for(maxC, kBlock), pl.n_t2, bt.nb), dim3(kBlock), 0, st, *w, *p, pl, in_scaled,
+             sc.cell_buf, bt);
   GJ_CHECK_LAUNCH("k_cell_gather");
   return 0;
 }
@@ -756,16 +781,16 @@ static bool lean_plan(const gj_world_desc* w, const gj_step_params* p, const Pla
 // n_giant_chunks chunks / n_giant_big multi-chunk groups of the lists), then the accumulators become fp32 sums
 static int launch_lean_group_pass(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const float* beta,
                                   const float* in, float* out_scaled, float* out_plain, const Scratch& sc, bool bwd,
-                                  cudaStream_t st);
+                                  cudaStream_t st, const Batch& bt);
 static int launch_lean_forward_sums(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const float* beta,
                                     const float* in, float* out_scaled, float* out_plain, const Scratch& sc,
-                                    cudaStream_t st) {
+                                    cudaStream_t st, const Batch& bt) {
   if (w->n_giant_chunks > 0) {
     gj_world_desc wg = *w;
     wg.n_small = 0;
     wg.n_chunks = w->n_giant_chunks;
     wg.n_big = w->n_giant_big;
-    if (int e = launch_lean_group_pass(&wg, p, pl, beta, in, out_scaled, out_plain, sc, false, st)) return e;
+    if (int e = launch_lean_group_pass(&wg, p, pl, beta, in, out_scaled, out_plain, sc, false, st, bt)) return e;
   }
   {
     ProfScope ps(K_GROUP_SMALL_F, st);
@@ -779,8 +804,8 @@ static int launch_lean_forward_sums(const gj_world_desc* w, const gj_step_params
         ++gr.n;
       }
     if (gr.n == 0) return 0;
-    launch_pdl(k_lean_scatter_finalize, dim3(blocks_for(gr.start[gr.n], kBlock)), dim3(kBlock), 0, st, *w, *p, pl, gr, beta, in,
-               sct, out_scaled, out_plain);
+    launch_pdl(k_lean_scatter_finalize, dim3(blocks_for(gr.start[gr.n], kBlock) * bt.nb), dim3(kBlock), 0, st, *w, *p, pl,
+               gr, beta, in, sct, out_scaled, out_plain, bt);
     GJ_CHECK_LAUNCH("k_lean_scatter_finalize");
   }
   return 0;
@@ -788,49 +813,60 @@ static int launch_lean_forward_sums(const gj_world_desc* w, const gj_step_params
 
 static int launch_lean_group_pass(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const float* beta,
                                   const float* in, float* out_scaled, float* out_plain, const Scratch& sc, bool bwd,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, const Batch& bt) {
   if (w->n_small > 0 || w->n_chunks > 0) {
     ProfScope ps(bwd ? K_GROUP_CHUNK_B : K_GROUP_CHUNK_F, st);
     const int chunk_blocks = w->n_chunks > 0 ? blocks_for(w->n_chunks * 32, kBlock) : 0;
     const int small_blocks = w->n_small > 0 ? blocks_for(w->n_small, kBlock) : 0;
-    launch_pdl(k_lean_group_sums, dim3(chunk_blocks + small_blocks), dim3(kBlock), 0, st, *w, *p, pl, beta, in, out_scaled,
-               out_plain, sc.part_a, chunk_blocks);
+    launch_pdl(k_lean_group_sums, dim3((chunk_blocks + small_blocks) * bt.nb), dim3(kBlock), 0, st, *w, *p, pl, beta, in,
+               out_scaled, out_plain, sc.part_a, chunk_blocks, bt);
     GJ_CHECK_LAUNCH("k_lean_group_sums");
   }
   if (w->n_big > 0) {
     ProfScope ps(bwd ? K_GROUP_FIX_B : K_GROUP_FIX_F, st);
-    launch_pdl(k_lean_group_fix, dim3(blocks_for(w->n_big * 32, kBlock)), dim3(kBlock), 0, st, *w, *p, pl, beta,
-               (const float*)sc.part_a, out_scaled, out_plain);
+    launch_pdl(k_lean_group_fix, dim3(blocks_for(w->n_big * 32, kBlock) * bt.nb), dim3(kBlock), 0, st, *w, *p, pl, beta,
+               (const float*)sc.part_a, out_scaled, out_plain, bt);
     GJ_CHECK_LAUNCH("k_lean_group_fix");
   }
   return 0;
 }
 
 // `next` != NULL: also run the transmission pass of the following step inside the agent kernel (pipelined family
-// only); returns 1 when it did
+// only); returns 1 when it did.  bt.nb > 1: a batched ensemble (pipelined kernels only; the caller has checked).
 static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, const LeanPlan& lp,
-                        const gj_fwd_io* io, const Scratch& sc, cudaStream_t st, const NextStep* next) {
+                        const gj_fwd_io* io, const Scratch& sc, cudaStream_t st, const NextStep* next,
+                        const Batch& bt = kNoBatch) {
   const bool quar = p->n_quar > 0;
+  const bool batch = bt.nb > 1;
   if (p->stage != GJ_STAGE_REST) {
     if (!p->t_ready) {
       ProfScope ps(K_TRANSMISSION, st);
-      static OccCache occ[2];
+      static OccCache occ[4];
       const Scatter sct{sc.sct_acc, sc.sct_dirty};
-      if (quar) launch_pdl(k_lean_transmission<true>, dim3(lean_grid(w, k_lean_transmission<true>, &occ[1])), dim3(kLeanThreads), 0, st, *w, *p, lp, *io, sc.tile_part, sct);
-      else launch_pdl(k_lean_transmission<false>, dim3(lean_grid(w, k_lean_transmission<false>, &occ[0])), dim3(kLeanThreads), 0, st, *w, *p, lp, *io, sc.tile_part, sct);
+#define GJ_K1(Q, B, I)                                                                                               \
+  launch_pdl(k_lean_transmission<Q, B>, dim3(lean_grid(w, k_lean_transmission<Q, B>, &occ[I], bt)), dim3(kLeanThreads), \
+             0, st, *w, *p, lp, *io, sc.tile_part, sct, bt)
+      if (batch) {
+        if (quar) GJ_K1(true, true, 3);
+        else GJ_K1(false, true, 2);
+      } else {
+        if (quar) GJ_K1(true, false, 1);
+        else GJ_K1(false, false, 0);
+      }
+#undef GJ_K1
       GJ_CHECK_LAUNCH("k_lean_transmission");
     }
     if (lp.has_generic)
       if (int e = launch_lean_forward_sums(w, p, pl, io->beta, quar ? io->Tq : io->T, io->S_scaled + lp.gen_base,
-                                           io->S_unscaled + lp.gen_base, sc, st))
+                                           io->S_unscaled + lp.gen_base, sc, st, bt))
         return e;
-    if (int e = launch_cell_groups(w, p, pl, io->beta, io->S_scaled, io->S_unscaled, sc, st)) return e;
+    if (int e = launch_cell_groups(w, p, pl, io->beta, io->S_scaled, io->S_unscaled, sc, st, bt)) return e;
   }
   if (p->stage == GJ_STAGE_SUMS) return 0;
-  if (int e = launch_cell_gather(w, p, pl, io->S_scaled, sc, st)) return e;
+  if (int e = launch_cell_gather(w, p, pl, io->S_scaled, sc, st, bt)) return e;
   if (pipe_enabled() && pipe_aligned_fwd(w, lp, io)) {
     ProfScope ps(K_AGENT_FWD, st);
-    static OccCache occ[8];
+    static OccCache occ[12];
     const bool diag = io->q || io->n;
     const size_t smem = next ? sizeof(PipeFwdSharedT<true>) : sizeof(PipeFwdSharedT<false>);
     NextStep nx;
@@ -840,24 +876,31 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
       nx.tile_part = sc.tile_part;   // consumed by this step's k_cell_groups before the agent kernel runs
       nx.sct = Scatter{sc.sct_acc, sc.sct_dirty};   // zeroed by this step's finalize pass, which has already run
     }
-#define GJ_PIPE_FWD(Q, D, X, I)                                                                                      \
-  launch_pdl(k_pipe_forward<Q, D, X>, dim3(pipe_grid(w, k_pipe_forward<Q, D, X>, kPipeThreads, smem, &occ[I])),         \
-             dim3(kPipeThreads), smem, st, *w, *p, lp, *io, (const float*)sc.cell_buf, sc.red_part, sc.tickets, nx)
-    if (next) {
-      if (quar && diag) GJ_PIPE_FWD(true, true, true, 7);
-      else if (quar) GJ_PIPE_FWD(true, false, true, 6);
-      else if (diag) GJ_PIPE_FWD(false, true, true, 5);
-      else GJ_PIPE_FWD(false, false, true, 4);
+#define GJ_PIPE_FWD(Q, D, X, B, I)                                                                                    \
+  launch_pdl(k_pipe_forward<Q, D, X, B>,                                                                              \
+             dim3(pipe_grid(w, k_pipe_forward<Q, D, X, B>, kPipeThreads, smem, &occ[I], bt)), dim3(kPipeThreads), smem, \
+             st, *w, *p, lp, *io, (const float*)sc.cell_buf, sc.red_part, sc.tickets, nx, bt)
+    if (batch) {
+      if (quar && diag) GJ_PIPE_FWD(true, true, false, true, 11);
+      else if (quar) GJ_PIPE_FWD(true, false, false, true, 10);
+      else if (diag) GJ_PIPE_FWD(false, true, false, true, 9);
+      else GJ_PIPE_FWD(false, false, false, true, 8);
+    } else if (next) {
+      if (quar && diag) GJ_PIPE_FWD(true, true, true, false, 7);
+      else if (quar) GJ_PIPE_FWD(true, false, true, false, 6);
+      else if (diag) GJ_PIPE_FWD(false, true, true, false, 5);
+      else GJ_PIPE_FWD(false, false, true, false, 4);
     } else {
-      if (quar && diag) GJ_PIPE_FWD(true, true, false, 3);
-      else if (quar) GJ_PIPE_FWD(true, false, false, 2);
-      else if (diag) GJ_PIPE_FWD(false, true, false, 1);
-      else GJ_PIPE_FWD(false, false, false, 0);
+      if (quar && diag) GJ_PIPE_FWD(true, true, false, false, 3);
+      else if (quar) GJ_PIPE_FWD(true, false, false, false, 2);
+      else if (diag) GJ_PIPE_FWD(false, true, false, false, 1);
+      else GJ_PIPE_FWD(false, false, false, false, 0);
     }
 #undef GJ_PIPE_FWD
     GJ_CHECK_LAUNCH("k_pipe_forward");
     return next ? 1 : 0;
   }
+  if (batch) return bad("batched step: the pipelined kernels are off or an array is not 16-byte aligned");
   {
     ProfScope ps(K_AGENT_FWD, st);
     static OccCache occ[4];
@@ -872,18 +915,29 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
 }
 
 static int lean_backward(const gj_world_desc* w, const gj_step_params* p, const Plan& pl, LeanPlan lp,
-                         const gj_bwd_io* io, const Scratch& sc, cudaStream_t st) {
+                         const gj_bwd_io* io, const Scratch& sc, cudaStream_t st, const Batch& bt = kNoBatch) {
   const bool quar = p->n_quar > 0;
+  const bool batch = bt.nb > 1;
   static OccCache occ_b[2], occ_g[2];
   int gather_grid = 1;
   const bool pipe = pipe_enabled() && pipe_aligned_bwd(w, lp, io);
+  if (batch && !pipe) return bad("batched step: the pipelined kernels are off or an array is not 16-byte aligned");
   if (p->stage != GJ_STAGE_REST) {
     if (pipe) {
       ProfScope ps(K_AGENT_BWD, st);
-      static OccCache occ[2];
+      static OccCache occ[4];
       const size_t smem = sizeof(PipeBwdShared);
-      if (quar) launch_pdl(k_pipe_backward<true>, dim3(pipe_grid(w, k_pipe_backward<true>, kBwdThreads, smem, &occ[1])), dim3(kBwdThreads), smem, st, *w, *p, lp, *io, sc.tile_part);
-      else launch_pdl(k_pipe_backward<false>, dim3(pipe_grid(w, k_pipe_backward<false>, kBwdThreads, smem, &occ[0])), dim3(kBwdThreads), smem, st, *w, *p, lp, *io, sc.tile_part);
+#define GJ_PIPE_BWD(Q, B, I)                                                                                          \
+  launch_pdl(k_pipe_backward<Q, B>, dim3(pipe_grid(w, k_pipe_backward<Q, B>, kBwdThreads, smem, &occ[I], bt)),          \
+             dim3(kBwdThreads), smem, st, *w, *p, lp, *io, sc.tile_part, bt)
+      if (batch) {
+        if (quar) GJ_PIPE_BWD(true, true, 3);
+        else GJ_PIPE_BWD(false, true, 2);
+      } else {
+        if (quar) GJ_PIPE_BWD(true, false, 1);
+        else GJ_PIPE_BWD(false, false, 0);
+      }
+#undef GJ_PIPE_BWD
       GJ_CHECK_LAUNCH("k_pipe_backward");
     } else {
       ProfScope ps(K_AGENT_BWD, st);
@@ -893,19 +947,30 @@ static int lean_backward(const gj_world_desc* w, const gj_step_params* p, const 
     }
     if (lp.has_generic)
       if (int e = launch_lean_group_pass(w, p, pl, io->beta, quar ? io->wq : io->w, io->cR + lp.gen_base,
-                                         io->R + lp.gen_base, sc, true, st))
+                                         io->R + lp.gen_base, sc, true, st, bt))
         return e;
-    if (int e = launch_cell_groups(w, p, pl, io->beta, io->cR, io->R, sc, st)) return e;
+    if (int e = launch_cell_groups(w, p, pl, io->beta, io->cR, io->R, sc, st, bt)) return e;
   }
   if (p->stage == GJ_STAGE_SUMS) return 0;
-  if (int e = launch_cell_gather(w, p, pl, io->cR, sc, st)) return e;
+  if (int e = launch_cell_gather(w, p, pl, io->cR, sc, st, bt)) return e;
   if (pipe) {
     ProfScope ps(K_AGENT_BWD_GATHER, st);
-    static OccCache occ[2];
+    static OccCache occ[4];
     const size_t smem = sizeof(PipeGatShared);
-    if (quar) launch_pdl(k_pipe_backward_gather<true>, dim3(gather_grid = pipe_grid(w, k_pipe_backward_gather<true>, kPipeThreads, smem, &occ[1])), dim3(kPipeThreads), smem, st, *w, *p, lp, *io, (const float*)sc.cell_buf, sc.dbeta_tile);
-    else launch_pdl(k_pipe_backward_gather<false>, dim3(gather_grid = pipe_grid(w, k_pipe_backward_gather<false>, kPipeThreads, smem, &occ[0])), dim3(kPipeThreads), smem, st, *w, *p, lp, *io, (const float*)sc.cell_buf, sc.dbeta_tile);
+#define GJ_PIPE_GAT(Q, B, I)                                                                                          \
+  launch_pdl(k_pipe_backward_gather<Q, B>,                                                                            \
+             dim3(gather_grid = pipe_grid(w, k_pipe_backward_gather<Q, B>, kPipeThreads, smem, &occ[I], bt)),          \
+             dim3(kPipeThreads), smem, st, *w, *p, lp, *io, (const float*)sc.cell_buf, sc.dbeta_tile, bt)
+    if (batch) {
+      if (quar) GJ_PIPE_GAT(true, true, 3);
+      else GJ_PIPE_GAT(false, true, 2);
+    } else {
+      if (quar) GJ_PIPE_GAT(true, false, 1);
+      else GJ_PIPE_GAT(false, false, 0);
+    }
+#undef GJ_PIPE_GAT
     GJ_CHECK_LAUNCH("k_pipe_backward_gather");
+    gather_grid /= bt.nb;   // the partials of ONE sample
   } else {
     ProfScope ps(K_AGENT_BWD_GATHER, st);
     if (quar) k_lean_backward_gather<true><<<(gather_grid = lean_grid(w, k_lean_backward_gather<true>, &occ_g[1])), kLeanThreads, 0, st>>>(*w, *p, lp, *io, sc.cell_buf, sc.dbeta_tile);
@@ -921,9 +986,9 @@ static int lean_backward(const gj_world_desc* w, const gj_step_params* p, const 
         dp.soff[k] = pl.tier[k] == GJ_TIER_GENERIC ? lp.gen_base + w->type_group_off[p->nets[k].type] : p->nets[k].s_off;
     }
     dp.n_range_parts = gather_grid;
-    dim3 grid2(kRedBlocks / 8, p->n_nets);
+    dim3 grid2(kRedBlocks / 8, p->n_nets, bt.nb);
     launch_pdl(k_dbeta, grid2, dim3(kBlock), 0, st, *w, *p, pl, dp, io->S_unscaled, (const float*)io->R,
-               (const double*)sc.dbeta_tile, sc.dbeta_part, sc.tickets, io->g_beta);
+               (const double*)sc.dbeta_tile, sc.dbeta_part, sc.tickets, io->g_beta, bt);
     GJ_CHECK_LAUNCH("k_dbeta");
   }
   return 0;
@@ -1316,10 +1381,33 @@ int gj_transmission_backward(int64_t n, float now, const float* tinf, const floa
   return 0;
 }
 
+// gj_batch -> the kernels' Batch, with the checks of the header
+static int make_batch(const gj_world_desc* w, const gj_step_params* p, const gj_batch* b, Batch* bt) {
+  if (!b) return bad("batch is NULL");
+  if (b->n_samples < 1 || b->n_samples > 1024) return bad("batch: n_samples out of range");
+  if (b->agent_stride < w->n_agents || (b->agent_stride & 3)) return bad("batch: agent_stride must be >= n_agents and a multiple of 4");
+  if ((int64_t)b->n_samples * b->agent_stride >= ((int64_t)1 << 32)) return bad("batch: n_samples * agent_stride must stay below 2^32");
+  if (b->scratch_stride < scratch_bytes(w) || (b->scratch_stride & 255)) return bad("batch: scratch_stride must be >= gj_scratch_bytes and a multiple of 256");
+  if (b->group_stride < 0 || b->beta_stride < 0 || b->red_stride < 0 || b->beta_stride > (1 << 20) || b->red_stride > (1 << 20))
+    return bad("batch: strides");
+  if (p->mode != GJ_MODE_STEP || p->stage != GJ_STAGE_ALL || p->phases != GJ_PHASE_ALL)
+    return bad("batch: only the whole fused step (GJ_MODE_STEP, GJ_PHASE_ALL, GJ_STAGE_ALL) is batched");
+  bt->nb = b->n_samples;
+  bt->sN = (uint32_t)b->agent_stride;
+  bt->sG = b->group_stride;
+  bt->sScr = b->scratch_stride;
+  bt->sBeta = (int)b->beta_stride;
+  bt->sRed = (int)b->red_stride;
+  return 0;
+}
+
 static int step_forward_impl(const gj_world_desc* w, const gj_step_params* p, const gj_step_params* next,
-                             const gj_fwd_io* io, void* stream) {
+                             const gj_fwd_io* io, void* stream, const gj_batch* batch = nullptr) {
   if (int e = check_world(w)) return e;
   if (!p || !io) return bad("params/io is NULL");
+  Batch bt = kNoBatch;
+  if (batch)
+    if (int e = make_batch(w, p, batch, &bt)) return e;
   if (p->n_stages > GJ_MAX_STAGES || p->n_age_bins > GJ_MAX_AGE_BINS || p->n_quar > GJ_MAX_QUAR) return bad("params sizes");
   if (!io->scratch) return bad("scratch is NULL");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1327,6 +1415,7 @@ static int step_forward_impl(const gj_world_desc* w, const gj_step_params* p, co
   if (N == 0) return 0;
   const Scratch sc = carve(w, io->scratch, nullptr);
   if (p->reset_scatter && w->n_groups > 0) {   // an unused look-ahead left its transmissions in the accumulators
+    if (batch) return bad("batch: reset_scatter is not supported (no look-ahead in batched steps)");
     cudaMemsetAsync(sc.sct_acc, 0, sizeof(unsigned long long) * (size_t)w->n_groups, st);
     cudaMemsetAsync(sc.sct_dirty, 0, (size_t)w->n_groups, st);
   }
@@ -1400,9 +1489,16 @@ static int step_forward_impl(const gj_world_desc* w, const gj_step_params* p, co
           have_next = aligned16(io->T_next) && aligned16(io->Tq_next);
         }
       }
+      if (batch) {
+        if (io->S_scaled && batch->n_samples > 1 && batch->group_stride < lp.gen_base + w->n_groups)
+          return bad("batch: group_stride smaller than the group-sum buffers");
+        if (p->t_ready) return bad("batch: t_ready (look-ahead) is not supported");
+        return lean_forward(w, &pp, pl, lp, io, sc, st, nullptr, bt);
+      }
       return lean_forward(w, &pp, pl, lp, io, sc, st, have_next ? &nx : nullptr);
     }
   }
+  if (batch) return bad("batch: this step does not run on the throughput-mode kernels (gj_step_plan = 0, injected noise, or no packed profile)");
   const int grid = (int)w->n_tiles;
   if (pp.stage != GJ_STAGE_REST) {
     {
@@ -1439,10 +1535,21 @@ int gj_step_forward_next(const gj_world_desc* w, const gj_step_params* p, const 
   return step_forward_impl(w, p, next, io, stream);
 }
 
-int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_bwd_io* io, void* stream) {
+int gj_step_forward_batch(const gj_world_desc* w, const gj_step_params* p, const gj_fwd_io* io, const gj_batch* batch,
+                          void* stream) {
+  if (!batch) return bad("batch is NULL");
+  const int rc = step_forward_impl(w, p, nullptr, io, stream, batch);
+  return rc > 0 ? 0 : rc;
+}
+
+static int step_backward_impl(const gj_world_desc* w, const gj_step_params* p, const gj_bwd_io* io, void* stream,
+                              const gj_batch* batch) {
   if (int e = check_world(w)) return e;
   if (!p || !io) return bad("params/io is NULL");
   if (!io->scratch) return bad("scratch is NULL");
+  Batch bt = kNoBatch;
+  if (batch)
+    if (int e = make_batch(w, p, batch, &bt)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t N = w->n_agents;
   if (N == 0) return 0;
@@ -1472,9 +1579,12 @@ int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_b
       if (!io->tinf || !io->inf || !io->cur || !io->nxt || !io->ttn || !io->tape_y0 || !io->stage_prob || !io->g_inf ||
           !io->g_tinf)
         return bad("fused step backward: state / tape arrays are NULL");
-      return lean_backward(w, &pp, pl, lp, io, sc, st);
+      if (batch && batch->n_samples > 1 && batch->group_stride < lp.gen_base + w->n_groups)
+        return bad("batch: group_stride smaller than the group-sum buffers");
+      return lean_backward(w, &pp, pl, lp, io, sc, st, bt);
     }
   }
+  if (batch) return bad("batch: this step does not run on the throughput-mode kernels (gj_step_plan = 0, injected noise, or no packed profile)");
   const int grid = (int)w->n_tiles;
   if (pp.stage != GJ_STAGE_REST) {
     {
@@ -1501,10 +1611,20 @@ int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_b
     dp.n_range_parts = w->n_tiles;
     dim3 grid2(kRedBlocks / 8, pp.n_nets);
     k_dbeta<<<grid2, kBlock, 0, st>>>(*w, pp, pl, dp, io->S_unscaled, io->R, sc.dbeta_tile, sc.dbeta_part, sc.tickets,
-                                      io->g_beta);
+                                      io->g_beta, kNoBatch);
     GJ_CHECK_LAUNCH("k_dbeta");
   }
   return 0;
+}
+
+int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_bwd_io* io, void* stream) {
+  return step_backward_impl(w, p, io, stream, nullptr);
+}
+
+int gj_step_backward_batch(const gj_world_desc* w, const gj_step_params* p, const gj_bwd_io* io, const gj_batch* batch,
+                           void* stream) {
+  if (!batch) return bad("batch is NULL");
+  return step_backward_impl(w, p, io, stream, batch);
 }
 
 int gj_philox_fill_at(uint64_t seed, uint32_t call_index, uint64_t first_agent, int64_t n, float* E, float* u, float* z,

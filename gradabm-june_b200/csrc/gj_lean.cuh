@@ -146,6 +146,13 @@ __device__ __forceinline__ TileRun lean_tiles(const gj_world_desc& w) {
   r.t1 = w.n_tiles * ((int64_t)blockIdx.x + 1) / gridDim.x;
   return r;
 }
+// ... of a batched launch: the run of this CTA among its sample's CTAs
+__device__ __forceinline__ TileRun lean_tiles(const gj_world_desc& w, const BatchCta& bc) {
+  TileRun r;
+  r.t0 = w.n_tiles * (int64_t)bc.bx / bc.gx;
+  r.t1 = w.n_tiles * ((int64_t)bc.bx + 1) / bc.gx;
+  return r;
+}
 // first tile after `tile` that lies in another cell (of any cell-tier type), clipped to the run  (CTA-uniform)
 __device__ __forceinline__ int64_t lean_segment_end(const LeanPlan& lp, int64_t tile, int64_t t1) {
   int64_t e = t1;
@@ -278,19 +285,26 @@ __device__ __forceinline__ float quar_mask(const gj_step_params& p, float cur) {
 #endif
 constexpr int kK1Batch = GJ_K1_BATCH;
 
-template <bool kQuar>
+template <bool kQuar, bool kBatch>
 __global__ void __launch_bounds__(kLeanThreads, GJ_K1_MINB) k_lean_transmission(gj_world_desc w, gj_step_params p, LeanPlan lp,
                                                                     gj_fwd_io io, float* __restrict__ tile_part,
-                                                                    Scatter sct) {
+                                                                    Scatter sct, Batch bt) {
   __shared__ ProbRow prob[200];
   pdl_launch();
   lean_load_prob<false>(prob, p, lp, io.leisure_prob);
   pdl_wait();
   __syncthreads();
+  const BatchCta bc = batch_cta<kBatch>(bt);
+  const uint32_t so = bc.so;   // batched ensemble: this sample's offset into the per-agent arrays (else 0)
+  if (kBatch) {
+    tile_part = scr_shift(tile_part, bt, bc.s);
+    sct.acc = scr_shift(sct.acc, bt, bc.s);
+    sct.dirty = scr_shift(sct.dirty, bt, bc.s);
+  }
   const float4* __restrict__ prof = reinterpret_cast<const float4*>(io.prof4);
   const float* __restrict__ g_inf = io.inf;
   const float* __restrict__ g_cur = io.cur;
-  const TileRun run = lean_tiles(w);
+  const TileRun run = lean_tiles(w, bc);
   for (int64_t tile = run.t0; tile < run.t1;) {
     const int64_t tend = lp.n_cell > 0 ? lean_segment_end(lp, tile, run.t1) : run.t1;
     const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tend];
@@ -302,8 +316,8 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_K1_MINB) k_lean_transmission(
 #pragma unroll
       for (int h = 0; h < kK1Batch; ++h) {  // the batch's streaming loads first
         const uint32_t a = base + h * kLeanThreads;
-        inf[h] = (a < a1) ? g_inf[a] : 0.0f;
-        cur[h] = (kQuar && a < a1) ? g_cur[a] : 0.0f;
+        inf[h] = (a < a1) ? g_inf[a + so] : 0.0f;
+        cur[h] = (kQuar && a < a1) ? g_cur[a + so] : 0.0f;
       }
       // the infectious few: ALL their dependent loads (infection time, packed profile, group word, class) are issued
       // before the first use — one exposed DRAM latency per batch instead of one per infectious agent
@@ -315,7 +329,7 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_K1_MINB) k_lean_transmission(
       for (int h = 0; h < kK1Batch; ++h) {
         const uint32_t a = base + h * kLeanThreads;
         const bool on = inf[h] != 0.0f;   // false beyond a1
-        tinf[h] = on ? io.tinf[a] : 0.0f;
+        tinf[h] = on ? io.tinf[a + so] : 0.0f;
         pf[h] = on ? prof[a] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         ent[h] = (on && lp.has_generic) ? w.ent1[a] : kEntNone;
         cls[h] = (on && lp.n_cell > 0) ? (int)w.cls[a] : 0;
@@ -326,11 +340,11 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_K1_MINB) k_lean_transmission(
         if (a >= a1) break;
         float T = 0.0f;
         if (inf[h] != 0.0f) T = lean_transmission<false>(p.now, tinf[h], pf[h]).coef * inf[h];
-        io.T[a] = T;
+        io.T[a + so] = T;
         float Tq = T;
         if (kQuar) {
           Tq = quar_mask(p, cur[h]) * T;
-          io.Tq[a] = Tq;
+          io.Tq[a + so] = Tq;
         }
         if (Tq != 0.0f) {   // cell-channel partial sums and the generic groups' accumulators
           if (lp.n_cell > 0) lean_channel_fma(acc, prob, cls[h], Tq, lp.n_cell);
@@ -445,15 +459,25 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_sums(gj_world_desc w, gj_
                                                             const float* __restrict__ beta,
                                                             const float* __restrict__ in, float* __restrict__ out_scaled,
                                                             float* __restrict__ out_plain, float* __restrict__ part,
-                                                            int chunk_blocks) {
+                                                            int chunk_blocks, Batch bt) {
   __shared__ LeanGroupShared gs;
   pdl_launch();
   pdl_wait();
+  uint32_t bx = blockIdx.x;
+  if (bt.nb > 1) {   // batched ensemble: block = unit * nb + sample (the samples share the member lists through L2)
+    const int s = (int)(bx % (uint32_t)bt.nb);
+    bx /= (uint32_t)bt.nb;
+    beta += (int64_t)s * bt.sBeta;
+    in += (int64_t)s * bt.sN;
+    out_scaled += (int64_t)s * bt.sG;
+    out_plain += (int64_t)s * bt.sG;
+    part = scr_shift(part, bt, s);
+  }
   lean_beta_sums(gs, w, p, pl, beta);
-  if ((int)blockIdx.x < chunk_blocks)
-    lean_group_chunk_body(w, gs, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, in, out_scaled, out_plain, part);
+  if ((int)bx < chunk_blocks)
+    lean_group_chunk_body(w, gs, ((int64_t)bx * blockDim.x + threadIdx.x) >> 5, in, out_scaled, out_plain, part);
   else
-    lean_group_small_body(w, gs, (int64_t)(blockIdx.x - chunk_blocks) * blockDim.x + threadIdx.x, in, out_scaled,
+    lean_group_small_body(w, gs, (int64_t)(bx - chunk_blocks) * blockDim.x + threadIdx.x, in, out_scaled,
                           out_plain);
 }
 
@@ -463,13 +487,22 @@ __global__ void __launch_bounds__(kBlock) k_lean_group_fix(gj_world_desc w, gj_s
                                                            const float* __restrict__ beta,
                                                            const float* __restrict__ part,
                                                            float* __restrict__ out_scaled,
-                                                           float* __restrict__ out_plain) {
+                                                           float* __restrict__ out_plain, Batch bt) {
   __shared__ LeanGroupShared gs;
   pdl_launch();
   pdl_wait();
+  uint32_t bx = blockIdx.x;
+  if (bt.nb > 1) {
+    const int s = (int)(bx % (uint32_t)bt.nb);
+    bx /= (uint32_t)bt.nb;
+    beta += (int64_t)s * bt.sBeta;
+    out_scaled += (int64_t)s * bt.sG;
+    out_plain += (int64_t)s * bt.sG;
+    part = scr_shift(part, bt, s);
+  }
   lean_beta_sums(gs, w, p, pl, beta);
   const int lane = threadIdx.x & 31;
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t i = ((int64_t)bx * blockDim.x + threadIdx.x) >> 5;
   if (i >= w.n_big) return;
   const uint32_t g = w.big_groups[i];
   const float b = lean_group_beta(gs, g);
@@ -491,12 +524,23 @@ __global__ void __launch_bounds__(kBlock) k_lean_scatter_finalize(gj_world_desc 
                                                                   GenericRanges gr, const float* __restrict__ beta,
                                                                   const float* __restrict__ in, Scatter sct,
                                                                   float* __restrict__ out_scaled,
-                                                                  float* __restrict__ out_plain) {
+                                                                  float* __restrict__ out_plain, Batch bt) {
   __shared__ LeanGroupShared gs;
   pdl_launch();
   pdl_wait();
+  uint32_t bx = blockIdx.x;
+  if (bt.nb > 1) {
+    const int s = (int)(bx % (uint32_t)bt.nb);
+    bx /= (uint32_t)bt.nb;
+    beta += (int64_t)s * bt.sBeta;
+    in += (int64_t)s * bt.sN;
+    out_scaled += (int64_t)s * bt.sG;
+    out_plain += (int64_t)s * bt.sG;
+    sct.acc = scr_shift(sct.acc, bt, s);
+    sct.dirty = scr_shift(sct.dirty, bt, s);
+  }
   lean_beta_sums(gs, w, p, pl, beta);
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = (int64_t)bx * blockDim.x + threadIdx.x;
   if (i >= gr.start[gr.n]) return;
   int r = 0;
 #pragma unroll
@@ -825,7 +869,9 @@ __device__ __forceinline__ void lean_backward_agent(const gj_step_params& p, con
                                                     float gcur_o, float gnxt_o, float gttn_o, float inv_tau, float dead,
                                                     float g_deaths, const float* __restrict__ gred_age,
                                                     const ProbRow* __restrict__ prob, float (&acc)[GJ_MAX_CHANNELS],
-                                                    const uint32_t* __restrict__ orig_id) {
+                                                    const uint32_t* __restrict__ orig_id, uint32_t soff = 0u) {
+    // soff: batched ensemble — this sample's offset into the per-sample arrays (outputs below); the agent's id in the
+    // world and in the noise stream stays `a`
     const int age = age_of(cls);
     const float n = signbit(ty) ? 1.0f : 0.0f;  // the tape's sign bit is the draw
     // symptoms^T: the draws (and the agent's id in the noise stream) are fetched only by the few agents whose
@@ -872,19 +918,20 @@ __device__ __forceinline__ void lean_backward_agent(const gj_step_params& p, con
     g_s += glam * X;
     // outputs
     const float wv = glam * s;
-    io.w[a] = wv;
+    const uint32_t ao = a + soff;
+    io.w[ao] = wv;
     float wqv = wv;
     if (kQuar) {
       wqv = glam * (quar_mask(p, cur) * s);
-      io.wq[a] = wqv;
+      io.wq[ao] = wqv;
     }
     if (wqv != 0.0f && lp.n_cell > 0) lean_channel_fma(acc, prob, cls, wqv, lp.n_cell);
-    if (io.g_s) io.g_s[a] = g_s;
-    io.g_inf[a] = gi;
-    io.g_tinf[a] = g_tinf;
-    if (io.g_cur) io.g_cur[a] = g_cur;
-    if (io.g_nxt) io.g_nxt[a] = g_nxt;
-    if (io.g_ttn) io.g_ttn[a] = g_ttn;
+    if (io.g_s) io.g_s[ao] = g_s;
+    io.g_inf[ao] = gi;
+    io.g_tinf[ao] = g_tinf;
+    if (io.g_cur) io.g_cur[ao] = g_cur;
+    if (io.g_nxt) io.g_nxt[ao] = g_nxt;
+    if (io.g_ttn) io.g_ttn[ao] = g_ttn;
 }
 
 // =====================================================================================================

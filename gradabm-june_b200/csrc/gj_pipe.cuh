@@ -213,9 +213,11 @@ struct PipeFwdSharedT {
   alignas(8) uint64_t full[kPipeStages];
 };
 
+// so: batched ensemble — this sample's offset into the per-sample arrays (a multiple of four agents: the copies stay
+// 16-byte aligned); the world's arrays are shared
 __device__ __forceinline__ void pipe_fwd_issue(PipeFwdStage& sg, uint64_t* bar, const gj_world_desc& w,
                                                const LeanPlan& lp, const gj_fwd_io& io, const float* Tr, int64_t tile,
-                                               bool has_gen, bool has_range) {
+                                               bool has_gen, bool has_range, uint32_t so = 0u) {
   const TileSpan t = tile_span(w, tile);
   uint32_t total = 6u * t.n4 + (t.hi16 - t.lo16);
   if (has_gen) total += t.n4;
@@ -224,29 +226,42 @@ __device__ __forceinline__ void pipe_fwd_issue(PipeFwdStage& sg, uint64_t* bar, 
   mbar_expect_tx(bar, total);
   const Copier c{bar};
   if (w.orig_id) c.f4(sg.oid, w.orig_id, t);
-  c.f4(sg.s, io.s, t);
-  c.f4(sg.inf, io.inf, t);
-  c.f4(sg.tinf, io.tinf, t);
-  c.f4(sg.cur, io.cur, t);
-  c.f4(sg.nxt, io.nxt, t);
-  c.f4(sg.ttn, io.ttn, t);
+  c.f4(sg.s, io.s + so, t);
+  c.f4(sg.inf, io.inf + so, t);
+  c.f4(sg.tinf, io.tinf + so, t);
+  c.f4(sg.cur, io.cur + so, t);
+  c.f4(sg.nxt, io.nxt + so, t);
+  c.f4(sg.ttn, io.ttn + so, t);
   if (has_gen) c.f4(sg.ent, w.ent1, t);
   if (has_range) {
     c.f4(sg.slot, lp.r_slot, t);
     if (!lp.r_pc_lut) c.f4(sg.rpc, lp.r_pc, t);
-    bulk_g2s(sg.T, Tr + t.tlo, (t.thi - t.tlo) * 4u, bar);
+    bulk_g2s(sg.T, Tr + so + t.tlo, (t.thi - t.tlo) * 4u, bar);
   }
   bulk_g2s(sg.cls, w.cls + t.lo16, t.hi16 - t.lo16, bar);
 }
 
-template <bool kQuar, bool kDiag, bool kNext>
+template <bool kQuar, bool kDiag, bool kNext, bool kBatch>
 __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc w, gj_step_params p, LeanPlan lp,
                                                                  gj_fwd_io io, const float* __restrict__ cell_buf,
                                                                  double* __restrict__ red_part,
-                                                                 unsigned int* __restrict__ ticket, NextStep nx) {
+                                                                 unsigned int* __restrict__ ticket, NextStep nx,
+                                                                 Batch bt) {
+  static_assert(!(kNext && kBatch), "the look-ahead transmission pass is not batched");
   extern __shared__ __align__(128) unsigned char pipe_smem[];
   PipeFwdSharedT<kNext>& sh = *reinterpret_cast<PipeFwdSharedT<kNext>*>(pipe_smem);
-  const TileRun run = lean_tiles(w);
+  const BatchCta bc = batch_cta<kBatch>(bt);
+  const uint32_t so = bc.so;
+  float* __restrict__ red_out = io.red;
+  const float* __restrict__ beta_in = io.beta;
+  if (kBatch) {   // this sample's slices of the scratch and of the small per-sample arrays
+    cell_buf = scr_shift(cell_buf, bt, bc.s);
+    red_part = scr_shift(red_part, bt, bc.s);
+    ticket = scr_shift(ticket, bt, bc.s);
+    if (red_out) red_out += (int64_t)bc.s * bt.sRed;
+    beta_in += (int64_t)bc.s * bt.sBeta;
+  }
+  const TileRun run = lean_tiles(w, bc);
   const float* __restrict__ Tr = (kQuar && !lp.r_house) ? io.Tq : io.T;
   const bool has_gen = lp.has_generic != 0, has_range = lp.n_range > 0;
   pdl_launch();
@@ -260,15 +275,15 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
     }
   }
   pdl_wait();   // everything below reads what earlier kernels of the stream wrote
-  if (threadIdx.x < p.n_nets) sh.beta[threadIdx.x] = io.beta[threadIdx.x];
+  if (threadIdx.x < p.n_nets) sh.beta[threadIdx.x] = beta_in[threadIdx.x];
   if (threadIdx.x < 100) sh.hist[threadIdx.x] = 0.0f;
   if (threadIdx.x == 0) sh.deaths = 0.0f;
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 0; i < kPipeStages; ++i)
-      if (run.t0 + i < run.t1) pipe_fwd_issue(sh.st[i], &sh.full[i], w, lp, io, Tr, run.t0 + i, has_gen, has_range);
+      if (run.t0 + i < run.t1) pipe_fwd_issue(sh.st[i], &sh.full[i], w, lp, io, Tr, run.t0 + i, has_gen, has_range, so);
   }
-  const float* __restrict__ SP = io.S_scaled + lp.gen_base;
+  const float* __restrict__ SP = io.S_scaled + lp.gen_base + (kBatch ? (int64_t)bc.s * bt.sG : (int64_t)0);
   const float dead = (float)(p.n_stages - 1);
   const float inv_tau = 1.0f / p.tau;
   const float beta_r = lp.n_range > 0 ? sh.beta[lp.r_net] : 0.0f;
@@ -318,7 +333,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
       const uint64_t ga = w.orig_id ? (uint64_t)sg.oid[i] : p.agent_offset + a;
       const float rpc = !has_range ? 0.0f : (lp.r_pc_lut ? ((sg.slot[i] == kNoSlot) ? 0.0f : sh.pc_lut[sg.slot[i] & 0xFFFFu])
                                                          : sg.rpc[i]);
-      const FwdOut o = lean_forward_agent<kQuar, kDiag>(p, lp, io, a, ga, hs, gv, Lc, beta_r, rpc,
+      const FwdOut o = lean_forward_agent<kQuar, kDiag>(p, lp, io, a + so, ga, hs, gv, Lc, beta_r, rpc,
                                                         sg.s[i], sg.inf[i], sg.tinf[i], sg.cur[i], sg.nxt[i], sg.ttn[i], cls,
                                                         inv_tau, dead, sh.hist, &sh.deaths);
       if (kNext) {   // TransmissionUpdater of the next step (same arithmetic as k_lean_transmission)
@@ -340,7 +355,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
       }
     }
     if (pipe_release() && tile + kPipeStages < run.t1)
-      pipe_fwd_issue(sg, &sh.full[stg], w, lp, io, Tr, tile + kPipeStages, has_gen, has_range);
+      pipe_fwd_issue(sg, &sh.full[stg], w, lp, io, Tr, tile + kPipeStages, has_gen, has_range, so);
     if (++stg == kPipeStages) {
       stg = 0;
       parity ^= 1u;
@@ -355,7 +370,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
       }
     }
   }
-  if (io.red) {
+  if (red_out) {
     __syncthreads();
     const int nr = 2 + p.n_age_bins;
     if ((int)threadIdx.x < nr) {
@@ -368,9 +383,9 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
         const int b = threadIdx.x - 2;
         for (int c = max(p.age_bins[b] + 1, 0); c < p.age_bins[b + 1] && c < 100; ++c) v += (double)sh.hist[c];
       }
-      red_part[(int64_t)blockIdx.x * kMaxRed + threadIdx.x] = v;
+      red_part[(int64_t)bc.bx * kMaxRed + threadIdx.x] = v;
     }
-    finish_partials<kMaxRed>(nr, red_part, gridDim.x, ticket, io.red);
+    finish_partials<kMaxRed>(nr, red_part, bc.gx, ticket, red_out);
   }
 }
 
@@ -394,18 +409,18 @@ struct BwdCot {
 };
 
 __device__ __forceinline__ void pipe_bwd_issue(PipeBwdStage& sg, uint64_t* bar, const gj_world_desc& w,
-                                               const gj_bwd_io& io, int64_t tile) {
+                                               const gj_bwd_io& io, int64_t tile, uint32_t so = 0u) {
   const TileSpan t = tile_span(w, tile);
   const uint32_t total = 7u * t.n4 + (t.hi16 - t.lo16);
   mbar_expect_tx(bar, total);
   const Copier c{bar};
-  c.f4(sg.s, io.s, t);
-  c.f4(sg.tinf, io.tinf, t);
-  c.f4(sg.cur, io.cur, t);
-  c.f4(sg.nxt, io.nxt, t);
-  c.f4(sg.ttn, io.ttn, t);
-  c.f4(sg.ty, io.tape_y0, t);
-  c.f4(sg.v, io.tape_v, t);
+  c.f4(sg.s, io.s + so, t);
+  c.f4(sg.tinf, io.tinf + so, t);
+  c.f4(sg.cur, io.cur + so, t);
+  c.f4(sg.nxt, io.nxt + so, t);
+  c.f4(sg.ttn, io.ttn + so, t);
+  c.f4(sg.ty, io.tape_y0 + so, t);
+  c.f4(sg.v, io.tape_v + so, t);
   bulk_g2s(sg.cls, w.cls + t.lo16, t.hi16 - t.lo16, bar);
 }
 
@@ -415,12 +430,20 @@ __device__ __forceinline__ void pipe_bwd_issue(PipeBwdStage& sg, uint64_t* bar, 
 constexpr int kBwdThreads = GJ_PIPE_BWD_THREADS;
 constexpr int kBwdPer = kPipeTile / kBwdThreads;
 constexpr int kBwdCtas = kBwdThreads == 256 ? 3 : 2;
-template <bool kQuar>
+template <bool kQuar, bool kBatch>
 __global__ void __launch_bounds__(kBwdThreads, kBwdCtas) k_pipe_backward(gj_world_desc w, gj_step_params p, LeanPlan lp,
-                                                                  gj_bwd_io io, float* __restrict__ tile_part) {
+                                                                  gj_bwd_io io, float* __restrict__ tile_part,
+                                                                  Batch bt) {
   extern __shared__ __align__(128) unsigned char pipe_smem[];
   PipeBwdShared& sh = *reinterpret_cast<PipeBwdShared*>(pipe_smem);
-  const TileRun run = lean_tiles(w);
+  const BatchCta bc = batch_cta<kBatch>(bt);
+  const uint32_t so = bc.so;
+  const float* __restrict__ g_red = io.g_red;
+  if (kBatch) {
+    tile_part = scr_shift(tile_part, bt, bc.s);
+    if (g_red) g_red += (int64_t)bc.s * bt.sRed;
+  }
+  const TileRun run = lean_tiles(w, bc);
   const BwdCot cot{{io.g_s_o, io.g_inf_o, io.g_tinf_o, io.g_cur_o, io.g_nxt_o, io.g_ttn_o}};
   pdl_launch();
   pipe_init_barriers(sh.full);
@@ -428,21 +451,21 @@ __global__ void __launch_bounds__(kBwdThreads, kBwdCtas) k_pipe_backward(gj_worl
   pdl_wait();   // everything below reads what earlier kernels of the stream wrote
   if (threadIdx.x < 100) {
     float g = 0.0f;
-    if (io.g_red) {
-      g = io.g_red[0];
+    if (g_red) {
+      g = g_red[0];
       const int age = threadIdx.x;
       for (int b = 0; b < p.n_age_bins; ++b)
-        if (age > p.age_bins[b] && age < p.age_bins[b + 1]) g += io.g_red[2 + b];
+        if (age > p.age_bins[b] && age < p.age_bins[b + 1]) g += g_red[2 + b];
     }
     sh.gred_age[threadIdx.x] = g;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 0; i < kPipeStages; ++i)
-      if (run.t0 + i < run.t1) pipe_bwd_issue(sh.st[i], &sh.full[i], w, io, run.t0 + i);
+      if (run.t0 + i < run.t1) pipe_bwd_issue(sh.st[i], &sh.full[i], w, io, run.t0 + i, so);
   }
   const float dead = (float)(p.n_stages - 1);
-  const float g_deaths = io.g_red ? io.g_red[1] / dead : 0.0f;
+  const float g_deaths = g_red ? g_red[1] / dead : 0.0f;
   const float inv_tau = 1.0f / p.tau;
   float acc[GJ_MAX_CHANNELS];
 #pragma unroll
@@ -466,7 +489,7 @@ __global__ void __launch_bounds__(kBwdThreads, kBwdCtas) k_pipe_backward(gj_worl
       const uint32_t a = a0 + threadIdx.x + h * kBwdThreads;
       const uint32_t al = a < a1 ? a : a0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) c[h][k] = cot.p[k] ? cot.p[k][al] : 0.0f;
+      for (int k = 0; k < 6; ++k) c[h][k] = cot.p[k] ? cot.p[k][al + so] : 0.0f;
     }
     const uint32_t sk = a0 & 3u, sk16 = a0 & 15u;
 #pragma unroll
@@ -476,10 +499,10 @@ __global__ void __launch_bounds__(kBwdThreads, kBwdCtas) k_pipe_backward(gj_worl
       if (a >= a1) break;
       lean_backward_agent<kQuar>(p, lp, io, a, sg.s[i], sg.tinf[i], sg.cur[i], sg.nxt[i], sg.ttn[i], sg.ty[i], sg.v[i],
                                  sg.cls[j + sk16], c[h][0], c[h][1], c[h][2], c[h][3], c[h][4], c[h][5], inv_tau, dead,
-                                 g_deaths, sh.gred_age, sh.prob, acc, w.orig_id);
+                                 g_deaths, sh.gred_age, sh.prob, acc, w.orig_id, so);
     }
     if (pipe_release() && tile + kPipeStages < run.t1)
-      pipe_bwd_issue(sg, &sh.full[stg], w, io, tile + kPipeStages);
+      pipe_bwd_issue(sg, &sh.full[stg], w, io, tile + kPipeStages, so);
     const bool ends_cell = lp.n_cell > 0 && (tile + 1 == run.t1 || (sh.next_flag[stg] & 1u));   // after the barrier
     if (++stg == kPipeStages) {
       stg = 0;
@@ -518,7 +541,7 @@ struct PipeGatShared {
 template <bool kQuar>
 __device__ __forceinline__ void pipe_gat_issue(PipeGatStage& sg, uint64_t* bar, const gj_world_desc& w,
                                                const LeanPlan& lp, const gj_bwd_io& io, const float* wr, int64_t tile,
-                                               bool has_gen, bool has_range) {
+                                               bool has_gen, bool has_range, uint32_t so = 0u) {
   const TileSpan t = tile_span(w, tile);
   uint32_t total = 4u * t.n4 + (t.hi16 - t.lo16);
   if (kQuar) total += t.n4;
@@ -526,29 +549,37 @@ __device__ __forceinline__ void pipe_gat_issue(PipeGatStage& sg, uint64_t* bar, 
   if (has_range) total += (lp.r_pc_lut ? 2u : 3u) * t.n4 + (t.thi - t.tlo) * 4u;
   mbar_expect_tx(bar, total);
   const Copier c{bar};
-  c.f4(sg.inf, io.inf, t);
-  c.f4(sg.tinf, io.tinf, t);
-  c.f4(sg.gi, io.g_inf, t);
-  c.f4(sg.gt, io.g_tinf, t);
-  if (kQuar) c.f4(sg.cur, io.cur, t);
+  c.f4(sg.inf, io.inf + so, t);
+  c.f4(sg.tinf, io.tinf + so, t);
+  c.f4(sg.gi, io.g_inf + so, t);
+  c.f4(sg.gt, io.g_tinf + so, t);
+  if (kQuar) c.f4(sg.cur, io.cur + so, t);
   if (has_gen) c.f4(sg.ent, w.ent1, t);
   if (has_range) {
     c.f4(sg.slot, lp.r_slot, t);
     if (!lp.r_pc_lut) c.f4(sg.rpc, lp.r_pc, t);
-    c.f4(sg.Tm, io.T_in, t);
-    bulk_g2s(sg.wr, wr + t.tlo, (t.thi - t.tlo) * 4u, bar);
+    c.f4(sg.Tm, io.T_in + so, t);
+    bulk_g2s(sg.wr, wr + so + t.tlo, (t.thi - t.tlo) * 4u, bar);
   }
   bulk_g2s(sg.cls, w.cls + t.lo16, t.hi16 - t.lo16, bar);
 }
 
-template <bool kQuar>
+template <bool kQuar, bool kBatch>
 __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward_gather(gj_world_desc w, gj_step_params p,
                                                                          LeanPlan lp, gj_bwd_io io,
                                                                          const float* __restrict__ cell_buf,
-                                                                         double* __restrict__ dbeta_part) {
+                                                                         double* __restrict__ dbeta_part, Batch bt) {
   extern __shared__ __align__(128) unsigned char pipe_smem[];
   PipeGatShared& sh = *reinterpret_cast<PipeGatShared*>(pipe_smem);
-  const TileRun run = lean_tiles(w);
+  const BatchCta bc = batch_cta<kBatch>(bt);
+  const uint32_t so = bc.so;
+  const float* __restrict__ beta_in = io.beta;
+  if (kBatch) {
+    cell_buf = scr_shift(cell_buf, bt, bc.s);
+    dbeta_part = scr_shift(dbeta_part, bt, bc.s);
+    beta_in += (int64_t)bc.s * bt.sBeta;
+  }
+  const TileRun run = lean_tiles(w, bc);
   const float* __restrict__ wr = (kQuar && !lp.r_house) ? io.wq : io.w;  // member values of the range network
   const bool has_gen = lp.has_generic != 0, has_range = lp.n_range > 0;
   pdl_launch();
@@ -556,13 +587,14 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward_gather(gj_wor
   lean_load_prob<false>(sh.prob, p, lp, io.leisure_prob);
   pipe_fill_pc_lut(sh.pc_lut);
   pdl_wait();   // everything below reads what earlier kernels of the stream wrote
-  if (threadIdx.x < p.n_nets) sh.beta[threadIdx.x] = io.beta[threadIdx.x];
+  if (threadIdx.x < p.n_nets) sh.beta[threadIdx.x] = beta_in[threadIdx.x];
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 0; i < kPipeStages; ++i)
-      if (run.t0 + i < run.t1) pipe_gat_issue<kQuar>(sh.st[i], &sh.full[i], w, lp, io, wr, run.t0 + i, has_gen, has_range);
+      if (run.t0 + i < run.t1)
+        pipe_gat_issue<kQuar>(sh.st[i], &sh.full[i], w, lp, io, wr, run.t0 + i, has_gen, has_range, so);
   }
-  const float* __restrict__ cRP = io.cR + lp.gen_base;
+  const float* __restrict__ cRP = io.cR + lp.gen_base + (kBatch ? (int64_t)bc.s * bt.sG : (int64_t)0);
   const float4* __restrict__ prof = reinterpret_cast<const float4*>(io.prof4);
   const float beta_r = lp.n_range > 0 ? sh.beta[lp.r_net] : 0.0f;
   double db[1] = {0.0};
@@ -606,19 +638,19 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_backward_gather(gj_wor
       const float gv = lean_generic_finish(w, cRP, ent[h], a, gen[h]);
       const float rpc = !has_range ? 0.0f : (lp.r_pc_lut ? ((sg.slot[i] == kNoSlot) ? 0.0f : sh.pc_lut[sg.slot[i] & 0xFFFFu])
                                                          : sg.rpc[i]);
-      lean_gather_agent<kQuar>(p, lp, io, a, R, gv, Lc, beta_r, rpc,
+      lean_gather_agent<kQuar>(p, lp, io, a + so, R, gv, Lc, beta_r, rpc,
                                has_range ? sg.Tm[i] : 0.0f, kQuar ? sg.cur[i] : 0.0f, sg.inf[i], sg.tinf[i], pf[h],
                                sg.gi[i], sg.gt[i], db[0]);
     }
     if (pipe_release() && tile + kPipeStages < run.t1)
-      pipe_gat_issue<kQuar>(sg, &sh.full[stg], w, lp, io, wr, tile + kPipeStages, has_gen, has_range);
+      pipe_gat_issue<kQuar>(sg, &sh.full[stg], w, lp, io, wr, tile + kPipeStages, has_gen, has_range, so);
     if (++stg == kPipeStages) {
       stg = 0;
       parity ^= 1u;
     }
   }
   if (lp.n_range > 0)
-    block_sums<double, 1, kPipeWarps>(db, 1, dbeta_part + (int64_t)blockIdx.x * GJ_MAX_RANGE_NETS);
+    block_sums<double, 1, kPipeWarps>(db, 1, dbeta_part + (int64_t)bc.bx * GJ_MAX_RANGE_NETS);
 }
 
 }  // namespace gj

@@ -31,6 +31,48 @@ struct Plan {
   const float* rpc[GJ_MAX_NETS];      //                 and per-agent contact probability
 };
 
+// ---- batched ensemble (gj_step_forward_batch / gj_step_backward_batch) ------------------------------------------
+// b independent samples on one world: sample s of a batched launch reads and writes every per-sample array at a fixed
+// stride behind sample 0's (gj_batch).  Persistent and 1-D kernels interleave the samples in the block index
+// (block = unit * nb + sample), so the CTAs that walk the same agent tiles / group lists run next to each other and
+// share the world's index data through L2; kernels with a 2-D grid take the sample from blockIdx.z.
+struct Batch {
+  int nb;          // samples
+  uint32_t sN;     // stride of the per-agent arrays (elements; nb * sN < 2^32)
+  int64_t sG;      // stride of the group-sum buffers (elements)
+  int64_t sScr;    // stride of the scratch buffers (bytes, multiple of 256)
+  int sBeta, sRed; // strides of beta / g_beta and red / g_red (elements)
+};
+struct BatchCta {
+  int s;           // sample of this CTA
+  uint32_t bx, gx; // its block index among the sample's CTAs, and how many those are
+  uint32_t so;     // s * sN: added to agent indices of per-sample arrays
+};
+template <bool kBatch>
+__device__ __forceinline__ BatchCta batch_cta(const Batch& bt) {
+  BatchCta c;
+  if (kBatch) {
+    c.s = (int)(blockIdx.x % (uint32_t)bt.nb);
+    c.bx = blockIdx.x / (uint32_t)bt.nb;
+    c.gx = gridDim.x / (uint32_t)bt.nb;
+    c.so = (uint32_t)c.s * bt.sN;
+  } else {
+    c.s = 0;
+    c.bx = blockIdx.x;
+    c.gx = gridDim.x;
+    c.so = 0u;
+  }
+  return c;
+}
+template <typename T>
+__device__ __forceinline__ T* scr_shift(T* p, const Batch& bt, int s) {
+  return reinterpret_cast<T*>(reinterpret_cast<char*>(p) + (int64_t)s * bt.sScr);
+}
+template <typename T>
+__device__ __forceinline__ const T* scr_shift(const T* p, const Batch& bt, int s) {
+  return reinterpret_cast<const T*>(reinterpret_cast<const char*>(p) + (int64_t)s * bt.sScr);
+}
+
 // ---- shared-memory tables ---------------------------------------------------------------------------
 struct TileTables {
   float prob[GJ_MAX_CHANNELS][200];  // attendance probability by (sex, age) class for today's day type
@@ -91,11 +133,12 @@ __device__ __forceinline__ void block_sums(T (&v)[kR], int nr, T* __restrict__ o
 template <int kR>
 __device__ __forceinline__ void finish_partials(int nr, const double* __restrict__ partials, int64_t n_part,
                                                 unsigned int* __restrict__ ticket, float* __restrict__ out) {
+  // n_part = number of CTAs taking a ticket (the whole grid, or one sample's CTAs of a batched launch)
   __shared__ bool last;
   __shared__ double sm[32];
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == (unsigned int)n_part - 1u);
   __syncthreads();
   if (!last) return;
   __threadfence();
@@ -164,9 +207,17 @@ __global__ void __launch_bounds__(kBlock) k_tile_transmission(gj_world_desc w, g
 __global__ void __launch_bounds__(kBlock) k_cell_groups(gj_world_desc w, gj_step_params p, Plan pl,
                                                         const float* __restrict__ beta,
                                                         const float* __restrict__ tile_part,
-                                                        float* __restrict__ out_scaled, float* __restrict__ out_plain) {
+                                                        float* __restrict__ out_scaled, float* __restrict__ out_plain,
+                                                        Batch bt) {
   pdl_launch();
   pdl_wait();
+  if (bt.nb > 1) {   // batched ensemble: sample blockIdx.z
+    const int s = blockIdx.z;
+    beta += (int64_t)s * bt.sBeta;
+    tile_part = scr_shift(tile_part, bt, s);
+    out_scaled += (int64_t)s * bt.sG;
+    out_plain += (int64_t)s * bt.sG;
+  }
   const int j = blockIdx.y;
   const int k = pl.t2_net[j];
   const gj_net net = p.nets[k];
@@ -188,9 +239,14 @@ __global__ void __launch_bounds__(kBlock) k_cell_groups(gj_world_desc w, gj_step
 // one thread per (cell channel, cell): sum over the cell's groups (agent edge order)
 __global__ void __launch_bounds__(kBlock) k_cell_gather(gj_world_desc w, gj_step_params p, Plan pl,
                                                         const float* __restrict__ in_scaled,
-                                                        float* __restrict__ cell_buf) {
+                                                        float* __restrict__ cell_buf, Batch bt) {
   pdl_launch();
   pdl_wait();
+  if (bt.nb > 1) {
+    const int s = blockIdx.z;
+    in_scaled += (int64_t)s * bt.sG;
+    cell_buf = scr_shift(cell_buf, bt, s);
+  }
   const int j = blockIdx.y;
   const gj_net net = p.nets[pl.t2_net[j]];
   const int t = net.type;

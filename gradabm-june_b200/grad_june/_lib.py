@@ -18,7 +18,7 @@ GJ_MAX_STAGES = 16
 GJ_MAX_QUAR = 4
 GJ_MAX_AGE_BINS = 8
 GJ_MAX_CHANNELS = 8
-GJ_ABI_VERSION = 9
+GJ_ABI_VERSION = 10
 
 KIND_PLAIN, KIND_HOUSEHOLD, KIND_LEISURE, KIND_CARE_VISIT = 0, 1, 2, 3
 PHASE_NETWORKS, PHASE_SAMPLE, PHASE_INFECT, PHASE_SYMPTOMS, PHASE_ALL = 1, 2, 4, 8, 15
@@ -110,6 +110,13 @@ class BwdIO(C.Structure):
     _fields_ = [(name, C.c_void_p) for name in _BWD_FIELDS]
 
 
+class Batch(C.Structure):
+    """gj_batch: strides of a batched ensemble call (gj_step_forward_batch / gj_step_backward_batch)."""
+    _fields_ = [("n_samples", C.c_int32), ("_pad0", C.c_int32), ("agent_stride", C.c_int64),
+                ("group_stride", C.c_int64), ("beta_stride", C.c_int64), ("red_stride", C.c_int64),
+                ("scratch_stride", C.c_int64)]
+
+
 class GradJuneLibraryError(RuntimeError):
     pass
 
@@ -184,6 +191,10 @@ def lib():
     L.gj_step_forward_next.argtypes = [C.POINTER(WorldDesc), C.POINTER(StepParams), C.POINTER(StepParams),
                                        C.POINTER(FwdIO), C.c_void_p]
     L.gj_step_backward.argtypes = [C.POINTER(WorldDesc), C.POINTER(StepParams), C.POINTER(BwdIO), C.c_void_p]
+    L.gj_step_forward_batch.argtypes = [C.POINTER(WorldDesc), C.POINTER(StepParams), C.POINTER(FwdIO), C.POINTER(Batch),
+                                        C.c_void_p]
+    L.gj_step_backward_batch.argtypes = [C.POINTER(WorldDesc), C.POINTER(StepParams), C.POINTER(BwdIO),
+                                         C.POINTER(Batch), C.c_void_p]
     L.gj_philox_fill_at.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]
     L.gj_step_plan.argtypes = [C.POINTER(WorldDesc), C.POINTER(StepParams), C.POINTER(C.c_int64), C.c_int]
@@ -238,6 +249,7 @@ def check(rc, what):
 EXPORTED_SYMBOLS = [
     "gj_abi_version", "gj_last_error", "gj_config", "gj_scratch_bytes", "gj_profile_prepare", "gj_profile_pack",
     "gj_transmission_forward", "gj_transmission_backward", "gj_step_forward", "gj_step_forward_next", "gj_step_backward",
+    "gj_step_forward_batch", "gj_step_backward_batch",
     "gj_philox_fill", "gj_philox_fill_at", "gj_step_plan", "gj_philox4x32_10", "gj_philox2x32_10", "gj_profile_enable", "gj_profile_read",
     "gj_profile_kernel_name", "gj_pipeline_enable", "gj_boundary_pack", "gj_boundary_unpack",
     "gj_peer_create", "gj_peer_handle", "gj_peer_connect", "gj_peer_exchange", "gj_peer_status", "gj_peer_destroy",

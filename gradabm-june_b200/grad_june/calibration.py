@@ -4,7 +4,9 @@ log-beta samples on one world, sharded across the GPUs of a box).
 The reference evaluates one sample per Python-driven run (example_scripts/run_model.py:6-11).  Here every rank holds
 a replica of the world and its own captured window (:class:`grad_june.graphed.GraphedRunner`); a batch ``[B, K]`` of
 log-beta vectors is dealt out round-robin, each rank replays its samples back to back (one graph launch per sample)
-and the losses and gradients are all-gathered — no collective on the data path.
+and the losses and gradients are all-gathered — no collective on the data path.  With ``batch=b`` every replay steps
+b of the rank's samples together ([N, b] batching, ``gj_step_forward_batch``): one read of the world's index data per
+b samples; ``loss_fn`` then returns one loss per sample.
 """
 from typing import Callable, Optional, Sequence
 
@@ -15,10 +17,11 @@ from .graphed import GraphedRunner
 
 class EnsembleEvaluator:
     def __init__(self, runner, loss_fn: Callable[[dict], torch.Tensor], networks: Optional[Sequence[str]] = None,
-                 seed: int = 0, process_group=None):
+                 seed: int = 0, process_group=None, batch: Optional[int] = None):
         import torch.distributed as dist
 
-        self.graphed = GraphedRunner(runner, loss_fn, networks=networks, seed=seed)
+        self.batch = int(batch) if batch else None
+        self.graphed = GraphedRunner(runner, loss_fn, networks=networks, seed=seed, batch=self.batch)
         self.names = self.graphed.names
         self.group = process_group
         self.distributed = dist.is_available() and dist.is_initialized()
@@ -35,7 +38,19 @@ class EnsembleEvaluator:
         B, K = log_betas.shape
         per = -(-B // self.world_size)                       # samples per rank, the last ones padded
         mine = torch.zeros(per, K + 1, device=dev)
-        for j in range(per):
+        if self.batch:
+            b = self.batch
+            ids = torch.arange(per, device=dev) * self.world_size + self.rank      # this rank's samples
+            ids = ids[ids < B]
+            for j0 in range(0, ids.numel(), b):
+                chunk = ids[j0:j0 + b]
+                lb = log_betas[chunk]
+                if chunk.numel() < b:                         # the last replay is padded with copies of its first row
+                    lb = torch.cat([lb, lb[:1].expand(b - chunk.numel(), K)])
+                loss, grads, _ = self.graphed(lb)
+                mine[j0:j0 + chunk.numel(), 0] = loss[: chunk.numel()]
+                mine[j0:j0 + chunk.numel(), 1:] = grads[: chunk.numel()]
+        for j in range(per if not self.batch else 0):
             i = j * self.world_size + self.rank               # round-robin: sample i goes to rank i % world_size
             if i >= B:
                 break

@@ -12,6 +12,13 @@ the NCCL all-reduces of a partitioned world — is capturable with ``torch.cuda.
 Noise: the Philox key and call indices are kernel arguments, so every replay draws the SAME noise (common random
 numbers across parameter samples — the usual variance reduction for calibration gradients); ``recapture(seed)``
 re-records the graph with another key.
+
+``batch=b`` captures a BATCHED window: b parameter samples advance together through
+``gj_step_forward_batch`` / ``gj_step_backward_batch`` — one read of the world's index data and of the infectiousness
+profile serves all b samples, and every kernel launch does b samples' work.  ``log_beta`` is then [b, K], ``loss_fn``
+receives result series of shape [T+1, b] and must return one loss per sample ([b]); the gradients come back as [b, K]
+(the samples are independent, so the gradient of the summed loss IS the per-sample gradient).  Sample r of a batched
+replay is bit-identical to an unbatched replay with ``log_beta[r]`` (same Philox key).
 """
 import warnings
 from typing import Callable, Optional, Sequence
@@ -23,16 +30,21 @@ from . import ops
 
 class GraphedRunner:
     def __init__(self, runner, loss_fn: Callable[[dict], torch.Tensor], networks: Optional[Sequence[str]] = None,
-                 seed: int = 0, warmup: int = 1):
+                 seed: int = 0, warmup: int = 1, batch: Optional[int] = None):
         self.runner = runner
         self.loss_fn = loss_fn
+        self.batch = int(batch) if batch else None
+        runner.batch = self.batch
         nets = runner.model.infection_networks.networks
         self.names = list(networks) if networks is not None else list(nets.keys())
         agent = runner.data["agent"]
         ops.require_cuda(agent.susceptibility, "data['agent'].susceptibility")
         self.device = agent.susceptibility.device
         init = [float(torch.as_tensor(nets[k].log_beta).detach().reshape(-1)[0]) for k in self.names]
-        self.log_beta = torch.tensor(init, dtype=torch.float32).to(self.device).requires_grad_(True)
+        self.log_beta = torch.tensor(init, dtype=torch.float32).to(self.device)
+        if self.batch:
+            self.log_beta = self.log_beta.repeat(self.batch, 1)          # [b, K]
+        self.log_beta.requires_grad_(True)
         # the networks that are NOT calibrated keep their log-betas as constants of the graph: they must already
         # live on the device (a host-to-device copy cannot be captured)
         for k, net in nets.items():
@@ -50,11 +62,14 @@ class GraphedRunner:
             # a network built with log_beta=nn.Parameter(...) holds it as a registered parameter, and nn.Module
             # refuses to assign a plain tensor over one: unregister it first
             nets[k]._parameters.pop("log_beta", None)
-            nets[k].log_beta = self.log_beta[i]
+            nets[k].log_beta = self.log_beta[:, i] if self.batch else self.log_beta[i]
         with ops.philox_seed(self.seed):
             results, is_infected = self.runner()
         loss = self.loss_fn(results)
-        loss.backward()
+        if self.batch and tuple(loss.shape) != (self.batch,):
+            raise ValueError(f"batched window: loss_fn must return one loss per sample, shape ({self.batch},); "
+                             f"got {tuple(loss.shape)}")
+        loss.sum().backward()
         part = self.runner.data.__dict__.get("_gj_partition")
         if part is not None and part.world_size > 1:
             # geographic partition: every rank holds the d/dbeta terms of the groups it owns; the sum over ranks
@@ -92,8 +107,8 @@ class GraphedRunner:
 
     @torch.no_grad()
     def __call__(self, log_beta: Optional[torch.Tensor] = None):
-        """Replay with ``log_beta`` ([K], any device; None = keep).  Returns (loss, d loss / d log_beta, results):
-        static device tensors that the next replay overwrites."""
+        """Replay with ``log_beta`` ([K], or [b, K] for a batched window; any device; None = keep).  Returns
+        (loss, d loss / d log_beta, results): static device tensors that the next replay overwrites."""
         if log_beta is not None:
             self.log_beta.copy_(log_beta.to(dtype=torch.float32), non_blocking=True)
         self.graph.replay()

@@ -157,11 +157,17 @@ def _interaction_active(policies, timer):
 
 def beta_vector(networks, policies, timer, device):
     """[K] vector of beta_eff = 10**log_beta * policy factors (base.py:36-42), differentiable wrt every
-    log_beta / factor tensor."""
+    log_beta / factor tensor.  A batched ensemble (``Runner.batch = b``) holds b values per log_beta: the result is
+    then [b, K]."""
     if not networks:
         return torch.zeros(0, device=device)
     device = torch.device(device)
     lbs = [net.log_beta for net in networks]
+    nb = max((lb.numel() for lb in lbs if torch.is_tensor(lb)), default=1)
+    if nb > 1:      # batched ensemble: networks that are not calibrated broadcast their scalar
+        cols = [net.beta_eff(policies, timer).to(device=device, dtype=torch.float32).reshape(-1).expand(nb)
+                for net in networks]
+        return torch.stack(cols, dim=1).contiguous()
     if (not _interaction_active(policies, timer)
             and all(torch.is_tensor(lb) and lb.device == device and lb.dtype == torch.float32 for lb in lbs)):
         # every log_beta already lives on the step's device: one stack + one pow instead of K of each

@@ -629,6 +629,222 @@ class _Step(torch.autograd.Function):
                 g_T_in if need[10] else None, g_q_in, g_n_in, g_frac if need[13] else None, None)
 
 
+# --------------------------------------------------------------------------------------
+# batched ensemble: b samples per call (gj_step_forward_batch / gj_step_backward_batch)
+# --------------------------------------------------------------------------------------
+# which stride every pointer field of the io structs moves by from one sample to the next (fields not listed are
+# shared by the samples: the lookup tables and the infectiousness profile)
+_AGENT_FIELDS = {"s", "inf", "tinf", "cur", "nxt", "ttn", "T_in", "q_in", "n_in", "s_o", "inf_o", "tinf_o", "cur_o",
+                 "nxt_o", "ttn_o", "T", "Tq", "q", "lam", "n", "tape_v", "tape_y0", "g_s_o", "g_inf_o", "g_tinf_o",
+                 "g_cur_o", "g_nxt_o", "g_ttn_o", "g_s", "g_inf", "g_tinf", "g_cur", "g_nxt", "g_ttn", "w", "wq"}
+_GROUP_FIELDS = {"S_scaled", "S_unscaled", "R", "cR"}
+
+
+def _scratch_batch(world: DeviceWorld, nb: int):
+    """Per-sample scratch buffers of a batched call: (tensor, stride in bytes)."""
+    stride = int(_lib.lib().gj_scratch_bytes(C.byref(world.desc())))
+    stride = (stride + 255) // 256 * 256
+    hit = world.__dict__.get("_scratch_b")
+    if hit is None or hit[0].numel() < nb * stride:
+        hit = world.__dict__["_scratch_b"] = (torch.zeros(nb * stride, dtype=torch.uint8, device=world.device), stride)
+    return hit
+
+
+def _row_calls(fn, what, world, desc, p, io, nb, strides, stream):
+    """A call the library does not batch (the seeding step): one ordinary call per sample on its slices."""
+    for r in range(nb):
+        row = type(io)()
+        for name, _ in io._fields_:
+            v = getattr(io, name)
+            if v:
+                v += r * strides.get(name, 0)
+            setattr(row, name, v)
+        with _on(world.device):
+            _lib.check(fn(C.byref(desc), C.byref(p), C.byref(row), stream), what)
+
+
+class _BatchStep(torch.autograd.Function):
+    """The fused step (and the seeding step) for a batch of b independent samples on one world: state tensors
+    [b, Np] (Np = n_agents rounded up to a multiple of 4; sample rows 16-byte aligned), beta [b, K], reductions
+    [b, 2 + bins].  The fused step is ONE library call (``gj_step_forward_batch``): the b samples share every read of
+    the world's index data and of the infectiousness profile; the seeding step (once per window) runs per sample.
+    All samples draw the same Philox stream (common random numbers), so sample r is bit-identical to an unbatched
+    run with the same seed and beta[r]."""
+
+    @staticmethod
+    def forward(ctx, static: StepStatic, spec: StepSpec, noise, beta, s, inf, tinf, cur, nxt, ttn, seed_fraction):
+        world = static.world
+        dev, N = world.device, world.n_agents
+        L = _lib.lib()
+        seed, call_index, E, u, z = noise
+        if E is not None or u is not None or z is not None:
+            raise _lib.GradJuneLibraryError("batched ensembles draw the in-kernel Philox noise (no injected arrays)")
+        nb, Np = s.shape
+        if Np % 4 or Np < N:
+            raise ValueError(f"batched state must be [b, Np] with Np >= n_agents and Np % 4 == 0, got {tuple(s.shape)}")
+        seed_mode = spec.mode == MODE_SEED
+        if EXACT_ORDER or spec.exact_order:
+            raise _lib.GradJuneLibraryError("batched ensembles run the throughput-mode kernels only")
+        if not seed_mode and (spec.phases != PHASE_ALL or step_plan(static, spec) != "throughput"):
+            raise _lib.GradJuneLibraryError(
+                "batched ensembles need the whole fused step on the throughput-mode kernels (gj_step_plan = 1): "
+                "renumber the world (Runner.get_data does) and use the built-in network kinds")
+        p, s_total = _fill_params(world, spec, static.symptoms, seed, call_index)
+        io = _lib.FwdIO()
+        keep = []
+
+        def put(name, t):
+            t = _f32(t, dev)
+            if t is not None:
+                keep.append(t)
+                setattr(io, name, t.data_ptr())
+            return t
+
+        def new(name):
+            t = torch.empty(nb, Np, dtype=torch.float32, device=dev)
+            if Np > N:
+                t[:, N:] = 0.0          # the kernels never touch the padding
+            setattr(io, name, t.data_ptr())
+            return t
+
+        put("leisure_prob", static.leisure_prob)
+        put("stage_prob", static.symptoms.stage_prob)
+        st = {}
+        for name, t in zip(_STATE, (s, inf, tinf, cur, nxt, ttn)):
+            st[name] = put(name, t)
+            if tuple(st[name].shape) != (nb, Np):
+                raise ValueError(f"batched state '{name}' has shape {tuple(st[name].shape)}, expected {(nb, Np)}")
+        out = {name: new(name) for name in ("s_o", "inf_o", "tinf_o", "cur_o", "nxt_o", "ttn_o")}
+        tape_y0 = new("tape_y0")
+        nr = 2 + p.n_age_bins
+        red = None
+        if spec.want_reductions:
+            red = torch.empty(nb, nr, dtype=torch.float32, device=dev)
+            io.red = red.data_ptr()
+        scratch, scr_stride = _scratch_batch(world, nb)
+        io.scratch = scratch.data_ptr()
+        desc = world.desc()
+        strides = {name: 4 * Np for name in _AGENT_FIELDS}
+        strides.update(red=4 * nr, scratch=scr_stride)
+        T = tape_v = S_un = None
+        sG = K = 0
+        if seed_mode:
+            seed_fraction = put("seed_fraction", seed_fraction)
+            if seed_fraction.numel() not in (1, nb):
+                raise ValueError("seed_fraction must hold 1 or b values")
+            strides["seed_fraction"] = 4 if seed_fraction.numel() == nb else 0
+            beta = None
+            _row_calls(L.gj_step_forward, "gj_step_forward", world, desc, p, io, nb, strides, _stream(dev))
+        else:
+            seed_fraction = None
+            beta = put("beta", beta)
+            K = p.n_nets
+            if tuple(beta.shape) != (nb, K):
+                raise ValueError(f"batched beta has shape {tuple(beta.shape)}, expected {(nb, K)}")
+            for name in ("maxinf", "shape", "rate", "shift", "k0", "prof4"):
+                put(name, getattr(static, name))
+            T = new("T")
+            io.Tq = _buffer(world, "Tq_b", nb * Np).data_ptr() if p.n_quar > 0 else T.data_ptr()
+            tape_v = new("tape_v")
+            sG = s_total + world.n_groups
+            io.S_scaled = _buffer(world, "S_scaled_b", nb * sG).data_ptr()
+            S_un = torch.empty(nb, max(sG, 1), dtype=torch.float32, device=dev)
+            io.S_unscaled = S_un.data_ptr()
+            bt = _lib.Batch(n_samples=nb, agent_stride=Np, group_stride=max(sG, 1), beta_stride=K, red_stride=nr,
+                            scratch_stride=scr_stride)
+            with _on(dev):
+                _lib.check(L.gj_step_forward_batch(C.byref(desc), C.byref(p), C.byref(io), C.byref(bt), _stream(dev)),
+                           "gj_step_forward_batch")
+        ctx.static, ctx.spec, ctx.noise_key = static, spec, (seed, call_index)
+        ctx.shape = (nb, Np, sG, K, nr)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(beta, st["s"], st["inf"], st["tinf"], st["cur"], st["nxt"], st["ttn"], T, seed_fraction,
+                              out["inf_o"], tape_v, tape_y0, S_un)
+        if T is not None:
+            ctx.mark_non_differentiable(T)
+        return (out["s_o"], out["inf_o"], out["tinf_o"], out["cur_o"], out["nxt_o"], out["ttn_o"], T, red)
+
+    @staticmethod
+    def backward(ctx, g_s_o, g_inf_o, g_tinf_o, g_cur_o, g_nxt_o, g_ttn_o, g_T, g_red):
+        static, spec = ctx.static, ctx.spec
+        world = static.world
+        dev = world.device
+        nb, Np, sG, K, nr = ctx.shape
+        beta, s, inf, tinf, cur, nxt, ttn, T, seed_fraction, inf_o, tape_v, tape_y0, S_un = ctx.saved_tensors
+        seed, call_index = ctx.noise_key
+        p, _ = _fill_params(world, spec, static.symptoms, seed, call_index)
+        seed_mode = spec.mode == MODE_SEED
+        L = _lib.lib()
+        io = _lib.BwdIO()
+        keep = []
+
+        def put(name, t):
+            t = _f32(t, dev)
+            if t is not None:
+                keep.append(t)
+                setattr(io, name, t.data_ptr())
+            return t
+
+        put("beta", beta), put("leisure_prob", static.leisure_prob), put("stage_prob", static.symptoms.stage_prob)
+        put("seed_fraction", seed_fraction)
+        for name, t in zip(_STATE, (s, inf, tinf, cur, nxt, ttn)):
+            put(name, t)
+        put("inf_o", inf_o), put("tape_y0", tape_y0)
+        for name, g in (("g_s_o", g_s_o), ("g_inf_o", g_inf_o), ("g_tinf_o", g_tinf_o), ("g_cur_o", g_cur_o),
+                        ("g_nxt_o", g_nxt_o), ("g_ttn_o", g_ttn_o), ("g_red", g_red)):
+            g = put(name, g)
+            if g is not None and name != "g_red" and tuple(g.shape) != (nb, Np):
+                raise ValueError(f"cotangent {name} has shape {tuple(g.shape)}, expected {(nb, Np)}")
+        need = ctx.needs_input_grad   # (static, spec, noise, beta, s, inf, tinf, cur, nxt, ttn, seed_fraction)
+
+        def new(name):
+            t = torch.empty(nb, Np, dtype=torch.float32, device=dev)
+            if Np > world.n_agents:
+                t[:, world.n_agents:] = 0.0
+            setattr(io, name, t.data_ptr())
+            return t
+
+        grads = {}
+        for i, name in enumerate(_STATE):
+            if need[4 + i] or (not seed_mode and name in ("inf", "tinf")):   # the gather pass accumulates into these two
+                grads[name] = new("g_" + name)
+        scratch, scr_stride = _scratch_batch(world, nb)
+        io.scratch = scratch.data_ptr()
+        desc = world.desc()
+        g_beta = g_frac = None
+        if seed_mode:
+            g_frac = torch.zeros(nb, dtype=torch.float32, device=dev)
+            io.g_seed_fraction = g_frac.data_ptr()
+            strides = {name: 4 * Np for name in _AGENT_FIELDS}
+            strides.update(g_red=4 * nr, scratch=scr_stride, g_seed_fraction=4,
+                           seed_fraction=4 if seed_fraction.numel() == nb else 0)
+            _row_calls(L.gj_step_backward, "gj_step_backward", world, desc, p, io, nb, strides, _stream(dev))
+            if seed_fraction.numel() != nb:
+                g_frac = g_frac.sum().reshape(seed_fraction.shape)    # one fraction shared by the samples
+            else:
+                g_frac = g_frac.reshape(seed_fraction.shape)
+        else:
+            for name in ("maxinf", "shape", "rate", "shift", "k0", "prof4"):
+                put(name, getattr(static, name))
+            put("T_in", T), put("tape_v", tape_v), put("S_unscaled", S_un)
+            g_beta = torch.zeros(nb, max(K, 1), dtype=torch.float32, device=dev)
+            io.g_beta = g_beta.data_ptr()
+            io.w = _buffer(world, "w_b", nb * Np).data_ptr()
+            io.wq = _buffer(world, "wq_b", nb * Np).data_ptr() if p.n_quar > 0 else io.w
+            io.R, io.cR = _buffer(world, "R_b", nb * sG).data_ptr(), _buffer(world, "cR_b", nb * sG).data_ptr()
+            bt = _lib.Batch(n_samples=nb, agent_stride=Np, group_stride=max(sG, 1), beta_stride=K, red_stride=nr,
+                            scratch_stride=scr_stride)
+            with _on(dev):
+                _lib.check(L.gj_step_backward_batch(C.byref(desc), C.byref(p), C.byref(io), C.byref(bt), _stream(dev)),
+                           "gj_step_backward_batch")
+            g_beta = g_beta[:, :K]
+        return (None, None, None, g_beta if need[3] else None,
+                grads.get("s") if need[4] else None, grads.get("inf") if need[5] else None,
+                grads.get("tinf") if need[6] else None, grads.get("cur") if need[7] else None,
+                grads.get("nxt") if need[8] else None, grads.get("ttn") if need[9] else None,
+                g_frac if (seed_mode and need[10]) else None)
+
+
 def infection_step(static: StepStatic, spec: StepSpec, beta, state: dict, T_in=None, q_in=None, n_in=None,
                    seed_fraction=None, noise=None, next_spec=None):
     """Run one (fused or partial) step.  ``state``: s, inf, tinf, cur, nxt, ttn (any may be None when
@@ -643,6 +859,15 @@ def infection_step(static: StepStatic, spec: StepSpec, beta, state: dict, T_in=N
             noise = NOISE.next(world.n_agents, world.device)
         else:
             noise = (0, 0, None, None, None)
+    if state.get("s") is not None and state["s"].dim() == 2:      # [b, Np]: a batched ensemble
+        if T_in is not None or q_in is not None or n_in is not None or static.exchange is not None:
+            raise _lib.GradJuneLibraryError("batched ensembles run the whole fused step on an unpartitioned world")
+        outs = _BatchStep.apply(static, spec, noise, beta, state["s"], state["inf"], state["tinf"], state["cur"],
+                                state["nxt"], state["ttn"], seed_fraction)
+        names = ("s", "inf", "tinf", "cur", "nxt", "ttn", "T", "red")
+        ret = dict(zip(names, outs))
+        ret.update(q=None, n=None, lam=None)
+        return ret
     outs = _Step.apply(static, spec, noise, beta, state.get("s"), state.get("inf"), state.get("tinf"),
                        state.get("cur"), state.get("nxt"), state.get("ttn"), T_in, q_in, n_in, seed_fraction, next_spec)
     names = ("s", "inf", "tinf", "cur", "nxt", "ttn", "T", "q", "n", "red", "lam")

@@ -44,6 +44,10 @@ class Runner(torch.nn.Module):
         self.population_by_age = self.get_people_by_age()
         self.save_path = Path(save_path)
         self.input_parameters = parameters
+        # batched ensemble: ``runner.batch = b`` makes ``forward()`` step b independent samples of the
+        # epidemic at once — the networks' ``log_beta`` then hold b values each, the state tensors are [b, Np] and
+        # every result series is [T+1, b].  All samples draw the same noise (common random numbers).
+        self.batch = None
         self.restore_initial_data()
 
     @classmethod
@@ -117,10 +121,22 @@ class Runner(torch.nn.Module):
         replaced it."""
         key = tuple(id(self.data_backup[k]) for k in _STATE_KEYS) + \
             tuple((id(self.data_backup["symptoms"][k]), self.data_backup["symptoms"][k]._version) for k in _SYMPTOM_KEYS)
+        key = key + (self.batch,)
         hit = self.__dict__.get("_window_start")
         if hit is None or hit[0] != key:
             state = {k: self.data_backup[k].detach() for k in _STATE_KEYS}
             sym = {k: self.data_backup["symptoms"][k].detach().to(torch.float32) for k in _SYMPTOM_KEYS}
+            if self.batch:      # b copies of the initial state, rows padded to a multiple of four agents
+                n = self.n_agents
+                n_pad = (n + 3) // 4 * 4
+
+                def rows(t):
+                    out = torch.zeros(self.batch, n_pad, dtype=torch.float32, device=t.device)
+                    out[:, :n] = t.to(torch.float32)
+                    return out
+
+                state = {k: rows(v) for k, v in state.items()}
+                sym = {k: rows(v) for k, v in sym.items()}
             hit = self.__dict__["_window_start"] = (key, state, sym)
         agent = self.data["agent"]
         for k in _STATE_KEYS:
@@ -150,6 +166,8 @@ class Runner(torch.nn.Module):
         timer.reset()
         if self.data["agent"].susceptibility.is_cuda:
             self._restore_for_window()
+        elif self.batch:
+            raise RuntimeError("batched ensembles run on a CUDA device only")
         else:
             self.restore_initial_data()
         reds = [self.set_initial_cases()]
@@ -163,23 +181,27 @@ class Runner(torch.nn.Module):
             data, red = model.step(data, timer, age_bins=self._age_bins_host, want_probs=False, next_timer=ahead)
             reds.append(red)
             dates.append(timer.date)
-        table = torch.stack(reds)                      # [T+1, 2 + n_bins]
+        table = torch.stack(reds)                      # [T+1, 2 + n_bins]   (batched: [T+1, b, 2 + n_bins])
         table = all_reduce_sum(table, data.__dict__.get("_gj_partition"))   # partitioned world: sum over ranks
         ex = data.__dict__.get("_gj_cache", {}).get("exchange")
         if ex is not None and not torch.cuda.is_current_stream_capturing():
             ex.check()      # a peer that never arrived at an exchange must not go unnoticed (once per window)
-        cases_per_timestep = table[:, 0]
-        data["results"]["deaths_per_timestep"] = table[:, 1]
+        cases_per_timestep = table[..., 0]
+        data["results"]["deaths_per_timestep"] = table[..., 1]
         results = {
             "dates": dates,
             "cases_per_timestep": cases_per_timestep,
             "daily_cases_per_timestep": torch.diff(
-                cases_per_timestep, prepend=torch.zeros(1, device=cases_per_timestep.device)),
+                cases_per_timestep, dim=0, prepend=torch.zeros_like(cases_per_timestep[:1])),
             "deaths_per_timestep": data["results"]["deaths_per_timestep"],
         }
         for i, key in enumerate(self._age_bins_host[1:]):
-            results[f"cases_by_age_{key:02d}"] = table[:, 2 + i]
-        return results, original_order(data, data["agent"].is_infected)
+            results[f"cases_by_age_{key:02d}"] = table[..., 2 + i]
+        is_infected = data["agent"].is_infected
+        if is_infected.dim() == 2:                      # batched: [b, Np] -> [b, n_agents] in the loaded order
+            is_infected = original_order(data, is_infected[:, : self.n_agents].t()).t()
+            return results, is_infected
+        return results, original_order(data, is_infected)
 
     def save_results(self, results, is_infected):
         self.save_path.mkdir(exist_ok=True, parents=True)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GJ_ABI_VERSION 9
+#define GJ_ABI_VERSION 10
 
 #define GJ_MAX_TYPES 8      /* edge types (household, company, school, university, care_home, leisure, ...) */
 #define GJ_MAX_NETS 16      /* infection networks active in one step */
@@ -371,6 +371,38 @@ int gj_step_forward_next(const gj_world_desc* w, const gj_step_params* p, const 
                          const gj_fwd_io* io, void* stream);
 /* reverse-mode derivative of gj_step_forward (replaces autograd's replay of the op tape) */
 int gj_step_backward(const gj_world_desc* w, const gj_step_params* p, const gj_bwd_io* io, void* stream);
+
+/* ---- batched ensemble [N, b] (BASELINE config 5; the reference evaluates one parameter sample per
+ * Python-driven run, example_scripts/run_model.py:6-11): ONE call steps `n_samples` independent epidemics on the same
+ * world.  `io` describes sample 0; sample s reads and writes every per-sample array at a fixed stride behind it:
+ *   per-agent arrays  (state in/out, T, Tq, tapes, q/lam/n, cotangents, w, wq)        + s * agent_stride  elements
+ *   group-sum buffers (S_scaled, S_unscaled, R, cR)                                   + s * group_stride  elements
+ *   beta, g_beta                                                                      + s * beta_stride   elements
+ *   red, g_red                                                                        + s * red_stride    elements
+ *   scratch                                                                           + s * scratch_stride bytes
+ * while the world (index words, classes, tiles), the packed infectiousness profile and the lookup tables are shared.
+ * The CTAs of the b samples that walk the same run of agent tiles are launched next to each other (block index =
+ * run * b + sample) and advance in step, so the tile's index words, class bytes and profile are fetched from HBM once
+ * and served to the other b-1 samples out of L2: one index read per b samples.  All samples draw the SAME Philox
+ * stream (seed, call_index): common random numbers across the parameter samples of an ensemble.  Sample s of a batched
+ * call is bit-identical to a gj_step_forward / gj_step_backward call on its slices.
+ * Requirements (else an error is returned, nothing runs): the whole fused step in throughput mode (gj_step_plan = 1,
+ * prof4 given, no injected noise, GJ_MODE_STEP, GJ_STAGE_ALL), the pipelined kernels enabled, agent_stride a multiple
+ * of 4 with every per-agent array 16-byte aligned, n_samples * agent_stride < 2^32, scratch_stride a multiple of 256
+ * and >= gj_scratch_bytes(). */
+typedef struct gj_batch {
+  int32_t n_samples;
+  int32_t _pad0;
+  int64_t agent_stride;
+  int64_t group_stride;
+  int64_t beta_stride;
+  int64_t red_stride;
+  int64_t scratch_stride;
+} gj_batch;
+int gj_step_forward_batch(const gj_world_desc* w, const gj_step_params* p, const gj_fwd_io* io, const gj_batch* batch,
+                          void* stream);
+int gj_step_backward_batch(const gj_world_desc* w, const gj_step_params* p, const gj_bwd_io* io, const gj_batch* batch,
+                           void* stream);
 
 /* ---- geographic partition: boundary groups (no counterpart in the reference, which is single-device)
  * Between GJ_STAGE_SUMS and GJ_STAGE_REST the caller all-reduces (NCCL, owned by the caller) the sums of the groups
