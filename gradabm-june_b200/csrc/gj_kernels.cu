@@ -570,7 +570,7 @@ static int build_channels(const gj_world_desc* w, const gj_step_params* p, Chann
   return 0;
 }
 
-static const Batch kNoBatch = {1, 0u, 0, 0, 0, 0};
+static const Batch kNoBatch = {1, 0u, 0, 0, 0, 0, nullptr};
 // grid of a persistent kernel in a batched launch: the resident wave is split between the samples (block = run * nb +
 // sample), at least one CTA and at most one per tile for each
 static inline int batch_grid(const gj_world_desc* w, int64_t resident, const Batch& bt) {
@@ -864,11 +864,17 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
   }
   if (p->stage == GJ_STAGE_SUMS) return 0;
   if (int e = launch_cell_gather(w, p, pl, io->S_scaled, sc, st, bt)) return e;
+  if (batch && bt.noise && pipe_enabled() && pipe_aligned_fwd(w, lp, io)) {   // the draw's noise, once for all samples
+    ProfScope pn(K_OTHER, st);
+    launch_pdl(k_batch_noise, dim3(agent_grid(w->n_agents)), dim3(kBlock), 0, st, *w, *p, const_cast<float*>(bt.noise));
+    GJ_CHECK_LAUNCH("k_batch_noise");
+  }
   if (pipe_enabled() && pipe_aligned_fwd(w, lp, io)) {
     ProfScope ps(K_AGENT_FWD, st);
     static OccCache occ[12];
     const bool diag = io->q || io->n;
-    const size_t smem = next ? sizeof(PipeFwdSharedT<true>) : sizeof(PipeFwdSharedT<false>);
+    const size_t smem = next ? sizeof(PipeFwdSharedT<true, false>)
+                             : (batch ? sizeof(PipeFwdSharedT<false, true>) : sizeof(PipeFwdSharedT<false, false>));
     NextStep nx;
     memset(&nx, 0, sizeof(nx));
     if (next) {
@@ -1398,6 +1404,8 @@ static int make_batch(const gj_world_desc* w, const gj_step_params* p, const gj_
   bt->sScr = b->scratch_stride;
   bt->sBeta = (int)b->beta_stride;
   bt->sRed = (int)b->red_stride;
+  bt->noise = b->noise;
+  if (b->noise && !aligned16(b->noise)) return bad("batch: noise must be 16-byte aligned");
   return 0;
 }
 

@@ -573,16 +573,19 @@ struct FwdRes {   // everything one agent's forward produces
   float tape_v, tape_y0, q, lam, n;
   float s_o, inf_o, tinf_o, cur_o, nxt_o, ttn_o;
 };
-// r0, r1: the agent's Philox2x32 pair (philox_step_pair); ga = its id in the noise stream
+// Gumbel noise of the draw from the agent's Philox2x32 pair (philox_step_pair): lg2 E0 - lg2 E1, E = -lg2 u
+__device__ __forceinline__ float lean_noise_dE(uint32_t r0, uint32_t r1) {
+  return lg2_fast(fmaxf(-lg2_fast(u01_open(r0)), kMinE2)) - lg2_fast(fmaxf(-lg2_fast(u01_open(r1)), kMinE2));
+}
+// dE: lean_noise_dE of the agent's Philox pair; ga = its id in the noise stream
 template <bool kQuar>
 __device__ __forceinline__ FwdRes lean_forward_core(const gj_step_params& p, const LeanPlan& lp,
-                                                    const float* __restrict__ stage_prob, uint64_t ga, uint32_t r0,
-                                                    uint32_t r1, float hs, float gv, float Lc, float beta_r, float rpc,
+                                                    const float* __restrict__ stage_prob, uint64_t ga, float dE,
+                                                    float hs, float gv, float Lc, float beta_r, float rpc,
                                                     float s, float inf, float tinf, float cur, float nxt, float ttn,
                                                     int cls, float inv_tau, float dead, float* __restrict__ hist,
                                                     float* __restrict__ deaths, float q_seed = -1.0f) {
   FwdRes o;
-  const float dE = lg2_fast(fmaxf(-lg2_fast(u01_open(r0)), kMinE2)) - lg2_fast(fmaxf(-lg2_fast(u01_open(r1)), kMinE2));
   const float rv = (beta_r * rpc) * hs;
   const float house = lp.r_house ? rv : 0.0f;
   const float plain = (gv + Lc) + (lp.r_house ? 0.0f : rv);
@@ -629,10 +632,15 @@ __device__ __forceinline__ FwdOut lean_forward_agent(const gj_step_params& p, co
                                                    uint32_t a, uint64_t ga, float hs, float gv, float Lc, float beta_r, float rpc,
                                                    float s, float inf, float tinf, float cur, float nxt, float ttn,
                                                    int cls, float inv_tau, float dead, float* __restrict__ hist,
-                                                   float* __restrict__ deaths) {
-  uint32_t r[2];
-  philox_step_pair(p.seed, p.call_index, ga, r);   // ga: the agent's id in the noise stream (noise_agent())
-  const FwdRes o = lean_forward_core<kQuar>(p, lp, io.stage_prob, ga, r[0], r[1], hs, gv, Lc, beta_r, rpc, s, inf, tinf,
+                                                   float* __restrict__ deaths, bool noise_given = false,
+                                                   float dE_given = 0.0f) {
+  float dE = dE_given;   // batched ensemble: evaluated once for all samples (k_batch_noise)
+  if (!noise_given) {
+    uint32_t r[2];
+    philox_step_pair(p.seed, p.call_index, ga, r);   // ga: the agent's id in the noise stream (noise_agent())
+    dE = lean_noise_dE(r[0], r[1]);
+  }
+  const FwdRes o = lean_forward_core<kQuar>(p, lp, io.stage_prob, ga, dE, hs, gv, Lc, beta_r, rpc, s, inf, tinf,
                                             cur, nxt, ttn, cls, inv_tau, dead, hist, deaths);
   io.tape_v[a] = o.tape_v;
   io.tape_y0[a] = o.tape_y0;
@@ -652,6 +660,19 @@ __device__ __forceinline__ FwdOut lean_forward_agent(const gj_step_params& p, co
   out.tinf = o.tinf_o;
   out.cur = o.cur_o;
   return out;
+}
+
+// batched ensemble: the draw's noise of every agent, once for all samples of the batch (gj_batch.noise)
+__global__ void __launch_bounds__(kBlock) k_batch_noise(gj_world_desc w, gj_step_params p, float* __restrict__ dE) {
+  pdl_launch();
+  pdl_wait();
+  const uint32_t N = (uint32_t)w.n_agents;
+  for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < N; a += gridDim.x * blockDim.x) {
+    const uint64_t ga = w.orig_id ? (uint64_t)w.orig_id[a] : p.agent_offset + a;
+    uint32_t r[2];
+    philox_step_pair(p.seed, p.call_index, ga, r);
+    dE[a] = lean_noise_dE(r[0], r[1]);
+  }
 }
 
 // =====================================================================================================
@@ -828,7 +849,7 @@ __global__ void __launch_bounds__(kLeanThreads, 4) k_lean_seed(gj_world_desc w, 
       const uint64_t ga = w.orig_id ? (uint64_t)oid[h] : p.agent_offset + a;
       uint32_t r[2];
       philox_step_pair(p.seed, p.call_index, ga, r);
-      const FwdRes o = lean_forward_core<false>(p, lp, io.stage_prob, ga, r[0], r[1], 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, s[h],
+      const FwdRes o = lean_forward_core<false>(p, lp, io.stage_prob, ga, lean_noise_dE(r[0], r[1]), 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, s[h],
                                                 inf[h], tinf[h], cur[h], nxt[h], ttn[h], cls[h], inv_tau, dead, hist,
                                                 &deaths, q_seed);
       io.tape_y0[a] = o.tape_y0;

@@ -194,15 +194,17 @@ __device__ __forceinline__ bool next_new_cell(const NextStep& nx, int64_t a, int
   for (int i = 0; i < nx.n_tc; ++i) changed = changed || (nx.tc[i][a] != nx.tc[i][b]);
   return changed;
 }
-struct alignas(16) PipeFwdStage {
+template <bool kBatch>
+struct alignas(16) PipeFwdStageT {
   float s[kPipeF], inf[kPipeF], tinf[kPipeF], cur[kPipeF], nxt[kPipeF], ttn[kPipeF], rpc[kPipeF];
   uint32_t ent[kPipeF], slot[kPipeF], oid[kPipeF];
   float T[kPipeH];
   uint8_t cls[kPipeTile + 32];
+  float dE[kBatch ? kPipeF : 4];   // batched ensemble: the draw's noise, shared by the samples (Batch::noise)
 };
-template <bool kNext>
+template <bool kNext, bool kBatch>
 struct PipeFwdSharedT {
-  PipeFwdStage st[kPipeStages];
+  PipeFwdStageT<kBatch> st[kPipeStages];
   ProbRow prob[200];
   ProbRow prob_next[kNext ? 200 : 1];   // transmission-side tables of the next step (look-ahead only)
   float L[2][200];
@@ -215,16 +217,20 @@ struct PipeFwdSharedT {
 
 // so: batched ensemble — this sample's offset into the per-sample arrays (a multiple of four agents: the copies stay
 // 16-byte aligned); the world's arrays are shared
-__device__ __forceinline__ void pipe_fwd_issue(PipeFwdStage& sg, uint64_t* bar, const gj_world_desc& w,
+template <bool kBatch>
+__device__ __forceinline__ void pipe_fwd_issue(PipeFwdStageT<kBatch>& sg, uint64_t* bar, const gj_world_desc& w,
                                                const LeanPlan& lp, const gj_fwd_io& io, const float* Tr, int64_t tile,
-                                               bool has_gen, bool has_range, uint32_t so = 0u) {
+                                               bool has_gen, bool has_range, uint32_t so = 0u,
+                                               const float* noise = nullptr) {
   const TileSpan t = tile_span(w, tile);
   uint32_t total = 6u * t.n4 + (t.hi16 - t.lo16);
+  if (kBatch && noise) total += t.n4;
   if (has_gen) total += t.n4;
   if (w.orig_id) total += t.n4;
   if (has_range) total += (lp.r_pc_lut ? 1u : 2u) * t.n4 + (t.thi - t.tlo) * 4u;
   mbar_expect_tx(bar, total);
   const Copier c{bar};
+  if (kBatch && noise) c.f4(sg.dE, noise, t);
   if (w.orig_id) c.f4(sg.oid, w.orig_id, t);
   c.f4(sg.s, io.s + so, t);
   c.f4(sg.inf, io.inf + so, t);
@@ -249,8 +255,9 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
                                                                  Batch bt) {
   static_assert(!(kNext && kBatch), "the look-ahead transmission pass is not batched");
   extern __shared__ __align__(128) unsigned char pipe_smem[];
-  PipeFwdSharedT<kNext>& sh = *reinterpret_cast<PipeFwdSharedT<kNext>*>(pipe_smem);
+  PipeFwdSharedT<kNext, kBatch>& sh = *reinterpret_cast<PipeFwdSharedT<kNext, kBatch>*>(pipe_smem);
   const BatchCta bc = batch_cta<kBatch>(bt);
+  const float* noise = kBatch ? bt.noise : nullptr;
   const uint32_t so = bc.so;
   float* __restrict__ red_out = io.red;
   const float* __restrict__ beta_in = io.beta;
@@ -281,7 +288,8 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 0; i < kPipeStages; ++i)
-      if (run.t0 + i < run.t1) pipe_fwd_issue(sh.st[i], &sh.full[i], w, lp, io, Tr, run.t0 + i, has_gen, has_range, so);
+      if (run.t0 + i < run.t1)
+        pipe_fwd_issue<kBatch>(sh.st[i], &sh.full[i], w, lp, io, Tr, run.t0 + i, has_gen, has_range, so, noise);
   }
   const float* __restrict__ SP = io.S_scaled + lp.gen_base + (kBatch ? (int64_t)bc.s * bt.sG : (int64_t)0);
   const float dead = (float)(p.n_stages - 1);
@@ -297,7 +305,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
   const float* L = sh.L[0];
   TileWalk tw = tile_walk_begin(w, lp, run);
   for (int64_t tile = run.t0; tile < run.t1; ++tile) {
-    PipeFwdStage& sg = sh.st[stg];
+    PipeFwdStageT<kBatch>& sg = sh.st[stg];
     PIPE_TILE_FACTS;
     mbar_wait(&sh.full[stg], parity);
     if (new_cell) {
@@ -335,7 +343,8 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
                                                          : sg.rpc[i]);
       const FwdOut o = lean_forward_agent<kQuar, kDiag>(p, lp, io, a + so, ga, hs, gv, Lc, beta_r, rpc,
                                                         sg.s[i], sg.inf[i], sg.tinf[i], sg.cur[i], sg.nxt[i], sg.ttn[i], cls,
-                                                        inv_tau, dead, sh.hist, &sh.deaths);
+                                                        inv_tau, dead, sh.hist, &sh.deaths, kBatch && noise != nullptr,
+                                                        (kBatch && noise) ? sg.dE[i] : 0.0f);
       if (kNext) {   // TransmissionUpdater of the next step (same arithmetic as k_lean_transmission)
         float T = 0.0f;
         if (o.inf != 0.0f) {
@@ -355,7 +364,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_pipe_forward(gj_world_desc 
       }
     }
     if (pipe_release() && tile + kPipeStages < run.t1)
-      pipe_fwd_issue(sg, &sh.full[stg], w, lp, io, Tr, tile + kPipeStages, has_gen, has_range, so);
+      pipe_fwd_issue<kBatch>(sg, &sh.full[stg], w, lp, io, Tr, tile + kPipeStages, has_gen, has_range, so, noise);
     if (++stg == kPipeStages) {
       stg = 0;
       parity ^= 1u;

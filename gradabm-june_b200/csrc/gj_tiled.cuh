@@ -42,6 +42,7 @@ struct Batch {
   int64_t sG;      // stride of the group-sum buffers (elements)
   int64_t sScr;    // stride of the scratch buffers (bytes, multiple of 256)
   int sBeta, sRed; // strides of beta / g_beta and red / g_red (elements)
+  const float* noise;  // [n_agents] the draw's Gumbel noise difference, evaluated once for all samples; NULL = in-kernel
 };
 struct BatchCta {
   int s;           // sample of this CTA

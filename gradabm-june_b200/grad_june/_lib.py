@@ -114,7 +114,7 @@ class Batch(C.Structure):
     """gj_batch: strides of a batched ensemble call (gj_step_forward_batch / gj_step_backward_batch)."""
     _fields_ = [("n_samples", C.c_int32), ("_pad0", C.c_int32), ("agent_stride", C.c_int64),
                 ("group_stride", C.c_int64), ("beta_stride", C.c_int64), ("red_stride", C.c_int64),
-                ("scratch_stride", C.c_int64)]
+                ("scratch_stride", C.c_int64), ("noise", C.c_void_p)]
 
 
 class GradJuneLibraryError(RuntimeError):

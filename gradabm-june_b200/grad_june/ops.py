@@ -5,6 +5,7 @@ classes call the same entry point with a sub-set of phases.  All tensors must li
 there is no CPU fallback.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass, field, replace
 from typing import Dict, List, Optional, Sequence
 
@@ -17,6 +18,9 @@ from .world import DeviceWorld
 
 TAU = 0.1
 EXACT_ORDER = False   # module-wide switch: run the reference-order kernels even in Philox mode
+# batched ensembles: evaluate the draw's noise once for all samples (gj_batch.noise); GJ_BATCH_OWN_NOISE=1 in the
+# environment makes every sample regenerate it (measurement switch; bit-identical results)
+BATCH_SHARED_NOISE = os.environ.get("GJ_BATCH_OWN_NOISE", "0") != "1"
 
 
 def require_cuda(t: torch.Tensor, what: str):
@@ -750,8 +754,10 @@ class _BatchStep(torch.autograd.Function):
             io.S_scaled = _buffer(world, "S_scaled_b", nb * sG).data_ptr()
             S_un = torch.empty(nb, max(sG, 1), dtype=torch.float32, device=dev)
             io.S_unscaled = S_un.data_ptr()
+            # the samples share the Philox stream: the draw's Gumbel noise is evaluated once per agent
+            noise_buf = _buffer(world, "noise_b", Np) if BATCH_SHARED_NOISE else None
             bt = _lib.Batch(n_samples=nb, agent_stride=Np, group_stride=max(sG, 1), beta_stride=K, red_stride=nr,
-                            scratch_stride=scr_stride)
+                            scratch_stride=scr_stride, noise=_ptr(noise_buf))
             with _on(dev):
                 _lib.check(L.gj_step_forward_batch(C.byref(desc), C.byref(p), C.byref(io), C.byref(bt), _stream(dev)),
                            "gj_step_forward_batch")

@@ -398,6 +398,11 @@ typedef struct gj_batch {
   int64_t beta_stride;
   int64_t red_stride;
   int64_t scratch_stride;
+  /* optional workspace of agent_stride floats.  All samples of a batch draw the same Philox stream, so the Gumbel
+   * noise of the infection draw (two Philox words and four log2 per agent) is the same for every sample: given this
+   * buffer, gj_step_forward_batch evaluates it ONCE per agent (one small kernel) and the b samples read it, instead
+   * of every sample regenerating it.  Same arithmetic: results are bit-identical.  NULL = every sample computes it. */
+  float* noise;
 } gj_batch;
 int gj_step_forward_batch(const gj_world_desc* w, const gj_step_params* p, const gj_fwd_io* io, const gj_batch* batch,
                           void* stream);
