@@ -846,7 +846,24 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
 #define GJ_K1(Q, B, I)                                                                                               \
   launch_pdl(k_lean_transmission<Q, B>, dim3(lean_grid(w, k_lean_transmission<Q, B>, &occ[I], bt)), dim3(kLeanThreads), \
              0, st, *w, *p, lp, *io, sc.tile_part, sct, bt)
-      if (batch) {
+#define GJ_K1C(Q, B, I)                                                                                              \
+  launch_pdl(k_lean_transmission_c<Q, B>, dim3(lean_grid(w, k_lean_transmission_c<Q, B>, &occ_c[I], bt)),              \
+             dim3(kLeanThreads), 0, st, *w, *p, lp, *io, sc.tile_part, sct, bt)
+      static OccCache occ_c[4];
+      static int compact = -1;   // GJ_K1C=0: the uncompacted pass (measurement switch)
+      if (compact < 0) {
+        const char* e = getenv("GJ_K1C");
+        compact = (e && e[0] == '0') ? 0 : 1;
+      }
+      if (compact) {
+        if (batch) {
+          if (quar) GJ_K1C(true, true, 3);
+          else GJ_K1C(false, true, 2);
+        } else {
+          if (quar) GJ_K1C(true, false, 1);
+          else GJ_K1C(false, false, 0);
+        }
+      } else if (batch) {
         if (quar) GJ_K1(true, true, 3);
         else GJ_K1(false, true, 2);
       } else {
@@ -854,6 +871,7 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
         else GJ_K1(false, false, 0);
       }
 #undef GJ_K1
+#undef GJ_K1C
       GJ_CHECK_LAUNCH("k_lean_transmission");
     }
     if (lp.has_generic)

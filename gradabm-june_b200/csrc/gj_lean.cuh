@@ -362,6 +362,120 @@ __global__ void __launch_bounds__(kLeanThreads, GJ_K1_MINB) k_lean_transmission(
 }
 
 // =====================================================================================================
+// K1c  the same pass with the infectious agents COMPACTED per warp.  K1 above is latency-bound: a warp keeps 64 agents
+//      in flight and sits out two dependent DRAM round trips per batch (is_infected, then the profile of the few
+//      infectious lanes) however few those lanes are.  Here a warp streams a chunk of 32 x GJ_K1C_PER agents with that
+//      many independent loads per lane, writes the zeros of everybody who is not infectious straight away, ballots, and then hands the
+//      chunk's infectious agents out densely, one per lane: ONE exposed round trip for the dependent loads of up to 32
+//      infectious agents.  Same arithmetic per agent (T is bit-identical to K1's); the per-thread partial sums of the
+//      cell channels are associated differently (another agent -> lane map).  The quarantine stage is read for the
+//      infectious agents only.
+// =====================================================================================================
+#ifndef GJ_K1C_MINB
+#define GJ_K1C_MINB 4
+#endif
+#ifndef GJ_K1C_PER
+#define GJ_K1C_PER 16   // measured on B200 (56 M agents): per x CTAs/SM = 16x4 0.152 ms, 8x5 0.161, 8x6 0.166, 12x5 0.165, 16x3 0.169, 16x5 0.168, 24x3 0.195, 4x8 0.188; K1: 0.208
+#endif
+constexpr int kK1cPer = GJ_K1C_PER;   // agents per lane and chunk
+
+template <bool kQuar, bool kBatch>
+__global__ void __launch_bounds__(kLeanThreads, GJ_K1C_MINB) k_lean_transmission_c(gj_world_desc w, gj_step_params p,
+                                                                                  LeanPlan lp, gj_fwd_io io,
+                                                                                  float* __restrict__ tile_part,
+                                                                                  Scatter sct, Batch bt) {
+  __shared__ ProbRow prob[200];
+  pdl_launch();
+  lean_load_prob<false>(prob, p, lp, io.leisure_prob);
+  pdl_wait();
+  __syncthreads();
+  const BatchCta bc = batch_cta<kBatch>(bt);
+  const uint32_t so = bc.so;
+  if (kBatch) {
+    tile_part = scr_shift(tile_part, bt, bc.s);
+    sct.acc = scr_shift(sct.acc, bt, bc.s);
+    sct.dirty = scr_shift(sct.dirty, bt, bc.s);
+  }
+  const float4* __restrict__ prof = reinterpret_cast<const float4*>(io.prof4);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr uint32_t kChunk = 32u * kK1cPer;
+  constexpr uint32_t kWarps = kLeanThreads / 32;
+  const TileRun run = lean_tiles(w, bc);
+  for (int64_t tile = run.t0; tile < run.t1;) {
+    const int64_t tend = lp.n_cell > 0 ? lean_segment_end(lp, tile, run.t1) : run.t1;
+    const uint32_t a0 = w.tile_begin[tile], a1 = w.tile_begin[tend];
+    float acc[GJ_MAX_CHANNELS];
+#pragma unroll
+    for (int j = 0; j < GJ_MAX_CHANNELS; ++j) acc[j] = 0.0f;
+    for (uint32_t cb = a0 + wid * kChunk; cb < a1; cb += kWarps * kChunk) {
+      float inf[kK1cPer];
+      unsigned int mask[kK1cPer];
+#pragma unroll
+      for (int j = 0; j < kK1cPer; ++j) {   // the chunk's streaming loads, all in flight
+        const uint32_t a = cb + j * 32 + lane;
+        inf[j] = (a < a1) ? io.inf[a + so] : 0.0f;
+      }
+      int total = 0;
+#pragma unroll
+      for (int j = 0; j < kK1cPer; ++j) {   // zeros for everybody who is not infectious; who is, by ballot
+        const uint32_t a = cb + j * 32 + lane;
+        const bool on = inf[j] != 0.0f;
+        mask[j] = __ballot_sync(0xffffffffu, on);
+        total += __popc(mask[j]);
+        if (a < a1 && !on) {
+          io.T[a + so] = 0.0f;
+          if (kQuar) io.Tq[a + so] = 0.0f;
+        }
+      }
+      for (int k0 = 0; k0 < total; k0 += 32) {   // the infectious agents, one per lane
+        int rem = k0 + lane, jsel = 0;
+        unsigned int m = 0u;
+        bool found = false;
+#pragma unroll
+        for (int j = 0; j < kK1cPer; ++j) {
+          const int c = __popc(mask[j]);
+          if (!found) {
+            if (rem < c) {
+              found = true;
+              m = mask[j];
+              jsel = j;
+            } else {
+              rem -= c;
+            }
+          }
+        }
+        if (!found) continue;
+        const uint32_t a = cb + jsel * 32 + __fns(m, 0u, rem + 1);
+        // every dependent load of the agent is issued before the first use
+        const float infv = io.inf[a + so];
+        const float tinf = io.tinf[a + so];
+        const float4 pf = prof[a];
+        const uint32_t ent = lp.has_generic ? w.ent1[a] : kEntNone;
+        const int cls = lp.n_cell > 0 ? (int)w.cls[a] : 0;
+        const float cur = kQuar ? io.cur[a + so] : 0.0f;
+        const float T = lean_transmission<false>(p.now, tinf, pf).coef * infv;
+        io.T[a + so] = T;
+        float Tq = T;
+        if (kQuar) {
+          Tq = quar_mask(p, cur) * T;
+          io.Tq[a + so] = Tq;
+        }
+        if (Tq != 0.0f) {
+          if (lp.n_cell > 0) lean_channel_fma(acc, prob, cls, Tq, lp.n_cell);
+          if (lp.has_generic) lean_scatter(w, sct, ent, a, Tq);
+        }
+      }
+    }
+    if (lp.n_cell > 0) {
+      block_sums<float, GJ_MAX_CHANNELS>(acc, lp.n_cell, tile_part + tile * GJ_MAX_CHANNELS);
+      for (int64_t i = threadIdx.x; i < (tend - tile - 1) * GJ_MAX_CHANNELS; i += kLeanThreads)
+        tile_part[(tile + 1) * GJ_MAX_CHANNELS + i] = 0.0f;
+    }
+    tile = tend;
+  }
+}
+
+// =====================================================================================================
 // K2  generic-tier group sums, one value per global group: plain = sum of member values,
 //     scaled = (sum of the betas of the type's networks) * pc_g * plain.  Forward: in = Tq; backward: in = wq.
 // =====================================================================================================
