@@ -1207,11 +1207,11 @@ int gj_abi_version(void) { return GJ_ABI_VERSION; }
 const char* gj_last_error(void) { return g_err; }
 
 int gj_config(int64_t* out, int n) {
-  const int64_t v[9] = {GJ_SMALL_GROUP,      GJ_CHUNK,          (int64_t)sizeof(gj_world_desc), (int64_t)sizeof(gj_step_params),
-                        (int64_t)sizeof(gj_fwd_io), (int64_t)sizeof(gj_bwd_io), kRedBlocks, GJ_TILE_AGENTS,
-                        GJ_SCATTER_MAX_GROUP};
-  for (int i = 0; i < n && i < 9; ++i) out[i] = v[i];
-  return 9;
+  const int64_t v[10] = {GJ_SMALL_GROUP,      GJ_CHUNK,          (int64_t)sizeof(gj_world_desc), (int64_t)sizeof(gj_step_params),
+                         (int64_t)sizeof(gj_fwd_io), (int64_t)sizeof(gj_bwd_io), kRedBlocks, GJ_TILE_AGENTS,
+                         GJ_SCATTER_MAX_GROUP, (int64_t)sizeof(gj_batch)};
+  for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
+  return 10;
 }
 
 int64_t gj_scratch_bytes(const gj_world_desc* w) { return w ? scratch_bytes(w) : -1; }

@@ -222,13 +222,14 @@ def lib():
     L.gj_world_last_error.restype = C.c_char_p
     L.gj_world_destroy.argtypes = [C.c_void_p]
     L.gj_memcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
-    cfg = (C.c_int64 * 9)()
-    L.gj_config(cfg, 9)
+    cfg = (C.c_int64 * 10)()
+    L.gj_config(cfg, 10)
     _config = {
         "small_group": cfg[0], "chunk": cfg[1], "red_blocks": cfg[6], "tile_agents": cfg[7], "scatter_max": cfg[8],
     }
     sizes = {"gj_world_desc": (cfg[2], C.sizeof(WorldDesc)), "gj_step_params": (cfg[3], C.sizeof(StepParams)),
-             "gj_fwd_io": (cfg[4], C.sizeof(FwdIO)), "gj_bwd_io": (cfg[5], C.sizeof(BwdIO))}
+             "gj_fwd_io": (cfg[4], C.sizeof(FwdIO)), "gj_bwd_io": (cfg[5], C.sizeof(BwdIO)),
+             "gj_batch": (cfg[9], C.sizeof(Batch))}
     for name, (c_size, py_size) in sizes.items():
         if c_size != py_size:
             raise GradJuneLibraryError(f"ABI mismatch for {name}: library {c_size} bytes, binding {py_size} bytes")

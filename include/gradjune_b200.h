@@ -338,7 +338,7 @@ int gj_abi_version(void);
 const char* gj_last_error(void);
 /* out[0]=GJ_SMALL_GROUP, out[1]=GJ_CHUNK, out[2]=sizeof(gj_world_desc), out[3]=sizeof(gj_step_params),
  * out[4]=sizeof(gj_fwd_io), out[5]=sizeof(gj_bwd_io), out[6]=reduction grid size, out[7]=GJ_TILE_AGENTS,
- * out[8]=GJ_SCATTER_MAX_GROUP */
+ * out[8]=GJ_SCATTER_MAX_GROUP, out[9]=sizeof(gj_batch) */
 int gj_config(int64_t* out, int n);
 /* bytes of the caller-provided scratch buffer (zero it once; the library leaves it zeroed) */
 int64_t gj_scratch_bytes(const gj_world_desc* w);

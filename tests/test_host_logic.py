@@ -317,3 +317,38 @@ def test_tier_policy_one_range_type_and_leisure_cells_only():
     tiers = dict(zip(data.venue_types(), _build(data).type_tier))
     assert tiers["household"] == W.TIER_RANGE and tiers["pair"] == W.TIER_GENERIC
     assert tiers["leisure"] == W.TIER_CELL and tiers["block"] == W.TIER_GENERIC
+
+
+def test_batched_ensemble_host_logic():
+    """Host side of the batched ensemble (no GPU): beta_vector turns per-network [b] log-betas into a [b, K] beta table
+    (uncalibrated scalars broadcast), differentiable per sample; the gj_batch binding has the library's layout; a
+    batched window on a CPU world is refused loudly."""
+    from grad_june import _lib
+    from grad_june.infection_networks import InfectionNetworks
+    from grad_june.infection_networks.base import beta_vector
+    from grad_june.default_config import default_parameters
+
+    params = default_parameters()
+    nets_mod = InfectionNetworks.from_parameters(params)
+    nets = list(nets_mod.networks.values())[:4]
+    b = 3
+    lb = torch.linspace(-0.3, 0.2, b * 2).reshape(b, 2).requires_grad_(True)
+    nets[0].log_beta = lb[:, 0]
+    nets[2].log_beta = lb[:, 1]
+    fixed1, fixed3 = float(nets[1].log_beta), float(nets[3].log_beta)
+    beta = beta_vector(nets, None, None, "cpu")
+    assert tuple(beta.shape) == (b, 4) and beta.is_contiguous()
+    assert torch.allclose(beta[:, 0], 10.0 ** lb[:, 0]) and torch.allclose(beta[:, 2], 10.0 ** lb[:, 1])
+    assert torch.allclose(beta[:, 1], torch.full((b,), 10.0 ** fixed1)) and torch.allclose(beta[:, 3], torch.full((b,), 10.0 ** fixed3))
+    (beta * torch.arange(1.0, b + 1).reshape(b, 1)).sum().backward()
+    expect = torch.log(torch.tensor(10.0)) * (10.0 ** lb.detach()) * torch.arange(1.0, b + 1).reshape(b, 1)
+    assert torch.allclose(lb.grad, expect, rtol=1e-6)
+    # unbatched call unchanged: [K]
+    for n in nets:
+        n.log_beta = torch.tensor(0.25)
+    assert tuple(beta_vector(nets, None, None, "cpu").shape) == (4,)
+    # binding layout = library layout (checked at load time as well)
+    cfg = (ctypes.c_int64 * 10)()
+    assert _lib.lib().gj_config(cfg, 10) == 10 and cfg[9] == ctypes.sizeof(_lib.Batch)
+    for sym in ("gj_step_forward_batch", "gj_step_backward_batch"):
+        assert hasattr(_lib.lib(), sym)
