@@ -61,7 +61,7 @@ with open(dst + "_kernels.csv", "w") as f:
 import datetime
 import json
 
-ids = {"k_lean_transmission": "transmission", "k_pipe_forward": "agent_forward", "k_lean_forward": "agent_forward",
+ids = {"k_lean_transmission": "transmission", "k_lean_transmission_c": "transmission", "k_pipe_forward": "agent_forward", "k_lean_forward": "agent_forward",
        "k_pipe_backward_gather": "backward_gather", "k_lean_backward_gather": "backward_gather",
        "k_pipe_backward": "agent_backward", "k_lean_backward": "agent_backward", "k_lean_group_sums": "group_sums",
        "k_lean_group_fix": "group_fix", "k_lean_scatter_finalize": "group_small<fwd>", "k_lean_seed": "seeding"}
@@ -91,7 +91,7 @@ json.dump({"agents": n_agents, "git": git, "when": datetime.datetime.now(datetim
 
 # ---- stall samples by source line for the agent kernels ---------------------------------------------
 for k in ("k_pipe_forward", "k_pipe_backward", "k_pipe_backward_gather", "k_lean_forward", "k_lean_backward",
-          "k_lean_backward_gather", "k_lean_transmission", "k_lean_group_sums"):
+          "k_lean_backward_gather", "k_lean_transmission", "k_lean_transmission_c", "k_lean_group_sums"):
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass",
                           "--kernel-name-base", "function", "--kernel-name", "regex:^" + k + "$", "--launch-count", "1"],
                          capture_output=True, text=True).stdout
