@@ -619,11 +619,14 @@ static int lean_grid(const gj_world_desc* w, K kernel, OccCache* cache, const Ba
 }
 
 // bulk-copy pipelined kernels (gj_pipe.cuh): on unless GJ_PIPE=0; they need 16-byte aligned per-agent arrays
-static int g_pipe_on = -1;   // bit 0: pipelined agent kernels, bit 1: look-ahead transmission pass
+static int g_pipe_on = -1;   // bit 0: pipelined agent kernels, bit 1: look-ahead transmission pass,
+                             // bit 2: the UNCOMPACTED transmission pass (k_lean_transmission instead of _c)
 static int pipe_flags() {
   if (g_pipe_on < 0) {
     const char* e = getenv("GJ_PIPE");
-    g_pipe_on = (e && e[0] >= '0' && e[0] <= '3') ? (e[0] - '0') : 1;   // look-ahead off: measured neutral
+    g_pipe_on = (e && e[0] >= '0' && e[0] <= '7') ? (e[0] - '0') : 1;   // look-ahead off: measured neutral
+    const char* c = getenv("GJ_K1C");
+    if (c && c[0] == '0') g_pipe_on |= 4;
   }
   return g_pipe_on;
 }
@@ -850,11 +853,7 @@ static int lean_forward(const gj_world_desc* w, const gj_step_params* p, const P
   launch_pdl(k_lean_transmission_c<Q, B>, dim3(lean_grid(w, k_lean_transmission_c<Q, B>, &occ_c[I], bt)),              \
              dim3(kLeanThreads), 0, st, *w, *p, lp, *io, sc.tile_part, sct, bt)
       static OccCache occ_c[4];
-      static int compact = -1;   // GJ_K1C=0: the uncompacted pass (measurement switch)
-      if (compact < 0) {
-        const char* e = getenv("GJ_K1C");
-        compact = (e && e[0] == '0') ? 0 : 1;
-      }
+      const bool compact = (pipe_flags() & 4) == 0;   // gj_pipeline_enable bit 2 / GJ_K1C=0: the uncompacted pass
       if (compact) {
         if (batch) {
           if (quar) GJ_K1C(true, true, 3);
@@ -1326,7 +1325,7 @@ int gj_peer_destroy(gj_peer* p) {
 
 int gj_pipeline_enable(int on) {
   const int prev = pipe_flags();
-  if (on >= 0) g_pipe_on = on & 3;
+  if (on >= 0) g_pipe_on = on & 7;
   return prev;
 }
 

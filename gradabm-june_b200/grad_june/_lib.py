@@ -259,11 +259,14 @@ EXPORTED_SYMBOLS = [
 ]
 
 
-def pipeline_enable(on=True, lookahead=False):
+def pipeline_enable(on=True, lookahead=False, uncompacted=False):
     """Bulk-copy pipelined agent kernels on/off (bit-identical results) and, with them, the fused transmission pass
-    of the following step (``lookahead``); returns the previous setting as (on, lookahead).  ``on=None`` queries."""
-    prev = lib().gj_pipeline_enable(-1 if on is None else ((1 if on else 0) | (2 if (on and lookahead) else 0)))
-    return bool(prev & 1), bool(prev & 2)
+    of the following step (``lookahead``); ``uncompacted`` selects the transmission pass without the per-warp
+    compaction of the infectious agents.  Returns the previous setting as (on, lookahead, uncompacted).
+    ``on=None`` queries."""
+    prev = lib().gj_pipeline_enable(-1 if on is None else ((1 if on else 0) | (2 if (on and lookahead) else 0)
+                                                           | (4 if uncompacted else 0)))
+    return bool(prev & 1), bool(prev & 2), bool(prev & 4)
 
 
 def profile_enable(on=True):

@@ -448,7 +448,9 @@ int gj_peer_destroy(gj_peer* peer);
  * and readable up to the next multiple of 16 bytes past its end (true of any allocator with >= 16-byte granules);
  * 0: register-batched loads.  Results are bit-identical.  on < 0 only queries.  Returns the previous setting.
  * Bit 1 of `on` (value 2, default clear: measured neutral on B200) allows gj_step_forward_next to
- * produce the look-ahead. */
+ * produce the look-ahead.  Bit 2 (value 4, default clear) selects the uncompacted transmission pass
+ * (k_lean_transmission) instead of the per-warp compacted one (k_lean_transmission_c): same T bit for bit, the
+ * partial sums of the cell channels associated differently. */
 int gj_pipeline_enable(int on);
 
 /* ---- measurement (bench.py): CUDA events recorded on the launching stream around every kernel ---- */

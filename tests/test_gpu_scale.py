@@ -278,6 +278,47 @@ def _compare_throughput_with_reference_order(n_agents, data, model, timer, state
     H.report("throughput vs reference-order kernels, one step: mask mismatches", int(len(mism)))
 
 
+@pytest.mark.parametrize("quarantine", [False, True])
+def test_compacted_transmission_pass(quarantine):
+    """k_lean_transmission_c (the infectious agents compacted per warp: the default) against k_lean_transmission on the
+    same mid-epidemic state and Philox stream: transmissions bit-identical; the per-thread partial sums of the leisure
+    channels are associated differently, so q agrees to fp32 rounding and draws differ only at near-ties."""
+    from grad_june import _lib, ops
+    n_agents = 250_003
+    params, data, model, timer, state = _setup(n_agents, seed=21)
+    if not quarantine:      # _setup's parameters carry an active quarantine policy
+        from grad_june.policies import Policies
+        params = dict(params)
+        params["policies"] = {}
+        model.policies = Policies.from_parameters(params)
+    assert model.kernel_family(data, timer) == "throughput"
+    outs = {}
+    prev = _lib.pipeline_enable(None)
+    try:
+        for uncompacted in (True, False):
+            _lib.pipeline_enable(True, lookahead=False, uncompacted=uncompacted)
+            for k in ("susceptibility", "is_infected", "infection_time"):
+                data["agent"][k] = state[k]
+            data["agent"].symptoms = {k: state[k] for k in ("current_stage", "next_stage", "time_to_next_stage")}
+            with ops.philox_seed(55):
+                _, red = model.step(data, timer, age_bins=(0, 18, 65, 100))
+            agent = data["agent"]
+            outs[uncompacted] = dict(T=agent.transmission.detach().clone(), q=agent["not_infected_probs"].detach().clone(),
+                                     n=agent["new_infected"].detach().clone(), red=red.detach().clone(),
+                                     cur=agent.symptoms["current_stage"].detach().clone())
+    finally:
+        _lib.pipeline_enable(*prev)
+    a, b = outs[True], outs[False]
+    assert int((a["T"] != 0).sum()) > 1000
+    assert torch.equal(a["T"], b["T"])
+    rel = ((a["q"] - b["q"]).abs() / a["q"].clamp_min(1e-30)).max()
+    assert float(rel) < 2e-6, float(rel)
+    flips = int((a["n"] != b["n"]).sum())
+    assert flips <= 2, flips
+    assert torch.allclose(a["red"], b["red"], atol=flips + 0.5)
+    H.report("compacted vs uncompacted transmission pass: draw flips", flips)
+
+
 def test_throughput_mode_bptt_window():
     """Five timesteps of Runner() + backward (BPTT through the fused step) in throughput mode against the
     reference-order kernels on the same Philox stream: identical trajectories (unless a near-tie flips an
