@@ -15,6 +15,17 @@ import torch
 from .graphed import GraphedRunner
 
 
+def ensemble_deal(n_samples: int, world_size: int, rank: int, batch: Optional[int] = None):
+    """Which samples ``rank`` evaluates, and in which replays: sample i goes to rank i % world_size (round-robin), a
+    rank's samples are taken ``batch`` at a time (one at a time without batching).  Returns (rows per rank in the
+    gathered table — the last ranks' rows may be padding — and the list of replays, each a list of sample indices).
+    Row j of rank r in the gathered table is sample j * world_size + r."""
+    per = -(-n_samples // world_size)
+    mine = [j * world_size + rank for j in range(per) if j * world_size + rank < n_samples]
+    step = int(batch) if batch else 1
+    return per, [mine[j0:j0 + step] for j0 in range(0, len(mine), step)]
+
+
 class EnsembleEvaluator:
     def __init__(self, runner, loss_fn: Callable[[dict], torch.Tensor], networks: Optional[Sequence[str]] = None,
                  seed: int = 0, process_group=None, batch: Optional[int] = None):
@@ -40,16 +51,17 @@ class EnsembleEvaluator:
         mine = torch.zeros(per, K + 1, device=dev)
         if self.batch:
             b = self.batch
-            ids = torch.arange(per, device=dev) * self.world_size + self.rank      # this rank's samples
-            ids = ids[ids < B]
-            for j0 in range(0, ids.numel(), b):
-                chunk = ids[j0:j0 + b]
-                lb = log_betas[chunk]
-                if chunk.numel() < b:                         # the last replay is padded with copies of its first row
-                    lb = torch.cat([lb, lb[:1].expand(b - chunk.numel(), K)])
+            _, replays = ensemble_deal(B, self.world_size, self.rank, b)
+            j0 = 0
+            for chunk in replays:                             # chunk: up to b sample indices of this rank
+                n = len(chunk)
+                lb = log_betas[torch.tensor(chunk, device=dev)]
+                if n < b:                                     # the last replay is padded with copies of its first row
+                    lb = torch.cat([lb, lb[:1].expand(b - n, K)])
                 loss, grads, _ = self.graphed(lb)
-                mine[j0:j0 + chunk.numel(), 0] = loss[: chunk.numel()]
-                mine[j0:j0 + chunk.numel(), 1:] = grads[: chunk.numel()]
+                mine[j0:j0 + n, 0] = loss[:n]
+                mine[j0:j0 + n, 1:] = grads[:n]
+                j0 += n
         for j in range(per if not self.batch else 0):
             i = j * self.world_size + self.rank               # round-robin: sample i goes to rank i % world_size
             if i >= B:

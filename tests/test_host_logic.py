@@ -352,3 +352,20 @@ def test_batched_ensemble_host_logic():
     assert _lib.lib().gj_config(cfg, 10) == 10 and cfg[9] == ctypes.sizeof(_lib.Batch)
     for sym in ("gj_step_forward_batch", "gj_step_backward_batch"):
         assert hasattr(_lib.lib(), sym)
+
+
+@pytest.mark.parametrize("n_samples,world_size,batch", [(5, 1, 2), (1024, 8, 8), (13, 4, 3), (7, 8, None), (16, 2, 1)])
+def test_ensemble_deal_covers_every_sample_once(n_samples, world_size, batch):
+    """EnsembleEvaluator's dealing of samples to ranks and replays: every sample evaluated exactly once, at most
+    ``batch`` per replay, and the gathered table's row (j, rank) is sample j * world_size + rank."""
+    from grad_june.calibration import ensemble_deal
+    seen = []
+    for rank in range(world_size):
+        per, replays = ensemble_deal(n_samples, world_size, rank, batch)
+        assert per == -(-n_samples // world_size)
+        flat = [i for chunk in replays for i in chunk]
+        assert all(1 <= len(chunk) <= (batch or 1) for chunk in replays)
+        assert flat == [j * world_size + rank for j in range(len(flat))]      # row j of this rank
+        assert len(flat) <= per
+        seen += flat
+    assert sorted(seen) == list(range(n_samples))
