@@ -369,3 +369,43 @@ def test_ensemble_deal_covers_every_sample_once(n_samples, world_size, batch):
         assert len(flat) <= per
         seen += flat
     assert sorted(seen) == list(range(n_samples))
+
+
+def test_batched_window_start_and_cpu_refusal():
+    """Runner.batch = b: the window starts from b copies of the backed-up state, rows padded to a multiple of four
+    agents (zeros), cached per batch size; a batched window on CPU tensors is refused (no CPU fallback)."""
+    from grad_june import GradJune, Timer
+    from grad_june.default_config import default_parameters
+    from grad_june.runner import Runner
+    from grad_june.world import make_synthetic_world
+    params = default_parameters()
+    params["system"]["device"] = "cpu"
+    params["timer"]["total_days"] = 2
+    torch.manual_seed(3)
+    data = Runner.get_data(params, data=make_synthetic_world(4001, seed=3, device="cpu", agents_per_super_area=1000))
+    n = len(data["agent"].id)
+    runner = Runner(model=GradJune.from_parameters(params), data=data, timer=Timer.from_parameters(params),
+                    log_fraction_initial_cases=-1.5, save_path="/tmp/gj_test_host", parameters=params)
+    runner.data_backup["infection_time"][5] = 2.5
+    runner.batch = 3
+    runner._restore_for_window()
+    agent = runner.data["agent"]
+    n_pad = (n + 3) // 4 * 4
+    for t in (agent.susceptibility, agent.is_infected, agent.infection_time, agent.symptoms["current_stage"],
+              agent.symptoms["next_stage"], agent.symptoms["time_to_next_stage"]):
+        assert tuple(t.shape) == (3, n_pad) and t.dtype == torch.float32 and t.is_contiguous()
+        assert torch.equal(t[0], t[2]) and float(t[:, n:].abs().sum()) == 0.0
+    assert torch.equal(agent.infection_time[1, :n], runner.data_backup["infection_time"])
+    assert torch.equal(agent.susceptibility[2, :n], torch.ones(n))
+    first = agent.susceptibility
+    runner._restore_for_window()
+    assert runner.data["agent"].susceptibility is first          # cached
+    runner.batch = 2
+    runner._restore_for_window()
+    assert tuple(runner.data["agent"].susceptibility.shape) == (2, n_pad)
+    runner.restore_initial_data()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        runner()
+    runner.batch = None
+    runner.restore_initial_data()
+    assert tuple(runner.data["agent"].susceptibility.shape) == (n,)
