@@ -381,7 +381,9 @@ def measure(args, ctx, scaling, graph, full=True):
     if B:
         # batched ensemble: every replay steps B of this rank's samples through gj_step_*_batch
         from grad_june.graphed import GraphedRunner
-        assert n_samples % B == 0, "--samples per GPU must be a multiple of --batch"
+        if n_samples % B:
+            raise SystemExit(f"--batch {B}: needs --parallelism ensemble with --samples a multiple of gpus x batch "
+                             f"(this rank has {n_samples} sample(s))")
         loss_fn_b = lambda r: r["cases_per_timestep"].sum(0) + r["deaths_per_timestep"].sum(0)   # noqa: E731
 
         def eager_batched(lb):          # the same window through the Python loop (per-kernel events need eager launches)
